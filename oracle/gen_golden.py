@@ -1,0 +1,250 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference (/root/reference/preds)
+through ``oracle/refharness``.  Run in the build container only:
+
+    python oracle/gen_golden.py
+
+TEST INFRASTRUCTURE.  The fixtures travel to the GPU box; the reference does not.
+Every case stores its inputs (X, y, theta, prior, injected normals) and the reference outputs:
+Jacobians (preds/gradients.py:20-46), likelihood Hessian (preds/likelihoods.py), the full GGN
+precision (preds/laplace.py:41-42), Sigma_chol for full/diag (preds/laplace.py:43-45,60), the
+Kronecker factors (preds/laplace.py:69-78), and the GLM / BNN predictives
+(preds/predictives.py:50-76, :12-28) for the injected draws.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refharness  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def randn(seed, *shape):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def flat(model):
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def kron_eps(model, S, seed):
+    eps = []
+    for i, p in enumerate(model.parameters()):
+        if p.dim() == 1:
+            eps.append(randn(seed + i, p.shape[0], S))
+        else:
+            eps.append(randn(seed + i, S, p.shape[0], p[0].numel()))
+    return eps
+
+
+def run_case(preds, name, model, lh, batches, Xte, prior, S, lh_desc, store_full=True):
+    """Run every hot-path entry of the reference on one configuration."""
+    from preds.laplace import Laplace
+    from preds.gradients import Jacobians
+    from preds.optimizers import GGN
+
+    out = {'lh': np.array(lh_desc), 'prior': np.array(prior, dtype=np.float64),
+           'theta': np_(flat(model)), 'Xte': np_(Xte), 'n_batches': np.array(len(batches))}
+    for i, (X, y) in enumerate(batches):
+        out['X%d' % i], out['y%d' % i] = np_(X), np_(y)
+    P = len(out['theta'])
+    K = model.output_size
+    is_gauss = type(lh).__name__ == 'GaussianLh'
+    can_backpack = type(lh).__name__ != 'BernoulliLh'
+
+    # Jacobians + GGN bundle of the first batch
+    X0, y0 = batches[0]
+    Js, f = Jacobians(model, X0)
+    out['Js0'], out['f0'] = np_(Js), np_(f)
+    Jb, Hess, rs, _ = GGN(model, lh, X0, y0, ret_f=True)
+    out['Hess0'], out['rs0'] = np_(Hess), np_(rs)
+
+    # full GGN precision exactly as preds/laplace.py:38-42
+    lap = Laplace(model, prior, lh)
+    precision = lap.expand_prior_precision('full')
+    for X, y in batches:
+        Jb, Hess, rs, _ = GGN(model, lh, X, y, ret_f=True)
+        precision += torch.einsum('mpk,mkl,mql->pq', Jb, Hess, Jb)
+    out['H_full'] = np_(precision)
+
+    eps_glm = randn(711, S, len(Xte), K)
+    eps_bnn = randn(712, P, S)
+    out['eps_glm'], out['eps_bnn'] = np_(eps_glm), np_(eps_bnn)
+
+    cov_types = ['full'] + (['diag', 'kron'] if can_backpack else [])
+    for cov in cov_types:
+        lap = Laplace(model, prior, lh)
+        lap.infer(batches, cov_type=cov)
+        if cov == 'kron':
+            kron = lap.Sigma_chol
+            for pi, qh in enumerate(kron.qhs):
+                for fi, m in enumerate(qh):
+                    out['kron_q_%d_%d' % (pi, fi)] = np_(m)
+        else:
+            out['Sigma_chol_' + cov] = np_(lap.Sigma_chol)
+        # GLM predictive
+        with refharness.inject_normals([eps_glm]):
+            res = lap.predictive_samples_glm(Xte, n_samples=S)
+        if is_gauss:
+            out['glm_fmu_' + cov], out['glm_fvar_' + cov] = np_(res[0]), np_(res[1])
+        else:
+            out['glm_' + cov] = np_(res)
+            from preds.predictives import functional_sampling_predictive  # moments via Gaussian
+            from preds.likelihoods import GaussianLh
+            Sig = lap.Sigma if cov != 'kron' else lap.Sigma_chol
+            fmu, fvar = functional_sampling_predictive(Xte, model, GaussianLh(), lap.mu, Sig, S)
+            out['glm_fmu_' + cov], out['glm_fvar_' + cov] = np_(fmu), np_(fvar)
+        # BNN predictive
+        if cov == 'kron':
+            eps_k = kron_eps(model, S, 900)
+            for i, e in enumerate(eps_k):
+                out['eps_kron_%d' % i] = np_(e)
+            with refharness.inject_normals(eps_k):
+                res = lap.predictive_samples_bnn(Xte, n_samples=S)
+            # dampened variant toggled after inference (experiments/imginference.py:160)
+            kron.dampen = True
+            with refharness.inject_normals(eps_k):
+                out['bnn_kron_dampen'] = np_(lap.predictive_samples_bnn(Xte, n_samples=S))
+            from preds.predictives import functional_sampling_predictive
+            from preds.likelihoods import GaussianLh
+            fmu, fvar = functional_sampling_predictive(Xte, model, GaussianLh(), lap.mu, kron, S)
+            out['glm_fvar_kron_dampen'] = np_(fvar)
+            kron.dampen = False
+        else:
+            with refharness.inject_normals([eps_bnn]):
+                res = lap.predictive_samples_bnn(Xte, n_samples=S)
+        out['bnn_' + cov] = np_(res)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('%-12s P=%d K=%d  %.1f KB' % (name, P, K, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
+
+
+def probe_case(preds, name):
+    """Full-size CIFAR10Net (reference tests' own fixture: seed 71, in_channels=2, n_out=3,
+    X seed 15 -- tests/test_jacobians.py:9-30): tensors too large to store, so the fixture
+    holds seeded random probes of them."""
+    from preds.models import CIFAR10Net
+    from preds.likelihoods import CategoricalLh
+    from preds.laplace import Laplace
+    from preds.gradients import Jacobians
+    torch.manual_seed(71)
+    model = CIFAR10Net(in_channels=2, n_out=3)
+    torch.manual_seed(15)
+    X = torch.randn(8, 2, 28, 28)
+    y = torch.softmax(randn(15, 8, 3), dim=1).argmax(dim=1)
+    theta = flat(model)
+    P = len(theta)
+    g = torch.Generator().manual_seed(4242)
+    idx = torch.randperm(P, generator=g)[:4096]
+    v = randn(4243, P)
+    out = {'theta_idx': np_(idx), 'theta_at_idx': np_(theta[idx]), 'theta_dot_v': np_(theta @ v),
+           'y': np_(y)}
+    Js, f = Jacobians(model, X)
+    out['f'] = np_(f)
+    out['Js_at_idx'] = np_(Js[:, idx, :])
+    out['Js_dot_v'] = np_(torch.einsum('npk,p->nk', Js, v))
+    lh = CategoricalLh()
+    lap = Laplace(model, 1.0, lh)
+    lap.infer([(X[:5], y[:5]), (X[5:], y[5:])], cov_type='diag')
+    prec = 1 / lap.Sigma_chol ** 2
+    out['diag_prec_at_idx'] = np_(prec[idx])
+    out['diag_prec_sum'] = np_(prec.double().sum())
+    lap = Laplace(model, 1.0, lh)
+    lap.infer([(X[:5], y[:5]), (X[5:], y[5:])], cov_type='kron')
+    for pi, qh in enumerate(lap.Sigma_chol.qhs):
+        for fi, m in enumerate(qh):
+            pv = randn(5000 + 10 * pi + fi, m.shape[0])
+            out['kron_q_%d_%d_mv' % (pi, fi)] = np_(m @ pv)
+            out['kron_q_%d_%d_tr' % (pi, fi)] = np_(m.diagonal().double().sum())
+    Xte = randn(16, 3, 2, 28, 28)
+    S = 4
+    eps_glm = randn(711, S, 3, 3)
+    with refharness.inject_normals([eps_glm]):
+        out['glm_kron'] = np_(lap.predictive_samples_glm(Xte, n_samples=S))
+    from preds.predictives import functional_sampling_predictive
+    from preds.likelihoods import GaussianLh
+    fmu, fvar = functional_sampling_predictive(Xte, model, GaussianLh(), lap.mu, lap.Sigma_chol, S)
+    out['glm_fmu_kron'], out['glm_fvar_kron'] = np_(fmu), np_(fvar)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('%-12s P=%d  %.1f KB' % (name, P, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
+
+
+def main():
+    preds = refharness.load()
+    from preds.models import MLPS
+    from preds.likelihoods import CategoricalLh, GaussianLh, BernoulliLh
+    from deepobs.pytorch.testproblems.testproblems_utils import tfconv2d, tfmaxpool2d
+    os.makedirs(OUT, exist_ok=True)
+
+    # (A) banana-shaped classifier (config 1 shape, narrower), two loader batches
+    torch.manual_seed(71)
+    model = MLPS(2, [10, 10], 2, 'tanh')
+    X = randn(15, 48, 2)
+    y = torch.randint(2, (48,), generator=torch.Generator().manual_seed(15))
+    run_case(preds, 'mlp_cls', model, CategoricalLh(), [(X[:32], y[:32]), (X[32:], y[32:])],
+             randn(16, 6, 2), 0.7, 5, 'categorical')
+
+    # (B) relu, K=3, single batch, confident logits (x6) to exercise the softmax clamp
+    torch.manual_seed(72)
+    model = MLPS(5, [12], 3, 'relu')
+    with torch.no_grad():
+        list(model.parameters())[-2].mul_(6.0)
+    X = randn(17, 40, 5) * 3
+    y = torch.randint(3, (40,), generator=torch.Generator().manual_seed(18))
+    run_case(preds, 'mlp_relu3', model, CategoricalLh(), [(X, y)], randn(19, 7, 5), 1.3, 6,
+             'categorical')
+
+    # (C) regression K=1 (GaussianLh): predictive returns moments
+    torch.manual_seed(73)
+    model = MLPS(3, [8], 1, 'tanh')
+    X = randn(20, 30, 3)
+    y = randn(21, 30, 1)
+    run_case(preds, 'mlp_reg', model, GaussianLh(0.6), [(X[:20], y[:20]), (X[20:], y[20:])],
+             randn(22, 5, 3), 2.0, 4, 'gaussian:0.6')
+
+    # (D) flatten + no bias
+    torch.manual_seed(74)
+    model = MLPS(16, [8, 6], 4, 'tanh', flatten=True, bias=False)
+    X = randn(23, 24, 1, 4, 4)
+    y = torch.randint(4, (24,), generator=torch.Generator().manual_seed(24))
+    run_case(preds, 'mlp_flat', model, CategoricalLh(), [(X, y)], randn(25, 5, 1, 4, 4), 0.5, 5,
+             'categorical')
+
+    # (E) Bernoulli K=1: full covariance only (preds/likelihoods.py:74-75)
+    torch.manual_seed(75)
+    model = MLPS(4, [7], 1, 'tanh')
+    X = randn(26, 36, 4)
+    y = torch.randint(2, (36, 1), generator=torch.Generator().manual_seed(27)).float()
+    run_case(preds, 'mlp_bern', model, BernoulliLh(), [(X, y)], randn(28, 5, 4), 1.0, 4,
+             'bernoulli')
+
+    # (F) tiny CNN from the same building blocks as preds/models.py:239-285
+    torch.manual_seed(76)
+    model = torch.nn.Sequential()
+    model.add_module('conv1', tfconv2d(2, 4, 3, tf_padding_type='same'))
+    model.add_module('relu1', torch.nn.ReLU())
+    model.add_module('pool1', tfmaxpool2d(3, stride=2, tf_padding_type='same'))
+    model.add_module('conv2', tfconv2d(4, 5, 3))
+    model.add_module('tanh2', torch.nn.Tanh())
+    model.add_module('flatten', torch.nn.Flatten())
+    model.add_module('dense', torch.nn.Linear(45, 3))
+    model.output_size = 3
+    X = randn(29, 20, 2, 9, 9)
+    y = torch.randint(3, (20,), generator=torch.Generator().manual_seed(30))
+    run_case(preds, 'cnn_tiny', model, CategoricalLh(), [(X[:12], y[:12]), (X[12:], y[12:])],
+             randn(31, 4, 2, 9, 9), 0.9, 5, 'categorical')
+
+    # (G) the reference tests' own CIFAR10Net fixture, probed
+    probe_case(preds, 'cifar10net_probe')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,519 @@
+"""CPU restatement ("port") of the Laplace-GGN hot path of aleximmer/BNN-predictions.
+
+TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this module, and only as
+the checker / the timed CPU baseline.  The product package (``bnn-predictions_b200/preds_b200``)
+never imports it and has no CPU fallback.
+
+Parity status: PINNED.  Every function below is checked (``tests/test_oracle_golden.py``)
+against fixtures in ``tests/golden/`` that were produced by running the UNMODIFIED reference
+(``/root/reference/preds``) through ``oracle/refharness`` with ``oracle/gen_golden.py``; in the
+build container the same tests also compare live against the reference.  The one part of the
+reference's arithmetic that lives in an absent third-party dependency is BackPACK 1.1.1
+(``requirements.txt:4``): ``BatchGrad`` is pinned by the reference's own
+``tests/test_jacobians.py:60-66`` (vs. pure autograd); ``DiagGGNExact`` by the identity
+``diag == diag(full GGN)``; ``KFLR`` for Linear layers and all biases by the N=1 identity
+``G (x) A == exact block``.  Conv-weight KFLR values (spatial pre-sum in G) follow the published
+BackPACK ``HBPConv2d`` definition and are *unpinned by any reference test* (SURVEY.md 8c).
+
+Everything is float32 torch on the CPU, written as plain functions with explicit
+standard-normal draws (``eps``) so the CUDA path can be fed identical numbers.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+CLAMP_EPS = 1e-7          # preds/likelihoods.py:4
+
+
+# ------------------------------------------------------------------------------------------
+# models  (preds/models.py:91-122, :239-285; deepobs tfconv2d/tfmaxpool2d semantics)
+# ------------------------------------------------------------------------------------------
+class SamePad2d(nn.Module):
+    """TF-"same" zero padding in front of a conv/pool with padding=0 (Appendix A of SURVEY.md):
+    out = ceil(in/stride); pad = max((out-1)*stride + k - in, 0); left/top = pad//2."""
+
+    def __init__(self, kernel, stride):
+        super().__init__()
+        self.kernel, self.stride = kernel, stride
+
+    def pads(self, H, W):
+        k, s = self.kernel, self.stride
+        ph = max((math.ceil(H / s) - 1) * s + k - H, 0)
+        pw = max((math.ceil(W / s) - 1) * s + k - W, 0)
+        return (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2)
+
+    def forward(self, x):
+        return F.pad(x, self.pads(x.shape[2], x.shape[3]))
+
+
+def make_mlps(input_size, hidden_sizes, output_size, activation='tanh', flatten=False, bias=True):
+    """Sequential MLP with module activations; restates preds/models.py:91-122."""
+    act = {'relu': nn.ReLU, 'tanh': nn.Tanh}[activation]
+    layers = [nn.Flatten()] if flatten else []
+    sizes = [input_size] + list(hidden_sizes)
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        layers += [nn.Linear(a, b, bias=bias), act()]
+    layers.append(nn.Linear(sizes[-1], output_size if output_size is not None else 1, bias=bias))
+    net = nn.Sequential(*layers)
+    net.output_size = output_size if output_size is not None else 1
+    return net
+
+
+def make_cifar10net(in_channels=3, n_out=10, use_tanh=False):
+    """DeepOBS 3c3d network; restates preds/models.py:239-285 (flat module list)."""
+    act = nn.Tanh if use_tanh else nn.ReLU
+    net = nn.Sequential(
+        nn.Conv2d(in_channels, 64, 5), nn.ReLU(), SamePad2d(3, 2), nn.MaxPool2d(3, 2),
+        nn.Conv2d(64, 96, 3), nn.ReLU(), SamePad2d(3, 2), nn.MaxPool2d(3, 2),
+        SamePad2d(3, 1), nn.Conv2d(96, 128, 3), nn.ReLU(), SamePad2d(3, 2), nn.MaxPool2d(3, 2),
+        nn.Flatten(),
+        nn.Linear(3 * 3 * 128, 512), act(), nn.Linear(512, 256), act(), nn.Linear(256, n_out))
+    for m in net.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.constant_(m.bias, 0.0)
+            nn.init.xavier_normal_(m.weight)
+        if isinstance(m, nn.Linear):
+            nn.init.constant_(m.bias, 0.0)
+            nn.init.xavier_uniform_(m.weight)
+    net.output_size = n_out
+    return net
+
+
+def n_params(model):
+    return sum(p.numel() for p in model.parameters())
+
+
+def get_theta(model):
+    return torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+
+
+def set_theta(model, theta):
+    off = 0
+    with torch.no_grad():
+        for p in model.parameters():
+            p.copy_(theta[off:off + p.numel()].reshape(p.shape))
+            off += p.numel()
+
+
+# ------------------------------------------------------------------------------------------
+# likelihoods  (preds/likelihoods.py)
+# ------------------------------------------------------------------------------------------
+class CategoricalLh:
+    name = 'categorical'
+
+    def inv_link(self, f):                       # :95-96
+        return torch.softmax(f, dim=-1)
+
+    def hessian(self, f):                        # :90-93  (clamped softmax)
+        p = self.inv_link(f).clamp(CLAMP_EPS, 1 - CLAMP_EPS)
+        return torch.diag_embed(p) - p.unsqueeze(2) * p.unsqueeze(1)
+
+    def residual(self, y, f):                    # :84-88
+        onehot = torch.zeros_like(f)
+        onehot[torch.arange(len(y)), y.long()] = 1
+        return onehot - self.inv_link(f)
+
+    def hess_factor(self):                       # :98-99  nn_loss -> (CE(sum), 1)
+        return 1.0
+
+    def loss_hessian_sqrt(self, f):
+        """BackPACK CrossEntropyLoss sqrt-Hessian, UNclamped softmax (Appendix A)."""
+        p = torch.softmax(f, dim=1)
+        sq = p.sqrt()
+        return torch.diag_embed(sq) - p.unsqueeze(2) * sq.unsqueeze(1)
+
+
+class GaussianLh:
+    name = 'gaussian'
+
+    def __init__(self, sigma_noise=1.0):
+        self.sigma_noise = sigma_noise
+
+    def inv_link(self, f):                       # :54-55
+        return f
+
+    def hessian(self, f):                        # :50-52
+        assert f.size(1) == 1
+        return torch.ones_like(f).unsqueeze(-1) / self.sigma_noise ** 2
+
+    def residual(self, y, f):                    # :47-48
+        return (y - f) / self.sigma_noise ** 2
+
+    def hess_factor(self):                       # :57-58  nn_loss -> (MSE(sum), 1/(2 s^2))
+        return 1.0 / (2 * self.sigma_noise ** 2)
+
+    def loss_hessian_sqrt(self, f):
+        """BackPACK MSELoss(sum) sqrt-Hessian: sqrt(2) I."""
+        N, K = f.shape
+        return math.sqrt(2.0) * torch.eye(K, dtype=f.dtype).expand(N, K, K).clone()
+
+
+class BernoulliLh:
+    name = 'bernoulli'
+
+    def inv_link(self, f):                       # :71-72
+        return torch.sigmoid(f)
+
+    def hessian(self, f):                        # :67-69
+        p = self.inv_link(f).clamp(CLAMP_EPS, 1 - CLAMP_EPS)
+        return p * (1 - p)
+
+    def residual(self, y, f):                    # :25-26
+        return y - self.inv_link(f)
+
+    def hess_factor(self):                       # :74-75
+        raise ValueError('No extendable nn loss for backpack in Bernoulli case')
+
+
+# ------------------------------------------------------------------------------------------
+# per-sample layer quantities (BackPACK BatchGrad / DiagGGNExact / KFLR, Appendix A)
+# ------------------------------------------------------------------------------------------
+def _param_layers(model):
+    return [m for m in model.modules() if isinstance(m, (nn.Linear, nn.Conv2d))]
+
+
+def _forward_recording(model, X):
+    """Forward pass keeping every parameterised layer's input and (graph-attached) output."""
+    rec, handles = [], []
+    for m in _param_layers(model):
+        handles.append(m.register_forward_hook(
+            lambda mod, inp, out, rec=rec: rec.append((mod, inp[0].detach(), out))))
+    try:
+        f = model(X)
+    finally:
+        for h in handles:
+            h.remove()
+    return f, rec
+
+
+def _unfold(m, a):
+    return F.unfold(a, m.kernel_size, dilation=m.dilation, padding=m.padding, stride=m.stride)
+
+
+def jacobians(model, X):
+    """Js [N,P,K] (K last; [N,P] when K == 1) and f [N,K]; restates preds/gradients.py:20-46
+    with BackPACK ``BatchGrad`` written out per layer (Linear: g (x) a; Conv2d: unfold-einsum)."""
+    K = model.output_size
+    N = X.shape[0]
+    cols, f_out = [], None
+    for k in range(K):
+        f, rec = _forward_recording(model, X)
+        if f_out is None:
+            f_out = f.detach()
+        target = f[:, k].sum() if K > 1 else f.sum()
+        grads = torch.autograd.grad(target, [out for (_, _, out) in rec])
+        per_param = {}
+        for (m, a, _), g in zip(rec, grads):
+            if isinstance(m, nn.Linear):
+                per_param[m.weight] = (g.unsqueeze(2) * a.unsqueeze(1)).reshape(N, -1)
+                if m.bias is not None:
+                    per_param[m.bias] = g
+            else:
+                go = g.reshape(N, g.shape[1], -1)
+                per_param[m.weight] = torch.einsum('nil,nol->noi', _unfold(m, a), go).reshape(N, -1)
+                if m.bias is not None:
+                    per_param[m.bias] = go.sum(2)
+        cols.append(torch.cat([per_param[p] for p in model.parameters()], dim=1))
+    if K > 1:
+        return torch.stack(cols, dim=2), f_out
+    return cols[0], f_out
+
+
+def ggn_bundle(model, lh, X, y=None):
+    """(Js [m,p,k], Hess [m,k,k], rs [m,k] | None, f); restates preds/optimizers.py:8-25."""
+    Js, f = jacobians(model, X)
+    Hess = lh.hessian(f)
+    m, p = Js.shape[:2]
+    rs = lh.residual(y, f) if y is not None else None
+    if Js.dim() == 2:
+        Js, Hess = Js.reshape(m, p, 1), Hess.reshape(m, 1, 1)
+        rs = rs.reshape(m, 1) if rs is not None else None
+    return Js, Hess, rs, f
+
+
+def _sqrt_ggn_backprop(model, lh, X):
+    """S_l[v, n, out, (H, W)] for every parameterised layer: the loss-Hessian square root
+    backpropagated to the layer outputs (BackPACK second-order convention, Appendix A)."""
+    f, rec = _forward_recording(model, X)
+    S = lh.loss_hessian_sqrt(f.detach())
+    outs = [out for (_, _, out) in rec]
+    per_v = [torch.autograd.grad(f, outs, grad_outputs=S[:, :, v], retain_graph=True)
+             for v in range(S.shape[2])]
+    Sl = [torch.stack([per_v[v][i] for v in range(S.shape[2])]).detach() for i in range(len(rec))]
+    return rec, Sl
+
+
+def diag_ggn_batch(model, lh, X):
+    """Flat exact GGN diagonal of one batch (no hess_factor); BackPACK ``DiagGGNExact`` as read
+    by preds/laplace.py:14-15,52-59."""
+    rec, Sls = _sqrt_ggn_backprop(model, lh, X)
+    out = {}
+    for (m, a, _), Sl in zip(rec, Sls):
+        V, N = Sl.shape[:2]
+        if isinstance(m, nn.Linear):
+            out[m.weight] = torch.einsum('vno,ni->oi', Sl ** 2, a ** 2)
+            if m.bias is not None:
+                out[m.bias] = (Sl ** 2).sum((0, 1))
+        else:
+            So = Sl.reshape(V, N, Sl.shape[2], -1)
+            JS = torch.einsum('nil,vnol->vnoi', _unfold(m, a), So)
+            out[m.weight] = (JS ** 2).sum((0, 1))
+            if m.bias is not None:
+                out[m.bias] = (So.sum(3) ** 2).sum((0, 1))
+    return torch.cat([out[p].reshape(-1) for p in model.parameters()])
+
+
+def kflr_batch(model, lh, X):
+    """Per-parameter Kronecker factors of one batch, [G, A] for weights / [G] for biases;
+    BackPACK ``KFLR`` as read by preds/laplace.py:73-78 (G sums over the batch, A is a batch mean)."""
+    rec, Sls = _sqrt_ggn_backprop(model, lh, X)
+    out = {}
+    for (m, a, _), Sl in zip(rec, Sls):
+        V, N = Sl.shape[:2]
+        if isinstance(m, nn.Linear):
+            G = torch.einsum('vni,vnj->ij', Sl, Sl)
+            A = a.t() @ a / N
+        else:
+            s = Sl.reshape(V, N, Sl.shape[2], -1).sum(3)
+            G = torch.einsum('vni,vnj->ij', s, s)
+            U = _unfold(m, a)
+            A = torch.einsum('bik,bjk->ij', U, U) / N
+        out[m.weight] = [G, A]
+        if m.bias is not None:
+            out[m.bias] = [G]
+    return [out[p] for p in model.parameters()]
+
+
+# ------------------------------------------------------------------------------------------
+# Kronecker-factored posterior  (preds/kron.py)
+# ------------------------------------------------------------------------------------------
+def symeig(M):
+    """Eigendecomposition from the UPPER triangle, eigenvalues clamped at 0, NaN -> 0;
+    restates preds/kron.py:146-173 (the jitter retry only triggers on LAPACK failure)."""
+    try:
+        L, W = torch.linalg.eigh(M, UPLO='U')
+    except RuntimeError:
+        L, W = torch.linalg.eigh(M + torch.eye(M.shape[0], dtype=M.dtype), UPLO='U')
+        L = L - 1.0
+    L = L.clamp(min=0.0)
+    L[torch.isnan(L)] = 0.0
+    W[torch.isnan(W)] = 0.0
+    return L, W
+
+
+class KronState:
+    """Plain container: qhs (precision factors), Ws/Lams (eigen), deltas, dampen."""
+
+    def __init__(self, model, delta, dampen=False):
+        self.qhs = []                                  # preds/kron.py:25-43
+        for p in model.parameters():
+            if p.dim() == 1:
+                self.qhs.append([torch.zeros(p.shape[0], p.shape[0])])
+            else:
+                m, n = p.shape[0], p[0].numel()
+                self.qhs.append([torch.zeros(m, m), torch.zeros(n, n)])
+        d = torch.as_tensor(delta)                     # :45-56
+        if d.dim() == 0 or (d.dim() == 1 and len(d) == 1):
+            self.deltas = d.reshape(-1)[:1].repeat(len(self.qhs))
+        elif d.dim() == 1:
+            if len(d) != len(self.qhs):
+                raise ValueError('Deltas do not match with parameter groups.')
+            self.deltas = d
+        else:
+            raise ValueError('Invalid dimensionality of delta.')
+        self.dampen = dampen
+        self.Ws = self.Lams = None
+
+    def update(self, krons, factor=1.0, batch_factor=1.0):      # :58-69
+        for kr, qh in zip(krons, self.qhs):
+            if len(kr) == 1:
+                qh[0] += kr[0] * factor
+            elif len(kr) == 2:
+                qh[0] += kr[0] * factor
+                qh[1] += kr[1] * batch_factor
+            else:
+                raise ValueError('..')
+
+    def decompose(self):                                        # :71-83
+        eig = [[symeig(m) for m in qh] for qh in self.qhs]
+        self.Lams = [[e[0] for e in pe] for pe in eig]
+        self.Ws = [[e[1] for e in pe] for pe in eig]
+
+    def sample(self, eps_list):
+        """theta-samples [S,P] ~ N(0, (G (x) A + delta I)^-1) from injected draws, one per
+        parameter in parameters() order: [p,S] for 1-factor, [S,m,n] for 2-factor; :85-110."""
+        parts = []
+        for l, w, delta, eps in zip(self.Lams, self.Ws, self.deltas, eps_list):
+            if len(l) == 1:
+                scale = torch.sqrt(1 / (l[0] + delta)).reshape(-1, 1)
+                parts.append((w[0] @ (scale * (w[0].t() @ eps))).t())
+            else:
+                (l1, l2), (W1, W2) = l, w
+                if self.dampen:
+                    D = torch.sqrt(1 / torch.outer(l1 + torch.sqrt(delta), l2 + torch.sqrt(delta)))
+                else:
+                    D = torch.sqrt(1 / (torch.outer(l1, l2) + delta))
+                z = (W1.t() @ eps @ W2) * D.unsqueeze(0)
+                z = W1 @ z @ W2.t()
+                parts.append(z.reshape(eps.shape[0], -1))
+        return torch.cat(parts, dim=1)
+
+    def functional_variance(self, Js):
+        """J Sigma J^T for Js [B,K,P]; restates preds/kron.py:112-143 (hess_factor = 1)."""
+        B, K, P = Js.shape
+        Jf = Js.reshape(B * K, P)
+        cur, SJ = 0, []
+        for l, w, delta in zip(self.Lams, self.Ws, self.deltas):
+            if len(l) == 1:
+                p = len(l[0])
+                inv = (1 / (l[0] + delta)).reshape(-1, 1)
+                Jp = Jf[:, cur:cur + p].t()
+                SJ.append((w[0] @ (inv * (w[0].t() @ Jp))).t())
+            else:
+                (l1, l2), (W1, W2) = l, w
+                m, n = len(l1), len(l2)
+                p = m * n
+                if self.dampen:
+                    Dinv = 1 / torch.outer(l1 + torch.sqrt(delta), l2 + torch.sqrt(delta))
+                else:
+                    Dinv = 1 / (torch.outer(l1, l2) + delta)
+                Jp = Jf[:, cur:cur + p].reshape(B * K, m, n)
+                Jp = (W1.t() @ Jp @ W2) * Dinv.unsqueeze(0)
+                SJ.append((W1 @ Jp @ W2.t()).reshape(B * K, p))
+            cur += p
+        SJ = torch.cat(SJ, dim=1).reshape(B, K, P)
+        return torch.bmm(Js, SJ.transpose(1, 2))
+
+
+# ------------------------------------------------------------------------------------------
+# Laplace.infer  (preds/laplace.py:30-82, :115-135)
+# ------------------------------------------------------------------------------------------
+def expand_prior_precision(prior_prec, P, cov_type):
+    pp = torch.as_tensor(prior_prec, dtype=torch.float32)
+    if pp.dim() == 0:
+        d = torch.ones(P) * pp
+        return torch.diag(d) if cov_type == 'full' else d
+    if pp.dim() == 1:
+        return torch.diag(pp) if cov_type == 'full' else pp.clone()
+    if pp.dim() == 2:
+        if cov_type == 'diag':
+            raise ValueError('Will not diagonalize non-diagonal prior.')
+        return pp.clone()
+    raise ValueError('Invalid shape for prior precision')
+
+
+def ggn_full_accumulate(model, lh, batches, precision):
+    """precision += sum_batches einsum('mpk,mkl,mql->pq'); preds/laplace.py:39-42."""
+    for X, y in batches:
+        Js, Hess, _, _ = ggn_bundle(model, lh, X, y)
+        precision += torch.einsum('mpk,mkl,mql->pq', Js, Hess, Js)
+    return precision
+
+
+def factorise_full(precision):
+    """chol(H) -> Sigma = cholesky_inverse -> chol(Sigma) (lower); preds/laplace.py:43-45."""
+    chol = torch.linalg.cholesky(precision)
+    Sigma = torch.cholesky_inverse(chol, upper=False)
+    return torch.linalg.cholesky(Sigma)
+
+
+def infer(model, prior_prec, lh, batches, cov_type='full', dampen_kron=False):
+    """Returns dict(mu, cov_type, and one of Sigma_chol [P,P] / Sigma_chol [P] / kron)."""
+    model.eval()
+    batches = list(batches)
+    P = n_params(model)
+    post = {'mu': get_theta(model), 'cov_type': cov_type}
+    if cov_type == 'full':
+        H = ggn_full_accumulate(model, lh, batches, expand_prior_precision(prior_prec, P, 'full'))
+        post['precision'] = H.clone()
+        post['Sigma_chol'] = factorise_full(H)
+    elif cov_type == 'diag':                                   # :47-60
+        hf = lh.hess_factor()
+        prec = expand_prior_precision(prior_prec, P, 'diag')
+        for X, _ in batches:
+            prec = prec + hf * diag_ggn_batch(model, lh, X)
+        post['precision'] = prec
+        post['Sigma_chol'] = torch.sqrt(1 / prec)
+    elif cov_type == 'kron':                                   # :62-80
+        hf = lh.hess_factor()
+        kron = KronState(model, prior_prec, dampen=dampen_kron)
+        N = sum(len(b[0]) for b in batches)
+        for X, y in batches:
+            kron.update(kflr_batch(model, lh, X), factor=hf, batch_factor=len(y) / N)
+        kron.decompose()
+        post['kron'] = kron
+    return post
+
+
+# ------------------------------------------------------------------------------------------
+# predictives  (preds/predictives.py:12-28, :50-76)
+# ------------------------------------------------------------------------------------------
+def glm_moments(model, X, post):
+    """f_mu [N,K], f_var [N,K,K]; restates preds/predictives.py:52-65."""
+    theta_star = get_theta(model)
+    Js, f = jacobians(model, X)
+    Js = Js.transpose(1, 2) if Js.dim() > 2 else Js.unsqueeze(1)
+    f_mu = f + Js @ (post['mu'] - theta_star)
+    if post['cov_type'] == 'kron':
+        f_var = post['kron'].functional_variance(Js)
+    elif post['cov_type'] == 'full':
+        Sigma = post['Sigma_chol'] @ post['Sigma_chol'].t()          # preds/laplace.py:111
+        f_var = torch.einsum('nkp,pq,ncq->nkc', Js, Sigma, Js)
+    else:
+        f_var = torch.einsum('nkp,p,ncp->nkc', Js, post['Sigma_chol'].square(), Js)
+    return f_mu, f_var
+
+
+def glm_predictive(model, lh, X, post, eps):
+    """softmax(f_mu + chol(f_var) eps) -> [S,N,K] for injected eps [S,N,K]; for GaussianLh
+    returns (f_mu, f_var) like preds/predictives.py:66-67.  Cholesky failure falls back to
+    the reference's diagonal branch (variance used as Normal scale, :73-76)."""
+    f_mu, f_var = glm_moments(model, X, post)
+    if isinstance(lh, GaussianLh):
+        return f_mu, f_var
+    try:
+        L = torch.linalg.cholesky(f_var)
+        fs = f_mu.unsqueeze(0) + torch.einsum('nkl,snl->snk', L, eps)
+    except RuntimeError:
+        scale = f_var.diagonal(dim1=1, dim2=2).clamp(1e-5)
+        fs = f_mu.unsqueeze(0) + scale.unsqueeze(0) * eps
+    return lh.inv_link(fs)
+
+
+def bnn_weight_samples(post, eps):
+    """theta samples [S,P]; eps is [P,S] (full/diag) or the per-parameter list (kron);
+    restates preds/predictives.py:14-20."""
+    if post['cov_type'] == 'kron':
+        covs = post['kron'].sample(eps)
+    elif post['cov_type'] == 'full':
+        covs = (post['Sigma_chol'] @ eps).t()
+    else:
+        covs = (post['Sigma_chol'].reshape(-1, 1) * eps).t()
+    return post['mu'] + covs
+
+
+def bnn_predictive(model, lh, X, post, eps):
+    """S forward passes at sampled weights -> [S,N,K]; restates preds/predictives.py:21-28."""
+    theta_star = get_theta(model)
+    samples = bnn_weight_samples(post, eps)
+    preds = []
+    with torch.no_grad():
+        for s in range(samples.shape[0]):
+            set_theta(model, samples[s])
+            preds.append(lh.inv_link(model(X)).detach())
+    set_theta(model, theta_star)
+    return torch.stack(preds)
+
+
+def kron_eps_shapes(model, S):
+    """Shapes of the draws Kron.sample consumes, in parameters() order (preds/kron.py:92,106)."""
+    shapes = []
+    for p in model.parameters():
+        if p.dim() == 1:
+            shapes.append((p.shape[0], S))
+        else:
+            shapes.append((S, p.shape[0], p[0].numel()))
+    return shapes
