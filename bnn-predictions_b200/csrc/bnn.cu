@@ -1,0 +1,198 @@
+// BNN predictive (preds/predictives.py:12-28), Kron.sample (preds/kron.py:85-110) and the small
+// dense helpers of the posterior code.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace bnnp {
+
+struct StoreThetaT {        // theta_s[s, p] = mu[p] + acc   for acc(p, s)
+  float* out; const float* mu; int64_t P;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t p, int64_t s, float acc, int) const { out[s * P + p] = mu[p] + acc; }
+};
+struct LoadLowerA {         // A(p, q) = L[p, q] for q <= p else 0 (Sigma_chol is lower triangular)
+  static constexpr bool K_CONTIG = true;
+  const float* L; int64_t P;
+  __device__ float operator()(int64_t p, int64_t q, int) const { return q <= p ? L[p * P + q] : 0.f; }
+};
+
+__global__ void sample_theta_diag_kernel(const float* __restrict__ sigma, const float* __restrict__ mu,
+                                         const float* __restrict__ eps, int64_t P, int64_t S,
+                                         float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * S) return;
+  int64_t p = i % P, s = i / P;
+  out[s * P + p] = mu[p] + sigma[p] * eps[p * S + s];
+}
+
+__global__ void axpy_kernel(int64_t n, float alpha, const float* __restrict__ x, float* __restrict__ y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(alpha, x[i], y[i]);
+}
+
+__global__ void scale_by_kernel(float* __restrict__ z, const float* __restrict__ D, int64_t per, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) z[i] *= D[i % per];
+}
+__global__ void kron_d_kernel(const float* __restrict__ l1, const float* __restrict__ l2, int m, int n,
+                              float delta, int dampen, float* __restrict__ D) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)m * n) return;
+  float a = l1[i / n], b = l2[i % n], v;
+  if (dampen) { float sd = sqrtf(delta); v = 1.f / ((a + sd) * (b + sd)); }
+  else v = 1.f / (a * b + delta);
+  D[i] = sqrtf(v);
+}
+struct StoreThetaGroup {    // theta_s[s, off + i*n + j] = mu[...] + acc, batch s, (i, j)
+  float* out; const float* mu; int64_t P, off; int n;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t i, int64_t j, float acc, int s) const {
+    int64_t p = off + i * n + j;
+    out[(int64_t)s * P + p] = (mu ? mu[p] : 0.f) + acc;
+  }
+};
+// 1-factor: t[i, s] = sqrt(1/(l[i]+delta)) * sum_k W[k, i] eps[k, s];  out[s, off+i] = mu + sum_k W[i,k] t[k,s]
+struct ScaleRowsStore {
+  float* t; int64_t S; const float* l; float delta;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t i, int64_t s, float acc, int) const { t[i * S + s] = acc * sqrtf(1.f / (l[i] + delta)); }
+};
+struct StoreThetaVec {
+  float* out; const float* mu; int64_t P, off;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t i, int64_t s, float acc, int) const { out[s * P + off + i] = (mu ? mu[off + i] : 0.f) + acc; }
+};
+
+}  // namespace bnnp
+using namespace bnnp;
+
+extern "C" int bnnp_sample_theta_full(const float* L, const float* mu, const float* eps, int64_t P,
+                                      int64_t S, float* theta_s, void* stream) {
+  if (!L || !mu || !eps || !theta_s || P <= 0 || S <= 0) return BNNP_ERR_INVALID;
+  return gemm_simt(P, S, P, 1, LoadLowerA{L, P}, LoadRowMajorB{eps, S, 0}, StoreThetaT{theta_s, mu, P},
+                   as_stream(stream));
+}
+
+extern "C" int bnnp_sample_theta_diag(const float* sigma, const float* mu, const float* eps, int64_t P,
+                                      int64_t S, float* theta_s, void* stream) {
+  if (!sigma || !mu || !eps || !theta_s || P <= 0 || S <= 0) return BNNP_ERR_INVALID;
+  sample_theta_diag_kernel<<<(unsigned)ceil_div64(P * S, 256), 256, 0, as_stream(stream)>>>(sigma, mu, eps, P, S, theta_s);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_kron_sample_group(const float* W1, const float* l1, const float* W2, const float* l2,
+                                      int m, int n, float delta, int dampen, const float* eps, int64_t S,
+                                      const float* mu, float* theta_s, int64_t P, int64_t off,
+                                      float* scratch, void* stream) {
+  if (!W1 || !l1 || !eps || !theta_s || !scratch || m <= 0 || S <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  if (!W2) {
+    // 1-factor (bias-like): eps [m, S]   preds/kron.py:88-93
+    float* t = scratch;
+    int rc = gemm_simt(m, S, m, 1, LoadColMajorA{W1, m, 0}, LoadRowMajorB{eps, S, 0},
+                       ScaleRowsStore{t, S, l1, delta}, st);
+    if (rc) return rc;
+    return gemm_simt(m, S, m, 1, LoadRowMajorA{W1, m, 0}, LoadRowMajorB{t, S, 0},
+                     StoreThetaVec{theta_s, mu, P, off}, st);
+  }
+  if (!l2 || n <= 0 || S > 65535) return BNNP_ERR_INVALID;
+  // 2-factor: eps [S, m, n]   preds/kron.py:94-109
+  const int64_t per = (int64_t)m * n;
+  float* T1 = scratch;                  // [S, m, n]
+  float* T2 = scratch + S * per;        // [S, m, n]
+  float* D = T2 + S * per;              // [m, n]
+  kron_d_kernel<<<(unsigned)ceil_div64(per, 256), 256, 0, st>>>(l1, l2, m, n, delta, dampen, D);
+  BNNP_LAUNCH_CHECK();
+  // T1 = eps W2 ; T2 = W1^T T1 ; T2 *= D ; T1 = T2 W2^T ; out = W1 T1
+  int rc = gemm_simt(m, n, n, (int)S, LoadRowMajorA{eps, n, per}, LoadRowMajorB{W2, n, 0},
+                     StoreAxpby{T1, n, per, 1.f, 0.f}, st);
+  if (rc) return rc;
+  rc = gemm_simt(m, n, m, (int)S, LoadColMajorA{W1, m, 0}, LoadRowMajorB{T1, n, per},
+                 StoreAxpby{T2, n, per, 1.f, 0.f}, st);
+  if (rc) return rc;
+  scale_by_kernel<<<(unsigned)ceil_div64(S * per, 256), 256, 0, st>>>(T2, D, per, S * per);
+  BNNP_LAUNCH_CHECK();
+  rc = gemm_simt(m, n, n, (int)S, LoadRowMajorA{T2, n, per}, LoadColMajorB{W2, n, 0},
+                 StoreAxpby{T1, n, per, 1.f, 0.f}, st);
+  if (rc) return rc;
+  return gemm_simt(m, n, m, (int)S, LoadRowMajorA{W1, m, 0}, LoadRowMajorB{T1, n, per},
+                   StoreThetaGroup{theta_s, mu, P, off, n}, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward passes at S sampled weight vectors
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t bnnp_bnn_forward_scratch_floats(const bnnp_op_t* ops, int n_ops, int64_t N, int64_t S) {
+  bnnp_plan_t plan;
+  (void)S;
+  if (bnnp_net_plan(ops, n_ops, N, 1, &plan) != BNNP_OK) return -1;
+  return plan.total_floats + N * plan.K + 64;
+}
+
+extern "C" int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const float* X, int64_t N,
+                                const float* theta_s, int64_t S, int64_t P, float* out, float* scratch,
+                                void* stream) {
+  if (!ops || !X || !theta_s || !out || !scratch || N <= 0 || S <= 0 || n_ops > BNNP_MAX_OPS) return BNNP_ERR_INVALID;
+  bnnp_plan_t plan;
+  int rc = bnnp_net_plan(ops, n_ops, N, 1, &plan);
+  if (rc) return rc;
+  if (plan.P != P) return BNNP_ERR_INVALID;
+  float* logits = scratch + plan.total_floats;
+  bnnp_op_t local[BNNP_MAX_OPS];
+  for (int64_t s = 0; s < S; ++s) {
+    for (int i = 0; i < n_ops; ++i) {
+      local[i] = ops[i];
+      if (is_param_op(ops[i])) {
+        local[i].weight = theta_s + s * P + ops[i].theta_off_w;
+        local[i].bias = ops[i].has_bias ? theta_s + s * P + ops[i].theta_off_b : nullptr;
+      }
+    }
+    rc = bnnp_net_forward(local, n_ops, &plan, X, N, scratch, logits, stream);
+    if (rc) return rc;
+    rc = bnnp_lik_inv_link(lik, logits, N, plan.K, out + s * N * plan.K, stream);
+    if (rc) return rc;
+  }
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dense helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int bnnp_sgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                          int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+                          void* stream) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  StoreAxpby ep{C, ldc, 0, alpha, beta};
+  if (!ta && !tb) return gemm_simt(M, N, K, 1, LoadRowMajorA{A, lda, 0}, LoadRowMajorB{B, ldb, 0}, ep, st);
+  if (!ta && tb) return gemm_simt(M, N, K, 1, LoadRowMajorA{A, lda, 0}, LoadColMajorB{B, ldb, 0}, ep, st);
+  if (ta && !tb) return gemm_simt(M, N, K, 1, LoadColMajorA{A, lda, 0}, LoadRowMajorB{B, ldb, 0}, ep, st);
+  return gemm_simt(M, N, K, 1, LoadColMajorA{A, lda, 0}, LoadColMajorB{B, ldb, 0}, ep, st);
+}
+
+extern "C" int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream) {
+  if (!x || !y || n <= 0) return BNNP_ERR_INVALID;
+  axpy_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, as_stream(stream)>>>(n, alpha, x, y);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" const char* bnnp_strerror(int code) {
+  switch (code) {
+    case BNNP_OK: return "ok";
+    case BNNP_ERR_INVALID: return "invalid argument";
+    case BNNP_ERR_UNSUPPORTED: return "unsupported layer type or size";
+    case BNNP_ERR_CUDA: return "CUDA error";
+    case BNNP_ERR_NO_DEVICE: return "no sm_100 device";
+    default: return "unknown error";
+  }
+}
+extern "C" int bnnp_version(void) { return 100; }
+extern "C" int bnnp_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return 0; }
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return p.major == 10 ? 1 : 0;
+}

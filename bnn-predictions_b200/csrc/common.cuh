@@ -1,0 +1,36 @@
+// Shared helpers for libbnnp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/bnnp_b200.h"
+
+#define BNNP_CUDA_CHECK(expr)                                         \
+  do {                                                                \
+    cudaError_t e__ = (expr);                                         \
+    if (e__ != cudaSuccess) {                                         \
+      fprintf(stderr, "[bnnp_b200] CUDA error %s at %s:%d\n",         \
+              cudaGetErrorString(e__), __FILE__, __LINE__);           \
+      return BNNP_ERR_CUDA;                                           \
+    }                                                                 \
+  } while (0)
+
+#define BNNP_LAUNCH_CHECK() BNNP_CUDA_CHECK(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline bool is_param_op(const bnnp_op_t& o) {
+  return o.kind == BNNP_OP_LINEAR || o.kind == BNNP_OP_CONV2D;
+}
+static inline bool is_elementwise_op(const bnnp_op_t& o) {
+  return o.kind == BNNP_OP_RELU || o.kind == BNNP_OP_TANH || o.kind == BNNP_OP_SIGMOID;
+}
+static inline int64_t op_in_size(const bnnp_op_t& o) { return (int64_t)o.in_c * o.in_h * o.in_w; }
+static inline int64_t op_out_size(const bnnp_op_t& o) { return (int64_t)o.out_c * o.out_h * o.out_w; }

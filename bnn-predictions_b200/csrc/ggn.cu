@@ -1,0 +1,521 @@
+// GGN accumulation from the saved layer factors (a_l, g_l) -- the Jacobian J_n is never read
+// from HBM; its tiles are synthesised inside the contraction kernels.
+//   full : H += sum_n J_n^T Lambda_n J_n            preds/laplace.py:42, preds/optimizers.py:94
+//   diag : d += factor * diag(...)                   preds/laplace.py:52-59 (BackPACK DiagGGNExact)
+//   kron : G_l += factor * sum s s^T, A_l += bf/N * sum a a^T   preds/laplace.py:73-78, kron.py:58-69
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gram_tc.cuh"
+
+namespace bnnp {
+
+// ------------------------------------------------------------------------------------------
+// shared functors
+// ------------------------------------------------------------------------------------------
+// implicit im2col of a conv input: U(pos, e) with e = (ci, a, b), pos = (oh, ow); batch b -> example b / V
+struct Im2col {
+  const float* in; int64_t ild; int V;
+  int Cin, H, W, OW, kh, kw, sh, sw, pl, pt;
+  __device__ float at(int64_t n, int pos, int e) const {
+    int b = e % kw, a = (e / kw) % kh, ci = e / (kw * kh);
+    int oh = pos / OW, ow = pos % OW;
+    int ih = oh * sh - pt + a, iw = ow * sw - pl + b;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
+    return in[n * ild + ((int64_t)ci * H + ih) * W + iw];
+  }
+};
+static Im2col make_im2col(const bnnp_op_t& o, const float* in, int64_t ild, int V) {
+  return Im2col{in, ild, V, o.in_c, o.in_h, o.in_w, o.out_w, o.kh, o.kw, o.stride_h, o.stride_w,
+                o.pad_l, o.pad_t};
+}
+
+static const float* op_input(const bnnp_op_t* ops, const bnnp_plan_t* plan, int i, const float* X,
+                             const float* ws, int64_t* ld) {
+  if (i == 0) { *ld = op_in_size(ops[0]); return X; }
+  *ld = plan->op[i - 1].act_ld;
+  return ws + plan->op[i - 1].act_off;
+}
+
+// ------------------------------------------------------------------------------------------
+// Jacobian materialisation  Js[n, p, v]
+// ------------------------------------------------------------------------------------------
+__global__ void jac_linear_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ A,
+                                  int64_t ald, int64_t N, int V, int m, int nin, int has_bias,
+                                  int64_t offw, int64_t offb, int64_t P, float* __restrict__ Js) {
+  int64_t per = (int64_t)m * (nin + (has_bias ? 1 : 0));
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * per * V) return;
+  int v = (int)(i % V);
+  int64_t e = (i / V) % per, n = i / (V * per);
+  int64_t p; float val;
+  if (e < (int64_t)m * nin) {
+    int u = (int)(e / nin), j = (int)(e % nin);
+    p = offw + e;
+    val = G[(n * V + v) * gld + u] * A[n * ald + j];
+  } else {
+    int u = (int)(e - (int64_t)m * nin);
+    p = offb + u;
+    val = G[(n * V + v) * gld + u];
+  }
+  Js[(n * P + p) * V + v] = val;
+}
+
+struct ConvGradA {     // A(co, pos) = gout[r, co, pos]
+  static constexpr bool K_CONTIG = true;
+  const float* g; int64_t gld; int L;
+  __device__ float operator()(int64_t co, int64_t pos, int r) const { return g[(int64_t)r * gld + co * L + pos]; }
+};
+struct ConvUnfoldB {   // B(pos, e) = unfold(in[n])[e, pos]
+  static constexpr bool K_CONTIG = false;
+  Im2col u;
+  __device__ float operator()(int64_t pos, int64_t e, int r) const { return u.at(r / u.V, (int)pos, (int)e); }
+};
+struct StoreJacConv {  // Js[n, offw + co*E + e, v]
+  float* Js; int64_t P, offw; int V, E;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t co, int64_t e, float acc, int r) const {
+    int64_t n = r / V; int v = r % V;
+    Js[(n * P + offw + co * E + e) * V + v] = acc;
+  }
+};
+struct StoreBlock {    // dst[r, co*E + e]   (per-row Jacobian block of one conv weight)
+  float* dst; int64_t ld; int E;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t co, int64_t e, float acc, int r) const {
+    dst[(int64_t)r * ld + co * E + e] = acc;
+  }
+};
+
+// s[r, co] = sum_pos gout[r, co, pos]
+__global__ void conv_possum_kernel(const float* __restrict__ g, int64_t gld, int64_t R, int Cout,
+                                   int L, float* __restrict__ s, int64_t sld) {
+  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  int lane = threadIdx.x % 32;
+  if (w >= R * Cout) return;
+  int64_t r = w / Cout; int co = (int)(w % Cout);
+  const float* p = g + r * gld + (int64_t)co * L;
+  float acc = 0.f;
+  for (int i = lane; i < L; i += 32) acc += p[i];
+  acc = warp_sum(acc);
+  if (lane == 0) s[r * sld + co] = acc;
+}
+
+// Js[n, offb + co, v] = sum_pos gout[(n,v), co, pos]
+__global__ void jac_conv_bias_direct(const float* __restrict__ g, int64_t gld, int64_t N, int V, int Cout,
+                                     int L, int64_t offb, int64_t P, float* __restrict__ Js) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * V * Cout) return;
+  int co = (int)(i % Cout); int64_t r = i / Cout; int64_t n = r / V; int v = (int)(r % V);
+  const float* p = g + r * gld + (int64_t)co * L;
+  float acc = 0.f;
+  for (int k = 0; k < L; ++k) acc += p[k];
+  Js[(n * P + offb + co) * V + v] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// full GGN, SIMT K-form:  H[p,q] += sum_{n,k} (Lambda G)[n,k,u(p)] a[n,c(p)] * G[n,k,u(q)] a[n,c(q)]
+// ------------------------------------------------------------------------------------------
+// per-parameter maps for Linear-only networks: unit column in G_cat, input column in A_cat
+__global__ void param_maps_kernel(int32_t* __restrict__ pu, int32_t* __restrict__ pc, int64_t off,
+                                  int m, int nin, int unit0, int col0, int is_bias) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t cnt = is_bias ? m : (int64_t)m * nin;
+  if (e >= cnt) return;
+  if (is_bias) { pu[off + e] = unit0 + (int)e; pc[off + e] = col0 + nin; }
+  else { pu[off + e] = unit0 + (int)(e / nin); pc[off + e] = col0 + (int)(e % nin); }
+}
+
+// GL[(n,k), u] = sum_l Lambda[n,k,l] G[(n,l), u]
+__global__ void lambda_g_kernel(const float* __restrict__ Lam, const float* __restrict__ G,
+                                int64_t N, int K, int M, float* __restrict__ GL) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K * M) return;
+  int u = (int)(i % M); int64_t r = i / M; int64_t n = r / K; int k = (int)(r % K);
+  float acc = 0.f;
+  for (int l = 0; l < K; ++l) acc = fmaf(Lam[(n * K + k) * K + l], G[(n * K + l) * M + u], acc);
+  GL[i] = acc;
+}
+
+struct JacOperand {       // J-like operand: X(p, r) = Gx[r, u(p)] * A[r / K, c(p)]
+  static constexpr bool K_CONTIG = false;
+  const float* Gx; const float* A; const int32_t* pu; const int32_t* pc;
+  int64_t gld, ald; int K;
+  __device__ float operator()(int64_t p, int64_t r, int) const {
+    return Gx[r * gld + pu[p]] * A[(r / K) * ald + pc[p]];
+  }
+};
+struct JacOperandB {      // same, (k, n) argument order
+  static constexpr bool K_CONTIG = false;
+  JacOperand j;
+  __device__ float operator()(int64_t r, int64_t q, int) const { return j(q, r, 0); }
+};
+struct AccumLower {
+  float* H; int64_t P;
+  __device__ bool skip(int64_t m0, int64_t n0, int bm, int) const { return m0 + bm - 1 < n0; }
+  __device__ void operator()(int64_t m, int64_t n, float acc, int) const { H[m * P + n] += acc; }
+};
+
+__global__ void symmetrize_kernel(float* __restrict__ H, int64_t P) {
+  __shared__ float tile[32][33];
+  int64_t bi = blockIdx.y, bj = blockIdx.x;     // destination tile (rows bi, cols bj), bi <= bj
+  if (bi > bj) return;
+  int tx = threadIdx.x, ty = threadIdx.y;
+  // load source tile (rows bj*32.., cols bi*32..)
+  for (int r = ty; r < 32; r += 8) {
+    int64_t sr = bj * 32 + r, sc = bi * 32 + tx;
+    tile[r][tx] = (sr < P && sc < P) ? H[sr * P + sc] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int64_t dr = bi * 32 + r, dc = bj * 32 + tx;
+    if (dr < P && dc < P && dr < dc) H[dr * P + dc] = tile[tx][r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// diag
+// ------------------------------------------------------------------------------------------
+// Q[n, u] = sum_v G[(n,v), u]^2
+__global__ void sqsum_v_kernel(const float* __restrict__ G, int64_t gld, int64_t N, int V, int M,
+                               float* __restrict__ Q) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * M) return;
+  int u = (int)(i % M); int64_t n = i / M;
+  float acc = 0.f;
+  for (int v = 0; v < V; ++v) { float g = G[(n * V + v) * gld + u]; acc = fmaf(g, g, acc); }
+  Q[i] = acc;
+}
+struct LoadQT {           // A(i, n) = Q[n, unit0 + i]
+  static constexpr bool K_CONTIG = false;
+  const float* Q; int64_t ld; int unit0;
+  __device__ float operator()(int64_t i, int64_t n, int) const { return Q[n * ld + unit0 + i]; }
+};
+struct LoadSq {           // B(n, j) = A[n, col0 + j]^2
+  static constexpr bool K_CONTIG = false;
+  const float* A; int64_t ld; int col0;
+  __device__ float operator()(int64_t n, int64_t j, int) const { float a = A[n * ld + col0 + j]; return a * a; }
+};
+struct AccumLinearParam { // (i, j) -> weight [m, nin] at offw, column nin -> bias at offb
+  float* d; int64_t offw, offb; int nin; int has_bias; float factor;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t i, int64_t j, float acc, int) const {
+    if (j < nin) d[offw + i * nin + j] += factor * acc;
+    else if (has_bias) d[offb + i] += factor * acc;
+  }
+};
+
+// conv weight diag: d[co, e] += factor * sum_r ( sum_pos gout[r,co,pos] U[r/V, e, pos] )^2
+// one block per 64x64 output tile, looping over all rows r (the per-sample Jacobian tile is
+// formed in registers, squared and accumulated -- never stored).
+__global__ void __launch_bounds__(G_THREADS)
+conv_diag_kernel(ConvGradA la, ConvUnfoldB lb, int64_t R, int Cout, int E, int L, float factor,
+                 float* __restrict__ d, int64_t offw) {
+  __shared__ float As[G_BK][G_BM + 4];
+  __shared__ float Bs[G_BK][G_BN + 4];
+  const int64_t m0 = (int64_t)blockIdx.y * G_BM, n0 = (int64_t)blockIdx.x * G_BN;
+  const int t = threadIdx.x;
+  const int tx = t % (G_BN / G_TN), ty = t / (G_BN / G_TN);
+  float tot[G_TM][G_TN];
+#pragma unroll
+  for (int i = 0; i < G_TM; ++i)
+#pragma unroll
+    for (int j = 0; j < G_TN; ++j) tot[i][j] = 0.f;
+  for (int64_t r = 0; r < R; ++r) {
+    float acc[G_TM][G_TN];
+#pragma unroll
+    for (int i = 0; i < G_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < G_TN; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < L; k0 += G_BK) {
+#pragma unroll
+      for (int i = 0; i < (G_BM * G_BK) / G_THREADS; ++i) {
+        int e = t + i * G_THREADS, kk = e % G_BK, mm = e / G_BK;
+        int64_t m = m0 + mm; int k = k0 + kk;
+        As[kk][mm] = (m < Cout && k < L) ? la(m, k, (int)r) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < (G_BN * G_BK) / G_THREADS; ++i) {
+        int e = t + i * G_THREADS, nn = e % G_BN, kk = e / G_BN;
+        int64_t n = n0 + nn; int k = k0 + kk;
+        Bs[kk][nn] = (n < E && k < L) ? lb(k, n, (int)r) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < G_BK; ++kk) {
+        float a[G_TM], b[G_TN];
+#pragma unroll
+        for (int i = 0; i < G_TM; ++i) a[i] = As[kk][ty * G_TM + i];
+#pragma unroll
+        for (int j = 0; j < G_TN; ++j) b[j] = Bs[kk][tx * G_TN + j];
+#pragma unroll
+        for (int i = 0; i < G_TM; ++i)
+#pragma unroll
+          for (int j = 0; j < G_TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < G_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < G_TN; ++j) tot[i][j] = fmaf(acc[i][j], acc[i][j], tot[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < G_TM; ++i)
+#pragma unroll
+    for (int j = 0; j < G_TN; ++j) {
+      int64_t m = m0 + ty * G_TM + i, n = n0 + tx * G_TN + j;
+      if (m < Cout && n < E) d[offw + m * E + n] += factor * tot[i][j];
+    }
+}
+
+// d[offb + co] += factor * sum_r s[r, co]^2
+__global__ void colsq_accum_kernel(const float* __restrict__ s, int64_t R, int C, float factor,
+                                   float* __restrict__ d) {
+  int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= C) return;
+  float acc = 0.f;
+  for (int64_t r = 0; r < R; ++r) { float v = s[r * C + co]; acc = fmaf(v, v, acc); }
+  d[co] += factor * acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// KFAC
+// ------------------------------------------------------------------------------------------
+struct LoadTA {            // A(i, r) = p[r*ld + c0 + i]
+  static constexpr bool K_CONTIG = false;
+  const float* p; int64_t ld; int c0;
+  __device__ float operator()(int64_t i, int64_t r, int) const { return p[r * ld + c0 + i]; }
+};
+struct LoadNB {            // B(r, j) = p[r*ld + c0 + j]
+  static constexpr bool K_CONTIG = false;
+  const float* p; int64_t ld; int c0;
+  __device__ float operator()(int64_t r, int64_t j, int) const { return p[r * ld + c0 + j]; }
+};
+struct AccumScaled {
+  float* C; int64_t ld; float alpha;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t m, int64_t n, float acc, int) const { C[m * ld + n] += alpha * acc; }
+};
+struct UnfoldTA {          // A(e, (n,pos)) = unfold(in[n])[e, pos]
+  static constexpr bool K_CONTIG = false;
+  Im2col u; int L;
+  __device__ float operator()(int64_t e, int64_t r, int) const { return u.at(r / L, (int)(r % L), (int)e); }
+};
+struct UnfoldNB {
+  static constexpr bool K_CONTIG = false;
+  Im2col u; int L;
+  __device__ float operator()(int64_t r, int64_t e, int) const { return u.at(r / L, (int)(r % L), (int)e); }
+};
+
+}  // namespace bnnp
+using namespace bnnp;
+
+static bool linear_only(const bnnp_op_t* ops, int n_ops) {
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_CONV2D || ops[i].kind == BNNP_OP_MAXPOOL2D || ops[i].kind == BNNP_OP_AVGPOOL2D)
+      return false;
+  return true;
+}
+
+static int build_param_maps(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int32_t* pu,
+                            int32_t* pc, cudaStream_t st) {
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    int64_t cnt = (int64_t)o.out_c * o.in_c;
+    param_maps_kernel<<<(unsigned)ceil_div64(cnt, 256), 256, 0, st>>>(pu, pc, o.theta_off_w, o.out_c, o.in_c,
+                                                                       q.lin_unit, q.lin_col, 0);
+    BNNP_LAUNCH_CHECK();
+    if (o.has_bias) {
+      param_maps_kernel<<<(unsigned)ceil_div64(o.out_c, 256), 256, 0, st>>>(pu, pc, o.theta_off_b, o.out_c,
+                                                                             o.in_c, q.lin_unit, q.lin_col, 1);
+      BNNP_LAUNCH_CHECK();
+    }
+  }
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_jacobians(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                              const float* X, const float* ws, float* Js, void* stream) {
+  if (!ops || !plan || !ws || !Js || N <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const int V = plan->K;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (!is_param_op(o)) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    const float* G = ws + q.grad_off;
+    if (o.kind == BNNP_OP_LINEAR) {
+      int64_t per = (int64_t)o.out_c * (o.in_c + (o.has_bias ? 1 : 0));
+      jac_linear_kernel<<<(unsigned)ceil_div64(N * per * V, 256), 256, 0, st>>>(
+          G, q.grad_ld, ws + plan->acat_off + q.lin_col, plan->Dtot, N, V, o.out_c, o.in_c, o.has_bias,
+          o.theta_off_w, o.theta_off_b, plan->P, Js);
+      BNNP_LAUNCH_CHECK();
+    } else {
+      int64_t ild; const float* in = op_input(ops, plan, i, X, ws, &ild);
+      if (!in) return BNNP_ERR_INVALID;
+      int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
+      if (N * V > 65535) return BNNP_ERR_UNSUPPORTED;
+      int rc = gemm_simt(o.out_c, E, L, (int)(N * V), ConvGradA{G, q.grad_ld, L},
+                         ConvUnfoldB{make_im2col(o, in, ild, V)},
+                         StoreJacConv{Js, plan->P, o.theta_off_w, V, E}, st);
+      if (rc) return rc;
+      if (o.has_bias) {
+        jac_conv_bias_direct<<<(unsigned)ceil_div64(N * V * o.out_c, 128), 128, 0, st>>>(
+            G, q.grad_ld, N, V, o.out_c, L, o.theta_off_b, plan->P, Js);
+        BNNP_LAUNCH_CHECK();
+      }
+    }
+  }
+  return BNNP_OK;
+}
+
+// ---------------------------------------------------------------------------- full
+extern "C" int64_t bnnp_ggn_full_scratch_floats(const bnnp_plan_t* plan, int64_t N, int engine) {
+  if (!plan) return 0;
+  int64_t simt = 2 * ((plan->P + 31) / 32 * 32) + N * plan->K * (int64_t)plan->Mtot + 64;
+  int64_t tc = gram_tc_scratch_floats(plan, N);
+  (void)engine;
+  return simt > tc ? simt : tc;
+}
+
+extern "C" int bnnp_ggn_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                   const float* ws, const float* Lambda, float* H, float* scratch,
+                                   int engine, void* stream) {
+  if (!ops || !plan || !ws || !Lambda || !H || !scratch || N <= 0) return BNNP_ERR_INVALID;
+  if (!linear_only(ops, n_ops)) return BNNP_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  if (engine == 0) engine = gram_tc_preferred(ops, n_ops, plan, N) ? 2 : 1;
+  if (engine == 2) return gram_tc_full_accum(ops, n_ops, plan, N, ws, Lambda, H, scratch, st);
+  const int K = plan->K, M = plan->Mtot;
+  const int64_t P = plan->P, Ppad = (P + 31) / 32 * 32;
+  int32_t* pu = reinterpret_cast<int32_t*>(scratch);
+  int32_t* pc = pu + Ppad;
+  float* GL = scratch + 2 * Ppad;
+  int rc = build_param_maps(ops, n_ops, plan, pu, pc, st);
+  if (rc) return rc;
+  const float* G = ws + plan->gcat_off;
+  const float* A = ws + plan->acat_off;
+  lambda_g_kernel<<<(unsigned)ceil_div64(N * K * M, 256), 256, 0, st>>>(Lambda, G, N, K, M, GL);
+  BNNP_LAUNCH_CHECK();
+  JacOperand ja{GL, A, pu, pc, M, plan->Dtot, K};
+  JacOperand jb{G, A, pu, pc, M, plan->Dtot, K};
+  return gemm_simt(P, P, N * K, 1, ja, JacOperandB{jb}, AccumLower{H, P}, st);
+}
+
+extern "C" int bnnp_symmetrize_lower(float* H, int64_t P, void* stream) {
+  if (!H || P <= 0) return BNNP_ERR_INVALID;
+  unsigned nb = (unsigned)ceil_div64(P, 32);
+  if (nb > 65535u) return BNNP_ERR_UNSUPPORTED;
+  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, as_stream(stream)>>>(H, P);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+// ---------------------------------------------------------------------------- diag
+extern "C" int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                                int64_t N, int V) {
+  int64_t need = N * (int64_t)plan->Mtot + 64;
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_CONV2D) need = need > N * V * ops[i].out_c + 64 ? need : N * V * ops[i].out_c + 64;
+  return need;
+}
+
+extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                   int V, const float* X, const float* ws, float factor, float* diag,
+                                   float* scratch, void* stream) {
+  if (!ops || !plan || !ws || !diag || !scratch || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const int M = plan->Mtot;
+  if (M > 0) {
+    sqsum_v_kernel<<<(unsigned)ceil_div64(N * M, 256), 256, 0, st>>>(ws + plan->gcat_off, M, N, V, M, scratch);
+    BNNP_LAUNCH_CHECK();
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (!is_param_op(o)) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    if (o.kind == BNNP_OP_LINEAR) {
+      int rc = gemm_simt(o.out_c, o.in_c + 1, N, 1, LoadQT{scratch, M, q.lin_unit},
+                         LoadSq{ws + plan->acat_off, plan->Dtot, q.lin_col},
+                         AccumLinearParam{diag, o.theta_off_w, o.theta_off_b, o.in_c, o.has_bias, factor}, st);
+      if (rc) return rc;
+    }
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_CONV2D) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    int64_t ild; const float* in = op_input(ops, plan, i, X, ws, &ild);
+    if (!in) return BNNP_ERR_INVALID;
+    int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
+    const float* G = ws + q.grad_off;
+    dim3 grid((unsigned)ceil_div64(E, G_BN), (unsigned)ceil_div64(o.out_c, G_BM));
+    conv_diag_kernel<<<grid, G_THREADS, 0, st>>>(ConvGradA{G, q.grad_ld, L},
+                                                 ConvUnfoldB{make_im2col(o, in, ild, V)}, N * V, o.out_c, E,
+                                                 L, factor, diag, o.theta_off_w);
+    BNNP_LAUNCH_CHECK();
+    if (o.has_bias) {
+      int64_t R = N * V;
+      conv_possum_kernel<<<(unsigned)ceil_div64(R * o.out_c * 32, 256), 256, 0, st>>>(G, q.grad_ld, R, o.out_c, L,
+                                                                                       scratch, o.out_c);
+      BNNP_LAUNCH_CHECK();
+      colsq_accum_kernel<<<(unsigned)ceil_div64(o.out_c, 64), 64, 0, st>>>(scratch, R, o.out_c, factor,
+                                                                          diag + o.theta_off_b);
+      BNNP_LAUNCH_CHECK();
+    }
+  }
+  return BNNP_OK;
+}
+
+// ---------------------------------------------------------------------------- kfac
+extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                            int64_t N, int V) {
+  int64_t need = 64;
+  (void)plan;
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_CONV2D) need = need > N * V * ops[i].out_c + 64 ? need : N * V * ops[i].out_c + 64;
+  return need;
+}
+
+extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
+                               const float* X, const float* ws, float factor, float batch_factor,
+                               float* const* factors, float* scratch, void* stream) {
+  if (!ops || !plan || !ws || !factors || !scratch || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const int64_t R = N * V;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (!is_param_op(o)) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    float* Gf = factors[2 * i];
+    float* Af = factors[2 * i + 1];
+    if (!Gf || !Af) return BNNP_ERR_INVALID;
+    const float* G = ws + q.grad_off;
+    if (o.kind == BNNP_OP_LINEAR) {
+      int rc = gemm_simt(o.out_c, o.out_c, R, 1, LoadTA{G, q.grad_ld, 0}, LoadNB{G, q.grad_ld, 0},
+                         AccumScaled{Gf, o.out_c, factor}, st);
+      if (rc) return rc;
+      const float* A = ws + plan->acat_off;
+      rc = gemm_simt(o.in_c, o.in_c, N, 1, LoadTA{A, plan->Dtot, q.lin_col}, LoadNB{A, plan->Dtot, q.lin_col},
+                     AccumScaled{Af, o.in_c, batch_factor / (float)N}, st);
+      if (rc) return rc;
+    } else {
+      int64_t ild; const float* in = op_input(ops, plan, i, X, ws, &ild);
+      if (!in) return BNNP_ERR_INVALID;
+      int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
+      conv_possum_kernel<<<(unsigned)ceil_div64(R * o.out_c * 32, 256), 256, 0, st>>>(G, q.grad_ld, R, o.out_c, L,
+                                                                                       scratch, o.out_c);
+      BNNP_LAUNCH_CHECK();
+      int rc = gemm_simt(o.out_c, o.out_c, R, 1, LoadTA{scratch, o.out_c, 0}, LoadNB{scratch, o.out_c, 0},
+                         AccumScaled{Gf, o.out_c, factor}, st);
+      if (rc) return rc;
+      Im2col u = make_im2col(o, in, ild, 1);
+      rc = gemm_simt(E, E, N * L, 1, UnfoldTA{u, L}, UnfoldNB{u, L},
+                     AccumScaled{Af, E, batch_factor / (float)N}, st);
+      if (rc) return rc;
+    }
+  }
+  return BNNP_OK;
+}

@@ -1,0 +1,661 @@
+// GLM predictive: f_mu = f + J (mu - theta*), f_var = J Sigma J^T, then the fused
+// Cholesky + sampling + inverse-link epilogue.  preds/predictives.py:50-76, preds/kron.py:112-143.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace bnnp {
+
+struct Im2colG {   // same implicit im2col as ggn.cu (kept local to this TU)
+  const float* in; int64_t ild; int V;
+  int Cin, H, W, OW, kh, kw, sh, sw, pl, pt;
+  __device__ float at(int64_t n, int pos, int e) const {
+    int b = e % kw, a = (e / kw) % kh, ci = e / (kw * kh);
+    int oh = pos / OW, ow = pos % OW;
+    int ih = oh * sh - pt + a, iw = ow * sw - pl + b;
+    if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
+    return in[n * ild + ((int64_t)ci * H + ih) * W + iw];
+  }
+};
+static Im2colG make_im2col_g(const bnnp_op_t& o, const float* in, int64_t ild, int V) {
+  return Im2colG{in, ild, V, o.in_c, o.in_h, o.in_w, o.out_w, o.kh, o.kw, o.stride_h, o.stride_w,
+                 o.pad_l, o.pad_t};
+}
+static const float* op_input_g(const bnnp_op_t* ops, const bnnp_plan_t* plan, int i, const float* X,
+                               const float* ws, int64_t* ld) {
+  if (i == 0) { *ld = op_in_size(ops[0]); return X; }
+  *ld = plan->op[i - 1].act_ld;
+  return ws + plan->op[i - 1].act_off;
+}
+
+__global__ void zero_kernel(float* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+// ---- per-row Jacobian block of a conv weight: Jb[r, co*E + e] -----------------------------
+struct ConvGradA2 {
+  static constexpr bool K_CONTIG = true;
+  const float* g; int64_t gld; int L;
+  __device__ float operator()(int64_t co, int64_t pos, int r) const { return g[(int64_t)r * gld + co * L + pos]; }
+};
+struct ConvUnfoldB2 {
+  static constexpr bool K_CONTIG = false;
+  Im2colG u;
+  __device__ float operator()(int64_t pos, int64_t e, int r) const { return u.at(r / u.V, (int)pos, (int)e); }
+};
+struct StoreBlock2 {
+  float* dst; int64_t ld; int E;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t co, int64_t e, float acc, int r) const { dst[(int64_t)r * ld + co * E + e] = acc; }
+};
+__global__ void conv_possum2_kernel(const float* __restrict__ g, int64_t gld, int64_t R, int Cout, int L,
+                                    float* __restrict__ s) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * Cout) return;
+  const float* p = g + (i / Cout) * gld + (i % Cout) * L;
+  float acc = 0.f;
+  for (int k = 0; k < L; ++k) acc += p[k];
+  s[i] = acc;
+}
+
+// ---- f_mu ---------------------------------------------------------------------------------
+// f_mu[n,k] += sum_u G[(n,k),u] * (sum_j a[n,j] dW[u,j] + db[u])
+__global__ void fmu_direct_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ A,
+                                  int64_t ald, const float* __restrict__ d, int64_t offw, int64_t offb,
+                                  int m, int nin, int has_bias, int K, int64_t N, float* __restrict__ fmu) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  int64_t n = i / K;
+  float acc = 0.f;
+  for (int u = 0; u < m; ++u) {
+    float t = has_bias ? d[offb + u] : 0.f;
+    for (int j = 0; j < nin; ++j) t = fmaf(A[n * ald + j], d[offw + (int64_t)u * nin + j], t);
+    acc = fmaf(G[i * gld + u], t, acc);
+  }
+  fmu[i] += acc;
+}
+
+// ---- f_var, full covariance (Linear-only) ---------------------------------------------------
+struct JacRowA {        // A((n,k), p) = G[(n,k), u(p)] * a[n, c(p)]
+  static constexpr bool K_CONTIG = true;
+  const float* G; const float* A; const int32_t* pu; const int32_t* pc; int64_t gld, ald; int K;
+  __device__ float operator()(int64_t r, int64_t p, int) const {
+    return G[r * gld + pu[p]] * A[(r / K) * ald + pc[p]];
+  }
+};
+// f_var[n,k,l] = sum_q T[(n,k), q] * J[(n,l), q]      one block per (n,k)
+__global__ void fvar_from_T_kernel(const float* __restrict__ T, JacRowA J, int64_t P, int K,
+                                   float* __restrict__ fvar) {
+  __shared__ float red[BNNP_MAX_K][8];
+  int64_t r = blockIdx.x;                    // (n,k)
+  int64_t n = r / K; int k = (int)(r % K);
+  float acc[BNNP_MAX_K];
+#pragma unroll
+  for (int l = 0; l < BNNP_MAX_K; ++l) acc[l] = 0.f;
+  for (int64_t q = threadIdx.x; q < P; q += blockDim.x) {
+    float t = T[r * P + q];
+    float a = J.A[n * J.ald + J.pc[q]];
+    int u = J.pu[q];
+    float ta = t * a;
+    for (int l = 0; l < K; ++l) acc[l] = fmaf(ta, J.G[(n * K + l) * J.gld + u], acc[l]);
+  }
+  int lane = threadIdx.x % 32, w = threadIdx.x / 32;
+  for (int l = 0; l < K; ++l) {
+    float v = warp_sum(acc[l]);
+    if (lane == 0) red[l][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float v = 0.f;
+    for (int i = 0; i < (int)(blockDim.x / 32); ++i) v += red[threadIdx.x][i];
+    fvar[(n * K + k) * K + threadIdx.x] = v;
+  }
+}
+__global__ void param_maps2_kernel(int32_t* __restrict__ pu, int32_t* __restrict__ pc, int64_t off,
+                                   int m, int nin, int unit0, int col0, int is_bias) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t cnt = is_bias ? m : (int64_t)m * nin;
+  if (e >= cnt) return;
+  if (is_bias) { pu[off + e] = unit0 + (int)e; pc[off + e] = col0 + nin; }
+  else { pu[off + e] = unit0 + (int)(e / nin); pc[off + e] = col0 + (int)(e % nin); }
+}
+
+// ---- f_var, diagonal ------------------------------------------------------------------------
+struct LoadSqA {        // A(n, j) = a[n, col0 + j]^2   (ones column included: j == nin)
+  static constexpr bool K_CONTIG = true;
+  const float* A; int64_t ld; int col0;
+  __device__ float operator()(int64_t n, int64_t j, int) const { float a = A[n * ld + col0 + j]; return a * a; }
+};
+struct LoadSigma2B {    // B(j, i) = sigma2[offw + i*nin + j], j == nin -> sigma2[offb + i]
+  static constexpr bool K_CONTIG = true;
+  const float* s; int64_t offw, offb; int nin, has_bias;
+  __device__ float operator()(int64_t j, int64_t i, int) const {
+    if (j < nin) return s[offw + i * nin + j];
+    return has_bias ? s[offb + i] : 0.f;
+  }
+};
+// fvar[n,k,l] += sum_u G[(n,k),u] G[(n,l),u] T[n,u]
+__global__ void fvar_weighted_gg_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ T,
+                                        int64_t tld, int64_t N, int K, int m, float* __restrict__ fvar) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K * K) return;
+  int l = (int)(i % K), k = (int)((i / K) % K); int64_t n = i / (K * K);
+  const float* gk = G + (n * K + k) * gld;
+  const float* gl = G + (n * K + l) * gld;
+  const float* t = T + n * tld;
+  float acc = 0.f;
+  for (int u = 0; u < m; ++u) acc = fmaf(gk[u] * gl[u], t[u], acc);
+  fvar[i] += acc;
+}
+// fvar[n,k,l] += sum_e w[e] * B[(n,k), e] * B[(n,l), e]        (w may be NULL -> 1)
+__global__ void fvar_weighted_block_kernel(const float* __restrict__ B, int64_t bld, const float* __restrict__ w,
+                                           int64_t E, int K, float* __restrict__ fvar) {
+  __shared__ float red[8];
+  int64_t i = blockIdx.x;            // (n,k,l)
+  int l = (int)(i % K), k = (int)((i / K) % K); int64_t n = i / (K * K);
+  const float* bk = B + (n * K + k) * bld;
+  const float* bl = B + (n * K + l) * bld;
+  float acc = 0.f;
+  for (int64_t e = threadIdx.x; e < E; e += blockDim.x) acc = fmaf(bk[e] * bl[e], w ? w[e] : 1.f, acc);
+  acc = warp_sum(acc);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int j = 0; j < (int)(blockDim.x / 32); ++j) v += red[j];
+    fvar[i] += v;
+  }
+}
+
+// ---- f_var, Kronecker ---------------------------------------------------------------------
+// Dinv[i, j] = 1/(l1[i] l2[j] + delta)   or dampened 1/((l1[i]+sqrt d)(l2[j]+sqrt d))   kron.py:130-134
+__global__ void kron_dinv_kernel(const float* __restrict__ l1, const float* __restrict__ l2, int m, int n,
+                                 float delta, int dampen, int take_sqrt, float* __restrict__ D) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)m * n) return;
+  float a = l1[i / n], b = l2[i % n], v;
+  if (dampen) { float sd = sqrtf(delta); v = 1.f / ((a + sd) * (b + sd)); }
+  else v = 1.f / (a * b + delta);
+  D[i] = take_sqrt ? sqrtf(v) : v;
+}
+__global__ void inv_shift_kernel(const float* __restrict__ l, int m, float delta, int take_sqrt,
+                                 float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  float v = 1.f / (l[i] + delta);
+  out[i] = take_sqrt ? sqrtf(v) : v;
+}
+struct LoadSqRows {     // A(n, j) = Ahat[n, j]^2
+  static constexpr bool K_CONTIG = true;
+  const float* A; int64_t ld;
+  __device__ float operator()(int64_t n, int64_t j, int) const { float a = A[n * ld + j]; return a * a; }
+};
+struct LoadDinvT {      // B(j, i) = Dinv[i, j]
+  static constexpr bool K_CONTIG = true;
+  const float* D; int n;
+  __device__ float operator()(int64_t j, int64_t i, int) const { return D[i * n + j]; }
+};
+// fvar[n,k,l] += sum_u w[u] Gh[(n,k),u] Gh[(n,l),u]
+__global__ void fvar_gg_const_kernel(const float* __restrict__ Gh, int64_t gld, const float* __restrict__ w,
+                                     int64_t N, int K, int m, float* __restrict__ fvar) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K * K) return;
+  int l = (int)(i % K), k = (int)((i / K) % K); int64_t n = i / (K * K);
+  const float* gk = Gh + (n * K + k) * gld;
+  const float* gl = Gh + (n * K + l) * gld;
+  float acc = 0.f;
+  for (int u = 0; u < m; ++u) acc = fmaf(gk[u] * gl[u], w[u], acc);
+  fvar[i] += acc;
+}
+
+// ---- sampling epilogue ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+  *hi = __umulhi(a, b);
+  return a * b;
+}
+// Philox4x32-10
+__device__ __forceinline__ uint4 philox4(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0, hi1;
+    uint32_t lo0 = mulhilo32(0xD2511F53u, ctr.x, &hi0);
+    uint32_t lo1 = mulhilo32(0xCD9E8D57u, ctr.z, &hi1);
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  float u2 = (float)b * 2.3283064365386963e-10f;
+  float r = sqrtf(-2.f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// One thread owns one input n (its K x K Cholesky factor lives in registers) and walks a slab of
+// samples; consecutive threads own consecutive n so the [S,N,K] stores of a warp are contiguous.
+template <int K>
+__global__ void __launch_bounds__(128)
+glm_sample_kernel(int lik, const float* __restrict__ fmu, const float* __restrict__ fvar,
+                  const float* __restrict__ eps, uint64_t seed, int64_t S, int64_t N,
+                  float* __restrict__ out, int32_t* __restrict__ status, int s_per_block) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float L[K * (K + 1) / 2];
+  float mu[K];
+  bool ok = true;
+  // lower Cholesky from the lower triangle of f_var[n]
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    mu[i] = fmu[n * K + i];
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      float s = fvar[(n * K + i) * K + j];
+#pragma unroll
+      for (int t = 0; t < j; ++t) s -= L[i * (i + 1) / 2 + t] * L[j * (j + 1) / 2 + t];
+      if (i == j) {
+        if (!(s > 0.f)) ok = false;
+        L[i * (i + 1) / 2 + j] = sqrtf(s);
+      } else {
+        L[i * (i + 1) / 2 + j] = s / L[j * (j + 1) / 2 + j];
+      }
+    }
+  }
+  if (blockIdx.y == 0) status[n] = ok ? 0 : 1;
+  int64_t s0 = (int64_t)blockIdx.y * s_per_block;
+  int64_t s1 = s0 + s_per_block < S ? s0 + s_per_block : S;
+  for (int64_t s = s0; s < s1; ++s) {
+    float e[K], f[K];
+    if (eps) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) e[i] = eps[(s * N + n) * K + i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < K; i += 4) {
+        uint64_t c = (uint64_t)(s * N + n);
+        uint4 r = philox4(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)(i / 4), 0u),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+        e[i] = a.x;
+        if (i + 1 < K) e[i + 1] = a.y;
+        if (i + 2 < K) e[i + 2] = b.x;
+        if (i + 3 < K) e[i + 3] = b.y;
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      float v = mu[i];
+#pragma unroll
+      for (int j = 0; j <= i; ++j) v = fmaf(L[i * (i + 1) / 2 + j], e[j], v);
+      f[i] = v;
+      mx = fmaxf(mx, v);
+    }
+    float* o = out + (s * N + n) * K;
+    if (lik == BNNP_LIK_CATEGORICAL) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < K; ++i) { f[i] = __expf(f[i] - mx); sum += f[i]; }
+      float inv = 1.f / sum;
+#pragma unroll
+      for (int i = 0; i < K; ++i) o[i] = f[i] * inv;
+    } else if (lik == BNNP_LIK_BERNOULLI) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) o[i] = 1.f / (1.f + __expf(-f[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < K; ++i) o[i] = f[i];
+    }
+  }
+}
+
+
+// Reference fallback when the batched Cholesky fails (preds/predictives.py:73-76):
+// Normal(f_mu, diag(f_var).clamp(1e-5)) -- the variance is used as the *scale* (reference quirk).
+__global__ void glm_sample_diag_kernel(int lik, const float* __restrict__ fmu, const float* __restrict__ fvar,
+                                       const float* __restrict__ eps, uint64_t seed, int64_t S, int64_t N,
+                                       int K, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // (s, n)
+  if (i >= S * N) return;
+  int64_t n = i % N;
+  float f[BNNP_MAX_K];
+  float mx = -INFINITY;
+  for (int k = 0; k < K; ++k) {
+    float e;
+    if (eps) e = eps[i * K + k];
+    else {
+      uint4 r = philox4(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)k, 1u),
+                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      e = box_muller(r.x, r.y).x;
+    }
+    float sc = fmaxf(fvar[(n * K + k) * K + k], 1e-5f);
+    f[k] = fmaf(sc, e, fmu[n * K + k]);
+    mx = fmaxf(mx, f[k]);
+  }
+  float* o = out + i * K;
+  if (lik == BNNP_LIK_CATEGORICAL) {
+    float sum = 0.f;
+    for (int k = 0; k < K; ++k) { f[k] = __expf(f[k] - mx); sum += f[k]; }
+    for (int k = 0; k < K; ++k) o[k] = f[k] / sum;
+  } else if (lik == BNNP_LIK_BERNOULLI) {
+    for (int k = 0; k < K; ++k) o[k] = 1.f / (1.f + __expf(-f[k]));
+  } else {
+    for (int k = 0; k < K; ++k) o[k] = f[k];
+  }
+}
+
+template <int K>
+static int launch_sample(int lik, const float* fmu, const float* fvar, const float* eps, uint64_t seed,
+                         int64_t S, int64_t N, float* out, int32_t* status, cudaStream_t st) {
+  unsigned gx = (unsigned)ceil_div64(N, 128);
+  // enough y-slabs to fill the machine (148 SMs x several CTAs), at least 8 samples per slab
+  int64_t want = (148 * 8 + gx - 1) / gx;
+  int64_t slabs = want < 1 ? 1 : want;
+  if (slabs > S) slabs = S;
+  int spb = (int)ceil_div64(S, slabs);
+  slabs = ceil_div64(S, spb);
+  if (slabs > 65535) return BNNP_ERR_UNSUPPORTED;
+  glm_sample_kernel<K><<<dim3(gx, (unsigned)slabs), 128, 0, st>>>(lik, fmu, fvar, eps, seed, S, N, out, status, spb);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+}  // namespace bnnp
+using namespace bnnp;
+
+static bool linear_only_g(const bnnp_op_t* ops, int n_ops) {
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_CONV2D || ops[i].kind == BNNP_OP_MAXPOOL2D || ops[i].kind == BNNP_OP_AVGPOOL2D)
+      return false;
+  return true;
+}
+static int zero(float* p, int64_t n, cudaStream_t st) {
+  zero_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p, n);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------ f_mu
+extern "C" int bnnp_glm_fmu(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                            const float* X, const float* ws, const float* f, const float* delta,
+                            float* f_mu, void* stream) {
+  if (!ops || !plan || !ws || !f || !f_mu || N <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  (void)X;
+  BNNP_CUDA_CHECK(cudaMemcpyAsync(f_mu, f, sizeof(float) * N * plan->K, cudaMemcpyDeviceToDevice, st));
+  if (!delta) return BNNP_OK;
+  if (!linear_only_g(ops, n_ops)) return BNNP_ERR_UNSUPPORTED;
+  const int K = plan->K;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    fmu_direct_kernel<<<(unsigned)ceil_div64(N * K, 128), 128, 0, st>>>(
+        ws + q.grad_off, q.grad_ld, ws + plan->acat_off + q.lin_col, plan->Dtot, delta, o.theta_off_w,
+        o.theta_off_b, o.out_c, o.in_c, o.has_bias, K, N, f_mu);
+    BNNP_LAUNCH_CHECK();
+  }
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------ full
+extern "C" int64_t bnnp_glm_fvar_full_scratch_floats(const bnnp_plan_t* plan, int64_t N) {
+  int64_t Ppad = (plan->P + 31) / 32 * 32;
+  return 2 * Ppad + N * plan->K * plan->P + 64;
+}
+
+extern "C" int bnnp_glm_fvar_full(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                  const float* ws, const float* Sigma, float* f_var, float* scratch,
+                                  void* stream) {
+  if (!ops || !plan || !ws || !Sigma || !f_var || !scratch || N <= 0) return BNNP_ERR_INVALID;
+  if (!linear_only_g(ops, n_ops)) return BNNP_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int K = plan->K;
+  const int64_t P = plan->P, Ppad = (P + 31) / 32 * 32;
+  int32_t* pu = reinterpret_cast<int32_t*>(scratch);
+  int32_t* pc = pu + Ppad;
+  float* T = scratch + 2 * Ppad;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    param_maps2_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * o.in_c, 256), 256, 0, st>>>(
+        pu, pc, o.theta_off_w, o.out_c, o.in_c, q.lin_unit, q.lin_col, 0);
+    BNNP_LAUNCH_CHECK();
+    if (o.has_bias) {
+      param_maps2_kernel<<<(unsigned)ceil_div64(o.out_c, 256), 256, 0, st>>>(pu, pc, o.theta_off_b, o.out_c, o.in_c,
+                                                                             q.lin_unit, q.lin_col, 1);
+      BNNP_LAUNCH_CHECK();
+    }
+  }
+  JacRowA J{ws + plan->gcat_off, ws + plan->acat_off, pu, pc, plan->Mtot, plan->Dtot, K};
+  int rc = gemm_simt(N * K, P, P, 1, J, LoadRowMajorB{Sigma, P, 0}, StoreAxpby{T, P, 0, 1.f, 0.f}, st);
+  if (rc) return rc;
+  fvar_from_T_kernel<<<(unsigned)(N * K), 256, 0, st>>>(T, J, P, K, f_var);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------ diag
+static int64_t conv_block_floats(const bnnp_op_t* ops, int n_ops, int64_t N, int K) {
+  int64_t mx = 0;
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_CONV2D) {
+      int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw;
+      int64_t v = N * K * (ops[i].out_c * E + ops[i].out_c);
+      mx = v > mx ? v : mx;
+    }
+  return mx;
+}
+
+extern "C" int64_t bnnp_glm_fvar_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                                     int64_t N) {
+  int64_t lin = N * (int64_t)plan->Mtot;
+  int64_t cv = conv_block_floats(ops, n_ops, N, plan->K);
+  return (lin > cv ? lin : cv) + 64;
+}
+
+extern "C" int bnnp_glm_fvar_diag(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                  const float* X, const float* ws, const float* sigma2, float* f_var,
+                                  float* scratch, void* stream) {
+  if (!ops || !plan || !ws || !sigma2 || !f_var || !scratch || N <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const int K = plan->K;
+  int rc = zero(f_var, N * K * K, st);
+  if (rc) return rc;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (!is_param_op(o)) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    const float* G = ws + q.grad_off;
+    if (o.kind == BNNP_OP_LINEAR) {
+      // T[n,u] = sum_j sigma2[u,j] a[n,j]^2 (+ sigma2_b[u])
+      rc = gemm_simt(N, o.out_c, o.in_c + 1, 1, LoadSqA{ws + plan->acat_off, plan->Dtot, q.lin_col},
+                     LoadSigma2B{sigma2, o.theta_off_w, o.theta_off_b, o.in_c, o.has_bias},
+                     StoreAxpby{scratch, o.out_c, 0, 1.f, 0.f}, st);
+      if (rc) return rc;
+      fvar_weighted_gg_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(G, q.grad_ld, scratch, o.out_c,
+                                                                                  N, K, o.out_c, f_var);
+      BNNP_LAUNCH_CHECK();
+    } else {
+      int64_t ild; const float* in = op_input_g(ops, plan, i, X, ws, &ild);
+      if (!in) return BNNP_ERR_INVALID;
+      int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
+      int64_t R = N * K, bw = (int64_t)o.out_c * E;
+      if (R > 65535) return BNNP_ERR_UNSUPPORTED;
+      float* Jb = scratch;
+      float* sb = scratch + R * bw;
+      rc = gemm_simt(o.out_c, E, L, (int)R, ConvGradA2{G, q.grad_ld, L}, ConvUnfoldB2{make_im2col_g(o, in, ild, K)},
+                     StoreBlock2{Jb, bw, E}, st);
+      if (rc) return rc;
+      fvar_weighted_block_kernel<<<(unsigned)(N * K * K), 256, 0, st>>>(Jb, bw, sigma2 + o.theta_off_w, bw, K, f_var);
+      BNNP_LAUNCH_CHECK();
+      if (o.has_bias) {
+        conv_possum2_kernel<<<(unsigned)ceil_div64(R * o.out_c, 128), 128, 0, st>>>(G, q.grad_ld, R, o.out_c, L, sb);
+        BNNP_LAUNCH_CHECK();
+        fvar_weighted_block_kernel<<<(unsigned)(N * K * K), 64, 0, st>>>(sb, o.out_c, sigma2 + o.theta_off_b,
+                                                                         o.out_c, K, f_var);
+        BNNP_LAUNCH_CHECK();
+      }
+    }
+  }
+  return BNNP_OK;
+}
+
+
+// ------------------------------------------------------------------------------------ kron block
+// One parameter group of Kron.functional_variance on a materialised Jacobian block
+// Jb[R, m*n] (row r = (b,k), row stride ldj):  f_var[b,k,l] += sum_ij M_k M_l Dinv,  M = W1^T J W2
+// (equal to bmm(J, (W1 ((W1^T J W2) * Dinv) W2^T)^T) of preds/kron.py:135-141).
+static int kron_fvar_block(const float* Jb, int64_t ldj, int64_t R, int K, int m, int n, const float* W1,
+                           const float* l1, const float* W2, const float* l2, float delta, int dampen,
+                           float* f_var, float* scratch, cudaStream_t st) {
+  const int64_t N = R / K;
+  int rc;
+  if (!W2) {   // 1-factor (bias-like): ghat = J W,  f_var += ghat diag(1/(l+delta)) ghat^T
+    float* gh = scratch;                 // [R, m]
+    float* db = gh + R * m;              // [m]
+    rc = gemm_simt(R, m, m, 1, LoadRowMajorA{Jb, ldj, 0}, LoadRowMajorB{W1, m, 0}, StoreAxpby{gh, m, 0, 1.f, 0.f}, st);
+    if (rc) return rc;
+    inv_shift_kernel<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(l1, m, delta, 0, db);
+    BNNP_LAUNCH_CHECK();
+    fvar_gg_const_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(gh, m, db, N, K, m, f_var);
+    BNNP_LAUNCH_CHECK();
+    return BNNP_OK;
+  }
+  if (R > 65535) return BNNP_ERR_UNSUPPORTED;
+  const int64_t bw = (int64_t)m * n;
+  float* T1 = scratch;                   // [R, m, n]
+  float* T2 = T1 + R * bw;               // [R, m, n]
+  float* D = T2 + R * bw;                // [m, n]
+  rc = gemm_simt(m, n, n, (int)R, LoadRowMajorA{Jb, n, ldj}, LoadRowMajorB{W2, n, 0},
+                 StoreAxpby{T1, n, bw, 1.f, 0.f}, st);
+  if (rc) return rc;
+  rc = gemm_simt(m, n, m, (int)R, LoadColMajorA{W1, m, 0}, LoadRowMajorB{T1, n, bw},
+                 StoreAxpby{T2, n, bw, 1.f, 0.f}, st);
+  if (rc) return rc;
+  kron_dinv_kernel<<<(unsigned)ceil_div64(bw, 256), 256, 0, st>>>(l1, l2, m, n, delta, dampen, 0, D);
+  BNNP_LAUNCH_CHECK();
+  fvar_weighted_block_kernel<<<(unsigned)(N * K * K), 256, 0, st>>>(T2, bw, D, bw, K, f_var);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_kron_fvar_block(const float* Jb, int64_t ldj, int K, int m, int n, const float* W1,
+                                    const float* l1, const float* W2, const float* l2, float delta,
+                                    int dampen, float* f_var, float* scratch, int64_t R, void* stream) {
+  if (!Jb || !W1 || !l1 || !f_var || !scratch || R <= 0 || K <= 0 || m <= 0 || R % K) return BNNP_ERR_INVALID;
+  if (W2 && (!l2 || n <= 0)) return BNNP_ERR_INVALID;
+  return kron_fvar_block(Jb, ldj, R, K, m, n, W1, l1, W2, l2, delta, dampen, f_var, scratch, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------ kron
+extern "C" int64_t bnnp_glm_fvar_kron_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                                     int64_t N) {
+  const int K = plan->K;
+  int64_t mx = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (!is_param_op(o)) continue;
+    int64_t m = o.out_c, n = (int64_t)o.in_c * o.kh * o.kw, v;
+    if (o.kind == BNNP_OP_LINEAR) v = N * n + N * K * m + N * m + m * n + m;
+    else v = 3 * N * K * m * n + 2 * N * K * m + m * n + m;
+    mx = v > mx ? v : mx;
+  }
+  return mx + 256;
+}
+
+extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                  const float* X, const float* ws, const float* const* eig,
+                                  const float* delta_w, const float* delta_b, int dampen, float* f_var,
+                                  float* scratch, void* stream) {
+  if (!ops || !plan || !ws || !eig || !delta_w || !delta_b || !f_var || !scratch || N <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const int K = plan->K;
+  const int64_t R = N * K;
+  int rc = zero(f_var, N * K * K, st);
+  if (rc) return rc;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (!is_param_op(o)) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    const float* W1 = eig[4 * i], *l1 = eig[4 * i + 1], *W2 = eig[4 * i + 2], *l2 = eig[4 * i + 3];
+    if (!W1 || !l1 || !W2 || !l2) return BNNP_ERR_INVALID;
+    const float* G = ws + q.grad_off;
+    const int m = o.out_c, n = o.in_c * o.kh * o.kw;
+    if (o.kind == BNNP_OP_LINEAR) {
+      // J_n,k = g (x) a  =>  W1^T J W2 = (W1^T g)(W2^T a)^T : rotate the factors, never the matrix
+      float* Ah = scratch;                 // [N, n]    a W2
+      float* Gh = Ah + N * n;              // [N*K, m]  g W1
+      float* T = Gh + R * m;               // [N, m]    Dinv (Ah^2)
+      float* D = T + N * m;                // [m, n]
+      float* db = D + (int64_t)m * n;      // [m]
+      rc = gemm_simt(N, n, n, 1, LoadRowMajorA{ws + plan->acat_off + q.lin_col, plan->Dtot, 0},
+                     LoadRowMajorB{W2, n, 0}, StoreAxpby{Ah, n, 0, 1.f, 0.f}, st);
+      if (rc) return rc;
+      rc = gemm_simt(R, m, m, 1, LoadRowMajorA{G, q.grad_ld, 0}, LoadRowMajorB{W1, m, 0},
+                     StoreAxpby{Gh, m, 0, 1.f, 0.f}, st);
+      if (rc) return rc;
+      kron_dinv_kernel<<<(unsigned)ceil_div64((int64_t)m * n, 256), 256, 0, st>>>(l1, l2, m, n, delta_w[i], dampen, 0, D);
+      BNNP_LAUNCH_CHECK();
+      rc = gemm_simt(N, m, n, 1, LoadSqRows{Ah, n}, LoadDinvT{D, n}, StoreAxpby{T, m, 0, 1.f, 0.f}, st);
+      if (rc) return rc;
+      fvar_weighted_gg_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(Gh, m, T, m, N, K, m, f_var);
+      BNNP_LAUNCH_CHECK();
+      if (o.has_bias) {
+        inv_shift_kernel<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(l1, m, delta_b[i], 0, db);
+        BNNP_LAUNCH_CHECK();
+        fvar_gg_const_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(Gh, m, db, N, K, m, f_var);
+        BNNP_LAUNCH_CHECK();
+      }
+    } else {
+      int64_t ild; const float* in = op_input_g(ops, plan, i, X, ws, &ild);
+      if (!in) return BNNP_ERR_INVALID;
+      if (R > 65535) return BNNP_ERR_UNSUPPORTED;
+      int L = o.out_h * o.out_w;
+      int64_t bw = (int64_t)m * n;
+      float* Jb = scratch;                 // [R, m, n]
+      float* sb = Jb + R * bw;             // [R, m]
+      float* rest = sb + R * m;
+      rc = gemm_simt(m, n, L, (int)R, ConvGradA2{G, q.grad_ld, L}, ConvUnfoldB2{make_im2col_g(o, in, ild, K)},
+                     StoreBlock2{Jb, bw, n}, st);
+      if (rc) return rc;
+      rc = kron_fvar_block(Jb, bw, R, K, m, n, W1, l1, W2, l2, delta_w[i], dampen, f_var, rest, st);
+      if (rc) return rc;
+      if (o.has_bias) {
+        conv_possum2_kernel<<<(unsigned)ceil_div64(R * m, 128), 128, 0, st>>>(G, q.grad_ld, R, m, L, sb);
+        BNNP_LAUNCH_CHECK();
+        rc = kron_fvar_block(sb, m, R, K, m, 0, W1, l1, nullptr, nullptr, delta_b[i], dampen, f_var, rest, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------ sample
+extern "C" int bnnp_glm_sample(int lik, const float* f_mu, const float* f_var, const float* eps,
+                               uint64_t seed, int64_t S, int64_t N, int K, float* out, int32_t* status,
+                               void* stream) {
+  if (!f_mu || !f_var || !out || !status || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+#define BNNP_CASE(KK) case KK: return launch_sample<KK>(lik, f_mu, f_var, eps, seed, S, N, out, status, st);
+  switch (K) {
+    BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
+    BNNP_CASE(9) BNNP_CASE(10) BNNP_CASE(11) BNNP_CASE(12) BNNP_CASE(13) BNNP_CASE(14) BNNP_CASE(15) BNNP_CASE(16)
+    default: return BNNP_ERR_UNSUPPORTED;
+  }
+#undef BNNP_CASE
+}
+
+extern "C" int bnnp_glm_sample_diag_fallback(int lik, const float* f_mu, const float* f_var, const float* eps,
+                                             uint64_t seed, int64_t S, int64_t N, int K, float* out,
+                                             void* stream) {
+  if (!f_mu || !f_var || !out || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  glm_sample_diag_kernel<<<(unsigned)ceil_div64(S * N, 128), 128, 0, as_stream(stream)>>>(lik, f_mu, f_var, eps, seed,
+                                                                                       S, N, K, out);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}

@@ -1,0 +1,142 @@
+// Likelihood terms of preds/likelihoods.py as device kernels (one thread per example; K <= 32).
+#include "common.cuh"
+
+namespace bnnp {
+
+constexpr float kClampEps = 1e-7f;     // preds/likelihoods.py:4
+
+__device__ __forceinline__ void softmax_row(const float* f, int K, float* p) {
+  float mx = f[0];
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, f[k]);
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) { p[k] = expf(f[k] - mx); s += p[k]; }
+  float inv = 1.f / s;
+  for (int k = 0; k < K; ++k) p[k] *= inv;
+}
+
+__global__ void lik_hessian_kernel(int lik, const float* __restrict__ f, int64_t N, int K,
+                                   float sigma2, float* __restrict__ L) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float* out = L + n * K * K;
+  if (lik == BNNP_LIK_CATEGORICAL) {
+    float p[BNNP_MAX_K];
+    softmax_row(f + n * K, K, p);
+    for (int k = 0; k < K; ++k) p[k] = fminf(fmaxf(p[k], kClampEps), 1.f - kClampEps);
+    for (int k = 0; k < K; ++k)
+      for (int l = 0; l < K; ++l) out[k * K + l] = (k == l ? p[k] : 0.f) - p[k] * p[l];
+  } else if (lik == BNNP_LIK_GAUSSIAN) {
+    out[0] = 1.f / sigma2;
+  } else {
+    float p = 1.f / (1.f + expf(-f[n]));
+    p = fminf(fmaxf(p, kClampEps), 1.f - kClampEps);
+    out[0] = p * (1.f - p);
+  }
+}
+
+// seed[n, v, k] = S_n[k, v];  CE: S = diag(sqrt p) - p sqrt(p)^T (unclamped), MSE: sqrt(2) I
+__global__ void lik_sqrt_seed_kernel(int lik, const float* __restrict__ f, int64_t N, int K,
+                                     float* __restrict__ seed) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float* out = seed + n * K * K;
+  if (lik == BNNP_LIK_CATEGORICAL) {
+    float p[BNNP_MAX_K];
+    softmax_row(f + n * K, K, p);
+    for (int v = 0; v < K; ++v) {
+      float sq = sqrtf(p[v]);
+      for (int k = 0; k < K; ++k) out[v * K + k] = (k == v ? sq : 0.f) - p[k] * sq;
+    }
+  } else {
+    for (int v = 0; v < K; ++v)
+      for (int k = 0; k < K; ++k) out[v * K + k] = (k == v) ? 1.41421356237309515f : 0.f;
+  }
+}
+
+__global__ void identity_seed_kernel(int64_t N, int K, float* __restrict__ seed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K * K) return;
+  int k = (int)(i % K), v = (int)((i / K) % K);
+  seed[i] = (k == v) ? 1.f : 0.f;
+}
+
+__global__ void lik_residual_kernel(int lik, const float* __restrict__ f, const void* __restrict__ y,
+                                    int64_t N, int K, float sigma2, float* __restrict__ rs) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  if (lik == BNNP_LIK_CATEGORICAL) {
+    float p[BNNP_MAX_K];
+    softmax_row(f + n * K, K, p);
+    int64_t label = reinterpret_cast<const int64_t*>(y)[n];
+    for (int k = 0; k < K; ++k) rs[n * K + k] = (k == label ? 1.f : 0.f) - p[k];
+  } else if (lik == BNNP_LIK_GAUSSIAN) {
+    const float* yy = reinterpret_cast<const float*>(y);
+    for (int k = 0; k < K; ++k) rs[n * K + k] = (yy[n * K + k] - f[n * K + k]) / sigma2;
+  } else {
+    const float* yy = reinterpret_cast<const float*>(y);
+    for (int k = 0; k < K; ++k) rs[n * K + k] = yy[n * K + k] - 1.f / (1.f + expf(-f[n * K + k]));
+  }
+}
+
+__global__ void lik_inv_link_kernel(int lik, const float* __restrict__ f, int64_t rows, int K,
+                                    float* __restrict__ out) {
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  if (lik == BNNP_LIK_CATEGORICAL) {
+    float p[BNNP_MAX_K];
+    softmax_row(f + n * K, K, p);
+    for (int k = 0; k < K; ++k) out[n * K + k] = p[k];
+  } else if (lik == BNNP_LIK_GAUSSIAN) {
+    for (int k = 0; k < K; ++k) out[n * K + k] = f[n * K + k];
+  } else {
+    for (int k = 0; k < K; ++k) out[n * K + k] = 1.f / (1.f + expf(-f[n * K + k]));
+  }
+}
+
+}  // namespace bnnp
+using namespace bnnp;
+
+static int check_lik(int lik, int K) {
+  if (lik < 0 || lik > 2 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  if (lik != BNNP_LIK_CATEGORICAL && K != 1 && lik == BNNP_LIK_BERNOULLI) return BNNP_ERR_INVALID;
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_lik_hessian(int lik, const float* f, int64_t N, int K, float sigma2,
+                                float* Lambda, void* stream) {
+  if (check_lik(lik, K) || !f || !Lambda || N <= 0) return BNNP_ERR_INVALID;
+  if (lik != BNNP_LIK_CATEGORICAL && K != 1) return BNNP_ERR_INVALID;   // preds/likelihoods.py:51
+  lik_hessian_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, as_stream(stream)>>>(lik, f, N, K, sigma2, Lambda);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_lik_sqrt_seed(int lik, const float* f, int64_t N, int K, float* seed, void* stream) {
+  if (check_lik(lik, K) || !f || !seed || N <= 0) return BNNP_ERR_INVALID;
+  if (lik == BNNP_LIK_BERNOULLI) return BNNP_ERR_INVALID;               // no nn_loss, :74-75
+  lik_sqrt_seed_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, as_stream(stream)>>>(lik, f, N, K, seed);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_identity_seed(int64_t N, int K, float* seed, void* stream) {
+  if (!seed || N <= 0 || K <= 0) return BNNP_ERR_INVALID;
+  identity_seed_kernel<<<(unsigned)ceil_div64(N * K * K, 256), 256, 0, as_stream(stream)>>>(N, K, seed);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_lik_residual(int lik, const float* f, const void* y, int64_t N, int K,
+                                 float sigma2, float* rs, void* stream) {
+  if (check_lik(lik, K) || !f || !y || !rs || N <= 0) return BNNP_ERR_INVALID;
+  lik_residual_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, as_stream(stream)>>>(lik, f, y, N, K, sigma2, rs);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_lik_inv_link(int lik, const float* f, int64_t rows, int K, float* out, void* stream) {
+  if (check_lik(lik, K) || !f || !out || rows <= 0) return BNNP_ERR_INVALID;
+  lik_inv_link_kernel<<<(unsigned)ceil_div64(rows, 128), 128, 0, as_stream(stream)>>>(lik, f, rows, K, out);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}

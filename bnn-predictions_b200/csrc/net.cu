@@ -1,0 +1,434 @@
+// Layer-factor pass: forward through the layer zoo saving every layer input, then one
+// backward sweep that propagates V columns at once (all K output Jacobians, or the V columns of
+// the loss-Hessian square root).  Replaces the K x (forward + BackPACK backward) loop of
+// preds/gradients.py:24-36 and the BackPACK second-order backward of preds/laplace.py:55-58,73-76.
+//
+// Linear layers live in two concatenated matrices so that later kernels can synthesise
+// Jacobian tiles on chip from one base pointer each:
+//   A_cat [N, Dtot]   : input of every Linear (+ a constant-1 column for its bias)
+//   G_cat [N*V, Mtot] : d f_v / d (pre-activation) of every Linear
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace bnnp {
+
+// ------------------------------------------------------------------------------------------
+// elementwise
+// ------------------------------------------------------------------------------------------
+__global__ void act_fwd_kernel(float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                               int kind) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  float* p = x + (i / cols) * ld + (i % cols);
+  float v = *p;
+  if (kind == BNNP_OP_RELU) v = v > 0.f ? v : 0.f;
+  else if (kind == BNNP_OP_TANH) v = tanhf(v);
+  else v = 1.f / (1.f + expf(-v));
+  *p = v;
+}
+
+// g[(n,v), c] *= act'(out[n, c])
+__global__ void act_bwd_kernel(float* __restrict__ g, int64_t gld, const float* __restrict__ out,
+                               int64_t old, int64_t N, int V, int64_t cols, int kind) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * V * cols) return;
+  int64_t c = i % cols, r = i / cols, n = r / V;
+  float o = out[n * old + c], d;
+  if (kind == BNNP_OP_RELU) d = o > 0.f ? 1.f : 0.f;
+  else if (kind == BNNP_OP_TANH) d = 1.f - o * o;
+  else d = o * (1.f - o);
+  g[r * gld + c] *= d;
+}
+
+__global__ void copy2d_kernel(float* __restrict__ dst, int64_t dld, const float* __restrict__ src,
+                              int64_t sld, int64_t rows, int64_t cols) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  dst[(i / cols) * dld + (i % cols)] = src[(i / cols) * sld + (i % cols)];
+}
+
+__global__ void fill_col_kernel(float* __restrict__ dst, int64_t ld, int64_t rows, float v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) dst[i * ld] = v;
+}
+
+static int copy2d(float* dst, int64_t dld, const float* src, int64_t sld, int64_t rows,
+                  int64_t cols, cudaStream_t st) {
+  int64_t n = rows * cols;
+  if (n == 0) return BNNP_OK;
+  copy2d_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(dst, dld, src, sld, rows, cols);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// conv / pool (direct form; one thread per output element)
+// ------------------------------------------------------------------------------------------
+struct ConvGeom {
+  int Cin, H, W, Cout, OH, OW, kh, kw, sh, sw, pl, pt;
+};
+static ConvGeom geom_of(const bnnp_op_t& o) {
+  return ConvGeom{o.in_c, o.in_h, o.in_w, o.out_c, o.out_h, o.out_w, o.kh, o.kw,
+                  o.stride_h, o.stride_w, o.pad_l, o.pad_t};
+}
+
+__global__ void conv_fwd_kernel(const float* __restrict__ in, int64_t ild, float* __restrict__ out,
+                                int64_t old, const float* __restrict__ Wt,
+                                const float* __restrict__ bias, int64_t N, ConvGeom g) {
+  int64_t per = (int64_t)g.Cout * g.OH * g.OW;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * per) return;
+  int64_t n = i / per, r = i % per;
+  int co = (int)(r / (g.OH * g.OW)), oh = (int)((r / g.OW) % g.OH), ow = (int)(r % g.OW);
+  const float* x = in + n * ild;
+  const float* w = Wt + (int64_t)co * g.Cin * g.kh * g.kw;
+  float acc = bias ? bias[co] : 0.f;
+  for (int ci = 0; ci < g.Cin; ++ci)
+    for (int a = 0; a < g.kh; ++a) {
+      int ih = oh * g.sh - g.pt + a;
+      if (ih < 0 || ih >= g.H) continue;
+      for (int b = 0; b < g.kw; ++b) {
+        int iw = ow * g.sw - g.pl + b;
+        if (iw < 0 || iw >= g.W) continue;
+        acc = fmaf(w[(ci * g.kh + a) * g.kw + b], x[((int64_t)ci * g.H + ih) * g.W + iw], acc);
+      }
+    }
+  out[n * old + r] = acc;
+}
+
+// gin[r, ci, ih, iw] = sum_{co,a,b} W[co,ci,a,b] * gout[r, co, oh, ow],  oh*sh - pt + a = ih
+__global__ void conv_bwd_data_kernel(const float* __restrict__ gout, int64_t gold,
+                                     float* __restrict__ gin, int64_t gild,
+                                     const float* __restrict__ Wt, int64_t R, ConvGeom g) {
+  int64_t per = (int64_t)g.Cin * g.H * g.W;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * per) return;
+  int64_t r = i / per, e = i % per;
+  int ci = (int)(e / (g.H * g.W)), ih = (int)((e / g.W) % g.H), iw = (int)(e % g.W);
+  const float* go = gout + r * gold;
+  float acc = 0.f;
+  for (int a = 0; a < g.kh; ++a) {
+    int th = ih + g.pt - a;
+    if (th < 0 || th % g.sh) continue;
+    int oh = th / g.sh;
+    if (oh >= g.OH) continue;
+    for (int b = 0; b < g.kw; ++b) {
+      int tw = iw + g.pl - b;
+      if (tw < 0 || tw % g.sw) continue;
+      int ow = tw / g.sw;
+      if (ow >= g.OW) continue;
+      for (int co = 0; co < g.Cout; ++co)
+        acc = fmaf(Wt[(((int64_t)co * g.Cin + ci) * g.kh + a) * g.kw + b],
+                   go[((int64_t)co * g.OH + oh) * g.OW + ow], acc);
+    }
+  }
+  gin[r * gild + e] = acc;
+}
+
+// Max pooling over a zero-padded input (deepobs tfmaxpool2d = ZeroPad2d + MaxPool2d(padding=0)):
+// window scanned row-major, strict '>' so the FIRST maximum wins (torch's rule); idx = ih*W+iw
+// of the winner or -1 when the winner is a padding zero.
+__global__ void maxpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
+                                   float* __restrict__ out, int64_t old, int32_t* __restrict__ idx,
+                                   int64_t N, ConvGeom g) {
+  int64_t per = (int64_t)g.Cout * g.OH * g.OW;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * per) return;
+  int64_t n = i / per, r = i % per;
+  int c = (int)(r / (g.OH * g.OW)), oh = (int)((r / g.OW) % g.OH), ow = (int)(r % g.OW);
+  const float* x = in + n * ild + (int64_t)c * g.H * g.W;
+  float best = -INFINITY;
+  int bi = -1;
+  for (int a = 0; a < g.kh; ++a) {
+    int ih = oh * g.sh - g.pt + a;
+    for (int b = 0; b < g.kw; ++b) {
+      int iw = ow * g.sw - g.pl + b;
+      bool inside = ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+      float v = inside ? x[ih * g.W + iw] : 0.f;      // outside = explicit zero padding
+      if (v > best || v != v) { best = v; bi = inside ? ih * g.W + iw : -1; }
+    }
+  }
+  out[n * old + r] = best;
+  idx[n * per + r] = bi;
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
+                                   float* __restrict__ gin, int64_t gild,
+                                   const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g) {
+  int64_t per = (int64_t)g.Cin * g.H * g.W;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * V * per) return;
+  int64_t r = i / per, e = i % per, n = r / V;
+  int c = (int)(e / (g.H * g.W)), ih = (int)((e / g.W) % g.H), iw = (int)(e % g.W);
+  int me = ih * g.W + iw;
+  int64_t operp = (int64_t)g.Cout * g.OH * g.OW;
+  const int32_t* id = idx + n * operp + (int64_t)c * g.OH * g.OW;
+  const float* go = gout + r * gold + (int64_t)c * g.OH * g.OW;
+  float acc = 0.f;
+  for (int a = 0; a < g.kh; ++a) {
+    int th = ih + g.pt - a;
+    if (th < 0 || th % g.sh) continue;
+    int oh = th / g.sh;
+    if (oh >= g.OH) continue;
+    for (int b = 0; b < g.kw; ++b) {
+      int tw = iw + g.pl - b;
+      if (tw < 0 || tw % g.sw) continue;
+      int ow = tw / g.sw;
+      if (ow >= g.OW) continue;
+      if (id[oh * g.OW + ow] == me) acc += go[oh * g.OW + ow];
+    }
+  }
+  gin[r * gild + e] = acc;
+}
+
+__global__ void avgpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
+                                   float* __restrict__ out, int64_t old, int64_t N, ConvGeom g) {
+  int64_t per = (int64_t)g.Cout * g.OH * g.OW;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * per) return;
+  int64_t n = i / per, r = i % per;
+  int c = (int)(r / (g.OH * g.OW)), oh = (int)((r / g.OW) % g.OH), ow = (int)(r % g.OW);
+  const float* x = in + n * ild + (int64_t)c * g.H * g.W;
+  float acc = 0.f;
+  for (int a = 0; a < g.kh; ++a)
+    for (int b = 0; b < g.kw; ++b) {
+      int ih = oh * g.sh - g.pt + a, iw = ow * g.sw - g.pl + b;
+      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) acc += x[ih * g.W + iw];
+    }
+  out[n * old + r] = acc / (float)(g.kh * g.kw);
+}
+
+__global__ void avgpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
+                                   float* __restrict__ gin, int64_t gild, int64_t R, ConvGeom g) {
+  int64_t per = (int64_t)g.Cin * g.H * g.W;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * per) return;
+  int64_t r = i / per, e = i % per;
+  int c = (int)(e / (g.H * g.W)), ih = (int)((e / g.W) % g.H), iw = (int)(e % g.W);
+  const float* go = gout + r * gold + (int64_t)c * g.OH * g.OW;
+  float acc = 0.f;
+  for (int a = 0; a < g.kh; ++a) {
+    int th = ih + g.pt - a;
+    if (th < 0 || th % g.sh) continue;
+    int oh = th / g.sh;
+    if (oh >= g.OH) continue;
+    for (int b = 0; b < g.kw; ++b) {
+      int tw = iw + g.pl - b;
+      if (tw < 0 || tw % g.sw) continue;
+      int ow = tw / g.sw;
+      if (ow >= g.OW) continue;
+      acc += go[oh * g.OW + ow];
+    }
+  }
+  gin[r * gild + e] = acc / (float)(g.kh * g.kw);
+}
+
+// Linear forward epilogue: out = acc + bias
+struct StoreBias {
+  float* p; int64_t ld; const float* bias;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t m, int64_t n, float acc, int) const {
+    p[m * ld + n] = acc + (bias ? bias[n] : 0.f);
+  }
+};
+
+}  // namespace bnnp
+
+using namespace bnnp;
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+static int next_param_op(const bnnp_op_t* ops, int n_ops, int i) {
+  for (int j = i + 1; j < n_ops; ++j) {
+    if (is_elementwise_op(ops[j]) || ops[j].kind == BNNP_OP_FLATTEN) continue;
+    return j;
+  }
+  return -1;
+}
+
+extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, bnnp_plan_t* plan) {
+  if (!ops || !plan || n_ops <= 0 || n_ops > BNNP_MAX_OPS || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
+  bnnp_plan_t P = {};
+  P.first_linear = -1;
+  int64_t nparam = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind < BNNP_OP_LINEAR || o.kind > BNNP_OP_SIGMOID) return BNNP_ERR_UNSUPPORTED;
+    if (i > 0 && op_in_size(o) != op_out_size(ops[i - 1])) return BNNP_ERR_INVALID;
+    if ((is_elementwise_op(o) || o.kind == BNNP_OP_FLATTEN)) {
+      if (i == 0) return BNNP_ERR_UNSUPPORTED;
+      if (op_in_size(o) != op_out_size(o)) return BNNP_ERR_INVALID;
+    }
+    if (is_param_op(o)) {
+      if (!o.weight) return BNNP_ERR_INVALID;
+      int64_t wn = (int64_t)o.out_c * o.in_c * o.kh * o.kw;
+      nparam += wn + (o.has_bias ? o.out_c : 0);
+    }
+    if (o.kind == BNNP_OP_LINEAR) {
+      if (o.in_h != 1 || o.in_w != 1 || o.kh != 1 || o.kw != 1) return BNNP_ERR_INVALID;
+      if (P.first_linear < 0) P.first_linear = i;
+      P.op[i].lin_col = P.Dtot;
+      P.op[i].lin_unit = P.Mtot;
+      P.Dtot += o.in_c + 1;
+      P.Mtot += o.out_c;
+      P.n_linear++;
+    } else {
+      P.op[i].lin_col = P.op[i].lin_unit = -1;
+    }
+  }
+  P.P = nparam;
+  P.K = (int32_t)op_out_size(ops[n_ops - 1]);
+  int64_t cur = 0;
+  auto take = [&](int64_t n) { int64_t o = cur; cur += (n + 31) / 32 * 32; return o; };
+  P.acat_off = take(N * (int64_t)P.Dtot);
+  P.gcat_off = take(N * V * (int64_t)P.Mtot);
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    bnnp_op_plan_t& q = P.op[i];
+    q.idx_off = -1;
+    if (is_elementwise_op(o) || o.kind == BNNP_OP_FLATTEN) {
+      q.act_off = P.op[i - 1].act_off; q.act_ld = P.op[i - 1].act_ld;
+      q.grad_off = P.op[i - 1].grad_off; q.grad_ld = P.op[i - 1].grad_ld;
+      continue;
+    }
+    int64_t osz = op_out_size(o);
+    int nx = next_param_op(ops, n_ops, i);
+    if (o.kind == BNNP_OP_LINEAR && nx >= 0 && ops[nx].kind == BNNP_OP_LINEAR) {
+      q.act_off = P.acat_off + P.op[nx].lin_col; q.act_ld = P.Dtot;
+    } else {
+      q.act_off = take(N * osz); q.act_ld = osz;
+    }
+    if (o.kind == BNNP_OP_LINEAR) {
+      q.grad_off = P.gcat_off + q.lin_unit; q.grad_ld = P.Mtot;
+    } else {
+      q.grad_off = take(N * V * osz); q.grad_ld = osz;
+    }
+    if (o.kind == BNNP_OP_MAXPOOL2D) q.idx_off = take(N * osz);
+  }
+  P.total_floats = cur;
+  *plan = P;
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                const float* X, int64_t N, float* ws, float* logits, void* stream) {
+  if (!ops || !plan || !X || !ws || N <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const float* in = X;
+  int64_t ild = op_in_size(ops[0]);
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    const bnnp_op_plan_t& q = plan->op[i];
+    float* out = ws + q.act_off;
+    int64_t osz = op_out_size(o);
+    unsigned blocks = (unsigned)ceil_div64(N * osz, 256);
+    switch (o.kind) {
+      case BNNP_OP_LINEAR: {
+        float* slice = ws + plan->acat_off + q.lin_col;
+        if (in != slice) {
+          int rc = copy2d(slice, plan->Dtot, in, ild, N, o.in_c, st);
+          if (rc) return rc;
+        }
+        fill_col_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(slice + o.in_c, plan->Dtot, N, 1.f);
+        BNNP_LAUNCH_CHECK();
+        int rc = gemm_simt(N, o.out_c, o.in_c, 1, LoadRowMajorA{slice, plan->Dtot, 0},
+                           LoadColMajorB{o.weight, o.in_c, 0},
+                           StoreBias{out, q.act_ld, o.has_bias ? o.bias : nullptr}, st);
+        if (rc) return rc;
+        break;
+      }
+      case BNNP_OP_CONV2D:
+        conv_fwd_kernel<<<blocks, 256, 0, st>>>(in, ild, out, q.act_ld, o.weight,
+                                                o.has_bias ? o.bias : nullptr, N, geom_of(o));
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_MAXPOOL2D:
+        maxpool_fwd_kernel<<<blocks, 256, 0, st>>>(in, ild, out, q.act_ld,
+                                                   reinterpret_cast<int32_t*>(ws) + q.idx_off, N, geom_of(o));
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_AVGPOOL2D:
+        avgpool_fwd_kernel<<<blocks, 256, 0, st>>>(in, ild, out, q.act_ld, N, geom_of(o));
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_RELU: case BNNP_OP_TANH: case BNNP_OP_SIGMOID:
+        act_fwd_kernel<<<blocks, 256, 0, st>>>(out, N, osz, q.act_ld, o.kind);
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_FLATTEN:
+        break;
+      default:
+        return BNNP_ERR_UNSUPPORTED;
+    }
+    in = out;
+    ild = q.act_ld;
+  }
+  if (logits) {
+    int rc = copy2d(logits, plan->K, in, ild, N, plan->K, st);
+    if (rc) return rc;
+  }
+  return BNNP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward (V columns)
+// ------------------------------------------------------------------------------------------
+extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                 const float* seed, int64_t N, int V, float* ws, void* stream) {
+  if (!ops || !plan || !seed || !ws || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  const int K = plan->K;
+  const int64_t R = N * V;
+  int first_param = -1;
+  for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { first_param = i; break; }
+  if (first_param < 0) return BNNP_ERR_INVALID;
+  {
+    const bnnp_op_plan_t& q = plan->op[n_ops - 1];
+    int rc = copy2d(ws + q.grad_off, q.grad_ld, seed, K, R, K, st);
+    if (rc) return rc;
+  }
+  for (int i = n_ops - 1; i > first_param; --i) {
+    const bnnp_op_t& o = ops[i];
+    const bnnp_op_plan_t& q = plan->op[i];
+    const bnnp_op_plan_t& qp = plan->op[i - 1];
+    float* gout = ws + q.grad_off;
+    float* gin = ws + qp.grad_off;
+    int64_t isz = op_in_size(o);
+    unsigned blocks = (unsigned)ceil_div64(R * isz, 256);
+    switch (o.kind) {
+      case BNNP_OP_LINEAR: {
+        int rc = gemm_simt(R, o.in_c, o.out_c, 1, LoadRowMajorA{gout, q.grad_ld, 0},
+                           LoadRowMajorB{o.weight, o.in_c, 0},
+                           StoreAxpby{gin, qp.grad_ld, 0, 1.f, 0.f}, st);
+        if (rc) return rc;
+        break;
+      }
+      case BNNP_OP_CONV2D:
+        conv_bwd_data_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, o.weight, R, geom_of(o));
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_MAXPOOL2D:
+        maxpool_bwd_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld,
+                                                   reinterpret_cast<const int32_t*>(ws) + q.idx_off, N, V, geom_of(o));
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_AVGPOOL2D:
+        avgpool_bwd_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, R, geom_of(o));
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_RELU: case BNNP_OP_TANH: case BNNP_OP_SIGMOID:
+        act_bwd_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, ws + q.act_off, q.act_ld, N, V, isz, o.kind);
+        BNNP_LAUNCH_CHECK();
+        break;
+      case BNNP_OP_FLATTEN:
+        break;
+      default:
+        return BNNP_ERR_UNSUPPORTED;
+    }
+  }
+  return BNNP_OK;
+}

@@ -1,0 +1,289 @@
+"""Host-side plumbing between ``nn.Module`` models and the C ABI: builds the network descriptor
+(``bnnp_op_t[]``), owns the torch-allocated workspace, and wraps each kernel entry point.
+
+No arithmetic of the hot path happens here; torch provides device memory and the stream only.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _cabi as cabi
+from ._cabi import lib, check, ptr, stream
+
+_ACT = {nn.ReLU: cabi.OP_RELU, nn.Tanh: cabi.OP_TANH, nn.Sigmoid: cabi.OP_SIGMOID}
+_IGNORED = (nn.Identity, nn.Dropout)        # model.eval() semantics (preds/laplace.py:35)
+
+
+def _pair(x):
+    return (x, x) if isinstance(x, int) else tuple(x)
+
+
+def _leaf_trace(model, sample):
+    """Run one example through the model recording (leaf module, in shape, out shape, padding)
+    in execution order.  deepobs-style ``ZeroPad2d`` paddings are set by forward-pre-hooks
+    (preds/models.py:250-266), so they are only known after a dry run."""
+    trace, handles = [], []
+
+    def hook(mod, inp, out):
+        pad = tuple(_pair4(mod.padding)) if isinstance(mod, nn.ZeroPad2d) else None
+        trace.append((mod, tuple(inp[0].shape[1:]), tuple(out.shape[1:]), pad))
+
+    for m in model.modules():
+        if len(list(m.children())) == 0:
+            handles.append(m.register_forward_hook(hook))
+    was_training = model.training
+    model.eval()
+    try:
+        with torch.no_grad():
+            model(sample)
+    finally:
+        for h in handles:
+            h.remove()
+        model.train(was_training)
+    return trace
+
+
+def _pair4(p):
+    return (p, p, p, p) if isinstance(p, int) else tuple(p)
+
+
+def _shape3(shape):
+    if len(shape) == 3:
+        return shape
+    if len(shape) == 1:
+        return (shape[0], 1, 1)
+    raise cabi.BnnpError('unsupported activation shape %s' % (shape,))
+
+
+class Net:
+    """Descriptor + workspace for one model on one device."""
+
+    def __init__(self, model):
+        self.model = model
+        self.params = list(model.parameters())
+        if not self.params:
+            raise ValueError('model has no parameters')
+        self.device = self.params[0].device
+        cabi.require_device(self.params[0])
+        self.P = sum(p.numel() for p in self.params)
+        self._sig = None
+        self._plans = {}
+        self._ws = None
+        self._scratch = None
+
+    # ------------------------------------------------------------------ descriptor
+    def _build(self, in_shape):
+        model = self.model
+        sample = torch.zeros((1,) + tuple(in_shape), device=self.device)
+        trace = _leaf_trace(model, sample)
+        offs, off = {}, 0
+        for p in self.params:
+            offs[id(p)] = off
+            off += p.numel()
+        ops, mods = [], []
+        pend_pad = (0, 0, 0, 0)
+        for mod, ishape, oshape, pad in trace:
+            if isinstance(mod, _IGNORED):
+                continue
+            if isinstance(mod, nn.ZeroPad2d):
+                pend_pad = tuple(a + b for a, b in zip(pend_pad, pad))
+                continue
+            op = cabi.Op()
+            if isinstance(mod, nn.ZeroPad2d):
+                continue
+            # input shape as seen by the op = shape before any folded padding
+            if any(pend_pad):
+                l, r, t, b = pend_pad
+                ishape = (ishape[0], ishape[1] - t - b, ishape[2] - l - r)
+            if isinstance(mod, nn.Linear):
+                if any(pend_pad):
+                    raise cabi.BnnpError('ZeroPad2d in front of Linear is unsupported')
+                if len(ishape) != 1:
+                    raise cabi.BnnpError('Linear expects a flattened input (got %s)' % (ishape,))
+                op.kind = cabi.OP_LINEAR
+                op.in_c, op.in_h, op.in_w = mod.in_features, 1, 1
+                op.out_c, op.out_h, op.out_w = mod.out_features, 1, 1
+                op.kh = op.kw = op.stride_h = op.stride_w = 1
+            elif isinstance(mod, nn.Conv2d):
+                if _pair(mod.dilation) != (1, 1) or mod.groups != 1 or mod.padding_mode != 'zeros':
+                    raise cabi.BnnpError('Conv2d with dilation/groups/non-zero padding mode is unsupported')
+                ph, pw = _pair(mod.padding)
+                op.kind = cabi.OP_CONV2D
+                op.in_c, op.in_h, op.in_w = ishape
+                op.out_c, op.out_h, op.out_w = oshape
+                op.kh, op.kw = _pair(mod.kernel_size)
+                op.stride_h, op.stride_w = _pair(mod.stride)
+                pend_pad = (pend_pad[0] + pw, pend_pad[1] + pw, pend_pad[2] + ph, pend_pad[3] + ph)
+            elif isinstance(mod, (nn.MaxPool2d, nn.AvgPool2d)):
+                is_max = isinstance(mod, nn.MaxPool2d)
+                if is_max and (_pair(mod.dilation) != (1, 1) or mod.ceil_mode):
+                    raise cabi.BnnpError('MaxPool2d with dilation/ceil_mode is unsupported')
+                if not is_max and (mod.ceil_mode or _pair(mod.padding) != (0, 0)):
+                    raise cabi.BnnpError('AvgPool2d with padding/ceil_mode is unsupported')
+                if is_max and _pair(mod.padding) != (0, 0):
+                    # torch pads max-pool with -inf, not zeros: not expressible as zero padding
+                    raise cabi.BnnpError('MaxPool2d(padding>0) is unsupported; use ZeroPad2d + padding=0')
+                op.kind = cabi.OP_MAXPOOL2D if is_max else cabi.OP_AVGPOOL2D
+                op.in_c, op.in_h, op.in_w = ishape
+                op.out_c, op.out_h, op.out_w = oshape
+                op.kh, op.kw = _pair(mod.kernel_size)
+                st = mod.stride if mod.stride is not None else mod.kernel_size
+                op.stride_h, op.stride_w = _pair(st)
+            elif type(mod) in _ACT:
+                if any(pend_pad):
+                    raise cabi.BnnpError('ZeroPad2d in front of an activation is unsupported')
+                op.kind = _ACT[type(mod)]
+                op.in_c, op.in_h, op.in_w = _shape3(ishape)
+                op.out_c, op.out_h, op.out_w = _shape3(oshape)
+            elif isinstance(mod, nn.Flatten):
+                op.kind = cabi.OP_FLATTEN
+                op.in_c, op.in_h, op.in_w = _shape3(ishape)
+                n = 1
+                for s in oshape:
+                    n *= s
+                op.out_c, op.out_h, op.out_w = n, 1, 1
+            else:
+                raise cabi.BnnpError('layer type %s is outside the supported zoo (Linear, Conv2d, ReLU, '
+                                     'Tanh, Sigmoid, MaxPool2d, AvgPool2d, ZeroPad2d, Flatten)'
+                                     % type(mod).__name__)
+            if op.kind in (cabi.OP_CONV2D, cabi.OP_MAXPOOL2D, cabi.OP_AVGPOOL2D):
+                op.pad_l, op.pad_r, op.pad_t, op.pad_b = pend_pad
+            pend_pad = (0, 0, 0, 0)
+            if op.kind in (cabi.OP_LINEAR, cabi.OP_CONV2D):
+                op.has_bias = int(mod.bias is not None)
+                op.theta_off_w = offs[id(mod.weight)]
+                op.theta_off_b = offs[id(mod.bias)] if mod.bias is not None else -1
+            ops.append(op)
+            mods.append(mod)
+        if len(ops) > cabi.MAX_OPS:
+            raise cabi.BnnpError('too many layers (%d > %d)' % (len(ops), cabi.MAX_OPS))
+        if not ops or ops[0].kind == cabi.OP_FLATTEN:
+            # a leading Flatten only reshapes the caller's tensor
+            while ops and ops[0].kind == cabi.OP_FLATTEN:
+                ops.pop(0)
+                mods.pop(0)
+        covered = sum((m.weight.numel() + (m.bias.numel() if m.bias is not None else 0))
+                      for m in mods if isinstance(m, (nn.Linear, nn.Conv2d)))
+        if covered != self.P:
+            raise cabi.BnnpError('model has parameters outside Linear/Conv2d layers (%d of %d covered)'
+                                 % (covered, self.P))
+        self.ops = (cabi.Op * len(ops))(*ops)
+        self.mods = mods
+        self.n_ops = len(ops)
+        self.in_size = ops[0].in_c * ops[0].in_h * ops[0].in_w
+        self.K = ops[-1].out_c * ops[-1].out_h * ops[-1].out_w
+        self.linear_only = all(o.kind not in (cabi.OP_CONV2D, cabi.OP_MAXPOOL2D, cabi.OP_AVGPOOL2D)
+                               for o in ops)
+        self._plans = {}
+        self._sig = tuple(in_shape)
+
+    def prepare(self, X):
+        """Validate / flatten the input batch, (re)build the descriptor, refresh weight pointers."""
+        cabi.require_device(self.params[0])
+        X = cabi.f32(X, self.device)
+        in_shape = tuple(X.shape[1:])
+        if self._sig != in_shape:
+            self._build(in_shape)
+        for op, mod in zip(self.ops, self.mods):
+            if op.kind in (cabi.OP_LINEAR, cabi.OP_CONV2D):
+                w = mod.weight
+                if w.dtype != torch.float32 or not w.is_contiguous():
+                    raise cabi.BnnpError('parameters must be contiguous float32')
+                op.weight = w.data_ptr()
+                op.bias = mod.bias.data_ptr() if mod.bias is not None else None
+        return X.reshape(X.shape[0], -1)
+
+    def plan(self, N, V):
+        key = (N, V)
+        if key not in self._plans:
+            pl = cabi.Plan()
+            check(lib.bnnp_net_plan(self.ops, self.n_ops, N, V, C.byref(pl)), 'bnnp_net_plan')
+            self._plans[key] = pl
+        return self._plans[key]
+
+    def workspace(self, plan):
+        n = int(plan.total_floats) + 64
+        if self._ws is None or self._ws.numel() < n:
+            self._ws = None
+            self._ws = torch.empty(n, dtype=torch.float32, device=self.device)
+        return self._ws
+
+    def scratch(self, n_floats):
+        n = int(n_floats) + 64
+        if self._scratch is None or self._scratch.numel() < n:
+            self._scratch = None
+            self._scratch = torch.empty(n, dtype=torch.float32, device=self.device)
+        return self._scratch
+
+    def release(self):
+        self._ws = None
+        self._scratch = None
+
+    # ------------------------------------------------------------------ passes
+    def forward(self, X2d, V):
+        """Forward N examples; returns (plan, ws, logits [N,K])."""
+        N = X2d.shape[0]
+        pl = self.plan(N, V)
+        ws = self.workspace(pl)
+        f = torch.empty(N, self.K, dtype=torch.float32, device=self.device)
+        check(lib.bnnp_net_forward(self.ops, self.n_ops, C.byref(pl), ptr(X2d), N, ptr(ws), ptr(f),
+                                   stream()), 'bnnp_net_forward')
+        return pl, ws, f
+
+    def backward(self, pl, ws, seed, N, V):
+        check(lib.bnnp_net_backward(self.ops, self.n_ops, C.byref(pl), ptr(seed), N, V, ptr(ws),
+                                    stream()), 'bnnp_net_backward')
+
+    def identity_seed(self, N):
+        seed = torch.empty(N, self.K, self.K, dtype=torch.float32, device=self.device)
+        check(lib.bnnp_identity_seed(N, self.K, ptr(seed), stream()), 'bnnp_identity_seed')
+        return seed
+
+    def jacobian_factors(self, X):
+        """forward + identity-seeded backward: the (a_l, g_l) factors of J for a batch."""
+        X2d = self.prepare(X)
+        N = X2d.shape[0]
+        pl, ws, f = self.forward(X2d, self.K)
+        self.backward(pl, ws, self.identity_seed(N), N, self.K)
+        return X2d, pl, ws, f
+
+    def sqrt_factors(self, X, lik_code):
+        """forward + backward seeded with the loss-Hessian square root (BackPACK convention)."""
+        X2d = self.prepare(X)
+        N = X2d.shape[0]
+        pl, ws, f = self.forward(X2d, self.K)
+        seed = torch.empty(N, self.K, self.K, dtype=torch.float32, device=self.device)
+        check(lib.bnnp_lik_sqrt_seed(lik_code, ptr(f), N, self.K, ptr(seed), stream()), 'bnnp_lik_sqrt_seed')
+        self.backward(pl, ws, seed, N, self.K)
+        return X2d, pl, ws, f
+
+    def materialise_jacobians(self, X):
+        X2d, pl, ws, f = self.jacobian_factors(X)
+        N = X2d.shape[0]
+        Js = torch.empty(N, self.P, self.K, dtype=torch.float32, device=self.device)
+        check(lib.bnnp_jacobians(self.ops, self.n_ops, C.byref(pl), N, ptr(X2d), ptr(ws), ptr(Js), stream()),
+              'bnnp_jacobians')
+        return Js, f
+
+
+_NETS = {}
+
+
+def net_for(model):
+    """One cached ``Net`` per model object (the model keeps its own parameters; we hold pointers)."""
+    key = id(model)
+    ent = _NETS.get(key)
+    if ent is None or ent.model is not model or ent.device != next(model.parameters()).device:
+        ent = Net(model)
+        _NETS[key] = ent
+    return ent
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*[p if p else None for p in ptrs])
+    return arr
+
+
+def float_array(vals):
+    return (C.c_float * len(vals))(*[float(v) for v in vals])

@@ -1,0 +1,146 @@
+"""GLM and BNN predictives with the signatures of ``preds/predictives.py`` plus the additive
+``eps=`` / ``seed=`` arguments used to inject the standard-normal draws (parity with the oracle).
+"""
+import ctypes as C
+import logging
+
+import torch
+from torch.nn.utils import parameters_to_vector
+
+from . import _cabi as cabi
+from ._cabi import lib, check, ptr, stream
+from ._engine import net_for, ptr_array, float_array
+from .kron import Kron
+from .likelihoods import GaussianLh
+
+# upper bound for per-call scratch; inputs are processed in chunks that respect it
+SCRATCH_BUDGET_FLOATS = 1 << 30
+
+
+def _kron_tables(net, kron):
+    """Per-op eigen pointers {W_G, lam_G, W_A, lam_A} and prior precisions for weight / bias."""
+    index = {id(p): i for i, p in enumerate(net.params)}
+    eig, dw, db = [], [], []
+    for op, mod in zip(net.ops, net.mods):
+        if op.kind in (cabi.OP_LINEAR, cabi.OP_CONV2D):
+            wi = index[id(mod.weight)]
+            eig += [ptr(kron.Ws[wi][0]), ptr(kron.Lams[wi][0]), ptr(kron.Ws[wi][1]), ptr(kron.Lams[wi][1])]
+            dw.append(float(kron.deltas[wi]))
+            db.append(float(kron.deltas[index[id(mod.bias)]]) if mod.bias is not None else 0.0)
+        else:
+            eig += [None] * 4
+            dw.append(0.0)
+            db.append(0.0)
+    return ptr_array(eig), float_array(dw), float_array(db)
+
+
+def glm_moments(X, model, mu, Sigma):
+    """f_mu [N,K] and f_var [N,K,K] of the linearised model (preds/predictives.py:52-65).
+    ``Sigma`` is the full covariance [P,P], the diagonal variances [P], or a ``Kron``."""
+    net = net_for(model)
+    theta_star = parameters_to_vector(model.parameters()).detach()
+    delta = (mu - theta_star).to(torch.float32).contiguous()
+    delta_ptr = ptr(delta) if bool((delta != 0).any()) else None
+    X = cabi.f32(X, net.device)
+    N, K, P = X.shape[0], None, net.P
+    net.prepare(X[:1])
+    K = net.K
+    # chunk size from the scratch the chosen structure needs per input
+    if isinstance(Sigma, Kron):
+        per = max(1, int(lib.bnnp_glm_fvar_kron_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(1, K)), 1)))
+        cap = 65535 // K
+    elif Sigma.dim() == 2:
+        per, cap = K * P + 1, 1 << 30
+    else:
+        per = max(1, int(lib.bnnp_glm_fvar_diag_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(1, K)), 1)))
+        cap = 65535 // K if not net.linear_only else 1 << 30
+    chunk = max(1, min(N, cap, SCRATCH_BUDGET_FLOATS // per))
+    f_mu = torch.empty(N, K, dtype=torch.float32, device=net.device)
+    f_var = torch.empty(N, K, K, dtype=torch.float32, device=net.device)
+    tables = _kron_tables(net, Sigma) if isinstance(Sigma, Kron) else None
+    for s in range(0, N, chunk):
+        Xc = X[s:s + chunk]
+        n = Xc.shape[0]
+        X2d, pl, ws, f = net.jacobian_factors(Xc)
+        fm, fv = f_mu[s:s + n], f_var[s:s + n]
+        check(lib.bnnp_glm_fmu(net.ops, net.n_ops, C.byref(pl), n, ptr(X2d), ptr(ws), ptr(f), delta_ptr,
+                               ptr(fm), stream()), 'bnnp_glm_fmu')
+        if isinstance(Sigma, Kron):
+            sc = net.scratch(lib.bnnp_glm_fvar_kron_scratch_floats(net.ops, net.n_ops, C.byref(pl), n))
+            check(lib.bnnp_glm_fvar_kron(net.ops, net.n_ops, C.byref(pl), n, ptr(X2d), ptr(ws), tables[0],
+                                         tables[1], tables[2], int(Sigma.dampen), ptr(fv), ptr(sc), stream()),
+                  'bnnp_glm_fvar_kron')
+        elif Sigma.dim() == 2:
+            sc = net.scratch(lib.bnnp_glm_fvar_full_scratch_floats(C.byref(pl), n))
+            check(lib.bnnp_glm_fvar_full(net.ops, net.n_ops, C.byref(pl), n, ptr(ws), ptr(Sigma), ptr(fv),
+                                         ptr(sc), stream()), 'bnnp_glm_fvar_full')
+        else:
+            sc = net.scratch(lib.bnnp_glm_fvar_diag_scratch_floats(net.ops, net.n_ops, C.byref(pl), n))
+            check(lib.bnnp_glm_fvar_diag(net.ops, net.n_ops, C.byref(pl), n, ptr(X2d), ptr(ws), ptr(Sigma),
+                                         ptr(fv), ptr(sc), stream()), 'bnnp_glm_fvar_diag')
+    return f_mu, f_var
+
+
+def functional_sampling_predictive(X, model, likelihood, mu, Sigma, mc_samples=1000, no_link=False,
+                                   eps=None, seed=None):
+    """GLM predictive (preds/predictives.py:50-76): regression returns (f_mu, f_var);
+    classification returns link(f_mu + chol(f_var) eps) of shape [S, N, K]."""
+    if not isinstance(Sigma, Kron):
+        Sigma = cabi.f32(Sigma, mu.device)
+    f_mu, f_var = glm_moments(X, model, mu, Sigma)
+    if type(likelihood) is GaussianLh:
+        return f_mu, f_var
+    N, K = f_mu.shape
+    S = int(mc_samples)
+    lik = cabi.LIK_GAUSSIAN if no_link else likelihood.code
+    out = torch.empty(S, N, K, dtype=torch.float32, device=f_mu.device)
+    status = torch.empty(N, dtype=torch.int32, device=f_mu.device)
+    if eps is not None:
+        eps = cabi.f32(eps, f_mu.device)
+        assert tuple(eps.shape) == (S, N, K)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())     # advances the global torch RNG
+    check(lib.bnnp_glm_sample(lik, ptr(f_mu), ptr(f_var), ptr(eps), seed, S, N, K, ptr(out), ptr(status),
+                              stream()), 'bnnp_glm_sample')
+    if bool(status.any()):
+        # MultivariateNormal would have raised for the whole batch (:70-76)
+        logging.warning('functional sampling covariance indefinite - use diagonal')
+        check(lib.bnnp_glm_sample_diag_fallback(lik, ptr(f_mu), ptr(f_var), ptr(eps), seed, S, N, K, ptr(out),
+                                                stream()), 'bnnp_glm_sample_diag_fallback')
+    return out
+
+
+def sample_weights(mu, Sigma_chol, mc_samples, eps=None):
+    """theta samples [S, P] (preds/predictives.py:14-20)."""
+    S, P = int(mc_samples), len(mu)
+    mu = cabi.f32(mu, mu.device)
+    if isinstance(Sigma_chol, Kron):
+        return Sigma_chol.sample(S, eps=eps, mu=mu)
+    Sigma_chol = cabi.f32(Sigma_chol, mu.device)
+    e = torch.randn(P, S, device=mu.device) if eps is None else cabi.f32(eps, mu.device)
+    assert tuple(e.shape) == (P, S)
+    out = torch.empty(S, P, dtype=torch.float32, device=mu.device)
+    if Sigma_chol.dim() == 2:
+        check(lib.bnnp_sample_theta_full(ptr(Sigma_chol), ptr(mu), ptr(e), P, S, ptr(out), stream()),
+              'bnnp_sample_theta_full')
+    else:
+        check(lib.bnnp_sample_theta_diag(ptr(Sigma_chol), ptr(mu), ptr(e), P, S, ptr(out), stream()),
+              'bnnp_sample_theta_diag')
+    return out
+
+
+def nn_sampling_predictive(X, model, likelihood, mu, Sigma_chol, mc_samples=100, no_link=False,
+                           eps=None):
+    """BNN predictive (preds/predictives.py:12-28): S forward passes at sampled weights,
+    [S, N, K].  The model's own parameters are never overwritten (the sampled weights are read
+    from the sample matrix), so there is nothing to restore."""
+    net = net_for(model)
+    samples = sample_weights(mu, Sigma_chol, mc_samples, eps=eps)
+    X2d = net.prepare(X)
+    N, S = X2d.shape[0], samples.shape[0]
+    lik = cabi.LIK_GAUSSIAN if no_link else likelihood.code
+    out = torch.empty(S, N, net.K, dtype=torch.float32, device=net.device)
+    sc = net.scratch(lib.bnnp_bnn_forward_scratch_floats(net.ops, net.n_ops, N, S))
+    check(lib.bnnp_bnn_forward(net.ops, net.n_ops, lik, ptr(X2d), N, ptr(samples), S, net.P, ptr(out),
+                               ptr(sc), stream()), 'bnnp_bnn_forward')
+    return out

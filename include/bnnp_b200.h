@@ -1,0 +1,238 @@
+/*
+ * bnnp_b200.h -- C ABI of libbnnp_b200.so: the B200 (sm_100a) implementation of the Laplace-GGN
+ * hot path of aleximmer/BNN-predictions.
+ *
+ * The reference has no FFI of its own (it is pure Python on torch + BackPACK), so the drop-in
+ * boundary is the `preds` Python API (bnn-predictions_b200/preds_b200 mirrors it) and this C ABI
+ * sits one level below: each entry point replaces one library call site of the reference, cited
+ * as  <file>:<line>  relative to the reference root.  See INTEGRATION.md for the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless marked [host];
+ *   - the caller allocates and owns every buffer (torch does, in our glue); nothing here
+ *     allocates or frees device memory and there is no global state;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is
+ *     asynchronous on that stream;
+ *   - float32 everywhere; matrices are row-major;
+ *   - return value: 0 = BNNP_OK, negative = error (bnnp_strerror()).  The Python glue turns
+ *     BNNP_ERR_INVALID into ValueError and everything else into RuntimeError.
+ */
+#ifndef BNNP_B200_H
+#define BNNP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNNP_OK                0
+#define BNNP_ERR_INVALID      -1   /* bad argument / shape */
+#define BNNP_ERR_UNSUPPORTED  -2   /* layer type or size outside what the kernels cover */
+#define BNNP_ERR_CUDA         -3   /* a CUDA runtime call or launch failed */
+#define BNNP_ERR_NO_DEVICE    -4
+
+#define BNNP_MAX_OPS  64
+#define BNNP_MAX_K    32           /* max #outputs handled by the register-resident K x K code */
+
+const char* bnnp_strerror(int code);
+int bnnp_version(void);
+/* 1 if a CUDA device of compute capability 10.x is visible, else 0 (never throws). */
+int bnnp_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Network descriptor: the layer zoo the Jacobians are taken over (preds/models.py:91-122 MLPS,
+ * :239-285 CIFAR10Net, :182-236 CIFAR100Net).  One entry per leaf module in execution order.
+ * A ZeroPad2d in front of a conv / pool (deepobs tf-"same" padding) is folded into pad_*.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+  BNNP_OP_LINEAR = 1, BNNP_OP_CONV2D = 2, BNNP_OP_RELU = 3, BNNP_OP_TANH = 4,
+  BNNP_OP_MAXPOOL2D = 5, BNNP_OP_AVGPOOL2D = 6, BNNP_OP_FLATTEN = 7, BNNP_OP_SIGMOID = 8
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t in_c, in_h, in_w;          /* per-example input shape; Linear: in_c = features, h = w = 1 */
+  int32_t out_c, out_h, out_w;
+  int32_t kh, kw, stride_h, stride_w;
+  int32_t pad_l, pad_r, pad_t, pad_b;
+  int32_t has_bias;
+  const float* weight;               /* [out_c, in_c*kh*kw]  (Linear: [out, in]) */
+  const float* bias;                 /* [out_c] or NULL */
+  int64_t theta_off_w, theta_off_b;  /* offsets of weight / bias in the flat parameter vector */
+} bnnp_op_t;
+
+/* Where each op's saved tensors live inside the caller-provided float workspace. */
+typedef struct {
+  int64_t act_off, act_ld;           /* output activation of example n at ws + act_off + n*act_ld */
+  int64_t grad_off, grad_ld;         /* d f_v / d output for row (n*V+v) at ws + grad_off + row*grad_ld */
+  int64_t idx_off;                   /* maxpool argmax (int32 view of ws) or -1 */
+  int32_t lin_col, lin_unit;         /* Linear: first column in A_cat / first unit column in G_cat */
+} bnnp_op_plan_t;
+
+typedef struct {
+  int64_t total_floats;              /* workspace size to allocate, in floats */
+  int64_t acat_off, gcat_off;        /* A_cat [N, Dtot] (layer inputs + a ones column per Linear),
+                                        G_cat [N*V, Mtot] (d f_v / d pre-activation of every Linear) */
+  int32_t Dtot, Mtot;
+  int32_t n_linear, first_linear;    /* #Linear ops and index of the first one */
+  int64_t P;                         /* total #parameters */
+  int32_t K;                         /* network outputs */
+  int32_t reserved;
+  bnnp_op_plan_t op[BNNP_MAX_OPS];
+} bnnp_plan_t;
+
+/* [host] Lay out the workspace for batches of N examples and V back-propagated columns. */
+int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, bnnp_plan_t* plan);
+
+/* Forward pass, saving every layer input (replaces model(data) inside preds/gradients.py:26 and
+ * preds/laplace.py:56,73).  X: [N, in_size]; logits: [N, K] (also written to the workspace). */
+int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                     const float* X, int64_t N, float* ws, float* logits, void* stream);
+
+/* Back-propagate V columns at once.  seed: [N, V, K], row (n,v) is the vector multiplied from the
+ * left onto d f/d(.).  seed = I gives output Jacobians (the K backward passes of
+ * preds/gradients.py:24-36); seed = S_n^T gives BackPACK's sqrt-GGN backprop (Appendix A). */
+int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                      const float* seed, int64_t N, int V, float* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Likelihood terms (preds/likelihoods.py).  lik: 0 categorical, 1 gaussian, 2 bernoulli.
+ * ---------------------------------------------------------------------------------------- */
+enum { BNNP_LIK_CATEGORICAL = 0, BNNP_LIK_GAUSSIAN = 1, BNNP_LIK_BERNOULLI = 2 };
+
+/* Lambda [N,K,K]: categorical diag(p)-pp^T with p = clamp(softmax f, 1e-7, 1-1e-7)
+ * (preds/likelihoods.py:90-93); gaussian 1/sigma2 (:50-52); bernoulli p(1-p) clamped (:67-69). */
+int bnnp_lik_hessian(int lik, const float* f, int64_t N, int K, float sigma2, float* Lambda,
+                     void* stream);
+/* seed [N,V=K,K] for the BackPACK loss-Hessian square root (unclamped softmax; MSE: sqrt(2) I). */
+int bnnp_lik_sqrt_seed(int lik, const float* f, int64_t N, int K, float* seed, void* stream);
+/* seed [N,K,K] = identity (Jacobian back-propagation). */
+int bnnp_identity_seed(int64_t N, int K, float* seed, void* stream);
+/* residual [N,K]: onehot(y) - softmax f (:84-88), (y-f)/sigma2 (:47-48), y - sigmoid f (:25-26).
+ * y is int64 labels for categorical, float [N,K] otherwise. */
+int bnnp_lik_residual(int lik, const float* f, const void* y, int64_t N, int K, float sigma2,
+                      float* rs, void* stream);
+/* out = inv_link(f) in place-capable: softmax over the last dim / identity / sigmoid. */
+int bnnp_lik_inv_link(int lik, const float* f, int64_t rows, int K, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Jacobians and GGN accumulation
+ * ---------------------------------------------------------------------------------------- */
+/* Materialise Js [N,P,K] (K last) from the saved factors -- API compatibility with
+ * preds/gradients.py:20-46; small shapes only.  Requires backward with V = K, seed = I. */
+int bnnp_jacobians(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                   const float* X, const float* ws, float* Js, void* stream);
+
+/* H[P,P] += sum_n J_n^T Lambda_n J_n  (preds/laplace.py:42, preds/optimizers.py:94), Linear-only
+ * networks.  Only tiles on/below the diagonal are touched; call bnnp_symmetrize_lower() once
+ * after the last batch.  engine: 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16 tensor cores.
+ * scratch: caller buffer of bnnp_ggn_full_scratch_floats() floats. */
+int64_t bnnp_ggn_full_scratch_floats(const bnnp_plan_t* plan, int64_t N, int engine);
+int bnnp_ggn_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                        const float* ws, const float* Lambda, float* H, float* scratch,
+                        int engine, void* stream);
+/* H[p,q] = H[q,p] for p < q. */
+int bnnp_symmetrize_lower(float* H, int64_t P, void* stream);
+
+/* diag[P] += factor * diag(sum_n J_n^T Lambda_n J_n) from a sqrt-seeded backward
+ * (BackPACK DiagGGNExact as read by preds/laplace.py:52-59). */
+int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                        int V, const float* X, const float* ws, float factor, float* diag,
+                        float* scratch, void* stream);
+int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                     int64_t N, int V);
+
+/* KFLR factors (preds/laplace.py:73-78 + preds/kron.py:58-69): for every parameterised op,
+ * G += factor * sum_{n,v} s s^T  and  A += batch_factor * (1/N) sum_n a a^T.
+ * factors: [host] array of 2*n_ops device pointers, {G_i, A_i} per op (NULL for other ops). */
+int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
+                    const float* X, const float* ws, float factor, float batch_factor,
+                    float* const* factors, float* scratch, void* stream);
+int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                 int64_t N, int V);
+
+/* ------------------------------------------------------------------------------------------
+ * GLM predictive (preds/predictives.py:50-76)
+ * ---------------------------------------------------------------------------------------- */
+/* f_mu[N,K] = f + J (mu - theta) (:58); delta = mu - theta [P] (may be NULL -> f_mu = f). */
+int bnnp_glm_fmu(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                 const float* X, const float* ws, const float* f, const float* delta, float* f_mu,
+                 void* stream);
+/* f_var[N,K,K] = J Sigma J^T, Sigma [P,P] (:63).  Linear-only networks. */
+int64_t bnnp_glm_fvar_full_scratch_floats(const bnnp_plan_t* plan, int64_t N);
+int bnnp_glm_fvar_full(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                       const float* ws, const float* Sigma, float* f_var, float* scratch,
+                       void* stream);
+/* f_var = J diag(sigma2) J^T (:65). */
+int bnnp_glm_fvar_diag(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                       const float* X, const float* ws, const float* sigma2, float* f_var,
+                       float* scratch, void* stream);
+int64_t bnnp_glm_fvar_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                          int64_t N);
+/* Kronecker functional variance (preds/kron.py:112-143) using the rank structure of the layer
+ * Jacobians.  eig: [host] 4*n_ops device pointers {W_G, lam_G, W_A, lam_A} per op;
+ * delta_w / delta_b: [host] prior precision per op for weight / bias group; dampen as :130-134. */
+int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                       const float* X, const float* ws, const float* const* eig,
+                       const float* delta_w, const float* delta_b, int dampen, float* f_var,
+                       float* scratch, void* stream);
+int64_t bnnp_glm_fvar_kron_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                          int64_t N);
+/* out[S,N,K] = inv_link(f_mu + chol(f_var) eps) (:69-72, MultivariateNormal.sample).  eps [S,N,K]
+ * injected draws, or NULL to draw in-kernel (Philox, `seed`).  status[N] (int32) = 0 ok,
+ * 1 = f_var[n] not positive definite (caller takes the reference's fallback, :73-76). */
+int bnnp_glm_sample(int lik, const float* f_mu, const float* f_var, const float* eps,
+                    uint64_t seed, int64_t S, int64_t N, int K, float* out, int32_t* status,
+                    void* stream);
+
+/* One parameter group of Kron.functional_variance on a MATERIALISED Jacobian block
+ * Jb[R, m*n] (row r = (b,k), row stride ldj) -- API compatibility with preds/kron.py:112-143
+ * (Kron.functional_variance(Js)).  W2 == NULL selects the 1-factor (bias) form on Jb[R, m].
+ * f_var[R/K, K, K] is accumulated into.  scratch: 2*R*m*n + m*n floats (1-factor: R*m + m). */
+int bnnp_kron_fvar_block(const float* Jb, int64_t ldj, int K, int m, int n, const float* W1,
+                         const float* l1, const float* W2, const float* l2, float delta, int dampen,
+                         float* f_var, float* scratch, int64_t R, void* stream);
+/* The reference's fallback when a K x K Cholesky fails (preds/predictives.py:73-76):
+ * out = inv_link(f_mu + clamp(diag f_var, 1e-5) * eps). */
+int bnnp_glm_sample_diag_fallback(int lik, const float* f_mu, const float* f_var, const float* eps,
+                                  uint64_t seed, int64_t S, int64_t N, int K, float* out,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BNN predictive (preds/predictives.py:12-28) and Kron sampling (preds/kron.py:85-110)
+ * ---------------------------------------------------------------------------------------- */
+/* theta_s[S,P] = mu + (L eps)^T for L [P,P] lower (full) or sigma [P] (diag); eps [P,S]. */
+int bnnp_sample_theta_full(const float* L, const float* mu, const float* eps, int64_t P,
+                           int64_t S, float* theta_s, void* stream);
+int bnnp_sample_theta_diag(const float* sigma, const float* mu, const float* eps, int64_t P,
+                           int64_t S, float* theta_s, void* stream);
+/* One parameter group of Kron.sample: out[s, off + (i*n+j)] = mu + W1((W1^T eps_s W2) * D)W2^T
+ * (2-factor, eps [S,m,n]) or W(sqrt(1/(l+delta)) * W^T eps) (1-factor, eps [m,S]).
+ * mu may be NULL (zero-mean draws as returned by Kron.sample).  scratch: 2*S*m*n + m*n floats. */
+int bnnp_kron_sample_group(const float* W1, const float* l1, const float* W2, const float* l2,
+                           int m, int n, float delta, int dampen, const float* eps, int64_t S,
+                           const float* mu, float* theta_s, int64_t P, int64_t off,
+                           float* scratch, void* stream);
+/* out[S,N,K] = inv_link(f(X; theta_s)) for all S weight samples (Linear-only networks run as
+ * batched-weight GEMMs; others loop over s).  ws: S-independent scratch sized by the call below. */
+int64_t bnnp_bnn_forward_scratch_floats(const bnnp_op_t* ops, int n_ops, int64_t N, int64_t S);
+int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const float* X, int64_t N,
+                     const float* theta_s, int64_t S, int64_t P, float* out, float* scratch,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small dense helpers used by the posterior code (preds/laplace.py:111, preds/kron.py:58-69)
+ * ---------------------------------------------------------------------------------------- */
+/* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 SIMT; ta/tb: 0 = as stored, 1 = transposed. */
+int bnnp_sgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+               int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+               void* stream);
+/* y += alpha * x  (Kron.update axpy, preds/kron.py:62-66). */
+int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNNP_B200_H */

@@ -1,0 +1,216 @@
+"""Parity of the CUDA path (preds_b200 -> C ABI -> sm_100a kernels) with (a) the committed golden
+fixtures produced by the unmodified reference and (b) the CPU oracle on the same inputs.
+
+Tolerance: 1e-4 relative (max |diff| / max |ref|), the north-star bound for fp32, stated per
+assert.  Integer / index work (max-pool arg-max routing) is covered through the CNN cases, whose
+Jacobians would differ at O(1) if a single index were routed differently.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _product(name):
+    import preds_b200
+    from preds_b200 import models
+    g = cases.load_golden(name)
+    model = cases.make_product_model(name, models)
+    port.set_theta(model, torch.from_numpy(g['theta']))
+    model = model.cuda()
+    lh = cases.make_lh(g['lh'], lib=preds_b200)
+    batches, Xte = cases.case_data(g)
+    return g, model, lh, batches, Xte, float(g['prior'])
+
+
+@pytest.mark.parametrize('name', cases.FULL_CASES)
+def test_jacobians_and_ggn_bundle(name):
+    from preds_b200 import Jacobians, GGN
+    g, model, lh, batches, Xte, prior = _product(name)
+    X0, y0 = batches[0]
+    Js, f = Jacobians(model, X0)
+    assert tuple(Js.shape) == g['Js0'].shape
+    assert cases.rel_err(f.cpu(), g['f0']) < 1e-5
+    assert cases.rel_err(Js.cpu(), g['Js0']) < 1e-5
+    Jb, Hess, rs, f2 = GGN(model, lh, X0, y0, ret_f=True)
+    assert cases.rel_err(Hess.cpu(), g['Hess0']) < 1e-5
+    assert cases.rel_err(rs.cpu(), g['rs0']) < 1e-5
+    assert Jb.dim() == 3 and Hess.dim() == 3
+
+
+@pytest.mark.parametrize('engine', [1, 2])
+@pytest.mark.parametrize('name', cases.MLP_CASES)
+def test_infer_full(name, engine):
+    from preds_b200 import Laplace
+    g, model, lh, batches, Xte, prior = _product(name)
+    lap = Laplace(model, prior, lh)
+    lap.ggn_engine = engine
+    lap.infer(batches, cov_type='full')
+    assert lap.inferred and lap.Sigma_chol.shape == (lap.P, lap.P)
+    assert cases.rel_err(lap.precision.cpu(), g['H_full']) < TOL
+    Sref = torch.from_numpy(g['Sigma_chol_full'])
+    assert cases.rel_err(lap.Sigma.cpu(), Sref @ Sref.t()) < TOL
+    assert cases.rel_err((lap.Sigma_chol @ lap.Sigma_chol.T).cpu(), Sref @ Sref.t()) < TOL
+    # GLM predictive with the reference's injected draws
+    eps = torch.from_numpy(g['eps_glm'])
+    out = lap.predictive_samples_glm(Xte, n_samples=eps.shape[0], eps=eps)
+    if lh.code == 1:
+        assert cases.rel_err(out[0].cpu(), g['glm_fmu_full']) < 1e-5
+        assert cases.rel_err(out[1].cpu(), g['glm_fvar_full']) < TOL
+    else:
+        assert tuple(out.shape) == g['glm_full'].shape
+        assert cases.rel_err(out.cpu(), g['glm_full']) < TOL
+    eb = torch.from_numpy(g['eps_bnn'])
+    out = lap.predictive_samples_bnn(Xte, n_samples=eb.shape[1], eps=eb)
+    assert cases.rel_err(out.cpu(), g['bnn_full']) < 5e-4
+
+
+def test_infer_full_rejects_cnn():
+    from preds_b200 import Laplace
+    from preds_b200._cabi import BnnpError
+    g, model, lh, batches, Xte, prior = _product('cnn_tiny')
+    with pytest.raises(BnnpError):
+        Laplace(model, prior, lh).infer(batches, cov_type='full')
+
+
+@pytest.mark.parametrize('name', [c for c in cases.FULL_CASES if c != 'mlp_bern'])
+def test_infer_diag(name):
+    from preds_b200 import Laplace
+    g, model, lh, batches, Xte, prior = _product(name)
+    lap = Laplace(model, prior, lh)
+    lap.infer(batches, cov_type='diag')
+    assert cases.rel_err(lap.Sigma_chol.cpu(), g['Sigma_chol_diag']) < 1e-5
+    eps = torch.from_numpy(g['eps_glm'])
+    out = lap.predictive_samples_glm(Xte, n_samples=eps.shape[0], eps=eps)
+    if lh.code == 1:
+        assert cases.rel_err(out[1].cpu(), g['glm_fvar_diag']) < TOL
+    else:
+        assert cases.rel_err(out.cpu(), g['glm_diag']) < TOL
+    eb = torch.from_numpy(g['eps_bnn'])
+    out = lap.predictive_samples_bnn(Xte, n_samples=eb.shape[1], eps=eb)
+    assert cases.rel_err(out.cpu(), g['bnn_diag']) < TOL
+
+
+@pytest.mark.parametrize('name', [c for c in cases.FULL_CASES if c != 'mlp_bern'])
+def test_infer_kron(name):
+    from preds_b200 import Laplace, Kron
+    from preds_b200.predictives import glm_moments
+    g, model, lh, batches, Xte, prior = _product(name)
+    lap = Laplace(model, prior, lh)
+    lap.infer(batches, cov_type='kron')
+    kron = lap.Sigma_chol
+    assert type(kron) is Kron and lap.Sigma is kron
+    for pi, qh in enumerate(kron.qhs):
+        for fi, m in enumerate(qh):
+            assert cases.rel_err(m.cpu(), g['kron_q_%d_%d' % (pi, fi)]) < 1e-5, (pi, fi)
+    fmu, fvar = glm_moments(Xte, model, lap.mu, kron)
+    assert cases.rel_err(fmu.cpu(), g['glm_fmu_kron']) < 1e-5
+    assert cases.rel_err(fvar.cpu(), g['glm_fvar_kron']) < TOL
+    eps = torch.from_numpy(g['eps_glm'])
+    if lh.code != 1:
+        out = lap.predictive_samples_glm(Xte, n_samples=eps.shape[0], eps=eps)
+        assert cases.rel_err(out.cpu(), g['glm_kron']) < TOL
+    ek = cases.kron_eps_from(g)
+    S = eps.shape[0]
+    out = lap.predictive_samples_bnn(Xte, n_samples=S, eps=ek)
+    assert cases.rel_err(out.cpu(), g['bnn_kron']) < TOL
+    # dampening toggled after inference (experiments/imginference.py:160)
+    kron.dampen = True
+    _, fvar_d = glm_moments(Xte, model, lap.mu, kron)
+    assert cases.rel_err(fvar_d.cpu(), g['glm_fvar_kron_dampen']) < TOL
+    out = lap.predictive_samples_bnn(Xte, n_samples=S, eps=ek)
+    assert cases.rel_err(out.cpu(), g['bnn_kron_dampen']) < TOL
+
+
+def test_cifar10net_probe():
+    """The reference tests' own CIFAR10Net fixture (seed 71, X seed 15): conv / max-pool /
+    dense Jacobians, diagonal GGN, KFLR factors and the Kron GLM predictive."""
+    from preds_b200 import CIFAR10Net, CategoricalLh, Jacobians, Laplace
+    from preds_b200.predictives import glm_moments
+    g = cases.load_golden('cifar10net_probe')
+    torch.manual_seed(71)
+    model = CIFAR10Net(in_channels=2, n_out=3).cuda()
+    torch.manual_seed(15)
+    X = torch.randn(8, 2, 28, 28)
+    y = torch.from_numpy(g['y'])
+    idx = torch.from_numpy(g['theta_idx'])
+    P = sum(p.numel() for p in model.parameters())
+    v = torch.randn(P, generator=torch.Generator().manual_seed(4243))
+    Js, f = Jacobians(model, X)
+    assert cases.rel_err(f.cpu(), g['f']) < 1e-5
+    assert cases.rel_err(Js[:, idx.cuda(), :].cpu(), g['Js_at_idx']) < 1e-5
+    assert cases.rel_err(torch.einsum('npk,p->nk', Js, v.cuda()).cpu(), g['Js_dot_v']) < 1e-4
+    del Js
+    lh = CategoricalLh()
+    batches = [(X[:5], y[:5]), (X[5:], y[5:])]
+    lap = Laplace(model, 1.0, lh)
+    lap.infer(batches, cov_type='diag')
+    assert cases.rel_err(lap.precision[idx.cuda()].cpu(), g['diag_prec_at_idx']) < 1e-5
+    assert abs(float(lap.precision.double().sum()) - float(g['diag_prec_sum'])) < 1e-4 * float(g['diag_prec_sum'])
+    lap = Laplace(model, 1.0, lh)
+    lap.infer(batches, cov_type='kron')
+    for pi, qh in enumerate(lap.Sigma_chol.qhs):
+        for fi, m in enumerate(qh):
+            pv = torch.randn(m.shape[0], generator=torch.Generator().manual_seed(5000 + 10 * pi + fi))
+            assert cases.rel_err((m @ pv.cuda()).cpu(), g['kron_q_%d_%d_mv' % (pi, fi)]) < 1e-4, (pi, fi)
+    Xte = torch.randn(3, 2, 28, 28, generator=torch.Generator().manual_seed(16))
+    fmu, fvar = glm_moments(Xte, model, lap.mu, lap.Sigma_chol)
+    assert cases.rel_err(fmu.cpu(), g['glm_fmu_kron']) < 1e-5
+    assert cases.rel_err(fvar.cpu(), g['glm_fvar_kron']) < TOL
+    eps = torch.randn(4, 3, 3, generator=torch.Generator().manual_seed(711))
+    out = lap.predictive_samples_glm(Xte, n_samples=4, eps=eps)
+    assert cases.rel_err(out.cpu(), g['glm_kron']) < TOL
+
+
+def test_oracle_same_inputs_midsize():
+    """CUDA path vs the CPU oracle on a banana-shaped (config 1) problem at a size the oracle
+    finishes in seconds: MLPS(2,[50,50],2), N=600, two loader batches, all three structures."""
+    from preds_b200 import MLPS, CategoricalLh, Laplace
+    torch.manual_seed(71)
+    model = MLPS(2, [50, 50], 2, 'tanh')
+    X = torch.randn(600, 2, generator=torch.Generator().manual_seed(15))
+    y = torch.randint(2, (600,), generator=torch.Generator().manual_seed(15))
+    Xte = torch.randn(64, 2, generator=torch.Generator().manual_seed(16))
+    batches = [(X[:400], y[:400]), (X[400:], y[400:])]
+    omodel = port.make_mlps(2, [50, 50], 2, 'tanh')
+    port.set_theta(omodel, port.get_theta(model))
+    olh = port.CategoricalLh()
+    model = model.cuda()
+    S = 16
+    eps = torch.randn(S, 64, 2, generator=torch.Generator().manual_seed(711))
+    for cov in ('full', 'diag', 'kron'):
+        post = port.infer(omodel, 1.0, olh, batches, cov)
+        lap = Laplace(model, 1.0, CategoricalLh())
+        lap.infer(batches, cov_type=cov)
+        if cov == 'full':
+            assert cases.rel_err(lap.precision.cpu(), post['precision']) < TOL
+        ref = port.glm_predictive(omodel, olh, Xte, post, eps)
+        out = lap.predictive_samples_glm(Xte, n_samples=S, eps=eps)
+        assert cases.rel_err(out.cpu(), ref) < TOL, cov
+
+
+def test_glm_sampler_philox_statistics():
+    """In-kernel Philox draws: sample mean/covariance of the logits match (f_mu, f_var)."""
+    from preds_b200._cabi import lib, check, ptr, stream, LIK_GAUSSIAN
+    N, K, S = 4, 3, 200000
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(N, K, K, generator=g)
+    fvar = (A @ A.transpose(1, 2) + 0.1 * torch.eye(K)).cuda().contiguous()
+    fmu = torch.randn(N, K, generator=g).cuda().contiguous()
+    out = torch.empty(S, N, K, device='cuda')
+    status = torch.empty(N, dtype=torch.int32, device='cuda')
+    check(lib.bnnp_glm_sample(LIK_GAUSSIAN, ptr(fmu), ptr(fvar), None, 1234, S, N, K, ptr(out), ptr(status), stream()))
+    assert int(status.sum()) == 0
+    assert float((out.mean(0) - fmu).abs().max()) < 0.02
+    for n in range(N):
+        cov = torch.cov(out[:, n, :].T)
+        assert float((cov - fvar[n]).abs().max()) < 0.05 * float(fvar[n].abs().max())
+    # a non-PD covariance is flagged and the reference's diagonal fallback is used
+    fvar[1] = -fvar[1]
+    check(lib.bnnp_glm_sample(LIK_GAUSSIAN, ptr(fmu), ptr(fvar), None, 1234, 8, N, K, ptr(out), ptr(status), stream()))
+    assert status.cpu().tolist() == [0, 1, 0, 0]
