@@ -83,33 +83,45 @@ struct JacRowA {        // A((n,k), p) = G[(n,k), u(p)] * a[n, c(p)]
     return G[r * gld + pu[p]] * A[(r / K) * ald + pc[p]];
   }
 };
-// f_var[n,k,l] = sum_q T[(n,k), q] * J[(n,l), q]      one block per (n,k)
-__global__ void fvar_from_T_kernel(const float* __restrict__ T, JacRowA J, int64_t P, int K,
-                                   float* __restrict__ fvar) {
-  __shared__ float red[BNNP_MAX_K][8];
-  int64_t r = blockIdx.x;                    // (n,k)
-  int64_t n = r / K; int k = (int)(r % K);
-  float acc[BNNP_MAX_K];
+// f_var[n,k,l] = sum_q T[(n,k), q] * J[(n,l), q]      one block per (n,k); K accumulators in registers
+template <int KK>
+__global__ void __launch_bounds__(256)
+fvar_from_T_kernel(const float* T, JacRowA J, int64_t P, float* __restrict__ fvar) {
+  __shared__ float red[KK][8];
+  const int64_t r = blockIdx.x;              // (n,k)
+  const int64_t n = r / KK;
+  const int k = (int)(r % KK);
+  float acc[KK];
 #pragma unroll
-  for (int l = 0; l < BNNP_MAX_K; ++l) acc[l] = 0.f;
-  for (int64_t q = threadIdx.x; q < P; q += blockDim.x) {
-    float t = T[r * P + q];
-    float a = J.A[n * J.ald + J.pc[q]];
-    int u = J.pu[q];
-    float ta = t * a;
-    for (int l = 0; l < K; ++l) acc[l] = fmaf(ta, J.G[(n * K + l) * J.gld + u], acc[l]);
+  for (int l = 0; l < KK; ++l) acc[l] = 0.f;
+  const float* Trow = T + r * P;
+  const float* Arow = J.A + n * J.ald;
+  const float* Grow = J.G + n * KK * J.gld;
+  for (int64_t q = threadIdx.x; q < P; q += 256) {
+    const float ta = Trow[q] * Arow[J.pc[q]];
+    const int u = J.pu[q];
+#pragma unroll
+    for (int l = 0; l < KK; ++l) acc[l] = fmaf(ta, Grow[l * J.gld + u], acc[l]);
   }
-  int lane = threadIdx.x % 32, w = threadIdx.x / 32;
-  for (int l = 0; l < K; ++l) {
-    float v = warp_sum(acc[l]);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int l = 0; l < KK; ++l) {
+    const float v = warp_sum(acc[l]);
     if (lane == 0) red[l][w] = v;
   }
   __syncthreads();
-  if (threadIdx.x < K) {
+  if (threadIdx.x < KK) {
     float v = 0.f;
-    for (int i = 0; i < (int)(blockDim.x / 32); ++i) v += red[threadIdx.x][i];
-    fvar[(n * K + k) * K + threadIdx.x] = v;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[threadIdx.x][i];
+    fvar[(n * KK + k) * KK + threadIdx.x] = v;
   }
+}
+template <int KK>
+static int launch_fvar_from_T(const float* T, const JacRowA& J, int64_t P, int64_t N, float* fvar, cudaStream_t st) {
+  fvar_from_T_kernel<KK><<<(unsigned)(N * KK), 256, 0, st>>>(T, J, P, fvar);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
 }
 __global__ void param_maps2_kernel(int32_t* __restrict__ pu, int32_t* __restrict__ pc, int64_t off,
                                    int m, int nin, int unit0, int col0, int is_bias) {
@@ -433,9 +445,13 @@ extern "C" int bnnp_glm_fvar_full(const bnnp_op_t* ops, int n_ops, const bnnp_pl
   JacRowA J{ws + plan->gcat_off, ws + plan->acat_off, pu, pc, plan->Mtot, plan->Dtot, K};
   int rc = gemm_simt(N * K, P, P, 1, J, LoadRowMajorB{Sigma, P, 0}, StoreAxpby{T, P, 0, 1.f, 0.f}, st);
   if (rc) return rc;
-  fvar_from_T_kernel<<<(unsigned)(N * K), 256, 0, st>>>(T, J, P, K, f_var);
-  BNNP_LAUNCH_CHECK();
-  return BNNP_OK;
+#define BNNP_CASE(KK) case KK: return launch_fvar_from_T<KK>(T, J, P, N, f_var, st);
+  switch (K) {
+    BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
+    BNNP_CASE(9) BNNP_CASE(10) BNNP_CASE(11) BNNP_CASE(12) BNNP_CASE(13) BNNP_CASE(14) BNNP_CASE(15) BNNP_CASE(16)
+    default: return BNNP_ERR_UNSUPPORTED;
+  }
+#undef BNNP_CASE
 }
 
 // ------------------------------------------------------------------------------------ diag

@@ -1,7 +1,583 @@
+// Full-GGN accumulation on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, B operand by
+// TMA, A operand synthesised on chip).  Replaces the dominant einsum of preds/laplace.py:42
+//     precision += einsum('mpk,mkl,mql->pq', Js, Hess, Js)
+// for Linear-only networks without ever forming Js.
+//
+// Algebra.  For a Linear layer  J_n[k, (i,j)] = g_n[k,i] * a_n[j]  (a_n[j] := 1 for the bias), so
+//     H[(i,j),(i',j')] = sum_n  C_n[i,i'] * a_n[j] * a'_n[j'],     C_n = G_n^T Lambda_n G_n  (M x M)
+// i.e. for every pair of units (i,i') a *weighted Gram* of the layer inputs.  Contracting the K
+// outputs into C_n first removes the factor K from the 2*N*K*P^2 flops of the einsum as written.
+//
+// Mapping.  One CTA tile = 128 consecutive parameter rows of layer l (weights then biases) x
+// two column tiles (units i'_a, i'_b of layer l') x the same <=256-wide range of j'.  Per 32-example
+// K-chunk:
+//   B  = X^T tile [wc x 32]  bf16 hi/lo, loaded by TMA (SWIZZLE_64B, K-major), shared by both units;
+//   A  = c_n[i(p), i'] * x_n[j(p)]  computed in fp32 by 8 generator warps, split into bf16 hi/lo and
+//        written to shared memory in the UMMA canonical K-major SWIZZLE_64B layout;
+//   D += Ah*Bh + Ah*Bl + Al*Bh   (3 tcgen05.mma kind::f16 per 16-wide K-step; products exact, fp32
+//        accumulation in TMEM => ~2^-17 relative per term, "fp32-grade" after summation).
+// Epilogue: tcgen05.ld -> registers -> H[p,q] += acc (tiles on/below the diagonal only).
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include "gram_tc.cuh"
+
 namespace bnnp {
-int64_t gram_tc_scratch_floats(const bnnp_plan_t*, int64_t) { return 0; }
-bool gram_tc_preferred(const bnnp_op_t*, int, const bnnp_plan_t*, int64_t) { return false; }
-int gram_tc_full_accum(const bnnp_op_t*, int, const bnnp_plan_t*, int64_t, const float*, const float*,
-                       float*, float*, cudaStream_t) { return BNNP_ERR_UNSUPPORTED; }
+namespace tc {
+
+constexpr int BK = 32;                 // examples per K-chunk (32 bf16 = 64 B = one SWIZZLE_64B row)
+constexpr int TILE_M = 128;
+constexpr int MAX_WC = 256;
+constexpr int STAGES = 3;
+constexpr int A_TERM_BYTES = TILE_M * BK * 2;            // 8 KB
+constexpr int A_STAGE_BYTES = 2 * 2 * A_TERM_BYTES;      // 2 accumulators x (hi, lo)
+constexpr int B_TERM_BYTES = MAX_WC * BK * 2;            // 16 KB
+constexpr int B_STAGE_BYTES = 2 * B_TERM_BYTES;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;   // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 384;       // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: generators + epilogue
+constexpr int GEN_WARP0 = 4;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (it == 64) t0 = clock64();
+    if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 8000000000LL) {
+      printf("[bnnp_b200] gram_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: 8-row groups of 64 B rows, 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address            bits [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (16B) bits [16,30)
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset        bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                            // layout type SWIZZLE_64B
+  return d;
+}
+// Instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+struct BlockArgs {
+  // row side (layer l)
+  int m, n, has_bias, unit0, col0;     // rows r in [0, m*n (+m)): r < m*n -> (i=r/n, j=r%n), else bias unit r-m*n
+  long long row_theta0;                // theta offset of row 0 (weights, biases follow contiguously)
+  // column side (layer l')
+  int mp, np, unit0p;                  // column tiles: unit i' in [0,mp), j' in [0,np)
+  long long col_theta0;
+  int wc, n_jt, n_pairs, n_rt;         // column tile width, #j' tiles, #unit pairs, #row tiles
+  int diag_block;                      // 1 when l == l' (skip tiles strictly above the diagonal)
+  int n_chunks, Mtot;
+  long long Npad, P;
+};
+
+// out(hi, lo) <- split of 8 fp32 values into bf16 pairs
+__device__ __forceinline__ void split8(const float* a, uint4& hi, uint4& lo) {
+  __nv_bfloat162 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]);
+    float2 hf = __bfloat1622float2(h[i]);
+    l[i] = __floats2bfloat162_rn(a[2 * i] - hf.x, a[2 * i + 1] - hf.y);
+  }
+  hi = *reinterpret_cast<uint4*>(h);
+  lo = *reinterpret_cast<uint4*>(l);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+               const float* __restrict__ XT32, const float* __restrict__ Ct, float* __restrict__ H,
+               int* __restrict__ tile_counter, BlockArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_a = bars;                    // [STAGES]  generators -> MMA
+  uint64_t* full_b = bars + STAGES;           // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + 2 * STAGES;        // [STAGES]  MMA (tcgen05.commit) -> TMA + generators
+  uint64_t* acc_full = bars + 3 * STAGES;     // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+  int* tile_slot = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_a[s], 8); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = args.n_pairs * args.n_jt * args.n_rt;
+  const int rows_total = args.m * args.n + (args.has_bias ? args.m : 0);
+  uint32_t stage = 0, phase = 0;       // smem ring position (every role walks the same sequence)
+  uint32_t acc_phase = 0;
+
+  for (;;) {
+    if (threadIdx.x == 0) *tile_slot = atomicAdd(tile_counter, 1);
+    __syncthreads();
+    const int tile = *tile_slot;
+    __syncthreads();
+    if (tile >= n_tiles) break;
+    const int rt = tile % args.n_rt;
+    const int jt = (tile / args.n_rt) % args.n_jt;
+    const int pair = tile / (args.n_rt * args.n_jt);
+    const int ipa = 2 * pair, ipb = 2 * pair + 1;
+    const int nacc = ipb < args.mp ? 2 : 1;
+    const int jc0 = jt * args.wc;
+    const int row0 = rt * TILE_M;
+    if (args.diag_block) {
+      // needed iff some (row, col) of the tile is on/below the diagonal of H
+      long long max_row = args.row_theta0 + (row0 + TILE_M - 1 < rows_total - 1 ? row0 + TILE_M - 1 : rows_total - 1);
+      long long min_col = args.col_theta0 + (long long)ipa * args.np + jc0;
+      if (max_row < min_col) continue;          // uniform across the CTA
+    }
+
+    if (warp == 0) {
+      // ===================== TMA producer: B = X^T rows [jc0, jc0+wc) of layer l', hi and lo =====================
+      if (lane == 0) {
+        uint32_t s = stage, ph = phase;
+        const uint32_t bytes = 2u * (uint32_t)args.wc * BK * 2u;
+        for (int c = 0; c < args.n_chunks; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* bdst = smem + s * STAGE_BYTES + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_b[s], bytes);
+          tma_load_2d(&map_bh, &full_b[s], bdst, c * BK, jc0);
+          tma_load_2d(&map_bl, &full_b[s], bdst + B_TERM_BYTES, c * BK, jc0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        uint32_t s = stage, ph = phase;
+        const uint32_t idesc = umma_idesc_bf16(args.wc);
+        for (int c = 0; c < args.n_chunks; ++c) {
+          mbar_wait(&full_a[s], ph);
+          mbar_wait(&full_b[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b0 = a0 + A_STAGE_BYTES;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            if (a < nacc) {
+              const uint32_t ah = a0 + a * 2 * A_TERM_BYTES, al = ah + A_TERM_BYTES;
+              const uint32_t d = tmem_base + a * MAX_WC;
+#pragma unroll
+              for (int ks = 0; ks < BK / 16; ++ks) {
+                const uint64_t dah = umma_desc_sw64(ah + ks * 32), dal = umma_desc_sw64(al + ks * 32);
+                const uint64_t dbh = umma_desc_sw64(b0 + ks * 32), dbl = umma_desc_sw64(b0 + B_TERM_BYTES + ks * 32);
+                umma_bf16(d, dah, dbh, idesc, (c | ks) ? 1u : 0u);
+                umma_bf16(d, dah, dbl, idesc, 1u);
+                umma_bf16(d, dal, dbh, idesc, 1u);
+              }
+            }
+          }
+          umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
+          if (c == args.n_chunks - 1) umma_commit(acc_full);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp >= GEN_WARP0) {
+      // ===================== A generators (then epilogue) =====================
+      const int gw = warp - GEN_WARP0;
+      const int g = lane & 3;                  // 16-byte K-group (8 examples) inside the 32-example chunk
+      // this thread's two rows: gw*16 + it*8 + lane/4
+      const float* xsrc[2];
+      const float* csrc[2][2];
+      bool rvalid[2];
+      uint32_t soff[2];
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int rl = gw * 16 + it * 8 + (lane >> 2);
+        const int r = row0 + rl;
+        rvalid[it] = r < rows_total;
+        int u = args.unit0, src = args.col0;
+        if (rvalid[it]) {
+          if (r < args.m * args.n) { u += r / args.n; src += r % args.n; }
+          else { u += r - args.m * args.n; src += args.n; }        // bias row: the constant-1 column
+        }
+        xsrc[it] = XT32 + (long long)src * args.Npad + g * 8;
+        csrc[0][it] = Ct + ((long long)(args.unit0p + ipa) * args.Mtot + u) * args.Npad + g * 8;
+        csrc[1][it] = Ct + ((long long)(args.unit0p + (nacc > 1 ? ipb : ipa)) * args.Mtot + u) * args.Npad + g * 8;
+        soff[it] = (uint32_t)((rl >> 3) * 512 + (rl & 7) * 64 + ((g ^ ((rl >> 1) & 3)) << 4));
+      }
+      uint32_t s = stage, ph = phase;
+      float4 xv[2][2], cv[2][2][2];
+      auto load_chunk = [&](int c) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const float4* xp = reinterpret_cast<const float4*>(xsrc[it] + c * BK);
+          xv[it][0] = __ldg(xp); xv[it][1] = __ldg(xp + 1);
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const float4* cp = reinterpret_cast<const float4*>(csrc[a][it] + c * BK);
+            cv[a][it][0] = __ldg(cp); cv[a][it][1] = __ldg(cp + 1);
+          }
+        }
+      };
+      load_chunk(0);
+      for (int c = 0; c < args.n_chunks; ++c) {
+        float4 x[2][2], cc[2][2][2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          x[it][0] = xv[it][0]; x[it][1] = xv[it][1];
+#pragma unroll
+          for (int a = 0; a < 2; ++a) { cc[a][it][0] = cv[a][it][0]; cc[a][it][1] = cv[a][it][1]; }
+        }
+        if (c + 1 < args.n_chunks) load_chunk(c + 1);      // software prefetch of the next chunk
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* abase = smem + s * STAGE_BYTES;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (a < nacc) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              float v[8];
+              const float* xf = reinterpret_cast<const float*>(&x[it][0]);
+              const float* cf = reinterpret_cast<const float*>(&cc[a][it][0]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = rvalid[it] ? xf[e] * cf[e] : 0.f;
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              uint8_t* dst = abase + a * 2 * A_TERM_BYTES + soff[it];
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + A_TERM_BYTES) = lo;
+            }
+          }
+        }
+        fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      // ---------------- epilogue: H[p, q] += D ----------------
+      mbar_wait(acc_full, acc_phase);
+      tc_fence_after();
+      const int a = gw >> 2, quarter = gw & 3;
+      if (a < nacc) {
+        const int rl = quarter * 32 + lane;
+        const int r = row0 + rl;
+        const bool rowok = r < rows_total;
+        const int ip = a == 0 ? ipa : ipb;
+        float* hrow = H + (args.row_theta0 + r) * args.P + args.col_theta0 + (long long)ip * args.np + jc0;
+        const int ncols = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
+        for (int c0 = 0; c0 < args.wc; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * MAX_WC + c0), v);
+          if (rowok) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (c0 + e < ncols) hrow[c0 + e] += __uint_as_float(v[e]);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    // every role advanced the ring by n_chunks stages
+    {
+      uint32_t adv = (uint32_t)args.n_chunks;
+      uint32_t tot = stage + adv;
+      phase ^= (tot / STAGES) & 1;
+      stage = tot % STAGES;
+      acc_phase ^= 1;
+    }
+    tc_fence_before();
+    __syncthreads();            // TMEM drained by the epilogue before the next tile's first MMA overwrites it
+    tc_fence_after();
+  }
+
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------- pre-kernels
+// XT32[c, n] = A[n, c];  XTh/XTl = bf16 hi/lo split;  zero for n >= N   (32x32 smem transpose)
+__global__ void transpose_split_kernel(const float* __restrict__ A, long long ald, long long N, int D,
+                                       long long Npad, float* __restrict__ XT32,
+                                       __nv_bfloat16* __restrict__ XTh, __nv_bfloat16* __restrict__ XTl) {
+  __shared__ float tile[32][33];
+  const long long n0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    long long n = n0 + i; int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && c < D) ? A[n * ald + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int c = c0 + i; long long n = n0 + threadIdx.x;
+    if (c < D && n < Npad) {
+      float v = tile[threadIdx.x][i];
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      XT32[c * Npad + n] = v;
+      XTh[c * Npad + n] = h;
+      XTl[c * Npad + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// GL[(n,k), u] = sum_l Lambda[n,k,l] G[(n,l), u]
+__global__ void tc_lambda_g_kernel(const float* __restrict__ Lam, const float* __restrict__ G, long long N,
+                                   int K, int M, float* __restrict__ GL) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K * M) return;
+  int u = (int)(i % M); long long r = i / M; long long n = r / K; int k = (int)(r % K);
+  float acc = 0.f;
+  for (int l = 0; l < K; ++l) acc = fmaf(Lam[(n * K + k) * K + l], G[(n * K + l) * M + u], acc);
+  GL[i] = acc;
+}
+
+// Ct[(u'*M + u), n] = sum_k GL[(n,k), u] * G[(n,k), u']   (0 for n >= N).  One block per 32 examples.
+__global__ void ct_kernel(const float* __restrict__ GL, const float* __restrict__ G, long long N, int K,
+                          int M, long long Npad, float* __restrict__ Ct) {
+  extern __shared__ float sh[];            // GL tile [32][K*M] and G tile [32][K*M]
+  float* sgl = sh;
+  float* sg = sh + 32 * K * M;
+  const long long n0 = (long long)blockIdx.x * 32;
+  const int KM = K * M;
+  for (int i = threadIdx.x; i < 32 * KM; i += blockDim.x) {
+    long long n = n0 + i / KM;
+    bool ok = n < N;
+    sgl[i] = ok ? GL[n * KM + i % KM] : 0.f;
+    sg[i] = ok ? G[n * KM + i % KM] : 0.f;
+  }
+  __syncthreads();
+  const int nl = threadIdx.x & 31;
+  for (int e = threadIdx.x >> 5; e < M * M; e += blockDim.x >> 5) {
+    int up = e / M, u = e % M;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(sgl[nl * KM + k * M + u], sg[nl * KM + k * M + up], acc);
+    Ct[(long long)e * Npad + n0 + nl] = acc;
+  }
+}
+
+// Bias columns (SIMT): H[row_theta0 + r, bias_theta0p + i'] += sum_n Ct[(u'_i' * M + u(r)), n] * XT32[src(r), n]
+// one warp per (r, i').
+__global__ void bias_cols_kernel(const float* __restrict__ XT32, const float* __restrict__ Ct,
+                                 float* __restrict__ H, BlockArgs a, long long bias_theta0p, int r_begin) {
+  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rows_total = a.m * a.n + (a.has_bias ? a.m : 0);
+  const long long nwork = (long long)(rows_total - r_begin) * a.mp;
+  if (w >= nwork) return;
+  const int r = r_begin + (int)(w / a.mp), ip = (int)(w % a.mp);
+  int u = a.unit0, src = a.col0;
+  if (r < a.m * a.n) { u += r / a.n; src += r % a.n; } else { u += r - a.m * a.n; src += a.n; }
+  const float* x = XT32 + (long long)src * a.Npad;
+  const float* c = Ct + ((long long)(a.unit0p + ip) * a.Mtot + u) * a.Npad;
+  float acc = 0.f;
+  for (long long n = lane; n < a.Npad; n += 32) acc = fmaf(c[n], x[n], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) H[(a.row_theta0 + r) * a.P + bias_theta0p + ip] += acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_b_map(CUtensorMap* map, const __nv_bfloat16* base, long long rows, long long Npad, int wc) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return BNNP_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)Npad, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)Npad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)wc};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstride, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[bnnp_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
+    return BNNP_ERR_CUDA;
+  }
+  return BNNP_OK;
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------- host side
+static inline long long pad_to(long long v, long long a) { return (v + a - 1) / a * a; }
+
+struct TcLayout {
+  long long Npad, off_counter, off_xt32, off_xth, off_xtl, off_gl, off_ct, total;
+};
+static TcLayout tc_layout(const bnnp_plan_t* plan, long long N) {
+  TcLayout L;
+  L.Npad = pad_to(N, 64);
+  long long D = plan->Dtot, M = plan->Mtot, K = plan->K;
+  long long cur = 0;
+  auto take = [&](long long floats) { long long o = cur; cur += pad_to(floats, 256); return o; };
+  L.off_counter = take(256);
+  L.off_xt32 = take(D * L.Npad);
+  L.off_xth = take((D * L.Npad + 1) / 2);
+  L.off_xtl = take((D * L.Npad + 1) / 2);
+  L.off_gl = take(N * K * M);
+  L.off_ct = take(M * M * L.Npad);
+  L.total = cur;
+  return L;
+}
+
+int64_t gram_tc_scratch_floats(const bnnp_plan_t* plan, int64_t N) { return tc_layout(plan, N).total + 256; }
+
+bool gram_tc_preferred(const bnnp_op_t*, int, const bnnp_plan_t* plan, int64_t N) {
+  // tiny problems are launch/padding bound on 128 x 256 tiles: keep them on the SIMT path
+  return plan->P >= 2048 && N >= 256 && 32LL * plan->K * plan->Mtot * 2 * 4 <= 200 * 1024;
+}
+
+int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, const float* ws,
+                       const float* Lambda, float* H, float* scratch, cudaStream_t st) {
+  using namespace tc;
+  const int K = plan->K, M = plan->Mtot, D = plan->Dtot;
+  if ((long long)32 * K * M * 2 * 4 > 200 * 1024) return BNNP_ERR_UNSUPPORTED;
+  // scratch must be 1 KB aligned for the tensor maps / vector loads
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~uintptr_t(1023));
+  const TcLayout L = tc_layout(plan, N);
+  int* counters = reinterpret_cast<int*>(base + L.off_counter);
+  float* XT32 = base + L.off_xt32;
+  __nv_bfloat16* XTh = reinterpret_cast<__nv_bfloat16*>(base + L.off_xth);
+  __nv_bfloat16* XTl = reinterpret_cast<__nv_bfloat16*>(base + L.off_xtl);
+  float* GL = base + L.off_gl;
+  float* Ct = base + L.off_ct;
+  const float* A = ws + plan->acat_off;
+  const float* G = ws + plan->gcat_off;
+
+  BNNP_CUDA_CHECK(cudaMemsetAsync(counters, 0, 256 * sizeof(int), st));
+  {
+    dim3 grid((unsigned)(L.Npad / 32), (unsigned)((D + 31) / 32));
+    transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(A, D, N, D, L.Npad, XT32, XTh, XTl);
+    BNNP_LAUNCH_CHECK();
+    tc_lambda_g_kernel<<<(unsigned)ceil_div64(N * K * M, 256), 256, 0, st>>>(Lambda, G, N, K, M, GL);
+    BNNP_LAUNCH_CHECK();
+    size_t sh = (size_t)2 * 32 * K * M * sizeof(float);
+    BNNP_CUDA_CHECK(cudaFuncSetAttribute(ct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    ct_kernel<<<(unsigned)(L.Npad / 32), 256, sh, st>>>(GL, G, N, K, M, L.Npad, Ct);
+    BNNP_LAUNCH_CHECK();
+  }
+  BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  int pair_idx = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].kind != BNNP_OP_LINEAR) continue;
+    for (int j = 0; j <= i; ++j) {
+      if (ops[j].kind != BNNP_OP_LINEAR) continue;
+      const bnnp_op_t& R = ops[i];
+      const bnnp_op_t& Cc = ops[j];
+      if (R.has_bias && R.theta_off_b != R.theta_off_w + (long long)R.out_c * R.in_c) return BNNP_ERR_UNSUPPORTED;
+      BlockArgs a;
+      a.m = R.out_c; a.n = R.in_c; a.has_bias = R.has_bias;
+      a.unit0 = plan->op[i].lin_unit; a.col0 = plan->op[i].lin_col; a.row_theta0 = R.theta_off_w;
+      a.mp = Cc.out_c; a.np = Cc.in_c; a.unit0p = plan->op[j].lin_unit; a.col_theta0 = Cc.theta_off_w;
+      int n_jt = (a.np + MAX_WC - 1) / MAX_WC;
+      a.wc = (((a.np + n_jt - 1) / n_jt) + 15) / 16 * 16;
+      a.n_jt = (a.np + a.wc - 1) / a.wc;
+      a.n_pairs = (a.mp + 1) / 2;
+      const int rows_total = a.m * a.n + (a.has_bias ? a.m : 0);
+      a.n_rt = (rows_total + TILE_M - 1) / TILE_M;
+      a.diag_block = (i == j);
+      a.n_chunks = (int)(L.Npad / BK);
+      a.Mtot = M; a.Npad = L.Npad; a.P = plan->P;
+      CUtensorMap mh, ml;
+      int rc = make_b_map(&mh, XTh + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, a.wc);
+      if (rc) return rc;
+      rc = make_b_map(&ml, XTl + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, a.wc);
+      if (rc) return rc;
+      if (pair_idx >= 256) return BNNP_ERR_UNSUPPORTED;
+      const long long n_tiles = (long long)a.n_pairs * a.n_jt * a.n_rt;
+      int grid = (int)(n_tiles < sms ? n_tiles : sms);
+      gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+      BNNP_LAUNCH_CHECK();
+      ++pair_idx;
+      // bias columns of layer l' (SIMT): all rows for l' < l, bias rows only on the diagonal block
+      if (Cc.has_bias) {
+        int r_begin = (i == j) ? a.m * a.n : 0;
+        long long nwork = (long long)(rows_total - r_begin) * a.mp;
+        if (nwork > 0) {
+          bias_cols_kernel<<<(unsigned)ceil_div64(nwork * 32, 256), 256, 0, st>>>(XT32, Ct, H, a, Cc.theta_off_b, r_begin);
+          BNNP_LAUNCH_CHECK();
+        }
+      }
+    }
+  }
+  return BNNP_OK;
+}
+
 }  // namespace bnnp
