@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the Laplace-GGN hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W   # reference CPU arm (oracle port)
+
+Workload (BASELINE.json configs[4], the largest single-GPU configuration): full-covariance GGN of
+MLPS(784,[75],10,'tanh',flatten=True), P = 59 635, K = 10, synthetic N(0,1) inputs of MNIST shape.
+One step = one loader batch of B examples through the hot path: forward, K-column backward,
+likelihood Hessian, tensor-core accumulation  H += sum_n J_n^T Lambda_n J_n  into the resident
+14.2 GB precision matrix.  `value` is device-timed with the batches resident in HBM; `e2e` is the
+same metric through `Laplace.infer(...)` with pinned HOST batches (H2D + a D2H read per step).
+The one-off factorisation is not part of this metric (timed separately, north star).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'bnn-predictions_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = 'ggn_accum_examples_per_s'
+UNIT = 'examples/s'
+MODEL = dict(input_size=784, hidden_sizes=[75], output_size=10, activation='tanh', flatten=True)
+P_PARAMS, K_OUT = 59635, 10
+WORKLOAD = 'cfg5 full-cov GGN, MLPS(784,[75],10,tanh) P=59635 K=10, synthetic MNIST-shape N(0,1)'
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def make_batches(n_batches, B, pinned=False):
+    out = []
+    for i in range(n_batches):
+        g = torch.Generator().manual_seed(15 + i)
+        X = torch.randn(B, 1, 28, 28, generator=g)
+        y = torch.randint(K_OUT, (B,), generator=g)
+        if pinned:
+            X, y = X.pin_memory(), y.pin_memory()
+        out.append((X, y))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_full_ggn_rate(sample, repeats, warmup):
+    """examples/s of the reference's full-GGN accumulation (Jacobians + einsum, preds/laplace.py:39-42)
+    restated in oracle/port.py, float32 torch on all host threads, on `sample` examples per step."""
+    from oracle import port
+    torch.manual_seed(71)
+    model = port.make_mlps(**MODEL)
+    lh = port.CategoricalLh()
+    g = torch.Generator().manual_seed(15)
+    X = torch.randn(sample, 1, 28, 28, generator=g)
+    y = torch.randint(K_OUT, (sample,), generator=g)
+    H = torch.zeros(P_PARAMS, P_PARAMS)
+    times = []
+    for it in range(warmup + repeats):
+        t0 = time.perf_counter()
+        port.ggn_full_accumulate(model, lh, [(X, y)], H)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sample / statistics.mean(times), statistics.mean(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    sample = args.cpu_sample
+    rate, sec = cpu_full_ggn_rate(sample, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch': sample},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': '%d examples per step (Jacobians + einsum into the 14.2 GB H), oracle/port.py' % sample},
+        'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from preds_b200 import Laplace, CategoricalLh, MLPS
+    from preds_b200._cabi import lib, check, ptr, stream
+    from preds_b200._engine import net_for
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B, K, W = args.batch, args.steps, args.warmup
+
+    torch.manual_seed(71)
+    model = MLPS(**MODEL).to(dev)
+    lh = CategoricalLh()
+    net = net_for(model)
+    n_distinct = 4
+    host = make_batches(n_distinct, B, pinned=True)
+    for i in range(n_distinct):        # different examples on every rank (sharded data set)
+        host[i][0].add_(0.01 * rank)
+    resident = [(X.to(dev), y.to(dev)) for X, y in host]
+    H = torch.zeros(P_PARAMS, P_PARAMS, device=dev)
+
+    def step(X):
+        X2d, pl, ws, f = net.jacobian_factors(X)
+        N = X2d.shape[0]
+        Lam = lh._hessian_nkk(f)
+        sc = net.scratch(lib.bnnp_ggn_full_scratch_floats(C.byref(pl), N, args.engine))
+        check(lib.bnnp_ggn_full_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H), ptr(sc),
+                                      args.engine, stream()), 'bnnp_ggn_full_accum')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(resident[i % n_distinct][0])
+    barrier()
+    H.zero_()
+    lib.bnnp_prof_enable(1)
+    launches0 = lib.bnnp_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(resident[i % n_distinct][0])
+    if world > 1:
+        dist.all_reduce(H)              # the path's one exchange step: sum of the local GGNs
+    check(lib.bnnp_symmetrize_lower(ptr(H), P_PARAMS, stream()), 'bnnp_symmetrize_lower')
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(lib.bnnp_launch_count() - launches0)
+    # dominant kernel: CUDA-event records of every gram_tc launch (recorded on the launching stream)
+    cap = 4096
+    pms, pex, pus = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+    nrec = lib.bnnp_prof_read(pms, pex, pus, cap)
+    lib.bnnp_prof_enable(0)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = K * B * world / (ms * 1e-3)
+    checksum = float(H.diagonal().double().sum())
+
+    # ---- e2e through the public API with pinned host batches (H2D inside, D2H read per step) ----
+    lap = Laplace(model, 1.0, lh)
+    lap.ggn_engine = args.engine
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    lap.infer([host[0]], cov_type='full', factorise=False)     # warm-up
+    float(lap.precision.diagonal().sum())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        lap.infer([host[i % n_distinct]], cov_type='full', factorise=False)
+        float(lap.precision.diagonal().sum())                  # device -> host read of the step's result
+    if world > 1:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = e2e_steps * B * world / e2e_s
+    lap.precision = None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    recs = [(pms[i], pex[i], pus[i]) for i in range(max(nrec, 0))]
+    roofline = None
+    if recs:
+        top = max(r[2] for r in recs)
+        dom = [r for r in recs if r[2] >= 0.5 * top]           # the (layer1, layer1) block launches
+        avg_ms = statistics.mean(r[0] for r in dom)
+        useful = statistics.mean(r[2] for r in dom)
+        executed = statistics.mean(r[1] for r in dom)
+        peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+        ach = useful / (avg_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'gram_tc_traffic.json')))['dram_bytes_per_launch']
+        except Exception:
+            pass
+        roofline = {
+            'bound': 'tensor', 'kernel': 'gram_tc_kernel', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': ach / peak, 'traffic': traffic, 'peak_source': pk_kind + ' bf16 dense (sustained)',
+            'kernel_ms_per_launch': avg_ms, 'kernel_share_of_step': sum(r[0] for r in recs) / ms,
+            'flops_note': 'achieved = useful bf16 MMA flops (3 split passes x 2*N*rows*cols of the computed '
+                          'lower-triangle tiles, padding excluded) / CUDA-event kernel time',
+            'executed_tflops_incl_padding': executed / (avg_ms * 1e-3) / 1e12,
+            'einsum_as_written_tflops': (2.0 * K_OUT * P_PARAMS ** 2 + 2.0 * P_PARAMS * K_OUT ** 2) * B / (ms / K * 1e-3) / 1e12,
+        }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        rate, sec = cpu_full_ggn_rate(args.cpu_sample, 1, 1)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '%d examples, Jacobians + einsum into the 14.2 GB H (oracle/port.py), %.1f s' % (args.cpu_sample, sec)}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16x2-split (fp32-grade) tensor cores, f32 accumulate', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'engine': 'tcgen05' if args.engine != 1 else 'simt',
+                   'l2': 'working set >> L2: the 14.2 GB H is read-modify-written every step',
+                   'timed_region': 'K steps + all-reduce of H (N>1) + symmetrise'},
+        'roofline': roofline, 'cpu_baseline': cpu,
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * 784 * 4 + B * 8,
+                'd2h_bytes_per_step': 4, 'steps': e2e_steps,
+                'call': "Laplace.infer([(X_pinned_host, y)], cov_type='full', factorise=False) + float(precision.trace)"},
+        'gpu_launches': launches, 'clocks': clocks, 'checksum_trace_H': checksum,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=6)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=8192)
+    ap.add_argument('--engine', type=int, default=2)
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--cpu-sample', type=int, default=24)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -188,6 +188,8 @@ extern "C" const char* bnnp_strerror(int code) {
     default: return "unknown error";
   }
 }
+unsigned long long g_bnnp_launches = 0;
+extern "C" uint64_t bnnp_launch_count(void) { return g_bnnp_launches; }
 extern "C" int bnnp_version(void) { return 100; }
 extern "C" int bnnp_device_ok(void) {
   int n = 0;

@@ -15,7 +15,13 @@
     }                                                                 \
   } while (0)
 
-#define BNNP_LAUNCH_CHECK() BNNP_CUDA_CHECK(cudaGetLastError())
+// every kernel launch of the library passes through here: counted for bench.py's gpu_launches
+extern unsigned long long g_bnnp_launches;
+#define BNNP_LAUNCH_CHECK()                 \
+  do {                                      \
+    ++g_bnnp_launches;                      \
+    BNNP_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

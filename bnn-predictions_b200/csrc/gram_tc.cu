@@ -392,28 +392,39 @@ __global__ void tc_lambda_g_kernel(const float* __restrict__ Lam, const float* _
   GL[i] = acc;
 }
 
-// Ct[(u'*M + u), n] = sum_k GL[(n,k), u] * G[(n,k), u']   (0 for n >= N).  One block per 32 examples.
+// Ct[(u'*M + u), n] = sum_k GL[(n,k), u] * G[(n,k), u']   (0 for n >= N).  One block per NB examples
+// (NB = 32 / 16 / 8, the largest whose two [NB, K*M] staging tiles fit in shared memory).
+template <int NB>
 __global__ void ct_kernel(const float* __restrict__ GL, const float* __restrict__ G, long long N, int K,
                           int M, long long Npad, float* __restrict__ Ct) {
-  extern __shared__ float sh[];            // GL tile [32][K*M] and G tile [32][K*M]
-  float* sgl = sh;
-  float* sg = sh + 32 * K * M;
-  const long long n0 = (long long)blockIdx.x * 32;
+  extern __shared__ float sh[];
   const int KM = K * M;
-  for (int i = threadIdx.x; i < 32 * KM; i += blockDim.x) {
+  float* sgl = sh;
+  float* sg = sh + NB * KM;
+  const long long n0 = (long long)blockIdx.x * NB;
+  for (int i = threadIdx.x; i < NB * KM; i += blockDim.x) {
     long long n = n0 + i / KM;
     bool ok = n < N;
     sgl[i] = ok ? GL[n * KM + i % KM] : 0.f;
     sg[i] = ok ? G[n * KM + i % KM] : 0.f;
   }
   __syncthreads();
-  const int nl = threadIdx.x & 31;
-  for (int e = threadIdx.x >> 5; e < M * M; e += blockDim.x >> 5) {
+  const int nl = threadIdx.x % NB;
+  for (int e = threadIdx.x / NB; e < M * M; e += blockDim.x / NB) {
     int up = e / M, u = e % M;
     float acc = 0.f;
     for (int k = 0; k < K; ++k) acc = fmaf(sgl[nl * KM + k * M + u], sg[nl * KM + k * M + up], acc);
     Ct[(long long)e * Npad + n0 + nl] = acc;
   }
+}
+template <int NB>
+static int launch_ct(const float* GL, const float* G, long long N, int K, int M, long long Npad, float* Ct,
+                     cudaStream_t st) {
+  size_t sh = (size_t)2 * NB * K * M * sizeof(float);
+  BNNP_CUDA_CHECK(cudaFuncSetAttribute(ct_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  ct_kernel<NB><<<(unsigned)(Npad / NB), 256, sh, st>>>(GL, G, N, K, M, Npad, Ct);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
 }
 
 // Bias columns (SIMT): H[row_theta0 + r, bias_theta0p + i'] += sum_n Ct[(u'_i' * M + u(r)), n] * XT32[src(r), n]
@@ -474,6 +485,38 @@ static int make_b_map(CUtensorMap* map, const __nv_bfloat16* base, long long row
 // ---------------------------------------------------------------- host side
 static inline long long pad_to(long long v, long long a) { return (v + a - 1) / a * a; }
 
+// Optional CUDA-event timing of every gram_tc_kernel launch (bench.py's live roofline number).
+struct GramProf {
+  bool on = false;
+  int n = 0;
+  static constexpr int CAP = 4096;
+  cudaEvent_t beg[CAP], end[CAP];
+  double executed[CAP], useful[CAP];
+  bool created = false;
+};
+static GramProf g_prof;
+
+// MMA flops of one launch: executed (padded 128 x wc tiles, 3 split passes) and useful (valid rows/cols only)
+static void gram_flops(const tc::BlockArgs& a, double* executed, double* useful) {
+  const long long rows_total = (long long)a.m * a.n + (a.has_bias ? a.m : 0);
+  double ex = 0, us = 0;
+  for (int pair = 0; pair < a.n_pairs; ++pair)
+    for (int jt = 0; jt < a.n_jt; ++jt)
+      for (int rt = 0; rt < a.n_rt; ++rt) {
+        const int ipa = 2 * pair, nacc = (2 * pair + 1 < a.mp) ? 2 : 1;
+        const long long row0 = (long long)rt * tc::TILE_M, jc0 = (long long)jt * a.wc;
+        if (a.diag_block) {
+          long long last = row0 + tc::TILE_M - 1 < rows_total - 1 ? row0 + tc::TILE_M - 1 : rows_total - 1;
+          if (a.row_theta0 + last < a.col_theta0 + (long long)ipa * a.np + jc0) continue;
+        }
+        long long vr = rows_total - row0 < tc::TILE_M ? rows_total - row0 : tc::TILE_M;
+        long long vc = a.np - jc0 < a.wc ? a.np - jc0 : a.wc;
+        ex += 3.0 * 2.0 * tc::TILE_M * a.wc * (double)a.Npad * nacc;
+        us += 3.0 * 2.0 * vr * vc * (double)a.Npad * nacc;
+      }
+  *executed = ex; *useful = us;
+}
+
 struct TcLayout {
   long long Npad, off_counter, off_xt32, off_xth, off_xtl, off_gl, off_ct, total;
 };
@@ -497,14 +540,14 @@ int64_t gram_tc_scratch_floats(const bnnp_plan_t* plan, int64_t N) { return tc_l
 
 bool gram_tc_preferred(const bnnp_op_t*, int, const bnnp_plan_t* plan, int64_t N) {
   // tiny problems are launch/padding bound on 128 x 256 tiles: keep them on the SIMT path
-  return plan->P >= 2048 && N >= 256 && 32LL * plan->K * plan->Mtot * 2 * 4 <= 200 * 1024;
+  return plan->P >= 2048 && N >= 256 && 8LL * plan->K * plan->Mtot * 2 * 4 <= 200 * 1024;
 }
 
 int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, const float* ws,
                        const float* Lambda, float* H, float* scratch, cudaStream_t st) {
   using namespace tc;
   const int K = plan->K, M = plan->Mtot, D = plan->Dtot;
-  if ((long long)32 * K * M * 2 * 4 > 200 * 1024) return BNNP_ERR_UNSUPPORTED;
+  if ((long long)8 * K * M * 2 * 4 > 200 * 1024) return BNNP_ERR_UNSUPPORTED;
   // scratch must be 1 KB aligned for the tensor maps / vector loads
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~uintptr_t(1023));
   const TcLayout L = tc_layout(plan, N);
@@ -524,10 +567,12 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
     BNNP_LAUNCH_CHECK();
     tc_lambda_g_kernel<<<(unsigned)ceil_div64(N * K * M, 256), 256, 0, st>>>(Lambda, G, N, K, M, GL);
     BNNP_LAUNCH_CHECK();
-    size_t sh = (size_t)2 * 32 * K * M * sizeof(float);
-    BNNP_CUDA_CHECK(cudaFuncSetAttribute(ct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    ct_kernel<<<(unsigned)(L.Npad / 32), 256, sh, st>>>(GL, G, N, K, M, L.Npad, Ct);
-    BNNP_LAUNCH_CHECK();
+    const long long per = 2LL * K * M * (long long)sizeof(float);
+    int rc;
+    if (32 * per <= 200 * 1024) rc = launch_ct<32>(GL, G, N, K, M, L.Npad, Ct, st);
+    else if (16 * per <= 200 * 1024) rc = launch_ct<16>(GL, G, N, K, M, L.Npad, Ct, st);
+    else rc = launch_ct<8>(GL, G, N, K, M, L.Npad, Ct, st);
+    if (rc) return rc;
   }
   BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0, sms = 148;
@@ -563,7 +608,17 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
       if (pair_idx >= 256) return BNNP_ERR_UNSUPPORTED;
       const long long n_tiles = (long long)a.n_pairs * a.n_jt * a.n_rt;
       int grid = (int)(n_tiles < sms ? n_tiles : sms);
+      const bool prof = g_prof.on && g_prof.n < GramProf::CAP;
+      if (prof) {
+        if (!g_prof.created) {
+          for (int e = 0; e < GramProf::CAP; ++e) { cudaEventCreate(&g_prof.beg[e]); cudaEventCreate(&g_prof.end[e]); }
+          g_prof.created = true;
+        }
+        gram_flops(a, &g_prof.executed[g_prof.n], &g_prof.useful[g_prof.n]);
+        cudaEventRecord(g_prof.beg[g_prof.n], st);
+      }
       gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+      if (prof) { cudaEventRecord(g_prof.end[g_prof.n], st); ++g_prof.n; }
       BNNP_LAUNCH_CHECK();
       ++pair_idx;
       // bias columns of layer l' (SIMT): all rows for l' < l, bias rows only on the diagonal block
@@ -581,3 +636,21 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
 }
 
 }  // namespace bnnp
+
+extern "C" int bnnp_prof_enable(int on) {
+  bnnp::g_prof.on = on != 0;
+  bnnp::g_prof.n = 0;
+  return BNNP_OK;
+}
+// Copies up to cap records {ms, executed flops, useful flops} of the gram launches since enable;
+// returns the number of records (or a negative error).
+extern "C" int bnnp_prof_read(float* ms, double* executed, double* useful, int cap) {
+  int n = bnnp::g_prof.n < cap ? bnnp::g_prof.n : cap;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(bnnp::g_prof.end[i]) != cudaSuccess) return BNNP_ERR_CUDA;
+    if (cudaEventElapsedTime(&ms[i], bnnp::g_prof.beg[i], bnnp::g_prof.end[i]) != cudaSuccess) return BNNP_ERR_CUDA;
+    executed[i] = bnnp::g_prof.executed[i];
+    useful[i] = bnnp::g_prof.useful[i];
+  }
+  return n;
+}

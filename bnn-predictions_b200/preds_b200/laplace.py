@@ -50,7 +50,7 @@ class Laplace:
         self.ggn_engine = 0          # 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16
 
     # ------------------------------------------------------------------------------ infer
-    def infer(self, train_loader, cov_type='full', dampen_kron=False, shard=None):
+    def infer(self, train_loader, cov_type='full', dampen_kron=False, shard=None, factorise=True):
         """Compute the posterior (preds/laplace.py:30-82).
 
         shard: None   -- single process, exactly the reference's semantics;
@@ -58,6 +58,9 @@ class Laplace:
                'presharded' -- the loader already yields this rank's examples only.
         In both sharded modes the accumulated factors are summed with ONE all-reduce and the
         prior is added once afterwards, so every rank ends with the same posterior.
+
+        factorise=False stops after the accumulation (``self.precision`` / the ``Kron`` factors
+        are set, ``Sigma_chol`` is not): the one-off factorisation is timed separately.
         """
         cabi.require_device(next(self.model.parameters()))
         self.mu = parameters_to_vector(self.model.parameters()).detach()
@@ -89,7 +92,8 @@ class Laplace:
                 acc += prior
             self.precision = acc
             t1.record()
-            self.Sigma_chol, self._Sigma = self._factorise_full(acc)
+            if factorise:
+                self.Sigma_chol, self._Sigma = self._factorise_full(acc)
         elif cov_type == 'diag':
             _, hess_factor = self.likelihood.nn_loss()
             prior = self.expand_prior_precision(cov_type)
@@ -100,7 +104,8 @@ class Laplace:
                 acc += prior
             self.precision = acc
             t1.record()
-            self.Sigma_chol = torch.sqrt(1 / acc)
+            if factorise:
+                self.Sigma_chol = torch.sqrt(1 / acc)
         elif cov_type == 'kron':
             _, hess_factor = self.likelihood.nn_loss()
             assert np.isscalar(self.prior_prec)
@@ -129,7 +134,8 @@ class Laplace:
                         m.copy_(flat[off:off + m.numel()].reshape(m.shape))
                         off += m.numel()
             t1.record()
-            precision.decompose()
+            if factorise:
+                precision.decompose()
             self.Sigma_chol = precision
         else:
             t1.record()
@@ -137,7 +143,7 @@ class Laplace:
         t2.synchronize()
         self.timings = {'accumulate_ms': t0.elapsed_time(t1), 'factorise_ms': t1.elapsed_time(t2)}
         net_for(self.model).release()
-        self.inferred = True
+        self.inferred = bool(factorise)
 
     def _accumulate_full(self, batches, H):
         net = net_for(self.model)

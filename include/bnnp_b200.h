@@ -232,6 +232,14 @@ int bnnp_sgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, con
 /* y += alpha * x  (Kron.update axpy, preds/kron.py:62-66). */
 int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): number of kernel launches issued by the library so far, and
+ * CUDA-event timing of the tensor-core gram launches (recorded on the launching stream).
+ * ---------------------------------------------------------------------------------------- */
+uint64_t bnnp_launch_count(void);
+int bnnp_prof_enable(int on);
+int bnnp_prof_read(float* ms, double* executed_flops, double* useful_flops, int cap);
+
 #ifdef __cplusplus
 }
 #endif
