@@ -292,7 +292,7 @@ def main():
     ap.add_argument('--steps', type=int, default=6)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=8192)
+    ap.add_argument('--batch', type=int, default=16384)
     ap.add_argument('--engine', type=int, default=2)
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-sample', type=int, default=24)

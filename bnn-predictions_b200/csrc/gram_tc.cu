@@ -105,6 +105,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B: 8-row groups of 64 B rows, 512 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
   uint64_t d = 0;
@@ -317,23 +330,36 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       // ---------------- epilogue: H[p, q] += D ----------------
+      // TMEM -> registers (thread = row) -> per-warp smem transpose -> coalesced read-modify-write of
+      // H (lane = column, 128 B per request, 8 rows in flight).  All MMAs of the tile have retired, so
+      // the stage-0 operand buffers are free to serve as the transpose scratch.
       mbar_wait(acc_full, acc_phase);
       tc_fence_after();
       const int a = gw >> 2, quarter = gw & 3;
       if (a < nacc) {
-        const int rl = quarter * 32 + lane;
-        const int r = row0 + rl;
-        const bool rowok = r < rows_total;
+        float* sc = reinterpret_cast<float*>(smem + gw * (32 * 33 * 4 + 128));     // [32][33]
         const int ip = a == 0 ? ipa : ipb;
-        float* hrow = H + (args.row_theta0 + r) * args.P + args.col_theta0 + (long long)ip * args.np + jc0;
         const int ncols = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
-        for (int c0 = 0; c0 < args.wc; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * MAX_WC + c0), v);
-          if (rowok) {
+        const int rbase = row0 + quarter * 32;
+        float* hbase = H + (args.row_theta0 + rbase) * args.P + args.col_theta0 + (long long)ip * args.np + jc0;
+        int nrows = rows_total - rbase;
+        nrows = nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * MAX_WC + c0), v);
+          __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (c0 + e < ncols) hrow[c0 + e] += __uint_as_float(v[e]);
+          for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
+          __syncwarp();
+          const bool colok = c0 + lane < ncols;
+          for (int r0 = 0; r0 < nrows; r0 += 8) {
+            float h[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              h[u] = (colok && r0 + u < nrows) ? hbase[(long long)(r0 + u) * args.P + c0 + lane] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (colok && r0 + u < nrows) hbase[(long long)(r0 + u) * args.P + c0 + lane] = h[u] + sc[(r0 + u) * 33 + lane];
           }
         }
       }

@@ -22,8 +22,11 @@ from ._engine import net_for, ptr_array
 from .kron import Kron
 from .predictives import functional_sampling_predictive, nn_sampling_predictive
 
-# examples per accumulation launch for the full GGN (loader batches are concatenated up to this)
-FULL_SUPERBATCH = 8192
+# Full GGN: loader batches are concatenated into super-batches of up to this many examples per
+# accumulation launch (bounded by FULL_SCRATCH_FLOATS of kernel scratch).  Every launch reads and
+# writes the lower half of H once, so longer launches amortise that epilogue.
+FULL_SUPERBATCH = 65536
+FULL_SCRATCH_FLOATS = 1 << 30
 
 
 def _dist():
@@ -166,12 +169,21 @@ class Laplace:
             check(lib.bnnp_ggn_full_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H),
                                           ptr(sc), self.ggn_engine, stream()), 'bnnp_ggn_full_accum')
 
+        limit = None
         for X, _ in batches:
             X = X.to(self.device)
-            pend.append(X)
-            n_pend += len(X)
-            if n_pend >= FULL_SUPERBATCH:
-                flush()
+            if limit is None:      # examples per launch from the scratch the engine needs per example
+                net.prepare(X[:1])
+                pl1 = net.plan(64, net.K)
+                per = max(1, int(lib.bnnp_ggn_full_scratch_floats(C.byref(pl1), 64, self.ggn_engine)) // 64)
+                limit = max(64, min(FULL_SUPERBATCH, FULL_SCRATCH_FLOATS // per))
+            while len(X) > 0:
+                take = min(len(X), limit - n_pend)
+                pend.append(X[:take])
+                n_pend += take
+                X = X[take:]
+                if n_pend >= limit:
+                    flush()
         flush()
         check(lib.bnnp_symmetrize_lower(ptr(H), self.P, stream()), 'bnnp_symmetrize_lower')
 
