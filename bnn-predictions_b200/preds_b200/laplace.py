@@ -21,6 +21,7 @@ from ._cabi import lib, check, ptr, stream
 from ._engine import net_for, ptr_array
 from .kron import Kron
 from .predictives import functional_sampling_predictive, nn_sampling_predictive
+from . import parallel
 
 # Full GGN: loader batches are concatenated into super-batches of up to this many examples per
 # accumulation launch (bounded by FULL_SCRATCH_FLOATS of kernel scratch).  Every launch reads and
@@ -76,7 +77,7 @@ class Laplace:
 
         def my_batches():
             for i, (X, y) in enumerate(train_loader):
-                if dist and shard == 'batches' and i % world != rank:
+                if dist and not parallel.owns_batch(i, shard, rank, world):
                     continue
                 yield X, y
 
@@ -91,8 +92,7 @@ class Laplace:
                 acc = acc.to(torch.float32).contiguous()
             self._accumulate_full(my_batches(), acc)
             if dist:
-                dist.all_reduce(acc)
-                acc += prior
+                parallel.reduce_sum_(acc, prior)
             self.precision = acc
             t1.record()
             if factorise:
@@ -103,8 +103,7 @@ class Laplace:
             acc = torch.zeros(self.P, device=self.device) if dist else prior.clone().to(torch.float32)
             self._accumulate_diag(my_batches(), acc, float(hess_factor))
             if dist:
-                dist.all_reduce(acc)
-                acc += prior
+                parallel.reduce_sum_(acc, prior)
             self.precision = acc
             t1.record()
             if factorise:
@@ -115,27 +114,14 @@ class Laplace:
             precision = Kron(self.model, self.prior_prec, dampen=dampen_kron)
             if type(train_loader) is list:
                 n_local = sum(len(a[0]) for i, a in enumerate(train_loader)
-                              if not (dist and shard == 'batches' and i % world != rank))
-                N = n_local
-                if dist:
-                    cnt = torch.tensor([float(n_local)], device=self.device, dtype=torch.float64)
-                    dist.all_reduce(cnt)
-                    N = int(cnt.item())
+                              if not dist or parallel.owns_batch(i, shard, rank, world))
+                N = parallel.global_count(n_local, self.device, enabled=bool(dist))
             else:
                 N = len(train_loader.dataset)
-                if dist and shard == 'presharded':
-                    cnt = torch.tensor([float(N)], device=self.device, dtype=torch.float64)
-                    dist.all_reduce(cnt)
-                    N = int(cnt.item())
+                N = parallel.global_count(N, self.device, enabled=bool(dist) and shard == 'presharded')
             self._accumulate_kron(my_batches(), precision, float(hess_factor), N)
             if dist:
-                flat = torch.cat([m.reshape(-1) for qh in precision.qhs for m in qh])   # one bucket
-                dist.all_reduce(flat)
-                off = 0
-                for qh in precision.qhs:
-                    for m in qh:
-                        m.copy_(flat[off:off + m.numel()].reshape(m.shape))
-                        off += m.numel()
+                parallel.reduce_factors_(precision.qhs)
             t1.record()
             if factorise:
                 precision.decompose()

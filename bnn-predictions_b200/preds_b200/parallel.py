@@ -30,8 +30,57 @@ def sharded_predictive(fn, X, n_samples, gather=True, **kw):
     out = fn(X[lo:hi], n_samples, **kw)
     if ws == 1 or not gather:
         return out
-    sizes = [shard_bounds(len(X), r, ws) for r in range(ws)]
-    parts = [torch.empty(out.shape[0], b - a, out.shape[2], dtype=out.dtype, device=out.device)
-             for a, b in sizes]
-    dist.all_gather(parts, out.contiguous())
-    return torch.cat(parts, dim=1)
+    # all_gather needs equal shapes: pad every block to the largest one, trim after the exchange
+    sizes = [b - a for a, b in (shard_bounds(len(X), r, ws) for r in range(ws))]
+    width = max(sizes)
+    mine = out.new_zeros(out.shape[0], width, out.shape[2])
+    mine[:, :out.shape[1]] = out
+    parts = [torch.empty_like(mine) for _ in range(ws)]
+    dist.all_gather(parts, mine)
+    return torch.cat([p[:, :n] for p, n in zip(parts, sizes)], dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# accumulation side: which loader batches a rank owns and the single exchange step.  These helpers
+# are device-agnostic (they are exercised with the gloo backend on CPU tensors in the tests and
+# with NCCL on the GPU box).
+# ----------------------------------------------------------------------------------------------
+def owns_batch(i, shard, rank, world_size):
+    """True if this rank processes loader batch i under the given sharding mode."""
+    return not (shard == 'batches' and world_size > 1 and i % world_size != rank)
+
+
+def global_count(n_local, device, enabled=True):
+    """Sum of the per-rank example counts (the N of the KFAC batch weight M/N)."""
+    import torch.distributed as dist
+    if not enabled or world()[1] == 1:
+        return int(n_local)
+    cnt = torch.tensor([float(n_local)], device=device, dtype=torch.float64)
+    dist.all_reduce(cnt)
+    return int(round(cnt.item()))
+
+
+def reduce_sum_(acc, prior=None):
+    """ONE all-reduce(sum) of a rank-local accumulator; the prior precision is added once, after
+    the reduce (never per rank)."""
+    import torch.distributed as dist
+    if world()[1] > 1:
+        dist.all_reduce(acc)
+    if prior is not None:
+        acc += prior
+    return acc
+
+
+def reduce_factors_(qhs):
+    """All Kronecker factors of all parameters in ONE flat bucket (one launch, one all-reduce)."""
+    import torch.distributed as dist
+    if world()[1] == 1:
+        return qhs
+    flat = torch.cat([m.reshape(-1) for qh in qhs for m in qh])
+    dist.all_reduce(flat)
+    off = 0
+    for qh in qhs:
+        for m in qh:
+            m.copy_(flat[off:off + m.numel()].reshape(m.shape))
+            off += m.numel()
+    return qhs

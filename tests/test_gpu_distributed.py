@@ -1,0 +1,83 @@
+"""Two-GPU run of the sharded path (NCCL): `Laplace.infer(shard='batches')` on 2 ranks must agree
+with the single-process result and leave bit-identical posteriors on both ranks; the sharded GLM
+predictive must agree with the unsharded one.  Skipped on boxes with fewer than 2 GPUs."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _problem():
+    from preds_b200 import MLPS
+    torch.manual_seed(71)
+    model = MLPS(4, [9, 7], 3, 'tanh')
+    g = torch.Generator().manual_seed(15)
+    X = torch.randn(90, 4, generator=g)
+    y = torch.randint(3, (90,), generator=g)
+    batches = [(X[:32], y[:32]), (X[32:64], y[32:64]), (X[64:80], y[64:80]), (X[80:], y[80:])]
+    Xte = torch.randn(9, 4, generator=g)
+    eps = torch.randn(5, 9, 3, generator=g)
+    return model, batches, Xte, eps
+
+
+def _worker(rank, world, port_no, out_dir):
+    for p in (ROOT, os.path.join(ROOT, 'bnn-predictions_b200')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from preds_b200 import Laplace, CategoricalLh, parallel
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port_no))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    model, batches, Xte, eps = _problem()
+    model = model.cuda()
+    res = {}
+    for cov in ('full', 'diag', 'kron'):
+        lap = Laplace(model, 0.6, CategoricalLh())
+        lap.infer(batches, cov_type=cov, shard='batches')
+        if cov == 'kron':
+            res[cov] = [[m.cpu() for m in qh] for qh in lap.Sigma_chol.qhs]
+        else:
+            res[cov] = lap.precision.cpu()
+        lo, hi = parallel.shard_bounds(len(Xte), rank, world)
+        out = parallel.sharded_predictive(
+            lambda xs, S: lap.predictive_samples_glm(xs, n_samples=S, eps=eps[:, lo:hi]), Xte, 5)
+        res['glm_' + cov] = out.cpu()
+    torch.save(res, os.path.join(out_dir, 'r%d.pt' % rank))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_infer_and_predictive(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from preds_b200 import Laplace, CategoricalLh
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), 'r%d.pt' % r), weights_only=False) for r in range(2)]
+    model, batches, Xte, eps = _problem()
+    model = model.cuda()
+    for cov in ('full', 'diag', 'kron'):
+        lap = Laplace(model, 0.6, CategoricalLh())
+        lap.infer(batches, cov_type=cov)
+        ref_glm = lap.predictive_samples_glm(Xte, n_samples=5, eps=eps).cpu()
+        for r in res:
+            if cov == 'kron':
+                for qa, qb in zip(r[cov], lap.Sigma_chol.qhs):
+                    for a, b in zip(qa, qb):
+                        assert torch.allclose(a, b.cpu(), rtol=1e-4, atol=1e-6)
+            else:
+                assert torch.allclose(r[cov], lap.precision.cpu(), rtol=1e-4, atol=1e-6)
+            assert torch.allclose(r['glm_' + cov], ref_glm, rtol=1e-3, atol=1e-5)
+        if cov != 'kron':
+            assert torch.equal(res[0][cov], res[1][cov])      # identical sums on every rank
