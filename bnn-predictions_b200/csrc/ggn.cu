@@ -208,8 +208,8 @@ struct AccumLinearParam { // (i, j) -> weight [m, nin] at offw, column nin -> bi
 // one block per 64x64 output tile, looping over all rows r (the per-sample Jacobian tile is
 // formed in registers, squared and accumulated -- never stored).
 __global__ void __launch_bounds__(G_THREADS)
-conv_diag_kernel(ConvGradA la, ConvUnfoldB lb, int64_t R, int Cout, int E, int L, float factor,
-                 float* __restrict__ d, int64_t offw) {
+conv_diag_kernel(ConvGradA la, ConvUnfoldB lb, int64_t R, int Cout, int E, int L,
+                 float* __restrict__ partial) {
   __shared__ float As[G_BK][G_BM + 4];
   __shared__ float Bs[G_BK][G_BN + 4];
   const int64_t m0 = (int64_t)blockIdx.y * G_BM, n0 = (int64_t)blockIdx.x * G_BN;
@@ -220,7 +220,9 @@ conv_diag_kernel(ConvGradA la, ConvUnfoldB lb, int64_t R, int Cout, int E, int L
   for (int i = 0; i < G_TM; ++i)
 #pragma unroll
     for (int j = 0; j < G_TN; ++j) tot[i][j] = 0.f;
-  for (int64_t r = 0; r < R; ++r) {
+  const int64_t rchunk = (R + gridDim.z - 1) / gridDim.z;
+  const int64_t rbeg = blockIdx.z * rchunk, rend = rbeg + rchunk < R ? rbeg + rchunk : R;
+  for (int64_t r = rbeg; r < rend; ++r) {
     float acc[G_TM][G_TN];
 #pragma unroll
     for (int i = 0; i < G_TM; ++i)
@@ -264,8 +266,18 @@ conv_diag_kernel(ConvGradA la, ConvUnfoldB lb, int64_t R, int Cout, int E, int L
 #pragma unroll
     for (int j = 0; j < G_TN; ++j) {
       int64_t m = m0 + ty * G_TM + i, n = n0 + tx * G_TN + j;
-      if (m < Cout && n < E) d[offw + m * E + n] += factor * tot[i][j];
+      if (m < Cout && n < E) partial[((int64_t)blockIdx.z * Cout + m) * E + n] = tot[i][j];
     }
+}
+
+// d[i] += factor * sum_z partial[z, i]   (fixed summation order: deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nz, int64_t n, float factor,
+                                       float* __restrict__ d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int z = 0; z < nz; ++z) acc += partial[(int64_t)z * n + i];
+  d[i] += factor * acc;
 }
 
 // d[offb + co] += factor * sum_r s[r, co]^2
@@ -414,11 +426,23 @@ extern "C" int bnnp_symmetrize_lower(float* H, int64_t P, void* stream) {
 }
 
 // ---------------------------------------------------------------------------- diag
+// row splits of the conv-diag kernel: enough CTAs to fill the machine a few times over
+static int conv_diag_splits(const bnnp_op_t& o, int64_t R) {
+  int64_t tiles = ceil_div64((int64_t)o.in_c * o.kh * o.kw, G_BN) * ceil_div64(o.out_c, G_BM);
+  int64_t nz = ceil_div64(148 * 4, tiles);
+  if (nz > R) nz = R;
+  if (nz > 64) nz = 64;
+  return (int)(nz < 1 ? 1 : nz);
+}
+
 extern "C" int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                                 int64_t N, int V) {
   int64_t need = N * (int64_t)plan->Mtot + 64;
   for (int i = 0; i < n_ops; ++i)
-    if (ops[i].kind == BNNP_OP_CONV2D) need = need > N * V * ops[i].out_c + 64 ? need : N * V * ops[i].out_c + 64;
+    if (ops[i].kind == BNNP_OP_CONV2D) {
+      int64_t v = N * V * ops[i].out_c + 64 + 64LL * ops[i].out_c * ops[i].in_c * ops[i].kh * ops[i].kw + 64;
+      need = need > v ? need : v;
+    }
   return need;
 }
 
@@ -451,10 +475,15 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     if (!in) return BNNP_ERR_INVALID;
     int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
     const float* G = ws + q.grad_off;
-    dim3 grid((unsigned)ceil_div64(E, G_BN), (unsigned)ceil_div64(o.out_c, G_BM));
+    const int nz = conv_diag_splits(o, N * V);
+    float* partial = scratch + N * V * (int64_t)o.out_c + 64;
+    dim3 grid((unsigned)ceil_div64(E, G_BN), (unsigned)ceil_div64(o.out_c, G_BM), (unsigned)nz);
     conv_diag_kernel<<<grid, G_THREADS, 0, st>>>(ConvGradA{G, q.grad_ld, L},
                                                  ConvUnfoldB{make_im2col(o, in, ild, V)}, N * V, o.out_c, E,
-                                                 L, factor, diag, o.theta_off_w);
+                                                 L, partial);
+    BNNP_LAUNCH_CHECK();
+    reduce_partials_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * E, 256), 256, 0, st>>>(
+        partial, nz, (int64_t)o.out_c * E, factor, diag + o.theta_off_w);
     BNNP_LAUNCH_CHECK();
     if (o.has_bias) {
       int64_t R = N * V;

@@ -125,6 +125,63 @@ __global__ void conv_bwd_data_kernel(const float* __restrict__ gout, int64_t gol
   gin[r * gild + e] = acc;
 }
 
+
+// ---- convolution as implicit GEMM through the tiled functor GEMM -------------------------------
+// forward:   out[n, co, pos] = bias[co] + sum_e W[co, e] * U_n[e, pos]          (batch = example n)
+struct ConvWA {            // A(co, e) = W[co, e]
+  static constexpr bool K_CONTIG = true;
+  const float* W; int E;
+  __device__ float operator()(int64_t co, int64_t e, int) const { return W[co * E + e]; }
+};
+struct ConvIm2colB {       // B(e, pos) = in[n, ci, oh*s - pt + a, ow*s - pl + b]  (0 outside)
+  static constexpr bool K_CONTIG = false;
+  const float* in; int64_t ild; ConvGeom g;
+  __device__ float operator()(int64_t e, int64_t pos, int n) const {
+    int b = (int)(e % g.kw), a = (int)((e / g.kw) % g.kh), ci = (int)(e / (g.kw * g.kh));
+    int oh = (int)(pos / g.OW), ow = (int)(pos % g.OW);
+    int ih = oh * g.sh - g.pt + a, iw = ow * g.sw - g.pl + b;
+    if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) return 0.f;
+    return in[(int64_t)n * ild + ((int64_t)ci * g.H + ih) * g.W + iw];
+  }
+};
+struct ConvStoreOut {
+  float* out; int64_t old; const float* bias; int L;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t co, int64_t pos, float acc, int n) const {
+    out[(int64_t)n * old + co * L + pos] = acc + (bias ? bias[co] : 0.f);
+  }
+};
+// backward data: gin[r, ci, ipos] = sum_{(co,a,b)} W[co,ci,a,b] * gout[r, co, oh, ow], oh*s - pt + a = ih
+struct ConvWtA {           // A(ci, (co,a,b)) = W[co, ci, a, b]
+  static constexpr bool K_CONTIG = false;
+  const float* W; int Cin, kk;
+  __device__ float operator()(int64_t ci, int64_t q, int) const {
+    int64_t co = q / kk, ab = q % kk;
+    return W[(co * Cin + ci) * kk + ab];
+  }
+};
+struct ConvGoutB {         // B((co,a,b), ipos) = gout[r, co, oh, ow] if the tap hits a valid output
+  static constexpr bool K_CONTIG = false;
+  const float* g; int64_t gld; ConvGeom c;
+  __device__ float operator()(int64_t q, int64_t ipos, int r) const {
+    int kk = c.kh * c.kw;
+    int co = (int)(q / kk), a = (int)((q % kk) / c.kw), b = (int)(q % c.kw);
+    int ih = (int)(ipos / c.W), iw = (int)(ipos % c.W);
+    int th = ih + c.pt - a, tw = iw + c.pl - b;
+    if (th < 0 || tw < 0 || th % c.sh || tw % c.sw) return 0.f;
+    int oh = th / c.sh, ow = tw / c.sw;
+    if (oh >= c.OH || ow >= c.OW) return 0.f;
+    return g[(int64_t)r * gld + ((int64_t)co * c.OH + oh) * c.OW + ow];
+  }
+};
+struct ConvStoreGin {
+  float* gin; int64_t gild; int HW;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t ci, int64_t ipos, float acc, int r) const {
+    gin[(int64_t)r * gild + ci * HW + ipos] = acc;
+  }
+};
+
 // Max pooling over a zero-padded input (deepobs tfmaxpool2d = ZeroPad2d + MaxPool2d(padding=0)):
 // window scanned row-major, strict '>' so the FIRST maximum wins (torch's rule); idx = ih*W+iw
 // of the winner or -1 when the winner is a padding zero.
@@ -341,11 +398,19 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
         if (rc) return rc;
         break;
       }
-      case BNNP_OP_CONV2D:
-        conv_fwd_kernel<<<blocks, 256, 0, st>>>(in, ild, out, q.act_ld, o.weight,
-                                                o.has_bias ? o.bias : nullptr, N, geom_of(o));
-        BNNP_LAUNCH_CHECK();
+      case BNNP_OP_CONV2D: {
+        const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
+        if (N <= 65535) {
+          int rc = gemm_simt(o.out_c, L, E, (int)N, ConvWA{o.weight, E}, ConvIm2colB{in, ild, geom_of(o)},
+                             ConvStoreOut{out, q.act_ld, o.has_bias ? o.bias : nullptr, L}, st);
+          if (rc) return rc;
+        } else {
+          conv_fwd_kernel<<<blocks, 256, 0, st>>>(in, ild, out, q.act_ld, o.weight,
+                                                  o.has_bias ? o.bias : nullptr, N, geom_of(o));
+          BNNP_LAUNCH_CHECK();
+        }
         break;
+      }
       case BNNP_OP_MAXPOOL2D:
         maxpool_fwd_kernel<<<blocks, 256, 0, st>>>(in, ild, out, q.act_ld,
                                                    reinterpret_cast<int32_t*>(ws) + q.idx_off, N, geom_of(o));
@@ -408,8 +473,15 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
         break;
       }
       case BNNP_OP_CONV2D:
-        conv_bwd_data_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, o.weight, R, geom_of(o));
-        BNNP_LAUNCH_CHECK();
+        if (R <= 65535) {
+          int rc = gemm_simt(o.in_c, (int64_t)o.in_h * o.in_w, (int64_t)o.out_c * o.kh * o.kw, (int)R,
+                             ConvWtA{o.weight, o.in_c, o.kh * o.kw}, ConvGoutB{gout, q.grad_ld, geom_of(o)},
+                             ConvStoreGin{gin, qp.grad_ld, o.in_h * o.in_w}, st);
+          if (rc) return rc;
+        } else {
+          conv_bwd_data_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, o.weight, R, geom_of(o));
+          BNNP_LAUNCH_CHECK();
+        }
         break;
       case BNNP_OP_MAXPOOL2D:
         maxpool_bwd_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld,
