@@ -1,0 +1,314 @@
+// Generic tensor-core GEMM with functor (generated) operands -- the tcgen05 counterpart of
+// gemm_simt.cuh:   acc(m, n) = sum_k A(m, k) * B(k, n),   fp32-grade via split-bf16 (3 MMAs).
+//
+// Both operands are *synthesised* by 8 generator warps from functors (strided matrices, squared
+// activations, implicit transposes ...): each value is computed in fp32, split into bf16 hi/lo and
+// written to shared memory in the UMMA canonical K-major SWIZZLE_64B layout.  One thread issues
+// tcgen05.mma (M = 128, N = tile width, K = 16, kind::f16) into one of two TMEM accumulator buffers;
+// four dedicated epilogue warps drain the other buffer (tcgen05.ld) concurrently.  Persistent CTAs
+// walk (batch, m-tile, n-tile, k-split) tiles round-robin.
+//
+// Operand functors:
+//   struct LA { static constexpr bool K_CONTIG;   // memory order: true = k fastest, false = m fastest
+//               __device__ void load8(int64_t m, int64_t k0, int64_t K, int batch, float* out) const; };
+//   (load8 returns A(m, k0..k0+7), zero beyond K; rows m >= M are never requested)
+//   struct LB { ... same with n in place of m:  B(k, n) = lb.load8(n, k0, ...) ... };
+// Epilogue functor:
+//   struct EP { __device__ void row(int64_t m, int64_t n0, const float* v, int nvalid, int batch, int ks) const; };
+//   (v[0..nvalid) = acc(m, n0 ..), called by the thread that owns row m, 32 columns at a time)
+#pragma once
+#include "tc_common.cuh"
+
+namespace bnnp {
+namespace tcg {
+
+using namespace bnnp::tcp;
+
+constexpr int BK = 32, TILE_M = 128, MAX_N = 256, STAGES = 4;
+constexpr int A_TERM = TILE_M * BK * 2, A_STAGE = 2 * A_TERM;      // hi + lo
+constexpr int B_TERM = MAX_N * BK * 2, B_STAGE = 2 * B_TERM;
+constexpr int STAGE_BYTES = A_STAGE + B_STAGE;                     // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int NUM_THREADS = 512;      // warp 1: MMA, warp 2: TMEM alloc, warps 4-11: generators, 12-15: epilogue
+constexpr int GEN_WARP0 = 4, EPI_WARP0 = 12;
+constexpr int kMaxChunksPerAccum = 128;   // 4096 K-elements per TMEM accumulation (truncation bias ~2e-5)
+
+struct Shape {
+  long long M, N, K;
+  int batch, wn, n_mt, n_nt, ksplit, chunks_total;
+};
+
+// generic fallback: eight scalar evaluations of f(m, k, batch)
+template <class F>
+__device__ __forceinline__ void load8_scalar(const F& f, int64_t m, int64_t k0, int64_t K, int batch, float* out) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? f(m, k0 + e, batch) : 0.f;
+}
+
+template <class LA, class LB, class EP>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(Shape sh, LA la, LB lb, EP ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES] generators -> MMA   (8 warp arrivals)
+  uint64_t* empty = bars + STAGES;             // [STAGES] MMA commit -> generators
+  uint64_t* acc_full = bars + 2 * STAGES;      // [2] MMA commit -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2; // [2] epilogue (4 warp arrivals) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_tiles = (long long)sh.batch * sh.n_mt * sh.n_nt * sh.ksplit;
+  uint32_t stage = 0, phase = 0;
+  uint32_t iter = 0;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+    const int ks = (int)(tile % sh.ksplit);
+    const int nt = (int)((tile / sh.ksplit) % sh.n_nt);
+    const int mt = (int)((tile / ((long long)sh.ksplit * sh.n_nt)) % sh.n_mt);
+    const int b = (int)(tile / ((long long)sh.ksplit * sh.n_nt * sh.n_mt));
+    const int c_beg = (int)((long long)sh.chunks_total * ks / sh.ksplit);
+    const int c_end = (int)((long long)sh.chunks_total * (ks + 1) / sh.ksplit);
+    const int n_chunks = c_end - c_beg;
+    const long long m0 = (long long)mt * TILE_M, n0 = (long long)nt * sh.wn;
+    const uint32_t buf = iter & 1, buf_phase = (iter >> 1) & 1;
+
+    if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        mbar_wait(&acc_empty[buf], buf_phase ^ 1);        // epilogue has drained this accumulator
+        tc_fence_after();
+        uint32_t s = stage, ph = phase;
+        const uint32_t idesc = umma_idesc_bf16(sh.wn);
+        const uint32_t d = tmem_base + buf * MAX_N;
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_STAGE;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t dah = umma_desc_sw64(a0 + kk * 32), dal = umma_desc_sw64(a0 + A_TERM + kk * 32);
+            const uint64_t dbh = umma_desc_sw64(b0 + kk * 32), dbl = umma_desc_sw64(b0 + B_TERM + kk * 32);
+            umma_bf16(d, dah, dbh, idesc, (c | kk) ? 1u : 0u);
+            umma_bf16(d, dah, dbl, idesc, 1u);
+            umma_bf16(d, dal, dbh, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          if (c == n_chunks - 1) umma_commit(&acc_full[buf]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
+      // ===================== operand generators =====================
+      const int gw = warp - GEN_WARP0;
+      const int n_items_a = 16;                            // warp-items covering the 128 x 32 A tile
+      // warp-items covering the wn x 32 B tile: 8 rows x 4 K-groups (k fastest) or 32 rows x 1 K-group
+      const int n_items_b = LB::K_CONTIG ? sh.wn / 8 : ((sh.wn + 31) / 32) * 4;
+      const int n_items = n_items_a + n_items_b;
+      uint32_t s = stage, ph = phase;
+      for (int c = 0; c < n_chunks; ++c) {
+        const long long k0 = (long long)(c_beg + c) * BK;
+        float vals[6][8];
+        uint32_t offs[6];
+        // 1) issue the loads of all of this warp's items (independent of the smem stage)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int it = gw + j * 8;
+          offs[j] = 0xFFFFFFFFu;
+          if (it < n_items) {
+            const bool isA = it < n_items_a;
+            const int wi = isA ? it : it - n_items_a;
+            int row, g;
+            if (isA ? LA::K_CONTIG : LB::K_CONTIG) { row = wi * 8 + (lane >> 2); g = lane & 3; }
+            else { row = (wi >> 2) * 32 + lane; g = wi & 3; }
+            const long long gr = (isA ? m0 : n0) + row;
+            const bool ok = gr < (isA ? sh.M : sh.N);
+            if (isA) { if (ok) la.load8(gr, k0 + g * 8, sh.K, b, vals[j]); }
+            else { if (ok) lb.load8(gr, k0 + g * 8, sh.K, b, vals[j]); }
+            if (!ok) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) vals[j][e] = 0.f;
+            }
+            offs[j] = (isA ? 0u : (uint32_t)A_STAGE) + sw64_offset(row, g);
+          }
+        }
+        // 2) wait for the stage, split to bf16 hi/lo and publish
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* base = smem + s * STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          if (offs[j] != 0xFFFFFFFFu) {
+            uint4 hi, lo;
+            split8(vals[j], hi, lo);
+            const uint32_t term = offs[j] >= (uint32_t)A_STAGE ? (uint32_t)B_TERM : (uint32_t)A_TERM;
+            *reinterpret_cast<uint4*>(base + offs[j]) = hi;
+            *reinterpret_cast<uint4*>(base + offs[j] + term) = lo;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    } else if (warp >= EPI_WARP0) {
+      // ===================== epilogue =====================
+      const int q = warp - EPI_WARP0;
+      mbar_wait(&acc_full[buf], buf_phase);
+      tc_fence_after();
+      const long long m = m0 + q * 32 + lane;
+      const long long ncols = sh.N - n0 < sh.wn ? sh.N - n0 : sh.wn;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
+        if (m < sh.M) {
+          const int nvalid = ncols - c0 < 32 ? (int)(ncols - c0) : 32;
+          ep.row(m, n0 + c0, reinterpret_cast<const float*>(v), nvalid, b, ks);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    // every role advanced the smem ring by n_chunks stages
+    const uint32_t tot = stage + (uint32_t)n_chunks;
+    phase ^= (tot / STAGES) & 1;
+    stage = tot % STAGES;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// pick the n-tile width: fewest tiles, then least padding (multiple of 16, <= 256)
+inline int pick_wn(long long N) {
+  long long nt = (N + MAX_N - 1) / MAX_N;
+  long long w = ((N + nt - 1) / nt + 15) / 16 * 16;
+  return (int)(w < 16 ? 16 : w);
+}
+
+template <class LA, class LB, class EP>
+inline int gemm_tc(long long M, long long N, long long K, int batch, LA la, LB lb, EP ep, int ksplit,
+                   cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return BNNP_OK;
+  Shape sh;
+  sh.M = M; sh.N = N; sh.K = K; sh.batch = batch;
+  sh.wn = pick_wn(N);
+  sh.n_mt = (int)((M + TILE_M - 1) / TILE_M);
+  sh.n_nt = (int)((N + sh.wn - 1) / sh.wn);
+  sh.chunks_total = (int)((K + BK - 1) / BK);
+  sh.ksplit = ksplit < 1 ? 1 : (ksplit > sh.chunks_total ? sh.chunks_total : ksplit);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  auto kern = gemm_tc_kernel<LA, LB, EP>;
+  BNNP_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const long long n_tiles = (long long)batch * sh.n_mt * sh.n_nt * sh.ksplit;
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(sh, la, lb, ep);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+// split-K factor that fills the machine for an M x N output with `chunks` K-chunks
+inline int pick_ksplit(long long M, long long N, long long K, int batch) {
+  long long tiles = (long long)batch * ((M + TILE_M - 1) / TILE_M) * ((N + pick_wn(N) - 1) / pick_wn(N));
+  long long chunks = (K + BK - 1) / BK;
+  long long want = (148 * 2 + tiles - 1) / tiles;
+  long long maxs = chunks / 16 > 0 ? chunks / 16 : 1;       // at least 16 chunks per split
+  long long s = want < maxs ? want : maxs;
+  long long need = (chunks + kMaxChunksPerAccum - 1) / kMaxChunksPerAccum;     // accuracy floor
+  if (s < need) s = need;
+  return (int)(s < 1 ? 1 : (s > 512 ? 512 : s));
+}
+
+// ---- stock operand functors -------------------------------------------------------------------
+struct TcRowMajor {        // X(r, k) = p[b*bs + r*ld + k]            (k contiguous)
+  static constexpr bool K_CONTIG = true;
+  const float* p; long long ld, bs;
+  __device__ __forceinline__ void load8(int64_t r, int64_t k0, int64_t K, int b, float* out) const {
+    const float* q = p + (long long)b * bs + r * ld + k0;
+    if (k0 + 8 <= K && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
+      float4 x = __ldg(reinterpret_cast<const float4*>(q)), y = __ldg(reinterpret_cast<const float4*>(q) + 1);
+      out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w; out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = y.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? __ldg(q + e) : 0.f;
+    }
+  }
+};
+struct TcColMajor {        // X(r, k) = p[b*bs + k*ld + r]            (r contiguous: transposed storage)
+  static constexpr bool K_CONTIG = false;
+  const float* p; long long ld, bs;
+  __device__ __forceinline__ void load8(int64_t r, int64_t k0, int64_t K, int b, float* out) const {
+    const float* q = p + (long long)b * bs + k0 * ld + r;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? __ldg(q + (long long)e * ld) : 0.f;
+  }
+};
+
+// ---- stock epilogues ----------------------------------------------------------------------------
+struct TcStoreAxpby {      // C = alpha*acc + beta*C
+  float* p; long long ld, bs; float alpha, beta;
+  __device__ __forceinline__ void row(int64_t m, int64_t n0, const float* v, int nvalid, int b, int) const {
+    float* q = p + (long long)b * bs + m * ld + n0;
+    // fully unrolled with predicates so that v[] stays in registers
+    if (beta == 0.f) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = alpha * v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = alpha * v[e] + beta * q[e];
+    }
+  }
+};
+struct TcStorePartial {    // ws[ks][b][m][n] = acc     (deterministic split-K: reduced afterwards)
+  float* ws; long long M, N; int batch;
+  __device__ __forceinline__ void row(int64_t m, int64_t n0, const float* v, int nvalid, int b, int ks) const {
+    float* q = ws + (((long long)ks * batch + b) * M + m) * N + n0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = v[e];
+  }
+};
+
+// C[b][m][n] = alpha * sum_ks ws[ks][b][m][n] + beta * C[b][m][n]   (fixed order)
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int ksplit, long long M, long long N,
+                                     int batch, float alpha, float beta, float* __restrict__ C, long long ldc,
+                                     long long bsc);
+
+template <class LA, class LB>
+inline int gemm_tc_splitk(long long M, long long N, long long K, int batch, LA la, LB lb, float alpha,
+                          float beta, float* C, long long ldc, long long bsc, float* ws, int ksplit,
+                          cudaStream_t st) {
+  long long chunks = (K + BK - 1) / BK;
+  // the TMEM accumulator truncates on every update: with scratch available never let one
+  // accumulation span more than kMaxChunksPerAccum K-chunks (partials are summed in fp32 RN)
+  if (ws && (chunks + kMaxChunksPerAccum - 1) / kMaxChunksPerAccum > ksplit)
+    ksplit = (int)((chunks + kMaxChunksPerAccum - 1) / kMaxChunksPerAccum);
+  if (ksplit <= 1 || !ws) return gemm_tc(M, N, K, batch, la, lb, TcStoreAxpby{C, ldc, bsc, alpha, beta}, 1, st);
+  if (ksplit > chunks) ksplit = (int)chunks;
+  int rc = gemm_tc(M, N, K, batch, la, lb, TcStorePartial{ws, M, N, batch}, ksplit, st);
+  if (rc) return rc;
+  long long tot = (long long)batch * M * N;
+  splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ws, ksplit, M, N, batch, alpha, beta, C, ldc, bsc);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+}  // namespace tcg
+}  // namespace bnnp

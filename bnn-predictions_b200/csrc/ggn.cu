@@ -411,9 +411,16 @@ extern "C" int bnnp_ggn_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
   const float* A = ws + plan->acat_off;
   lambda_g_kernel<<<(unsigned)ceil_div64(N * K * M, 256), 256, 0, st>>>(Lambda, G, N, K, M, GL);
   BNNP_LAUNCH_CHECK();
-  JacOperand ja{GL, A, pu, pc, M, plan->Dtot, K};
-  JacOperand jb{G, A, pu, pc, M, plan->Dtot, K};
-  return gemm_simt(P, P, N * K, 1, ja, JacOperandB{jb}, AccumLower{H, P}, st);
+  // one fp32 accumulator per output never sums more than 4096 examples in sequence; the segments
+  // are combined through H (hierarchical summation keeps the long sum at fp32-reference quality)
+  for (int64_t n0 = 0; n0 < N; n0 += 4096) {
+    const int64_t nn = N - n0 < 4096 ? N - n0 : 4096;
+    JacOperand ja{GL + n0 * K * M, A + n0 * plan->Dtot, pu, pc, M, plan->Dtot, K};
+    JacOperand jb{G + n0 * K * M, A + n0 * plan->Dtot, pu, pc, M, plan->Dtot, K};
+    rc = gemm_simt(P, P, nn * K, 1, ja, JacOperandB{jb}, AccumLower{H, P}, st);
+    if (rc) return rc;
+  }
+  return BNNP_OK;
 }
 
 extern "C" int bnnp_symmetrize_lower(float* H, int64_t P, void* stream) {

@@ -87,6 +87,8 @@ _SIGS = {
     'bnnp_bnn_forward': (_I, [_OPS, _I, _I, _P, _L, _P, _L, _L, _P, _P, _V]),
     'bnnp_sgemm': (_I, [_I, _I, _L, _L, _L, _F, _P, _L, _P, _L, _F, _P, _L, _V]),
     'bnnp_axpy': (_I, [_L, _F, _P, _P, _V]),
+    'bnnp_sgemm_tc_scratch_floats': (_L, [_L, _L, _L]),
+    'bnnp_sgemm_tc': (_I, [_I, _I, _L, _L, _L, _F, _P, _L, _P, _L, _F, _P, _L, _P, _V]),
     'bnnp_launch_count': (C.c_uint64, []),
     'bnnp_prof_enable': (_I, [_I]),
     'bnnp_prof_read': (_I, [C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), _I]),

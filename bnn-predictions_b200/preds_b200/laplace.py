@@ -24,9 +24,9 @@ from .predictives import functional_sampling_predictive, nn_sampling_predictive
 from . import parallel
 
 # Full GGN: loader batches are concatenated into super-batches of up to this many examples per
-# accumulation launch (bounded by FULL_SCRATCH_FLOATS of kernel scratch).  Every launch reads and
-# writes the lower half of H once, so longer launches amortise that epilogue.
-FULL_SUPERBATCH = 65536
+# accumulation call (bounded by FULL_SCRATCH_FLOATS of kernel scratch).  Inside the library one
+# accumulator never sums more than 4096 examples (hierarchical fp32 summation through H).
+FULL_SUPERBATCH = 16384
 FULL_SCRATCH_FLOATS = 1 << 30
 
 

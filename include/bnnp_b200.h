@@ -229,6 +229,12 @@ int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const float* X, i
 int bnnp_sgemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
                void* stream);
+/* Same contract on the tensor cores (tcgen05, split-bf16 = fp32-grade, operands synthesised on chip).
+ * scratch (may be NULL): bnnp_sgemm_tc_scratch_floats() floats enabling deterministic split-K. */
+int64_t bnnp_sgemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K);
+int bnnp_sgemm_tc(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                  int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+                  float* scratch, void* stream);
 /* y += alpha * x  (Kron.update axpy, preds/kron.py:62-66). */
 int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream);
 
