@@ -10,11 +10,16 @@
 //
 // Operand functors:
 //   struct LA { static constexpr bool K_CONTIG;   // memory order: true = k fastest, false = m fastest
-//               __device__ void load8(int64_t m, int64_t k0, int64_t K, int batch, float* out) const; };
+//               using Row = ...;                   // per-row handle, computed once per tile
+//               __device__ Row row(int64_t m, int batch) const;
+//               __device__ void load8(const Row&, int64_t k0, int64_t K, float* out) const; };
 //   (load8 returns A(m, k0..k0+7), zero beyond K; rows m >= M are never requested)
-//   struct LB { ... same with n in place of m:  B(k, n) = lb.load8(n, k0, ...) ... };
+//   struct LB { ... same with n in place of m:  B(k, n) = lb.load8(lb.row(n, b), k0, ...) ... };
 // Epilogue functor:
-//   struct EP { __device__ void row(int64_t m, int64_t n0, const float* v, int nvalid, int batch, int ks) const; };
+//   struct EP { struct State {...};                       // per-thread scratch carried across one tile row
+//               __device__ void begin(State&) const;
+//               __device__ void row(State&, int64_t m, int64_t n0, const float* v, int nvalid, int batch, int ks) const;
+//               __device__ void end(State&, int64_t m, int batch, int ks) const; };
 //   (v[0..nvalid) = acc(m, n0 ..), called by the thread that owns row m, 32 columns at a time)
 #pragma once
 #include "tc_common.cuh"
@@ -74,9 +79,10 @@ gemm_tc_kernel(Shape sh, LA la, LB lb, EP ep) {
   uint32_t iter = 0;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+    // m-tile fastest: CTAs that run concurrently share the same B (n-tile) operand through L2
     const int ks = (int)(tile % sh.ksplit);
-    const int nt = (int)((tile / sh.ksplit) % sh.n_nt);
-    const int mt = (int)((tile / ((long long)sh.ksplit * sh.n_nt)) % sh.n_mt);
+    const int mt = (int)((tile / sh.ksplit) % sh.n_mt);
+    const int nt = (int)((tile / ((long long)sh.ksplit * sh.n_mt)) % sh.n_nt);
     const int b = (int)(tile / ((long long)sh.ksplit * sh.n_nt * sh.n_mt));
     const int c_beg = (int)((long long)sh.chunks_total * ks / sh.ksplit);
     const int c_end = (int)((long long)sh.chunks_total * (ks + 1) / sh.ksplit);
@@ -111,49 +117,75 @@ gemm_tc_kernel(Shape sh, LA la, LB lb, EP ep) {
       }
     } else if (warp >= GEN_WARP0 && warp < EPI_WARP0) {
       // ===================== operand generators =====================
+      // 8 warps; per K-chunk each warp fills 2 warp-items of the 128 x 32 A tile (items gw, gw+8) and up
+      // to 4 of the wn x 32 B tile.  A warp-item is 8 rows x 4 K-groups (k-contiguous operand: 128 B per
+      // row) or 32 rows x 1 K-group (row-contiguous operand); every lane owns one 16-byte K-group.
       const int gw = warp - GEN_WARP0;
-      const int n_items_a = 16;                            // warp-items covering the 128 x 32 A tile
-      // warp-items covering the wn x 32 B tile: 8 rows x 4 K-groups (k fastest) or 32 rows x 1 K-group
       const int n_items_b = LB::K_CONTIG ? sh.wn / 8 : ((sh.wn + 31) / 32) * 4;
-      const int n_items = n_items_a + n_items_b;
+      typename LA::Row ha[2];
+      typename LB::Row hb[4];
+      uint32_t offa[2], offb[4];
+      int ga[2], gb[4];
+      bool oka[2], okb[4], useb[4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int wi = gw + j * 8;
+        int row;
+        if (LA::K_CONTIG) { row = wi * 8 + (lane >> 2); ga[j] = lane & 3; }
+        else { row = (wi >> 2) * 32 + lane; ga[j] = wi & 3; }
+        oka[j] = m0 + row < sh.M;
+        ha[j] = la.row(oka[j] ? m0 + row : 0, b);
+        offa[j] = sw64_offset(row, ga[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int wi = gw + j * 8;
+        useb[j] = wi < n_items_b;
+        int row;
+        if (LB::K_CONTIG) { row = wi * 8 + (lane >> 2); gb[j] = lane & 3; }
+        else { row = (wi >> 2) * 32 + lane; gb[j] = wi & 3; }
+        okb[j] = useb[j] && n0 + row < sh.N;
+        hb[j] = lb.row(okb[j] ? n0 + row : 0, b);
+        offb[j] = (uint32_t)A_STAGE + sw64_offset(row, gb[j]);
+      }
       uint32_t s = stage, ph = phase;
       for (int c = 0; c < n_chunks; ++c) {
         const long long k0 = (long long)(c_beg + c) * BK;
-        float vals[6][8];
-        uint32_t offs[6];
-        // 1) issue the loads of all of this warp's items (independent of the smem stage)
+        float va[2][8], vb[4][8];
+        // 1) issue all loads of this chunk (independent of the smem stage)
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          const int it = gw + j * 8;
-          offs[j] = 0xFFFFFFFFu;
-          if (it < n_items) {
-            const bool isA = it < n_items_a;
-            const int wi = isA ? it : it - n_items_a;
-            int row, g;
-            if (isA ? LA::K_CONTIG : LB::K_CONTIG) { row = wi * 8 + (lane >> 2); g = lane & 3; }
-            else { row = (wi >> 2) * 32 + lane; g = wi & 3; }
-            const long long gr = (isA ? m0 : n0) + row;
-            const bool ok = gr < (isA ? sh.M : sh.N);
-            if (isA) { if (ok) la.load8(gr, k0 + g * 8, sh.K, b, vals[j]); }
-            else { if (ok) lb.load8(gr, k0 + g * 8, sh.K, b, vals[j]); }
-            if (!ok) {
+        for (int j = 0; j < 2; ++j) {
+          if (oka[j]) la.load8(ha[j], k0 + ga[j] * 8, sh.K, va[j]);
+          else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) vals[j][e] = 0.f;
-            }
-            offs[j] = (isA ? 0u : (uint32_t)A_STAGE) + sw64_offset(row, g);
+            for (int e = 0; e < 8; ++e) va[j][e] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (okb[j]) lb.load8(hb[j], k0 + gb[j] * 8, sh.K, vb[j]);
+          else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) vb[j][e] = 0.f;
           }
         }
         // 2) wait for the stage, split to bf16 hi/lo and publish
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* base = smem + s * STAGE_BYTES;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          if (offs[j] != 0xFFFFFFFFu) {
+        for (int j = 0; j < 2; ++j) {
+          uint4 hi, lo;
+          split8(va[j], hi, lo);
+          *reinterpret_cast<uint4*>(base + offa[j]) = hi;
+          *reinterpret_cast<uint4*>(base + offa[j] + A_TERM) = lo;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (useb[j]) {
             uint4 hi, lo;
-            split8(vals[j], hi, lo);
-            const uint32_t term = offs[j] >= (uint32_t)A_STAGE ? (uint32_t)B_TERM : (uint32_t)A_TERM;
-            *reinterpret_cast<uint4*>(base + offs[j]) = hi;
-            *reinterpret_cast<uint4*>(base + offs[j] + term) = lo;
+            split8(vb[j], hi, lo);
+            *reinterpret_cast<uint4*>(base + offb[j]) = hi;
+            *reinterpret_cast<uint4*>(base + offb[j] + B_TERM) = lo;
           }
         }
         fence_proxy_async();
@@ -168,14 +200,17 @@ gemm_tc_kernel(Shape sh, LA la, LB lb, EP ep) {
       tc_fence_after();
       const long long m = m0 + q * 32 + lane;
       const long long ncols = sh.N - n0 < sh.wn ? sh.N - n0 : sh.wn;
+      typename EP::State est;
+      ep.begin(est);
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
         if (m < sh.M) {
           const int nvalid = ncols - c0 < 32 ? (int)(ncols - c0) : 32;
-          ep.row(m, n0 + c0, reinterpret_cast<const float*>(v), nvalid, b, ks);
+          ep.row(est, m, n0 + c0, reinterpret_cast<const float*>(v), nvalid, b, ks);
         }
       }
+      if (m < sh.M) ep.end(est, m, b, ks);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -240,12 +275,19 @@ inline int pick_ksplit(long long M, long long N, long long K, int batch) {
 // ---- stock operand functors -------------------------------------------------------------------
 struct TcRowMajor {        // X(r, k) = p[b*bs + r*ld + k]            (k contiguous)
   static constexpr bool K_CONTIG = true;
+  using Row = const float*;
   const float* p; long long ld, bs;
-  __device__ __forceinline__ void load8(int64_t r, int64_t k0, int64_t K, int b, float* out) const {
-    const float* q = p + (long long)b * bs + r * ld + k0;
-    if (k0 + 8 <= K && ((reinterpret_cast<uintptr_t>(q) & 15) == 0)) {
-      float4 x = __ldg(reinterpret_cast<const float4*>(q)), y = __ldg(reinterpret_cast<const float4*>(q) + 1);
-      out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w; out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = y.w;
+  __device__ __forceinline__ Row row(int64_t r, int b) const { return p + (long long)b * bs + r * ld; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+    const float* q = rw + k0;
+    if (k0 + 8 <= K) {
+      if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(q)), y = __ldg(reinterpret_cast<const float4*>(q) + 1);
+        out[0] = x.x; out[1] = x.y; out[2] = x.z; out[3] = x.w; out[4] = y.x; out[5] = y.y; out[6] = y.z; out[7] = y.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[e] = __ldg(q + e);
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? __ldg(q + e) : 0.f;
@@ -254,18 +296,31 @@ struct TcRowMajor {        // X(r, k) = p[b*bs + r*ld + k]            (k contigu
 };
 struct TcColMajor {        // X(r, k) = p[b*bs + k*ld + r]            (r contiguous: transposed storage)
   static constexpr bool K_CONTIG = false;
+  using Row = const float*;
   const float* p; long long ld, bs;
-  __device__ __forceinline__ void load8(int64_t r, int64_t k0, int64_t K, int b, float* out) const {
-    const float* q = p + (long long)b * bs + k0 * ld + r;
+  __device__ __forceinline__ Row row(int64_t r, int b) const { return p + (long long)b * bs + r; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+    const float* q = rw + k0 * ld;
+    if (k0 + 8 <= K) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? __ldg(q + (long long)e * ld) : 0.f;
+      for (int e = 0; e < 8; ++e) out[e] = __ldg(q + (long long)e * ld);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? __ldg(q + (long long)e * ld) : 0.f;
+    }
   }
 };
 
 // ---- stock epilogues ----------------------------------------------------------------------------
-struct TcStoreAxpby {      // C = alpha*acc + beta*C
+struct TcNoState {
+  struct State {};
+  __device__ __forceinline__ void begin(State&) const {}
+  __device__ __forceinline__ void end(State&, int64_t, int, int) const {}
+};
+struct TcStoreAxpby : TcNoState {      // C = alpha*acc + beta*C
   float* p; long long ld, bs; float alpha, beta;
-  __device__ __forceinline__ void row(int64_t m, int64_t n0, const float* v, int nvalid, int b, int) const {
+  __host__ __device__ TcStoreAxpby(float* p_, long long ld_, long long bs_, float a_, float b_) : p(p_), ld(ld_), bs(bs_), alpha(a_), beta(b_) {}
+  __device__ __forceinline__ void row(State&, int64_t m, int64_t n0, const float* v, int nvalid, int b, int) const {
     float* q = p + (long long)b * bs + m * ld + n0;
     // fully unrolled with predicates so that v[] stays in registers
     if (beta == 0.f) {
@@ -277,9 +332,10 @@ struct TcStoreAxpby {      // C = alpha*acc + beta*C
     }
   }
 };
-struct TcStorePartial {    // ws[ks][b][m][n] = acc     (deterministic split-K: reduced afterwards)
+struct TcStorePartial : TcNoState {    // ws[ks][b][m][n] = acc     (deterministic split-K: reduced afterwards)
   float* ws; long long M, N; int batch;
-  __device__ __forceinline__ void row(int64_t m, int64_t n0, const float* v, int nvalid, int b, int ks) const {
+  __host__ __device__ TcStorePartial(float* w_, long long M_, long long N_, int b_) : ws(w_), M(M_), N(N_), batch(b_) {}
+  __device__ __forceinline__ void row(State&, int64_t m, int64_t n0, const float* v, int nvalid, int b, int ks) const {
     float* q = ws + (((long long)ks * batch + b) * M + m) * N + n0;
 #pragma unroll
     for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = v[e];

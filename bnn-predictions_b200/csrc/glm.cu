@@ -2,6 +2,7 @@
 // Cholesky + sampling + inverse-link epilogue.  preds/predictives.py:50-76, preds/kron.py:112-143.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace bnnp {
 
@@ -30,6 +31,11 @@ static const float* op_input_g(const bnnp_op_t* ops, const bnnp_plan_t* plan, in
 __global__ void zero_kernel(float* p, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.f;
+}
+static int zero(float* p, int64_t n, cudaStream_t st) {
+  zero_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p, n);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
 }
 
 // ---- per-row Jacobian block of a conv weight: Jb[r, co*E + e] -----------------------------
@@ -130,6 +136,121 @@ __global__ void param_maps2_kernel(int32_t* __restrict__ pu, int32_t* __restrict
   if (e >= cnt) return;
   if (is_bias) { pu[off + e] = unit0 + (int)e; pc[off + e] = col0 + nin; }
   else { pu[off + e] = unit0 + (int)(e / nin); pc[off + e] = col0 + (int)(e % nin); }
+}
+
+
+// ---- f_var, full covariance on tensor cores (structured) --------------------------------------
+//   T[n,u,u'] = sum_{p in unit u} sum_{q in unit u'} a~[n,j(p)] Sigma[p,q] a~[n,j(q)]
+//   f_var[n,k,l] = sum_{u,u'} G[n,k,u] T[n,u,u'] G[n,l,u']
+// One gemm_tc launch per layer l' (batch = its units u'):  Y_u'[n,p] = sum_q a~[n,j(q)] Sigma[p,q]
+// with the row-dot  T[n,u(p),u'] += a~[n,j(p)] * Y_u'[n,p]  fused into the epilogue.
+struct SigmaUnitB {       // B(k, p) for batch u':  Sigma[p, theta(u',k)],  k < nin: weight (u',k), k == nin: bias u'
+  static constexpr bool K_CONTIG = true;
+  struct Row { const float* w; const float* bias; };
+  const float* Sigma; long long P, offw, offb; int nin, has_bias;
+  __device__ __forceinline__ Row row(int64_t p, int up) const {
+    const float* r = Sigma + p * P;
+    return Row{r + offw + (long long)up * nin, r + offb + up};
+  }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t, float* out) const {
+    const float* w = rw.w + k0;
+    if (k0 + 8 <= nin) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = __ldg(w + e);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int64_t k = k0 + e;
+        out[e] = (k < nin) ? __ldg(w + e) : ((k == nin && has_bias) ? __ldg(rw.bias) : 0.f);
+      }
+    }
+  }
+};
+struct RowDotT {          // epilogue: T[n, u(p), u'] += a~[n, c(p)] * acc(n, p), flushed once per run of equal u
+  struct State { float acc; int u; };
+  float* T; const float* A; const int32_t* pu; const int32_t* pc; long long ald; int Mtot, unit0p;
+  __device__ __forceinline__ void begin(State& s) const { s.acc = 0.f; s.u = -1; }
+  __device__ __forceinline__ void flush(State& s, int64_t n, int up) const {
+    if (s.u >= 0) atomicAdd(T + ((long long)n * Mtot + s.u) * Mtot + unit0p + up, s.acc);
+  }
+  __device__ __forceinline__ void row(State& s, int64_t n, int64_t p0, const float* v, int nvalid, int up, int) const {
+    const float* __restrict__ a = A + n * ald;
+    float prod[32];
+    int uu[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {          // all loads first (no atomic in between)
+      const bool ok = e < nvalid;
+      const int64_t p = p0 + (ok ? e : 0);
+      uu[e] = ok ? __ldg(pu + p) : -2;
+      prod[e] = __ldg(a + __ldg(pc + p)) * v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (uu[e] != -2) {
+        if (uu[e] != s.u) { flush(s, n, up); s.u = uu[e]; s.acc = 0.f; }
+        s.acc += prod[e];
+      }
+    }
+  }
+  __device__ __forceinline__ void end(State& s, int64_t n, int up, int) const { flush(s, n, up); s.u = -1; }
+};
+// f_var[n,k,l] = sum_{u,u'} G[(n,k),u] T[n,u,u'] G[(n,l),u']     one block per input
+__global__ void fvar_from_units_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ T,
+                                       int K, int M, float* __restrict__ fvar) {
+  extern __shared__ float shm[];          // R[K][M]
+  const int64_t n = blockIdx.x;
+  const float* Tn = T + n * M * M;
+  for (int i = threadIdx.x; i < K * M; i += blockDim.x) {
+    const int k = i / M, up = i % M;
+    float acc = 0.f;
+    for (int u = 0; u < M; ++u) acc = fmaf(G[(n * K + k) * gld + u], Tn[u * M + up], acc);
+    shm[i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+    const int k = i / K, l = i % K;
+    float acc = 0.f;
+    for (int up = 0; up < M; ++up) acc = fmaf(shm[k * M + up], G[(n * K + l) * gld + up], acc);
+    fvar[n * K * K + i] = acc;
+  }
+}
+
+static int glm_fvar_full_tc(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, const float* ws,
+                            const float* Sigma, float* f_var, float* scratch, cudaStream_t st) {
+  const int K = plan->K, M = plan->Mtot;
+  const int64_t P = plan->P, Ppad = (P + 31) / 32 * 32;
+  int32_t* pu = reinterpret_cast<int32_t*>(scratch);
+  int32_t* pc = pu + Ppad;
+  float* T = scratch + 2 * Ppad;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    param_maps2_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * o.in_c, 256), 256, 0, st>>>(
+        pu, pc, o.theta_off_w, o.out_c, o.in_c, q.lin_unit, q.lin_col, 0);
+    BNNP_LAUNCH_CHECK();
+    if (o.has_bias) {
+      param_maps2_kernel<<<(unsigned)ceil_div64(o.out_c, 256), 256, 0, st>>>(pu, pc, o.theta_off_b, o.out_c, o.in_c,
+                                                                             q.lin_unit, q.lin_col, 1);
+      BNNP_LAUNCH_CHECK();
+    }
+  }
+  int rc = zero(T, N * M * M, st);
+  if (rc) return rc;
+  const float* A = ws + plan->acat_off;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    const int kdim = o.in_c + (o.has_bias ? 1 : 0);
+    rc = tcg::gemm_tc(N, P, kdim, o.out_c, tcg::TcRowMajor{A + q.lin_col, plan->Dtot, 0},
+                      SigmaUnitB{Sigma, P, o.theta_off_w, o.theta_off_b, o.in_c, o.has_bias},
+                      RowDotT{T, A, pu, pc, plan->Dtot, M, q.lin_unit}, 1, st);
+    if (rc) return rc;
+  }
+  fvar_from_units_kernel<<<(unsigned)N, 256, (size_t)K * M * sizeof(float), st>>>(ws + plan->gcat_off, M, T, K, M, f_var);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
 }
 
 // ---- f_var, diagonal ------------------------------------------------------------------------
@@ -383,11 +504,6 @@ static bool linear_only_g(const bnnp_op_t* ops, int n_ops) {
       return false;
   return true;
 }
-static int zero(float* p, int64_t n, cudaStream_t st) {
-  zero_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(p, n);
-  BNNP_LAUNCH_CHECK();
-  return BNNP_OK;
-}
 
 // ------------------------------------------------------------------------------------ f_mu
 extern "C" int bnnp_glm_fmu(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
@@ -413,17 +529,24 @@ extern "C" int bnnp_glm_fmu(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* 
 }
 
 // ------------------------------------------------------------------------------------ full
-extern "C" int64_t bnnp_glm_fvar_full_scratch_floats(const bnnp_plan_t* plan, int64_t N) {
+static bool fvar_full_use_tc(const bnnp_plan_t* plan, int engine) {
+  if (engine == 1) return false;
+  if (engine == 2) return true;
+  return plan->P >= 4096;                 // tiny posteriors: the SIMT path is launch-bound anyway
+}
+extern "C" int64_t bnnp_glm_fvar_full_scratch_floats(const bnnp_plan_t* plan, int64_t N, int engine) {
   int64_t Ppad = (plan->P + 31) / 32 * 32;
+  if (fvar_full_use_tc(plan, engine)) return 2 * Ppad + N * (int64_t)plan->Mtot * plan->Mtot + 64;
   return 2 * Ppad + N * plan->K * plan->P + 64;
 }
 
 extern "C" int bnnp_glm_fvar_full(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                                   const float* ws, const float* Sigma, float* f_var, float* scratch,
-                                  void* stream) {
+                                  int engine, void* stream) {
   if (!ops || !plan || !ws || !Sigma || !f_var || !scratch || N <= 0) return BNNP_ERR_INVALID;
   if (!linear_only_g(ops, n_ops)) return BNNP_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
+  if (fvar_full_use_tc(plan, engine)) return glm_fvar_full_tc(ops, n_ops, plan, N, ws, Sigma, f_var, scratch, st);
   const int K = plan->K;
   const int64_t P = plan->P, Ppad = (P + 31) / 32 * 32;
   int32_t* pu = reinterpret_cast<int32_t*>(scratch);

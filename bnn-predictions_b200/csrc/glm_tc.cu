@@ -1,0 +1,378 @@
+// GLM predictive, full covariance, on tensor cores with TMA-fed operands.
+//
+//   f_var[n] = J_n Sigma J_n^T        (preds/predictives.py:63, einsum('nkp,pq,ncq->nkc'))
+//
+// For Linear layers J_n[k,(i,j)] = g_n[k,i] a_n[j], hence
+//   f_var[n,k,l] = sum_{u,u'} G[n,k,u] T[n,u,u'] G[n,l,u'],
+//   T[n,u,u']    = sum_{p in unit u} a~_n[j(p)] * Y_u'[n,p],    Y_u'[n,p] = sum_{q in unit u'} Sigma[p,q] a~_n[j(q)].
+// Y is a plain GEMM per unit u' (M = inputs, N = all P parameters, K = inputs of the unit's layer) whose
+// operands are ordinary matrices: the activations and Sigma itself.  Both are pre-split into bf16 hi/lo
+// copies with 16-byte aligned rows and streamed by TMA (SWIZZLE_64B boxes) straight into the UMMA
+// layout -- no generator warps.  Y never leaves the chip: the epilogue multiplies each accumulator row
+// by a~_n[j(p)] and reduces over the columns of a unit (adding the unit's bias column, a rank-one term,
+// from the fp32 Sigma on the way).  P^2 MACs per input instead of the reference's K*P^2.
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace bnnp {
+namespace glmtc {
+
+using namespace bnnp::tcp;
+
+constexpr int BK = 32, TILE_M = 128, MAX_N = 256, STAGES = 4;
+constexpr int A_TERM = TILE_M * BK * 2, A_STAGE = 2 * A_TERM;
+constexpr int B_TERM = MAX_N * BK * 2, B_STAGE = 2 * B_TERM;
+constexpr int STAGE_BYTES = A_STAGE + B_STAGE;               // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int NUM_THREADS = 256;     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
+constexpr int EPI_WARP0 = 4;
+
+struct Args {
+  long long N, P;                    // inputs, parameters
+  int n_units, nin, has_bias;        // units of the column-side layer l', its fan-in
+  long long offw, offb;              // theta offsets of layer l' weights / biases
+  int unit0p;                        // global index of the layer's first unit
+  int unit_first, unit_step, delta;  // this launch covers units unit_first + i*unit_step (same K-start misalignment delta)
+  int wn, n_mt, n_nt, n_chunks;
+  long long ald; int Mtot;
+  const float* Sigma; const float* A; const int32_t* pu; const int32_t* pc; float* T;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                    const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
+                    Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                        // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + STAGES;              // [STAGES] MMA commit -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;       // [2]
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_tiles = (long long)args.n_units * args.n_nt * args.n_mt;
+  uint32_t stage = 0, phase = 0, iter = 0;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+    // input tile fastest: concurrently running CTAs stream the same Sigma tile (shared through L2)
+    const int mt = (int)(tile % args.n_mt);
+    const int nt = (int)((tile / args.n_mt) % args.n_nt);
+    const int up = args.unit_first + args.unit_step * (int)(tile / ((long long)args.n_mt * args.n_nt));
+    const long long m0 = (long long)mt * TILE_M, n0 = (long long)nt * args.wn;
+    const uint32_t buf = iter & 1, buf_phase = (iter >> 1) & 1;
+
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t s = stage, ph = phase;
+        const uint32_t bytes = (uint32_t)(A_STAGE + 2 * args.wn * BK * 2);
+        // first Sigma column of unit u', moved down to a 16-byte boundary (the activation copy is shifted by delta)
+        const int kcol0 = (int)(args.offw + (long long)up * args.nin) - args.delta;
+        for (int c = 0; c < args.n_chunks; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* base = smem + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], bytes);
+          tma_load_2d(&map_ah, &full[s], base, c * BK, (int)m0);
+          tma_load_2d(&map_al, &full[s], base + A_TERM, c * BK, (int)m0);
+          tma_load_2d(&map_sh, &full[s], base + A_STAGE, kcol0 + c * BK, (int)n0);
+          tma_load_2d(&map_sl, &full[s], base + A_STAGE + B_TERM, kcol0 + c * BK, (int)n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        mbar_wait(&acc_empty[buf], buf_phase ^ 1);
+        tc_fence_after();
+        uint32_t s = stage, ph = phase;
+        const uint32_t idesc = umma_idesc_bf16(args.wn);
+        const uint32_t d = tmem_base + buf * MAX_N;
+        for (int c = 0; c < args.n_chunks; ++c) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), b0 = a0 + A_STAGE;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t dah = umma_desc_sw64(a0 + kk * 32), dal = umma_desc_sw64(a0 + A_TERM + kk * 32);
+            const uint64_t dbh = umma_desc_sw64(b0 + kk * 32), dbl = umma_desc_sw64(b0 + B_TERM + kk * 32);
+            umma_bf16(d, dah, dbh, idesc, (c | kk) ? 1u : 0u);
+            umma_bf16(d, dah, dbl, idesc, 1u);
+            umma_bf16(d, dal, dbh, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          if (c == args.n_chunks - 1) umma_commit(&acc_full[buf]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp >= EPI_WARP0) {
+      // epilogue: T[n, u(p), u'] += a~[n, c(p)] * (Y[n,p] + Sigma[p, bias(u')])
+      const int q = warp - EPI_WARP0;
+      mbar_wait(&acc_full[buf], buf_phase);
+      tc_fence_after();
+      const long long n = m0 + q * 32 + lane;
+      const bool rowok = n < args.N;
+      const long long ncols = args.P - n0 < args.wn ? args.P - n0 : args.wn;
+      const float* __restrict__ arow = args.A + (rowok ? n : 0) * args.ald;
+      // bias column of unit u' = row (offb + u') of the symmetric Sigma: contiguous in p
+      const float* __restrict__ sbias = args.Sigma + (args.offb + up) * args.P;
+      float* trow = args.T + ((rowok ? n : 0) * args.Mtot) * (long long)args.Mtot + args.unit0p + up;
+      float acc = 0.f;
+      int ucur = -1;
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
+        if (rowok) {
+          // phase 1: every load of the chunk is issued before any atomic (nothing to serialise on)
+          float prod[32];
+          int uu[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const bool ok = c0 + e < ncols;
+            const long long p = n0 + c0 + (ok ? e : 0);
+            uu[e] = ok ? __ldg(args.pu + p) : -2;
+            const int col = __ldg(args.pc + p);
+            float y = __uint_as_float(v[e]);
+            if (args.has_bias) y += __ldg(sbias + p);
+            prod[e] = __ldg(arow + col) * y;
+          }
+          // phase 2: run-length reduction over units, one atomic per run
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (uu[e] != -2) {
+              if (uu[e] != ucur) {
+                if (ucur >= 0) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
+                ucur = uu[e]; acc = 0.f;
+              }
+              acc += prod[e];
+            }
+          }
+        }
+      }
+      if (rowok && ucur >= 0) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    const uint32_t tot = stage + (uint32_t)args.n_chunks;
+    phase ^= (tot / STAGES) & 1;
+    stage = tot % STAGES;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// dst_hi/lo[r, c] = bf16 split of src[r*lds + c] for c < cols, 0 for cols <= c < cpad
+__global__ void split_bf16_kernel(const float* __restrict__ src, long long lds, long long rows, long long cols,
+                                  long long cpad, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                  int shift) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cpad) return;
+  long long r = i / cpad, c = i % cpad - shift;
+  float v = (c >= 0 && c < cols) ? src[r * lds + c] : 0.f;
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// bf16 matrix [rows, cols] with row stride ld elements, boxes [box_rows x 32]
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return BNNP_ERR_CUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[bnnp_b200] cuTensorMapEncodeTiled failed: %d\n", (int)r);
+    return BNNP_ERR_CUDA;
+  }
+  return BNNP_OK;
+}
+
+}  // namespace glmtc
+}  // namespace bnnp
+
+using namespace bnnp;
+using namespace bnnp::glmtc;
+
+static inline long long up8(long long v) { return (v + 7) / 8 * 8; }
+static inline long long up32(long long v) { return (v + 31) / 32 * 32; }
+
+// Split a fp32 matrix into bf16 hi/lo copies with a 16-byte aligned row pitch (cpad = roundup8(cols)).
+extern "C" int bnnp_split_bf16(const float* src, int64_t lds, int64_t rows, int64_t cols, void* hi, void* lo,
+                               void* stream) {
+  if (!src || !hi || !lo || rows <= 0 || cols <= 0) return BNNP_ERR_INVALID;
+  const long long cpad = up8(cols);
+  split_bf16_kernel<<<(unsigned)ceil_div64(rows * cpad, 256), 256, 0, as_stream(stream)>>>(
+      src, lds, rows, cols, cpad, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), 0);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+// scratch layout (floats): [maps 2*Ppad ints][T N*M*M][per-layer activation splits]
+extern "C" int64_t bnnp_glm_fvar_full_tma_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                                         int64_t N) {
+  const int64_t Ppad = (plan->P + 31) / 32 * 32;
+  int64_t act = 0;
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_LINEAR) act += 8 * (N * up32(ops[i].in_c + 8) + 64);   // <= 8 shifted copies, hi + lo bf16
+  return 2 * Ppad + N * (int64_t)plan->Mtot * plan->Mtot + act + 1024;
+}
+
+__global__ void glmtc_param_maps_kernel(int32_t* __restrict__ pu, int32_t* __restrict__ pc, int64_t off, int m,
+                                        int nin, int unit0, int col0, int is_bias) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t cnt = is_bias ? m : (int64_t)m * nin;
+  if (e >= cnt) return;
+  if (is_bias) { pu[off + e] = unit0 + (int)e; pc[off + e] = col0 + nin; }
+  else { pu[off + e] = unit0 + (int)(e / nin); pc[off + e] = col0 + (int)(e % nin); }
+}
+__global__ void glmtc_zero_kernel(float* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+// f_var[n,k,l] = sum_{u,u'} G[(n,k),u] T[n,u,u'] G[(n,l),u']
+__global__ void glmtc_fvar_from_units_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ T,
+                                             int K, int M, float* __restrict__ fvar) {
+  extern __shared__ float shm[];
+  const int64_t n = blockIdx.x;
+  const float* Tn = T + n * M * M;
+  for (int i = threadIdx.x; i < K * M; i += blockDim.x) {
+    const int k = i / M, up = i % M;
+    float acc = 0.f;
+    for (int u = 0; u < M; ++u) acc = fmaf(G[(n * K + k) * gld + u], Tn[u * M + up], acc);
+    shm[i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) {
+    const int k = i / K, l = i % K;
+    float acc = 0.f;
+    for (int up = 0; up < M; ++up) acc = fmaf(shm[k * M + up], G[(n * K + l) * gld + up], acc);
+    fvar[n * K * K + i] = acc;
+  }
+}
+
+// Sigma: fp32 [P,P]; Sh/Sl: its bf16 hi/lo split with row pitch roundup8(P) (bnnp_split_bf16).
+extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                      const float* ws, const float* Sigma, const void* Sh, const void* Sl,
+                                      float* f_var, float* scratch, void* stream) {
+  if (!ops || !plan || !ws || !Sigma || !Sh || !Sl || !f_var || !scratch || N <= 0) return BNNP_ERR_INVALID;
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_CONV2D || ops[i].kind == BNNP_OP_MAXPOOL2D || ops[i].kind == BNNP_OP_AVGPOOL2D)
+      return BNNP_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int K = plan->K, M = plan->Mtot;
+  const int64_t P = plan->P, Ppad = (P + 31) / 32 * 32, Ppitch = up8(P);
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255));
+  int32_t* pu = reinterpret_cast<int32_t*>(base);
+  int32_t* pc = pu + Ppad;
+  float* T = base + 2 * Ppad;
+  float* act = T + ((N * (int64_t)M * M + 63) / 64) * 64;
+  const float* A = ws + plan->acat_off;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    glmtc_param_maps_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * o.in_c, 256), 256, 0, st>>>(
+        pu, pc, o.theta_off_w, o.out_c, o.in_c, q.lin_unit, q.lin_col, 0);
+    BNNP_LAUNCH_CHECK();
+    if (o.has_bias) {
+      glmtc_param_maps_kernel<<<(unsigned)ceil_div64(o.out_c, 256), 256, 0, st>>>(pu, pc, o.theta_off_b, o.out_c,
+                                                                                  o.in_c, q.lin_unit, q.lin_col, 1);
+      BNNP_LAUNCH_CHECK();
+    }
+  }
+  glmtc_zero_kernel<<<(unsigned)ceil_div64(N * (int64_t)M * M, 256), 256, 0, st>>>(T, N * (int64_t)M * M);
+  BNNP_LAUNCH_CHECK();
+  BNNP_CUDA_CHECK(cudaFuncSetAttribute(glm_fvar_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CUtensorMap msh, msl;
+  Args a;
+  a.N = N; a.P = P; a.ald = plan->Dtot; a.Mtot = M;
+  a.Sigma = Sigma; a.A = A; a.pu = pu; a.pc = pc; a.T = T;
+  {
+    long long nt = (P + MAX_N - 1) / MAX_N;
+    a.wn = (int)(((P + nt - 1) / nt + 15) / 16 * 16);
+    a.n_nt = (int)((P + a.wn - 1) / a.wn);
+    a.n_mt = (int)((N + TILE_M - 1) / TILE_M);
+  }
+  int rc = make_map(&msh, Sh, P, P, Ppitch, a.wn);
+  if (rc) return rc;
+  rc = make_map(&msl, Sl, P, P, Ppitch, a.wn);
+  if (rc) return rc;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    // TMA boxes must start on a 16-byte boundary, i.e. at a Sigma column that is a multiple of 8.  The K-range
+    // of unit u' starts at offw + u'*nin; units are grouped by the misalignment delta of that start (periodic in
+    // u'), and each group reads a copy of the layer's activations shifted right by delta (zero filled), so that
+    // the Sigma columns pulled in below the unit's range meet zeros.
+    int g8 = o.in_c % 8, period = 1;
+    if (g8) { int a_ = g8, b_ = 8; while (b_) { int t = a_ % b_; a_ = b_; b_ = t; } period = 8 / a_; }
+    for (int grp = 0; grp < period && grp < o.out_c; ++grp) {
+      const int delta = (int)((o.theta_off_w + (long long)grp * o.in_c) % 8);
+      const long long apitch = up32(o.in_c + delta);
+      __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(act);
+      __nv_bfloat16* al = ah + N * apitch;
+      act += N * apitch + 64;
+      split_bf16_kernel<<<(unsigned)ceil_div64(N * apitch, 256), 256, 0, st>>>(A + q.lin_col, plan->Dtot, N, o.in_c,
+                                                                               apitch, ah, al, delta);
+      BNNP_LAUNCH_CHECK();
+      CUtensorMap mah, mal;
+      rc = make_map(&mah, ah, N, apitch, apitch, TILE_M);
+      if (rc) return rc;
+      rc = make_map(&mal, al, N, apitch, apitch, TILE_M);
+      if (rc) return rc;
+      a.unit_first = grp; a.unit_step = period; a.delta = delta;
+      a.n_units = (o.out_c - grp + period - 1) / period;
+      a.nin = o.in_c; a.has_bias = o.has_bias;
+      a.offw = o.theta_off_w; a.offb = o.has_bias ? o.theta_off_b : 0; a.unit0p = q.lin_unit;
+      a.n_chunks = (o.in_c + delta + BK - 1) / BK;
+      const long long n_tiles = (long long)a.n_units * a.n_nt * a.n_mt;
+      const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+      glm_fvar_tma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, msh, msl, a);
+      BNNP_LAUNCH_CHECK();
+      if (getenv("BNNP_DEBUG_SYNC")) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        fprintf(stderr, "[bnnp debug] glm_fvar_tma op %d grp %d delta %d: units %d nin %d wn %d n_nt %d n_mt %d chunks %d -> %s\n",
+                i, grp, delta, a.n_units, a.nin, a.wn, a.n_nt, a.n_mt, a.n_chunks, cudaGetErrorString(e));
+        if (e != cudaSuccess) return BNNP_ERR_CUDA;
+      }
+    }
+  }
+  glmtc_fvar_from_units_kernel<<<(unsigned)N, 256, (size_t)K * M * sizeof(float), st>>>(ws + plan->gcat_off, M, T, K,
+                                                                                       M, f_var);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}

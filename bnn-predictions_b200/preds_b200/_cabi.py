@@ -70,8 +70,11 @@ _SIGS = {
     'bnnp_kfac_accum': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _F, C.POINTER(_P), _P, _V]),
     'bnnp_kfac_scratch_floats': (_L, [_OPS, _I, _PLAN, _L, _I]),
     'bnnp_glm_fmu': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _P, _V]),
-    'bnnp_glm_fvar_full_scratch_floats': (_L, [_PLAN, _L]),
-    'bnnp_glm_fvar_full': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _V]),
+    'bnnp_glm_fvar_full_scratch_floats': (_L, [_PLAN, _L, _I]),
+    'bnnp_glm_fvar_full': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _I, _V]),
+    'bnnp_split_bf16': (_I, [_P, _L, _L, _L, _P, _P, _V]),
+    'bnnp_glm_fvar_full_tma_scratch_floats': (_L, [_OPS, _I, _PLAN, _L]),
+    'bnnp_glm_fvar_full_tma': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _P, _P, _V]),
     'bnnp_glm_fvar_diag': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _P, _V]),
     'bnnp_glm_fvar_diag_scratch_floats': (_L, [_OPS, _I, _PLAN, _L]),
     'bnnp_glm_fvar_kron': (_I, [_OPS, _I, _PLAN, _L, _P, _P, C.POINTER(_P), C.POINTER(_F),

@@ -180,6 +180,8 @@ class Laplace:
         chol = torch.linalg.cholesky(H)
         Sigma = torch.cholesky_inverse(chol, upper=False)
         del chol
+        if not Sigma.is_contiguous() and Sigma.T.is_contiguous():
+            Sigma = Sigma.T            # column-major result of potri: symmetric, so the transpose view is free
         return torch.linalg.cholesky(Sigma), Sigma
 
     def _accumulate_diag(self, batches, diag, hess_factor):

@@ -15,6 +15,24 @@ from .likelihoods import GaussianLh
 
 # upper bound for per-call scratch; inputs are processed in chunks that respect it
 SCRATCH_BUDGET_FLOATS = 1 << 30
+# full-covariance GLM engines: 1 SIMT (as written), 2 tcgen05 with generated operands, 3 tcgen05 + TMA
+FULL_TMA_MIN_P = 4096
+_SPLIT_CACHE = {}
+
+
+def sigma_split(Sigma):
+    """bf16 hi/lo copies of the covariance (row pitch roundup8(P)) for the TMA-fed GLM kernel,
+    made once per posterior and cached (keyed on the tensor's storage and version)."""
+    key = (Sigma.data_ptr(), Sigma._version, tuple(Sigma.shape))
+    if _SPLIT_CACHE.get('key') != key:
+        _SPLIT_CACHE.clear()
+        P = Sigma.shape[0]
+        pitch = (P + 7) // 8 * 8
+        hi = torch.empty(P, pitch, dtype=torch.bfloat16, device=Sigma.device)
+        lo = torch.empty(P, pitch, dtype=torch.bfloat16, device=Sigma.device)
+        check(lib.bnnp_split_bf16(ptr(Sigma), P, P, P, ptr(hi), ptr(lo), stream()), 'bnnp_split_bf16')
+        _SPLIT_CACHE.update(key=key, hi=hi, lo=lo)
+    return _SPLIT_CACHE['hi'], _SPLIT_CACHE['lo']
 
 
 def _kron_tables(net, kron):
@@ -34,10 +52,12 @@ def _kron_tables(net, kron):
     return ptr_array(eig), float_array(dw), float_array(db)
 
 
-def glm_moments(X, model, mu, Sigma):
+def glm_moments(X, model, mu, Sigma, engine=0):
     """f_mu [N,K] and f_var [N,K,K] of the linearised model (preds/predictives.py:52-65).
     ``Sigma`` is the full covariance [P,P], the diagonal variances [P], or a ``Kron``."""
     net = net_for(model)
+    if torch.is_tensor(Sigma) and Sigma.dim() == 2 and not Sigma.is_contiguous() and Sigma.T.is_contiguous():
+        Sigma = Sigma.T                # covariance is symmetric: take the contiguous view, no copy
     theta_star = parameters_to_vector(model.parameters()).detach()
     delta = (mu - theta_star).to(torch.float32).contiguous()
     delta_ptr = ptr(delta) if bool((delta != 0).any()) else None
@@ -50,7 +70,14 @@ def glm_moments(X, model, mu, Sigma):
         per = max(1, int(lib.bnnp_glm_fvar_kron_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(1, K)), 1)))
         cap = 65535 // K
     elif Sigma.dim() == 2:
-        per, cap = K * P + 1, 1 << 30
+        if engine == 0:
+            engine = 3 if P >= FULL_TMA_MIN_P else 1
+        if engine == 3:
+            per = max(1, int(lib.bnnp_glm_fvar_full_tma_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(64, K)), 64)) // 64)
+            split = sigma_split(Sigma)
+        else:
+            per = max(1, int(lib.bnnp_glm_fvar_full_scratch_floats(C.byref(net.plan(64, K)), 64, engine)) // 64)
+        cap = 1 << 30
     else:
         per = max(1, int(lib.bnnp_glm_fvar_diag_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(1, K)), 1)))
         cap = 65535 // K if not net.linear_only else 1 << 30
@@ -70,10 +97,14 @@ def glm_moments(X, model, mu, Sigma):
             check(lib.bnnp_glm_fvar_kron(net.ops, net.n_ops, C.byref(pl), n, ptr(X2d), ptr(ws), tables[0],
                                          tables[1], tables[2], int(Sigma.dampen), ptr(fv), ptr(sc), stream()),
                   'bnnp_glm_fvar_kron')
+        elif Sigma.dim() == 2 and engine == 3:
+            sc = net.scratch(lib.bnnp_glm_fvar_full_tma_scratch_floats(net.ops, net.n_ops, C.byref(pl), n))
+            check(lib.bnnp_glm_fvar_full_tma(net.ops, net.n_ops, C.byref(pl), n, ptr(ws), ptr(Sigma), ptr(split[0]),
+                                             ptr(split[1]), ptr(fv), ptr(sc), stream()), 'bnnp_glm_fvar_full_tma')
         elif Sigma.dim() == 2:
-            sc = net.scratch(lib.bnnp_glm_fvar_full_scratch_floats(C.byref(pl), n))
+            sc = net.scratch(lib.bnnp_glm_fvar_full_scratch_floats(C.byref(pl), n, engine))
             check(lib.bnnp_glm_fvar_full(net.ops, net.n_ops, C.byref(pl), n, ptr(ws), ptr(Sigma), ptr(fv),
-                                         ptr(sc), stream()), 'bnnp_glm_fvar_full')
+                                         ptr(sc), engine, stream()), 'bnnp_glm_fvar_full')
         else:
             sc = net.scratch(lib.bnnp_glm_fvar_diag_scratch_floats(net.ops, net.n_ops, C.byref(pl), n))
             check(lib.bnnp_glm_fvar_diag(net.ops, net.n_ops, C.byref(pl), n, ptr(X2d), ptr(ws), ptr(Sigma),

@@ -160,11 +160,23 @@ int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_pla
 int bnnp_glm_fmu(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                  const float* X, const float* ws, const float* f, const float* delta, float* f_mu,
                  void* stream);
-/* f_var[N,K,K] = J Sigma J^T, Sigma [P,P] (:63).  Linear-only networks. */
-int64_t bnnp_glm_fvar_full_scratch_floats(const bnnp_plan_t* plan, int64_t N);
+/* f_var[N,K,K] = J Sigma J^T, Sigma [P,P] symmetric (:63).  Linear-only networks.
+ * engine: 0 auto, 1 SIMT (T = J Sigma as written), 2 tcgen05 structured
+ * (T[n,u,u'] = a^T Sigma_uu' a' per unit pair: P^2 instead of K P^2 MACs per input). */
+int64_t bnnp_glm_fvar_full_scratch_floats(const bnnp_plan_t* plan, int64_t N, int engine);
 int bnnp_glm_fvar_full(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                        const float* ws, const float* Sigma, float* f_var, float* scratch,
-                       void* stream);
+                       int engine, void* stream);
+/* The same on TMA-fed tensor cores: Sigma_hi / Sigma_lo are the bf16 hi/lo split of Sigma with a
+ * 16-byte aligned row pitch of roundup8(P) elements, made once per posterior by bnnp_split_bf16()
+ * (dst pitch = roundup8(cols)).  No generator warps: activations and Sigma stream through TMA. */
+int bnnp_split_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* hi, void* lo,
+                    void* stream);
+int64_t bnnp_glm_fvar_full_tma_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                              int64_t N);
+int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                           const float* ws, const float* Sigma, const void* Sigma_hi, const void* Sigma_lo,
+                           float* f_var, float* scratch, void* stream);
 /* f_var = J diag(sigma2) J^T (:65). */
 int bnnp_glm_fvar_diag(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                        const float* X, const float* ws, const float* sigma2, float* f_var,

@@ -217,3 +217,26 @@ def test_glm_sampler_philox_statistics():
     fvar[1] = -fvar[1]
     check(lib.bnnp_glm_sample(LIK_GAUSSIAN, ptr(fmu), ptr(fvar), None, 1234, 8, N, K, ptr(out), ptr(status), stream()))
     assert status.cpu().tolist() == [0, 1, 0, 0]
+
+
+@pytest.mark.parametrize('engine', [1, 2, 3])
+@pytest.mark.parametrize('arch', [(20, [30, 12], 5, 70), (64, [40], 10, 300), (3, [4], 1, 9)])
+def test_glm_fvar_full_engines(arch, engine):
+    """J Sigma J^T on all engines (SIMT as written / tcgen05 generated / tcgen05 TMA-fed) vs fp64 from materialised
+    Jacobians: ragged tile tails, several layers (cross-layer unit pairs), K = 1."""
+    from preds_b200 import MLPS, Jacobians
+    from preds_b200.predictives import glm_moments
+    din, hid, K, N = arch
+    torch.manual_seed(3)
+    model = MLPS(din, hid, K, 'tanh').cuda()
+    P = sum(p.numel() for p in model.parameters())
+    X = torch.randn(N, din, device='cuda')
+    A = torch.randn(P, P, device='cuda') / P ** 0.5
+    Sigma = (A @ A.T + 0.05 * torch.eye(P, device='cuda')).contiguous()
+    mu = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    Js, f = Jacobians(model, X)
+    Jt = (Js.transpose(1, 2) if Js.dim() == 3 else Js.unsqueeze(1)).double()
+    ref = torch.einsum('nkp,pq,ncq->nkc', Jt, Sigma.double(), Jt)
+    fmu, fvar = glm_moments(X, model, mu, Sigma, engine=engine)
+    assert cases.rel_err(fmu.cpu(), f.cpu()) < 1e-6
+    assert cases.rel_err(fvar.cpu(), ref.cpu()) < (1e-5 if engine == 1 else 3e-5)
