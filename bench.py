@@ -208,6 +208,7 @@ def run_ours(args):
         ms = float(t.item())
     value = K * B * world / (ms * 1e-3)
     checksum = float(H.diagonal().double().sum())
+    lap = None
 
     # ---- e2e through the public API with pinned host batches (H2D inside, D2H read per step) ----
     lap = Laplace(model, 1.0, lh)
@@ -229,6 +230,50 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_value = e2e_steps * B * world / e2e_s
     lap.precision = None
+
+    # ---- secondary: the one-off factorisation (timed separately) and the GLM predictive ----------
+    secondary = None
+    if not args.no_glm:
+        from preds_b200.predictives import glm_moments
+        H.diagonal().add_(1.0)                       # prior precision (added once, after the reduce)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        barrier()
+        ev[0].record()
+        Sigma_chol, Sigma = lap._factorise_full(H)
+        ev[1].record()
+        del H
+        lap.mu = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        lap.Sigma_chol, lap._Sigma, lap.inferred = Sigma_chol, Sigma, True
+        nte, S = args.glm_inputs, args.glm_samples
+        Xte_host = torch.randn(nte, 1, 28, 28, generator=torch.Generator().manual_seed(16 + rank)).pin_memory()
+        Xte = Xte_host.to(dev)
+        lap.predictive_samples_glm(Xte[:256], n_samples=8, seed=1)          # warm-up (also builds the Sigma split)
+        barrier()
+        ev[2].record()
+        out = lap.predictive_samples_glm(Xte, n_samples=S, seed=2)
+        ev[3].record()
+        barrier()
+        t0 = time.perf_counter()
+        out = lap.predictive_samples_glm(Xte_host, n_samples=S, seed=3)     # host inputs -> H2D inside
+        pmean = out.mean(0).cpu()                                           # what the drivers keep (imginference.py:45)
+        e2e_glm_s = time.perf_counter() - t0
+        glm_ms = ev[2].elapsed_time(ev[3])
+        if world > 1:
+            t = torch.tensor([glm_ms, e2e_glm_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            glm_ms, e2e_glm_s = float(t[0]), float(t[1])
+        secondary = {
+            'factorise_full_ms': ev[0].elapsed_time(ev[1]),
+            'factorise_note': 'one-off chol(H), cholesky_inverse, chol(Sigma) via cuSOLVER (torch.linalg), P=59635',
+            'glm_predictive': {
+                'metric': 'glm_predictive_input_samples_per_s', 'value': nte * S * world / (glm_ms * 1e-3),
+                'unit': '(inputs x samples)/s', 'inputs_per_gpu': nte, 'samples': S, 'ms': glm_ms,
+                'e2e_value': nte * S * world / e2e_glm_s,
+                'e2e_note': 'pinned host inputs -> predictive_samples_glm -> .mean(0) read back',
+                'prob_rows_sum_to_one': float((pmean.sum(1) - 1).abs().max()),
+                'scaling': 'test inputs sharded across ranks, no collective',
+            },
+        }
 
     if rank != 0:
         if world > 1:
@@ -279,7 +324,7 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * 784 * 4 + B * 8,
                 'd2h_bytes_per_step': 4, 'steps': e2e_steps,
                 'call': "Laplace.infer([(X_pinned_host, y)], cov_type='full', factorise=False) + float(precision.trace)"},
-        'gpu_launches': launches, 'clocks': clocks, 'checksum_trace_H': checksum,
+        'gpu_launches': launches, 'clocks': clocks, 'checksum_trace_H': checksum, 'secondary': secondary,
     }
     print(json.dumps(line))
     if world > 1:
@@ -297,6 +342,9 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--cpu-sample', type=int, default=24)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-glm', action='store_true')
+    ap.add_argument('--glm-inputs', type=int, default=10000)
+    ap.add_argument('--glm-samples', type=int, default=1000)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
