@@ -5,6 +5,7 @@
 //   kron : G_l += factor * sum s s^T, A_l += bf/N * sum a a^T   preds/laplace.py:73-78, kron.py:58-69
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "gram_tc.cuh"
 
 namespace bnnp {
@@ -203,6 +204,31 @@ struct AccumLinearParam { // (i, j) -> weight [m, nin] at offw, column nin -> bi
     else if (has_bias) d[offb + i] += factor * acc;
   }
 };
+
+struct TcColMajorSq {      // X(j, k = example n) = A[n*ld + j]^2   (diag path: squared layer inputs)
+  static constexpr bool K_CONTIG = false;
+  using Row = const float*;
+  const float* p; long long ld;
+  __device__ __forceinline__ Row row(int64_t r, int) const { return p + r; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+    const float* q = rw + k0 * ld;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = (k0 + e < K) ? __ldg(q + (long long)e * ld) : 0.f;
+      out[e] = v * v;
+    }
+  }
+};
+// d[offw + i*nin + j] += factor * T[i, j] (j < nin),  d[offb + i] += factor * T[i, nin]
+__global__ void diag_scatter_kernel(const float* __restrict__ T, int m, int nin, int has_bias, int64_t offw,
+                                    int64_t offb, float factor, float* __restrict__ d) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)m * (nin + 1)) return;
+  int i = (int)(e / (nin + 1)), j = (int)(e % (nin + 1));
+  if (j < nin) d[offw + (int64_t)i * nin + j] += factor * T[e];
+  else if (has_bias) d[offb + i] += factor * T[e];
+}
+constexpr long long kTcMinMacsG = 1LL << 25;
 
 // conv weight diag: d[co, e] += factor * sum_r ( sum_pos gout[r,co,pos] U[r/V, e, pos] )^2
 // one block per 64x64 output tile, looping over all rows r (the per-sample Jacobian tile is
@@ -445,12 +471,19 @@ static int conv_diag_splits(const bnnp_op_t& o, int64_t R) {
 extern "C" int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                                 int64_t N, int V) {
   int64_t need = N * (int64_t)plan->Mtot + 64;
-  for (int i = 0; i < n_ops; ++i)
+  int64_t lin = 0;
+  for (int i = 0; i < n_ops; ++i) {
     if (ops[i].kind == BNNP_OP_CONV2D) {
       int64_t v = N * V * ops[i].out_c + 64 + 64LL * ops[i].out_c * ops[i].in_c * ops[i].kh * ops[i].kw + 64;
       need = need > v ? need : v;
     }
-  return need;
+    if (ops[i].kind == BNNP_OP_LINEAR) {
+      int64_t mm = ops[i].out_c, nn = ops[i].in_c + 1;
+      int64_t v = (1 + tcg::pick_ksplit(mm, nn, N, 1)) * mm * nn + 128;
+      lin = lin > v ? lin : v;
+    }
+  }
+  return need + lin + 64;
 }
 
 extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
@@ -468,10 +501,25 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     if (!is_param_op(o)) continue;
     const bnnp_op_plan_t& q = plan->op[i];
     if (o.kind == BNNP_OP_LINEAR) {
-      int rc = gemm_simt(o.out_c, o.in_c + 1, N, 1, LoadQT{scratch, M, q.lin_unit},
-                         LoadSq{ws + plan->acat_off, plan->Dtot, q.lin_col},
-                         AccumLinearParam{diag, o.theta_off_w, o.theta_off_b, o.in_c, o.has_bias, factor}, st);
-      if (rc) return rc;
+      int rc;
+      if ((long long)o.out_c * (o.in_c + 1) * N >= kTcMinMacsG) {
+        // T[i, j] = sum_n Q[n, i] a[n, j]^2 on the tensor cores (split-K partials -> T), then scatter into d
+        const long long mm = o.out_c, nn = o.in_c + 1;
+        float* T = scratch + N * (int64_t)M + 64;
+        float* wsk = T + mm * nn + 64;
+        rc = tcg::gemm_tc_splitk(mm, nn, N, 1, tcg::TcColMajor{scratch + q.lin_unit, M, 0},
+                                 TcColMajorSq{ws + plan->acat_off + q.lin_col, plan->Dtot}, 1.f, 0.f, T, nn, 0, wsk,
+                                 tcg::pick_ksplit(mm, nn, N, 1), st);
+        if (rc) return rc;
+        diag_scatter_kernel<<<(unsigned)ceil_div64(mm * nn, 256), 256, 0, st>>>(T, o.out_c, o.in_c, o.has_bias,
+                                                                               o.theta_off_w, o.theta_off_b, factor, diag);
+        BNNP_LAUNCH_CHECK();
+      } else {
+        rc = gemm_simt(o.out_c, o.in_c + 1, N, 1, LoadQT{scratch, M, q.lin_unit},
+                       LoadSq{ws + plan->acat_off, plan->Dtot, q.lin_col},
+                       AccumLinearParam{diag, o.theta_off_w, o.theta_off_b, o.in_c, o.has_bias, factor}, st);
+        if (rc) return rc;
+      }
     }
   }
   for (int i = 0; i < n_ops; ++i) {
@@ -506,13 +554,25 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
 }
 
 // ---------------------------------------------------------------------------- kfac
-extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
-                                            int64_t N, int V) {
+// scratch layout of the KFAC pass: [conv position-sums][split-K partials of the tensor-core Grams]
+static int64_t kfac_conv_floats(const bnnp_op_t* ops, int n_ops, int64_t N, int V) {
   int64_t need = 64;
-  (void)plan;
   for (int i = 0; i < n_ops; ++i)
     if (ops[i].kind == BNNP_OP_CONV2D) need = need > N * V * ops[i].out_c + 64 ? need : N * V * ops[i].out_c + 64;
   return need;
+}
+extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                            int64_t N, int V) {
+  (void)plan;
+  int64_t part = 0;
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_LINEAR) {
+      int64_t m = ops[i].out_c, n = ops[i].in_c;
+      int64_t a = (int64_t)tcg::pick_ksplit(m, m, N * V, 1) * m * m, b = (int64_t)tcg::pick_ksplit(n, n, N, 1) * n * n;
+      part = part > a ? part : a;
+      part = part > b ? part : b;
+    }
+  return kfac_conv_floats(ops, n_ops, N, V) + part + 128;
 }
 
 extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
@@ -530,12 +590,23 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
     if (!Gf || !Af) return BNNP_ERR_INVALID;
     const float* G = ws + q.grad_off;
     if (o.kind == BNNP_OP_LINEAR) {
-      int rc = gemm_simt(o.out_c, o.out_c, R, 1, LoadTA{G, q.grad_ld, 0}, LoadNB{G, q.grad_ld, 0},
-                         AccumScaled{Gf, o.out_c, factor}, st);
+      int rc;
+      float* wsk = scratch + kfac_conv_floats(ops, n_ops, N, V);
+      if ((long long)o.out_c * o.out_c * R >= kTcMinMacsG)
+        rc = tcg::gemm_tc_splitk(o.out_c, o.out_c, R, 1, tcg::TcColMajor{G, q.grad_ld, 0}, tcg::TcColMajor{G, q.grad_ld, 0},
+                                 factor, 1.f, Gf, o.out_c, 0, wsk, tcg::pick_ksplit(o.out_c, o.out_c, R, 1), st);
+      else
+        rc = gemm_simt(o.out_c, o.out_c, R, 1, LoadTA{G, q.grad_ld, 0}, LoadNB{G, q.grad_ld, 0},
+                       AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       const float* A = ws + plan->acat_off;
-      rc = gemm_simt(o.in_c, o.in_c, N, 1, LoadTA{A, plan->Dtot, q.lin_col}, LoadNB{A, plan->Dtot, q.lin_col},
-                     AccumScaled{Af, o.in_c, batch_factor / (float)N}, st);
+      if ((long long)o.in_c * o.in_c * N >= kTcMinMacsG)
+        rc = tcg::gemm_tc_splitk(o.in_c, o.in_c, N, 1, tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0},
+                                 tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0}, batch_factor / (float)N, 1.f, Af, o.in_c,
+                                 0, wsk, tcg::pick_ksplit(o.in_c, o.in_c, N, 1), st);
+      else
+        rc = gemm_simt(o.in_c, o.in_c, N, 1, LoadTA{A, plan->Dtot, q.lin_col}, LoadNB{A, plan->Dtot, q.lin_col},
+                       AccumScaled{Af, o.in_c, batch_factor / (float)N}, st);
       if (rc) return rc;
     } else {
       int64_t ild; const float* in = op_input(ops, plan, i, X, ws, &ild);

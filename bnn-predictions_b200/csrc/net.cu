@@ -9,6 +9,7 @@
 //   G_cat [N*V, Mtot] : d f_v / d (pre-activation) of every Linear
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace bnnp {
 
@@ -289,6 +290,20 @@ struct StoreBias {
   }
 };
 
+// tensor-core epilogue of the Linear forward: out = acc + bias
+struct TcStoreBias : tcg::TcNoState {
+  float* p; long long ld; const float* bias;
+  __host__ __device__ TcStoreBias(float* p_, long long ld_, const float* b_) : p(p_), ld(ld_), bias(b_) {}
+  __device__ __forceinline__ void row(State&, int64_t m, int64_t n0, const float* v, int nvalid, int, int) const {
+    float* q = p + m * ld + n0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e < nvalid) q[e] = v[e] + (bias ? __ldg(bias + n0 + e) : 0.f);
+  }
+};
+// contractions below this many MACs stay on the SIMT path (a 128 x 256 tensor-core tile would be mostly padding)
+constexpr long long kTcMinMacs = 1LL << 25;
+
 }  // namespace bnnp
 
 using namespace bnnp;
@@ -325,10 +340,11 @@ extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, 
     if (o.kind == BNNP_OP_LINEAR) {
       if (o.in_h != 1 || o.in_w != 1 || o.kh != 1 || o.kw != 1) return BNNP_ERR_INVALID;
       if (P.first_linear < 0) P.first_linear = i;
+      // every layer slice starts on a 16-byte boundary (vectorised operand loads); padding columns are zero
       P.op[i].lin_col = P.Dtot;
       P.op[i].lin_unit = P.Mtot;
-      P.Dtot += o.in_c + 1;
-      P.Mtot += o.out_c;
+      P.Dtot += (o.in_c + 1 + 3) / 4 * 4;
+      P.Mtot += (o.out_c + 3) / 4 * 4;
       P.n_linear++;
     } else {
       P.op[i].lin_col = P.op[i].lin_unit = -1;
@@ -375,6 +391,8 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
                                 const float* X, int64_t N, float* ws, float* logits, void* stream) {
   if (!ops || !plan || !X || !ws || N <= 0) return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
+  if (plan->Dtot > 0)
+    BNNP_CUDA_CHECK(cudaMemsetAsync(ws + plan->acat_off, 0, sizeof(float) * N * plan->Dtot, st));
   const float* in = X;
   int64_t ild = op_in_size(ops[0]);
   for (int i = 0; i < n_ops; ++i) {
@@ -392,9 +410,15 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
         }
         fill_col_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(slice + o.in_c, plan->Dtot, N, 1.f);
         BNNP_LAUNCH_CHECK();
-        int rc = gemm_simt(N, o.out_c, o.in_c, 1, LoadRowMajorA{slice, plan->Dtot, 0},
-                           LoadColMajorB{o.weight, o.in_c, 0},
-                           StoreBias{out, q.act_ld, o.has_bias ? o.bias : nullptr}, st);
+        int rc;
+        if ((long long)N * o.out_c * o.in_c >= kTcMinMacs)
+          rc = tcg::gemm_tc(N, o.out_c, o.in_c, 1, tcg::TcRowMajor{slice, plan->Dtot, 0},
+                            tcg::TcRowMajor{o.weight, o.in_c, 0},
+                            TcStoreBias(out, q.act_ld, o.has_bias ? o.bias : nullptr), 1, st);
+        else
+          rc = gemm_simt(N, o.out_c, o.in_c, 1, LoadRowMajorA{slice, plan->Dtot, 0},
+                         LoadColMajorB{o.weight, o.in_c, 0},
+                         StoreBias{out, q.act_ld, o.has_bias ? o.bias : nullptr}, st);
         if (rc) return rc;
         break;
       }
@@ -451,6 +475,8 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
   int first_param = -1;
   for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { first_param = i; break; }
   if (first_param < 0) return BNNP_ERR_INVALID;
+  if (plan->Mtot > 0)
+    BNNP_CUDA_CHECK(cudaMemsetAsync(ws + plan->gcat_off, 0, sizeof(float) * R * plan->Mtot, st));
   {
     const bnnp_op_plan_t& q = plan->op[n_ops - 1];
     int rc = copy2d(ws + q.grad_off, q.grad_ld, seed, K, R, K, st);
@@ -466,9 +492,15 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
     unsigned blocks = (unsigned)ceil_div64(R * isz, 256);
     switch (o.kind) {
       case BNNP_OP_LINEAR: {
-        int rc = gemm_simt(R, o.in_c, o.out_c, 1, LoadRowMajorA{gout, q.grad_ld, 0},
-                           LoadRowMajorB{o.weight, o.in_c, 0},
-                           StoreAxpby{gin, qp.grad_ld, 0, 1.f, 0.f}, st);
+        int rc;
+        if ((long long)R * o.in_c * o.out_c >= kTcMinMacs)
+          rc = tcg::gemm_tc(R, o.in_c, o.out_c, 1, tcg::TcRowMajor{gout, q.grad_ld, 0},
+                            tcg::TcColMajor{o.weight, o.in_c, 0},
+                            tcg::TcStoreAxpby(gin, qp.grad_ld, 0, 1.f, 0.f), 1, st);
+        else
+          rc = gemm_simt(R, o.in_c, o.out_c, 1, LoadRowMajorA{gout, q.grad_ld, 0},
+                         LoadRowMajorB{o.weight, o.in_c, 0},
+                         StoreAxpby{gin, qp.grad_ld, 0, 1.f, 0.f}, st);
         if (rc) return rc;
         break;
       }

@@ -28,6 +28,11 @@ from . import parallel
 # accumulator never sums more than 4096 examples (hierarchical fp32 summation through H).
 FULL_SUPERBATCH = 16384
 FULL_SCRATCH_FLOATS = 1 << 30
+# kron / diag: loader batches are likewise concatenated (G sums over examples and A is weighted by
+# M/N, so the factors do not depend on how the examples are batched) up to this many examples and
+# this much layer-factor workspace.
+FACTOR_SUPERBATCH = 4096
+FACTOR_WORKSPACE_FLOATS = 1 << 30
 
 
 def _dist():
@@ -184,10 +189,31 @@ class Laplace:
             Sigma = Sigma.T            # column-major result of potri: symmetric, so the transpose view is free
         return torch.linalg.cholesky(Sigma), Sigma
 
-    def _accumulate_diag(self, batches, diag, hess_factor):
+    def _superbatches(self, batches):
+        """Concatenate loader batches into super-batches bounded by FACTOR_SUPERBATCH examples and
+        FACTOR_WORKSPACE_FLOATS of layer-factor workspace; yields (X, n_examples) on the device."""
         net = net_for(self.model)
+        pend, n_pend, limit = [], 0, None
         for X, _ in batches:
             X = X.to(self.device)
+            if limit is None:
+                net.prepare(X[:1])
+                per = max(1, int(net.plan(64, net.K).total_floats) // 64)
+                limit = max(1, min(FACTOR_SUPERBATCH, FACTOR_WORKSPACE_FLOATS // per))
+            while len(X) > 0:
+                take = min(len(X), limit - n_pend)
+                pend.append(X[:take])
+                n_pend += take
+                X = X[take:]
+                if n_pend >= limit:
+                    yield (torch.cat(pend) if len(pend) > 1 else pend[0]), n_pend
+                    pend, n_pend = [], 0
+        if pend:
+            yield (torch.cat(pend) if len(pend) > 1 else pend[0]), n_pend
+
+    def _accumulate_diag(self, batches, diag, hess_factor):
+        net = net_for(self.model)
+        for X, _ in self._superbatches(batches):
             X2d, pl, ws, f = net.sqrt_factors(X, self.likelihood.code)
             N = X2d.shape[0]
             sc = net.scratch(lib.bnnp_ggn_diag_scratch_floats(net.ops, net.n_ops, C.byref(pl), N, net.K))
@@ -198,9 +224,7 @@ class Laplace:
         net = net_for(self.model)
         index = {id(p): i for i, p in enumerate(net.params)}
         table = None
-        for X, y in batches:
-            M = len(y)
-            X = X.to(self.device)
+        for X, M in self._superbatches(batches):
             X2d, pl, ws, f = net.sqrt_factors(X, self.likelihood.code)
             if table is None:
                 ptrs = []

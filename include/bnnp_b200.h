@@ -74,7 +74,8 @@ typedef struct {
 typedef struct {
   int64_t total_floats;              /* workspace size to allocate, in floats */
   int64_t acat_off, gcat_off;        /* A_cat [N, Dtot] (layer inputs + a ones column per Linear),
-                                        G_cat [N*V, Mtot] (d f_v / d pre-activation of every Linear) */
+                                        G_cat [N*V, Mtot] (d f_v / d pre-activation of every Linear);
+                                        each layer's slice is padded to a multiple of 4 columns (zeros) */
   int32_t Dtot, Mtot;
   int32_t n_linear, first_linear;    /* #Linear ops and index of the first one */
   int64_t P;                         /* total #parameters */

@@ -58,12 +58,12 @@ def test_net_plan_layout():
     plan = _cabi.Plan()
     assert _cabi.lib.bnnp_net_plan(ops, len(ops), 64, 10, C.byref(plan)) == 0
     assert plan.P == P == 59635 and plan.K == 10
-    assert plan.Dtot == 784 + 1 + 75 + 1 and plan.Mtot == 85 and plan.n_linear == 2
+    assert plan.Dtot == 788 + 76 and plan.Mtot == 76 + 12 and plan.n_linear == 2   # slices padded to 4
     # layer 1 writes straight into layer 2's slice of A_cat; tanh is in place; logits are standalone
     assert plan.op[0].act_off == plan.acat_off + plan.op[2].lin_col and plan.op[0].act_ld == plan.Dtot
     assert plan.op[1].act_off == plan.op[0].act_off
     assert plan.op[2].act_ld == 10
-    assert plan.op[0].grad_off == plan.gcat_off and plan.op[2].grad_off == plan.gcat_off + 75
+    assert plan.op[0].grad_off == plan.gcat_off and plan.op[2].grad_off == plan.gcat_off + 76
     assert plan.total_floats >= 64 * plan.Dtot + 640 * plan.Mtot + 640
 
 

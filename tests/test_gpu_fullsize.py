@@ -1,0 +1,64 @@
+"""Size-independent properties at BASELINE.json's full size (config 5: P = 59 635, K = 10), where the
+CPU oracle cannot finish: symmetry, a checksum of checksums (trace of the full GGN == sum of the
+diagonal-GGN path), and linearity (H v against an independent fp64 evaluation of
+sum_n J_n^T Lambda_n (J_n v) from the layer factors)."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg5_full_ggn_properties():
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip('needs ~45 GB of free device memory')
+    from preds_b200 import Laplace, CategoricalLh, MLPS
+    from preds_b200._engine import net_for
+    torch.manual_seed(71)
+    model = MLPS(784, [75], 10, 'tanh', flatten=True).cuda()
+    P = sum(p.numel() for p in model.parameters())
+    assert P == 59635
+    g = torch.Generator().manual_seed(15)
+    N = 6000                                    # > one 4096-example accumulation segment, ragged tail
+    X = torch.randn(N, 1, 28, 28, generator=g)
+    y = torch.randint(10, (N,), generator=g)
+    lh = CategoricalLh()
+    lap = Laplace(model, 0.0, lh)
+    lap.ggn_engine = 2
+    lap.infer([(X[:2500], y[:2500]), (X[2500:], y[2500:])], cov_type='full', factorise=False)
+    H = lap.precision
+    # (1) symmetry (exact after the mirror)
+    idx = torch.randint(0, P, (4096,), device='cuda')
+    jdx = torch.randint(0, P, (4096,), device='cuda')
+    assert torch.equal(H[idx, jdx], H[jdx, idx])
+    # (2) checksum of checksums: trace(full) == sum(diag path); the diag path uses BackPACK's
+    #     unclamped softmax, the full path the clamped one -> agree to ~1e-5
+    lapd = Laplace(model, 0.0, lh)
+    lapd.infer([(X, y)], cov_type='diag', factorise=False)
+    d_full = H.diagonal().double()
+    d_diag = lapd.precision.double()
+    assert float((d_full - d_diag).abs().max() / d_diag.abs().max()) < 1e-4
+    assert abs(float(d_full.sum() / d_diag.sum()) - 1) < 5e-5
+    # (3) linearity: H v vs fp64 sum_n J_n^T Lambda_n J_n v from the factors (independent of the gram kernel)
+    net = net_for(model)
+    X2d, pl, ws, f = net.jacobian_factors(X.cuda())
+    K, M, D = net.K, pl.Mtot, pl.Dtot
+    A = ws[pl.acat_off: pl.acat_off + N * D].reshape(N, D).double()
+    G = ws[pl.gcat_off: pl.gcat_off + N * K * M].reshape(N, K, M).double()
+    Lam = lh._hessian_nkk(f).double()
+    v = torch.randn(P, generator=torch.Generator().manual_seed(5)).cuda().double()
+    W1, b1 = v[:58800].reshape(75, 784), v[58800:58875]
+    W2, b2 = v[58875:59625].reshape(10, 75), v[59625:]
+    c2, u2 = pl.op[2].lin_col, pl.op[2].lin_unit        # layer slices are padded to multiples of 4
+    a1, a2 = A[:, :784], A[:, c2:c2 + 75]
+    g1, g2 = G[:, :, :75], G[:, :, u2:u2 + 10]
+    Jv = torch.einsum('nki,ni->nk', g1, a1 @ W1.T + b1) + torch.einsum('nki,ni->nk', g2, a2 @ W2.T + b2)
+    w = torch.einsum('nkl,nl->nk', Lam, Jv)
+    t1 = torch.einsum('nk,nki->ni', w, g1)
+    t2 = torch.einsum('nk,nki->ni', w, g2)
+    ref = torch.cat([(t1.T @ a1).reshape(-1), t1.sum(0), (t2.T @ a2).reshape(-1), t2.sum(0)])
+    Hv = (H.double() @ v) if False else torch.cat([(H[i:i + 4096].double() @ v) for i in range(0, P, 4096)])
+    assert float((Hv - ref).abs().max() / ref.abs().max()) < 1e-4
+    net.release()
