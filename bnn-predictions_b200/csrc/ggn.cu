@@ -230,6 +230,15 @@ __global__ void diag_scatter_kernel(const float* __restrict__ T, int m, int nin,
 }
 constexpr long long kTcMinMacsG = 1LL << 25;
 
+// U[(n,pos), e] = unfold(in[n])[e, pos]   (row pitch Epad = roundup4(E), zero padded)
+__global__ void im2col_kernel(Im2col u, int64_t N, int L, int E, int Epad, float* __restrict__ U) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * L * Epad) return;
+  const int e = (int)(i % Epad);
+  const int64_t rp = i / Epad;
+  U[i] = e < E ? u.at(rp / L, (int)(rp % L), e) : 0.f;
+}
+
 // conv weight diag: d[co, e] += factor * sum_r ( sum_pos gout[r,co,pos] U[r/V, e, pos] )^2
 // one block per 64x64 output tile, looping over all rows r (the per-sample Jacobian tile is
 // formed in registers, squared and accumulated -- never stored).
@@ -565,13 +574,19 @@ extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, con
                                             int64_t N, int V) {
   (void)plan;
   int64_t part = 0;
-  for (int i = 0; i < n_ops; ++i)
+  for (int i = 0; i < n_ops; ++i) {
     if (ops[i].kind == BNNP_OP_LINEAR) {
       int64_t m = ops[i].out_c, n = ops[i].in_c;
       int64_t a = (int64_t)tcg::pick_ksplit(m, m, N * V, 1) * m * m, b = (int64_t)tcg::pick_ksplit(n, n, N, 1) * n * n;
       part = part > a ? part : a;
       part = part > b ? part : b;
     }
+    if (ops[i].kind == BNNP_OP_CONV2D) {
+      int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
+      int64_t v = N * L * ((E + 3) / 4 * 4) + 64 + (int64_t)tcg::pick_ksplit(E, E, N * L, 1) * E * E;
+      part = part > v ? part : v;
+    }
+  }
   return kfac_conv_floats(ops, n_ops, N, V) + part + 128;
 }
 
@@ -619,8 +634,19 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
                          AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       Im2col u = make_im2col(o, in, ild, 1);
-      rc = gemm_simt(E, E, N * L, 1, UnfoldTA{u, L}, UnfoldNB{u, L},
-                     AccumScaled{Af, E, batch_factor / (float)N}, st);
+      if ((long long)E * E * N * L >= kTcMinMacsG) {
+        // materialise the unfolded input once, then A += (bf/N) U^T U as a tensor-core Gram (split-K)
+        const int Epad = (E + 3) / 4 * 4;
+        float* U = scratch + kfac_conv_floats(ops, n_ops, N, V);
+        float* wsk = U + N * L * (int64_t)Epad + 64;
+        im2col_kernel<<<(unsigned)ceil_div64(N * L * (int64_t)Epad, 256), 256, 0, st>>>(u, N, L, E, Epad, U);
+        BNNP_LAUNCH_CHECK();
+        rc = tcg::gemm_tc_splitk(E, E, N * L, 1, tcg::TcColMajor{U, Epad, 0}, tcg::TcColMajor{U, Epad, 0},
+                                 batch_factor / (float)N, 1.f, Af, E, 0, wsk, tcg::pick_ksplit(E, E, N * L, 1), st);
+      } else {
+        rc = gemm_simt(E, E, N * L, 1, UnfoldTA{u, L}, UnfoldNB{u, L},
+                       AccumScaled{Af, E, batch_factor / (float)N}, st);
+      }
       if (rc) return rc;
     }
   }

@@ -290,6 +290,56 @@ struct StoreBias {
   }
 };
 
+// ---- convolution backward-data on tensor cores ----------------------------------------------------
+//   dU[(r,pos), e] = sum_co gout[r, co, pos] * W[co, e]          (plain GEMM, K = Cout)
+//   gin[r, ci, ih, iw] = sum_{a,b} dU[(r, pos(ih,iw,a,b)), (ci,a,b)]   (col2im as a gather)
+// dU is stored transposed, [r, e, pos], so that both its write and the gather are coalesced.
+struct ConvGoutRowsA {     // A(m = (r,pos), k = co) = gout[r, co, pos]
+  static constexpr bool K_CONTIG = false;
+  using Row = const float*;
+  const float* g; long long gld; int L;
+  __device__ __forceinline__ Row row(int64_t m, int) const { return g + (m / L) * gld + (m % L); }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? __ldg(rw + (k0 + e) * L) : 0.f;
+  }
+};
+struct ConvStoreDUt : tcg::TcNoState {    // dUt[(r*E + e)*L + pos] = acc(m = (r,pos), e)
+  float* d; int E, L;
+  __host__ __device__ ConvStoreDUt(float* d_, int E_, int L_) : d(d_), E(E_), L(L_) {}
+  __device__ __forceinline__ void row(State&, int64_t m, int64_t e0, const float* v, int nvalid, int, int) const {
+    float* q = d + ((m / L) * E + e0) * L + (m % L);
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e < nvalid) q[(long long)e * L] = v[e];
+  }
+};
+__global__ void col2im_gather_kernel(const float* __restrict__ dUt, float* __restrict__ gin, int64_t gild,
+                                     int64_t R, ConvGeom g) {
+  const int64_t per = (int64_t)g.Cin * g.H * g.W;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * per) return;
+  const int64_t r = i / per, e = i % per;
+  const int ci = (int)(e / (g.H * g.W)), ih = (int)((e / g.W) % g.H), iw = (int)(e % g.W);
+  const int L = g.OH * g.OW, kk = g.kh * g.kw;
+  const float* base = dUt + (r * ((int64_t)g.Cin * kk) + (int64_t)ci * kk) * L;
+  float acc = 0.f;
+  for (int a = 0; a < g.kh; ++a) {
+    const int th = ih + g.pt - a;
+    if (th < 0 || th % g.sh) continue;
+    const int oh = th / g.sh;
+    if (oh >= g.OH) continue;
+    for (int b = 0; b < g.kw; ++b) {
+      const int tw = iw + g.pl - b;
+      if (tw < 0 || tw % g.sw) continue;
+      const int ow = tw / g.sw;
+      if (ow >= g.OW) continue;
+      acc += base[(int64_t)(a * g.kw + b) * L + oh * g.OW + ow];
+    }
+  }
+  gin[r * gild + e] = acc;
+}
+
 // tensor-core epilogue of the Linear forward: out = acc + bias
 struct TcStoreBias : tcg::TcNoState {
   float* p; long long ld; const float* bias;
@@ -378,6 +428,20 @@ extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, 
       q.grad_off = take(N * V * osz); q.grad_ld = osz;
     }
     if (o.kind == BNNP_OP_MAXPOOL2D) q.idx_off = take(N * osz);
+  }
+  // scratch of the tensor-core conv backward-data path: the largest [N*V, E, L] over the conv ops that
+  // have to propagate a gradient to their input (every conv but the first parameterised op)
+  P.conv_scratch_off = -1;
+  {
+    int first_param = -1;
+    for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { first_param = i; break; }
+    int64_t need = 0;
+    for (int i = first_param + 1; i < n_ops; ++i)
+      if (ops[i].kind == BNNP_OP_CONV2D) {
+        int64_t v = N * V * (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw * ops[i].out_h * ops[i].out_w;
+        need = need > v ? need : v;
+      }
+    if (need > 0) P.conv_scratch_off = take(need);
   }
   P.total_floats = cur;
   *plan = P;
@@ -505,7 +569,15 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
         break;
       }
       case BNNP_OP_CONV2D:
-        if (R <= 65535) {
+        if (plan->conv_scratch_off >= 0 && (long long)R * o.out_c * o.out_h * o.out_w * o.in_c * o.kh * o.kw >= kTcMinMacs) {
+          const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
+          float* dUt = ws + plan->conv_scratch_off;
+          int rc = tcg::gemm_tc(R * L, E, o.out_c, 1, ConvGoutRowsA{gout, q.grad_ld, L}, tcg::TcColMajor{o.weight, E, 0},
+                                ConvStoreDUt(dUt, E, L), 1, st);
+          if (rc) return rc;
+          col2im_gather_kernel<<<blocks, 256, 0, st>>>(dUt, gin, qp.grad_ld, R, geom_of(o));
+          BNNP_LAUNCH_CHECK();
+        } else if (R <= 65535) {
           int rc = gemm_simt(o.in_c, (int64_t)o.in_h * o.in_w, (int64_t)o.out_c * o.kh * o.kw, (int)R,
                              ConvWtA{o.weight, o.in_c, o.kh * o.kw}, ConvGoutB{gout, q.grad_ld, geom_of(o)},
                              ConvStoreGin{gin, qp.grad_ld, o.in_h * o.in_w}, st);

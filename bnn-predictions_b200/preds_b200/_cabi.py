@@ -37,7 +37,7 @@ class Plan(C.Structure):
     _fields_ = [('total_floats', C.c_int64), ('acat_off', C.c_int64), ('gcat_off', C.c_int64),
                 ('Dtot', C.c_int32), ('Mtot', C.c_int32), ('n_linear', C.c_int32),
                 ('first_linear', C.c_int32), ('P', C.c_int64), ('K', C.c_int32),
-                ('reserved', C.c_int32), ('op', OpPlan * MAX_OPS)]
+                ('reserved', C.c_int32), ('conv_scratch_off', C.c_int64), ('op', OpPlan * MAX_OPS)]
 
 
 if not os.path.exists(LIB_PATH):
