@@ -307,7 +307,7 @@ def run_ours(args):
         }
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # reported at N=1 only (rank 0)
         torch.set_num_threads(os.cpu_count())
         rate, sec = cpu_full_ggn_rate(args.cpu_sample, 1, 1)
         cpu = {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',

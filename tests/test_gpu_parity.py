@@ -240,3 +240,39 @@ def test_glm_fvar_full_engines(arch, engine):
     fmu, fvar = glm_moments(X, model, mu, Sigma, engine=engine)
     assert cases.rel_err(fmu.cpu(), f.cpu()) < 1e-6
     assert cases.rel_err(fvar.cpu(), ref.cpu()) < (1e-5 if engine == 1 else 3e-5)
+
+
+@pytest.mark.parametrize('arch', [
+    dict(din=7, hid=[5], K=3, N=33, bias=True, act='tanh'),            # everything smaller than one tile
+    dict(din=130, hid=[17], K=4, N=200, bias=True, act='relu'),        # row-tile tails, relu masks
+    dict(din=64, hid=[40, 24], K=5, N=700, bias=True, act='tanh'),     # cross-layer blocks, N % 64 != 0
+    dict(din=300, hid=[9], K=2, N=97, bias=False, act='tanh'),         # no bias rows / columns, 2 column tiles
+    dict(din=33, hid=[20, 11, 6], K=1, N=150, bias=True, act='tanh'),  # K = 1 (regression-shaped Lambda), 4 layers
+    dict(din=20, hid=[16], K=3, N=9000, bias=True, act='tanh'),        # three 4096-example accumulation segments
+])
+def test_full_ggn_tensor_core_shape_sweep(arch):
+    """gram_tc (engine 2) vs fp64 sum_n J^T Lambda J from materialised Jacobians, and vs the SIMT engine."""
+    from preds_b200 import MLPS, CategoricalLh, GaussianLh, Laplace, Jacobians
+    torch.manual_seed(11)
+    model = MLPS(arch['din'], arch['hid'], arch['K'], arch['act'], bias=arch['bias']).cuda()
+    P = sum(p.numel() for p in model.parameters())
+    N, K = arch['N'], arch['K']
+    g = torch.Generator().manual_seed(12)
+    X = torch.randn(N, arch['din'], generator=g).cuda()
+    lh = GaussianLh(0.8) if K == 1 else CategoricalLh()
+    y = torch.randn(N, 1, generator=g).cuda() if K == 1 else torch.randint(K, (N,), generator=g).cuda()
+    H64 = torch.zeros(P, P, dtype=torch.float64, device='cuda')
+    for s in range(0, N, 1024):
+        Js, f = Jacobians(model, X[s:s + 1024])
+        Jd = (Js if Js.dim() == 3 else Js.unsqueeze(2)).double()
+        H64 += torch.einsum('mpk,mkl,mql->pq', Jd, lh.Hessian(f).double().reshape(len(f), K, K), Jd)
+    errs = {}
+    for eng in (1, 2):
+        lap = Laplace(model, 0.0, lh)
+        lap.ggn_engine = eng
+        lap.infer([(X[:N // 3], y[:N // 3]), (X[N // 3:], y[N // 3:])], cov_type='full', factorise=False)
+        H = lap.precision.double()
+        assert torch.equal(lap.precision, lap.precision.T)
+        errs[eng] = float((H - H64).abs().max() / H64.abs().max())
+    assert errs[1] < 1e-5, errs
+    assert errs[2] < 3e-5, errs
