@@ -12,6 +12,7 @@
 // by a~_n[j(p)] and reduces over the columns of a unit (adding the unit's bias column, a rank-one term,
 // from the fp32 Sigma on the way).  P^2 MACs per input instead of the reference's K*P^2.
 #include <stdlib.h>
+#include <vector>
 #include "tc_common.cuh"
 
 namespace bnnp {
@@ -36,6 +37,7 @@ struct Args {
   int wn, n_mt, n_nt, n_chunks;
   long long ald; int Mtot;
   const float* Sigma; const float* A; const int32_t* pu; const int32_t* pc; float* T;
+  const long long* tile_start;       // [n_units + 1] prefix of tiles per unit of this launch (lower triangle only)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -63,13 +65,20 @@ glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long n_tiles = (long long)args.n_units * args.n_nt * args.n_mt;
+  // T[n,u,u'] is symmetric: for unit u' only the parameter rows from the unit's own first weight onward are
+  // needed (units u >= u' of the layer, its later biases, all later layers); tile_start[] is the prefix of the
+  // per-unit tile counts.  Entries above the diagonal receive partial sums and are never read.
+  const long long n_tiles = args.tile_start[args.n_units];
   uint32_t stage = 0, phase = 0, iter = 0;
+  int ui = 0;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+    while (args.tile_start[ui + 1] <= tile) ++ui;                 // tiles are visited in increasing order
+    const int up = args.unit_first + args.unit_step * ui;
+    const int nt0 = (int)((args.offw + (long long)up * args.nin) / args.wn);
+    const long long local = tile - args.tile_start[ui];
     // input tile fastest: concurrently running CTAs stream the same Sigma tile (shared through L2)
-    const int mt = (int)(tile % args.n_mt);
-    const int nt = (int)((tile / args.n_mt) % args.n_nt);
-    const int up = args.unit_first + args.unit_step * (int)(tile / ((long long)args.n_mt * args.n_nt));
+    const int mt = (int)(local % args.n_mt);
+    const int nt = nt0 + (int)(local / args.n_mt);
     const long long m0 = (long long)mt * TILE_M, n0 = (long long)nt * args.wn;
     const uint32_t buf = iter & 1, buf_phase = (iter >> 1) & 1;
 
@@ -237,14 +246,14 @@ extern "C" int bnnp_split_bf16(const float* src, int64_t lds, int64_t rows, int6
   return BNNP_OK;
 }
 
-// scratch layout (floats): [maps 2*Ppad ints][T N*M*M][per-layer activation splits]
+// scratch layout (floats): [maps 2*Ppad ints][T N*M*M][tile prefix tables][per-layer activation splits]
 extern "C" int64_t bnnp_glm_fvar_full_tma_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                                          int64_t N) {
   const int64_t Ppad = (plan->P + 31) / 32 * 32;
   int64_t act = 0;
   for (int i = 0; i < n_ops; ++i)
     if (ops[i].kind == BNNP_OP_LINEAR) act += 8 * (N * up32(ops[i].in_c + 8) + 64);   // <= 8 shifted copies, hi + lo bf16
-  return 2 * Ppad + N * (int64_t)plan->Mtot * plan->Mtot + act + 1024;
+  return 2 * Ppad + N * (int64_t)plan->Mtot * plan->Mtot + act + 2 * (int64_t)(plan->Mtot + 64) * 8 + 4096;
 }
 
 __global__ void glmtc_param_maps_kernel(int32_t* __restrict__ pu, int32_t* __restrict__ pc, int64_t off, int m,
@@ -259,7 +268,7 @@ __global__ void glmtc_zero_kernel(float* p, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.f;
 }
-// f_var[n,k,l] = sum_{u,u'} G[(n,k),u] T[n,u,u'] G[(n,l),u']
+// f_var[n,k,l] = sum_{u,u'} G[(n,k),u] Tsym[n,u,u'] G[(n,l),u'],  Tsym read from the lower triangle (u >= u')
 __global__ void glmtc_fvar_from_units_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ T,
                                              int K, int M, float* __restrict__ fvar) {
   extern __shared__ float shm[];
@@ -268,7 +277,7 @@ __global__ void glmtc_fvar_from_units_kernel(const float* __restrict__ G, int64_
   for (int i = threadIdx.x; i < K * M; i += blockDim.x) {
     const int k = i / M, up = i % M;
     float acc = 0.f;
-    for (int u = 0; u < M; ++u) acc = fmaf(G[(n * K + k) * gld + u], Tn[u * M + up], acc);
+    for (int u = 0; u < M; ++u) acc = fmaf(G[(n * K + k) * gld + u], u >= up ? Tn[u * M + up] : Tn[up * M + u], acc);
     shm[i] = acc;
   }
   __syncthreads();
@@ -295,7 +304,9 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
   int32_t* pu = reinterpret_cast<int32_t*>(base);
   int32_t* pc = pu + Ppad;
   float* T = base + 2 * Ppad;
-  float* act = T + ((N * (int64_t)M * M + 63) / 64) * 64;
+  long long* prefix_dev = reinterpret_cast<long long*>(T + ((N * (int64_t)M * M + 63) / 64) * 64);
+  float* act = reinterpret_cast<float*>(prefix_dev + (M + 64) * 8);
+  long long prefix_used = 0;
   const float* A = ws + plan->acat_off;
   for (int i = 0; i < n_ops; ++i) {
     const bnnp_op_t& o = ops[i];
@@ -359,7 +370,19 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
       a.nin = o.in_c; a.has_bias = o.has_bias;
       a.offw = o.theta_off_w; a.offb = o.has_bias ? o.theta_off_b : 0; a.unit0p = q.lin_unit;
       a.n_chunks = (o.in_c + delta + BK - 1) / BK;
-      const long long n_tiles = (long long)a.n_units * a.n_nt * a.n_mt;
+      // per-unit tile counts (lower triangle): n-tiles from the one holding the unit's first weight row
+      std::vector<long long> prefix(a.n_units + 1, 0);
+      for (int ui = 0; ui < a.n_units; ++ui) {
+        const long long up = grp + (long long)period * ui;
+        const long long nt0 = (o.theta_off_w + up * o.in_c) / a.wn;
+        prefix[ui + 1] = prefix[ui] + (a.n_nt - nt0) * a.n_mt;
+      }
+      if (prefix_used + a.n_units + 1 > (long long)(M + 64) * 8) return BNNP_ERR_UNSUPPORTED;
+      BNNP_CUDA_CHECK(cudaMemcpyAsync(prefix_dev + prefix_used, prefix.data(), sizeof(long long) * (a.n_units + 1),
+                                      cudaMemcpyHostToDevice, st));
+      a.tile_start = prefix_dev + prefix_used;
+      prefix_used += a.n_units + 1;
+      const long long n_tiles = prefix[a.n_units];
       const int grid = (int)(n_tiles < sms ? n_tiles : sms);
       glm_fvar_tma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, msh, msl, a);
       BNNP_LAUNCH_CHECK();
