@@ -1,0 +1,160 @@
+"""Edge cases of the drop-in API on the GPU, each checked against the CPU oracle on the same inputs:
+single-example and ragged loader batches, vector / matrix priors, unknown cov_type, n_samples = 1,
+host-resident inputs, shifted posterior mean (mu != theta*), Sigmoid / AvgPool / stride-2 layers."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import port
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _pair(din=5, hid=(7,), K=3, act='tanh', bias=True, seed=71):
+    from preds_b200 import MLPS
+    torch.manual_seed(seed)
+    model = MLPS(din, list(hid), K, act, bias=bias)
+    omodel = port.make_mlps(din, list(hid), K, act, bias=bias)
+    port.set_theta(omodel, port.get_theta(model))
+    return model.cuda(), omodel
+
+
+def _data(N, din, K, seed=15):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(N, din, generator=g), torch.randint(K, (N,), generator=g)
+
+
+@pytest.mark.parametrize('cov', ['full', 'kron', 'diag'])
+def test_ragged_and_single_example_batches(cov):
+    from preds_b200 import Laplace, CategoricalLh
+    model, omodel = _pair()
+    X, y = _data(23, 5, 3)
+    batches = [(X[:1], y[:1]), (X[1:9], y[1:9]), (X[9:22], y[9:22]), (X[22:], y[22:])]   # sizes 1, 8, 13, 1
+    post = port.infer(omodel, 0.5, port.CategoricalLh(), batches, cov)
+    lap = Laplace(model, 0.5, CategoricalLh())
+    lap.infer(batches, cov_type=cov)
+    Xte, _ = _data(1, 5, 3, seed=16)                                                       # a single test input
+    eps = torch.randn(1, 1, 3, generator=torch.Generator().manual_seed(1))                # a single sample
+    ref = port.glm_predictive(omodel, port.CategoricalLh(), Xte, post, eps)
+    out = lap.predictive_samples_glm(Xte, n_samples=1, eps=eps)
+    assert tuple(out.shape) == (1, 1, 3)
+    assert cases.rel_err(out.cpu(), ref) < TOL
+
+
+def test_vector_and_matrix_priors_full():
+    from preds_b200 import Laplace, CategoricalLh
+    model, omodel = _pair()
+    X, y = _data(30, 5, 3)
+    P = port.n_params(omodel)
+    g = torch.Generator().manual_seed(3)
+    vec = torch.rand(P, generator=g) + 0.5
+    A = torch.randn(P, P, generator=g) * 0.05
+    mat = A @ A.T + torch.diag(vec)
+    for prior in (vec, mat):
+        post = port.infer(omodel, prior, port.CategoricalLh(), [(X, y)], 'full')
+        keep = prior.clone()
+        lap = Laplace(model, prior.cuda(), CategoricalLh())
+        lap.infer([(X, y)], cov_type='full')
+        assert cases.rel_err(lap.precision.cpu(), post['precision']) < TOL
+        assert torch.equal(prior, keep)                          # the caller's prior is never mutated
+    post = port.infer(omodel, vec, port.CategoricalLh(), [(X, y)], 'diag')
+    lap = Laplace(model, vec.cuda(), CategoricalLh())
+    lap.infer([(X, y)], cov_type='diag')
+    assert cases.rel_err(lap.Sigma_chol.cpu(), post['Sigma_chol']) < 1e-5
+    lap = Laplace(model, mat.cuda(), CategoricalLh())
+    with pytest.raises(ValueError, match='Will not diagonalize'):
+        lap.infer([(X, y)], cov_type='diag')
+    with pytest.raises(AssertionError):                         # kron needs a scalar prior (preds/laplace.py:66)
+        Laplace(model, vec.cuda(), CategoricalLh()).infer([(X, y)], cov_type='kron')
+
+
+def test_unknown_cov_type_and_guards():
+    """An unknown cov_type silently does nothing but marks the object inferred (preds/laplace.py:37-82)."""
+    from preds_b200 import Laplace, CategoricalLh, BernoulliLh
+    model, _ = _pair()
+    X, y = _data(8, 5, 3)
+    lap = Laplace(model, 1.0, CategoricalLh())
+    with pytest.raises(ValueError, match='Need to infer first'):
+        lap.predictive_samples_bnn(X)
+    lap.infer([(X, y)], cov_type='lowrank')
+    assert lap.inferred and lap.Sigma_chol is None
+    with pytest.raises(ValueError):                             # Bernoulli has no nn_loss -> full only (:74-75)
+        Laplace(model, 1.0, BernoulliLh()).infer([(X, y)], cov_type='diag')
+
+
+def test_host_inputs_and_dataloader():
+    """Inputs may live on the host (the reference moves them, preds/laplace.py:40) and the loader may be
+    a DataLoader (N from len(loader.dataset), :68)."""
+    from preds_b200 import Laplace, CategoricalLh
+    from torch.utils.data import DataLoader, TensorDataset
+    model, omodel = _pair()
+    X, y = _data(50, 5, 3)
+    loader = DataLoader(TensorDataset(X, y), batch_size=16, shuffle=False)
+    post = port.infer(omodel, 1.0, port.CategoricalLh(), list(loader), 'kron')
+    lap = Laplace(model, 1.0, CategoricalLh())
+    lap.infer(loader, cov_type='kron')
+    for qa, qb in zip(lap.Sigma_chol.qhs, post['kron'].qhs):
+        for a, b in zip(qa, qb):
+            assert cases.rel_err(a.cpu(), b) < 1e-5
+    Xte, _ = _data(4, 5, 3, seed=16)
+    out_host = lap.predictive_samples_glm(Xte, n_samples=3, seed=7)
+    out_dev = lap.predictive_samples_glm(Xte.cuda(), n_samples=3, seed=7)
+    assert torch.equal(out_host, out_dev)                       # same Philox stream, same inputs
+
+
+def test_shifted_posterior_mean():
+    """f_mu = f + J (mu - theta*) when the posterior mean was moved (preds/predictives.py:58)."""
+    from preds_b200 import Laplace, CategoricalLh
+    from preds_b200.predictives import glm_moments
+    model, omodel = _pair()
+    X, y = _data(30, 5, 3)
+    post = port.infer(omodel, 1.0, port.CategoricalLh(), [(X, y)], 'full')
+    lap = Laplace(model, 1.0, CategoricalLh())
+    lap.infer([(X, y)], cov_type='full')
+    shift = 0.05 * torch.randn(lap.P, generator=torch.Generator().manual_seed(2))
+    post['mu'] = post['mu'] + shift
+    lap.mu = lap.mu + shift.cuda()
+    Xte, _ = _data(6, 5, 3, seed=16)
+    fmu_o, fvar_o = port.glm_moments(omodel, Xte, post)
+    fmu, fvar = glm_moments(Xte, model, lap.mu, lap.Sigma)
+    assert cases.rel_err(fmu.cpu(), fmu_o) < 1e-5
+    assert cases.rel_err(fvar.cpu(), fvar_o) < TOL
+
+
+def test_other_layer_types():
+    """Sigmoid, AvgPool2d, a stride-2 'same' convolution and ReLU without bias: Jacobians vs autograd."""
+    from preds_b200 import Jacobians
+    from preds_b200.models import tfconv2d
+    torch.manual_seed(5)
+    net = nn.Sequential()
+    net.add_module('conv1', tfconv2d(2, 4, 3, stride=(2, 2), tf_padding_type='same', bias=False))
+    net.add_module('act1', nn.Sigmoid())
+    net.add_module('avg', nn.AvgPool2d(kernel_size=(2, 2)))
+    net.add_module('flatten', nn.Flatten())
+    net.add_module('dense1', nn.Linear(4 * 2 * 2, 6, bias=False))
+    net.add_module('relu', nn.ReLU())
+    net.add_module('dense2', nn.Linear(6, 2))
+    net.output_size = 2
+    X = torch.randn(5, 2, 7, 7)
+    out = net(X)
+    P = sum(p.numel() for p in net.parameters())
+    naive = torch.empty(5, P, 2)
+    for i in range(5):
+        for k in range(2):
+            g = torch.autograd.grad(out[i, k], list(net.parameters()), retain_graph=True)
+            naive[i, :, k] = torch.cat([t.reshape(-1) for t in g])
+    Js, f = Jacobians(net.cuda(), X)
+    assert torch.allclose(f.cpu(), out.detach(), atol=1e-5)
+    assert float((Js.cpu() - naive).abs().max()) < 1e-5
+
+
+def test_unsupported_layers_fail_loudly():
+    from preds_b200 import Jacobians
+    from preds_b200._cabi import BnnpError
+    net = nn.Sequential(nn.Linear(4, 4), nn.GELU(), nn.Linear(4, 2)).cuda()
+    net.output_size = 2
+    with pytest.raises(BnnpError, match='outside the supported zoo'):
+        Jacobians(net, torch.randn(3, 4))
