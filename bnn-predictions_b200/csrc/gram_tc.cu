@@ -121,7 +121,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
       // ===================== MMA issuer =====================
       if (lane == 0) {
         uint32_t s = stage, ph = phase;
-        const uint32_t idesc = umma_idesc_bf16(args.wc);
+        // the ragged last column tile issues a narrower MMA (the TMA box keeps its full height; rows past the
+        // layer's fan-in arrive as zeros and are simply not multiplied)
+        const int wvalid = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
+        const uint32_t idesc = umma_idesc_bf16((wvalid + 15) / 16 * 16);
         for (int c = 0; c < args.n_chunks; ++c) {
           mbar_wait(&full_a[s], ph);
           mbar_wait(&full_b[s], ph);
@@ -261,14 +264,14 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
           for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
           __syncwarp();
           const bool colok = c0 + lane < ncols;
-          for (int r0 = 0; r0 < nrows; r0 += 16) {
-            float h[16];
+          {
+            float h[32];                       // all 32 rows of this warp in flight before the first add
 #pragma unroll
-            for (int u = 0; u < 16; ++u)
-              h[u] = (colok && r0 + u < nrows) ? hbase[(long long)(r0 + u) * args.P + c0 + lane] : 0.f;
+            for (int u = 0; u < 32; ++u)
+              h[u] = (colok && u < nrows) ? hbase[(long long)u * args.P + c0 + lane] : 0.f;
 #pragma unroll
-            for (int u = 0; u < 16; ++u)
-              if (colok && r0 + u < nrows) hbase[(long long)(r0 + u) * args.P + c0 + lane] = h[u] + sc[(r0 + u) * 33 + lane];
+            for (int u = 0; u < 32; ++u)
+              if (colok && u < nrows) hbase[(long long)u * args.P + c0 + lane] = h[u] + sc[u * 33 + lane];
           }
         }
       }
@@ -448,7 +451,7 @@ static void gram_flops(const tc::BlockArgs& a, double* executed, double* useful)
         }
         long long vr = rows_total - row0 < tc::TILE_M ? rows_total - row0 : tc::TILE_M;
         long long vc = a.np - jc0 < a.wc ? a.np - jc0 : a.wc;
-        ex += 3.0 * 2.0 * tc::TILE_M * a.wc * (double)a.n_chunks * tc::BK * nacc;
+        ex += 3.0 * 2.0 * tc::TILE_M * ((vc + 15) / 16 * 16) * (double)a.n_chunks * tc::BK * nacc;
         us += 3.0 * 2.0 * vr * vc * (double)a.n_chunks * tc::BK * nacc;
       }
   *executed = ex; *useful = us;
@@ -528,8 +531,21 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
       a.m = R.out_c; a.n = R.in_c; a.has_bias = R.has_bias;
       a.unit0 = plan->op[i].lin_unit; a.col0 = plan->op[i].lin_col; a.row_theta0 = R.theta_off_w;
       a.mp = Cc.out_c; a.np = Cc.in_c; a.unit0p = plan->op[j].lin_unit; a.col_theta0 = Cc.theta_off_w;
-      int n_jt = (a.np + MAX_WC - 1) / MAX_WC;
-      a.wc = (((a.np + n_jt - 1) / n_jt) + 15) / 16 * 16;
+      // column tile width: widest box (<= 256, multiple of 16) whose tiling of np wastes the least MMA work
+      // when the last tile issues a narrower instruction (e.g. 784 = 3 x 224 + 112 instead of 4 x 208)
+      {
+        int best_w = 16; long long best_cost = -1;
+        for (int w = 256; w >= 64; w -= 16) {
+          const int nj = (a.np + w - 1) / w;
+          const int last = a.np - (nj - 1) * w;
+          const int last16 = (last + 15) / 16 * 16;
+          // executed MMA columns (a very narrow last tile is smem-bound: count it as >= 64) + ~64 columns worth of
+          // per-tile generator / epilogue work
+          const long long cost = (long long)(nj - 1) * w + (last16 < 64 ? 64 : last16) + 64LL * nj;
+          if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
+        }
+        a.wc = a.np < 64 ? (a.np + 15) / 16 * 16 : best_w;
+      }
       a.n_jt = (a.np + a.wc - 1) / a.wc;
       a.n_pairs = (a.mp + 1) / 2;
       const int rows_total = a.m * a.n + (a.has_bias ? a.m : 0);

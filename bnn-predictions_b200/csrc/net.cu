@@ -340,6 +340,34 @@ __global__ void col2im_gather_kernel(const float* __restrict__ dUt, float* __res
   gin[r * gild + e] = acc;
 }
 
+// ---- convolution forward on tensor cores: out[(n,pos), co] = sum_e U[(n,pos), e] W[co, e] + bias ----
+__global__ void im2col_fwd_kernel(const float* __restrict__ in, int64_t ild, int64_t N, ConvGeom g, int E, int Epad,
+                                  float* __restrict__ U) {
+  const int L = g.OH * g.OW;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * L * Epad) return;
+  const int e = (int)(i % Epad);
+  const int64_t rp = i / Epad;
+  float v = 0.f;
+  if (e < E) {
+    const int b = e % g.kw, a = (e / g.kw) % g.kh, ci = e / (g.kw * g.kh);
+    const int pos = (int)(rp % L), oh = pos / g.OW, ow = pos % g.OW;
+    const int ih = oh * g.sh - g.pt + a, iw = ow * g.sw - g.pl + b;
+    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = in[(rp / L) * ild + ((int64_t)ci * g.H + ih) * g.W + iw];
+  }
+  U[i] = v;
+}
+struct ConvStoreOutT : tcg::TcNoState {   // out[n*old + co*L + pos] = acc(m = (n,pos), co) + bias[co]
+  float* out; long long old; const float* bias; int L;
+  __host__ __device__ ConvStoreOutT(float* o_, long long old_, const float* b_, int L_) : out(o_), old(old_), bias(b_), L(L_) {}
+  __device__ __forceinline__ void row(State&, int64_t m, int64_t c0, const float* v, int nvalid, int, int) const {
+    float* q = out + (m / L) * old + c0 * L + (m % L);
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e < nvalid) q[(long long)e * L] = v[e] + (bias ? __ldg(bias + c0 + e) : 0.f);
+  }
+};
+
 // tensor-core epilogue of the Linear forward: out = acc + bias
 struct TcStoreBias : tcg::TcNoState {
   float* p; long long ld; const float* bias;
@@ -429,16 +457,18 @@ extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, 
     }
     if (o.kind == BNNP_OP_MAXPOOL2D) q.idx_off = take(N * osz);
   }
-  // scratch of the tensor-core conv backward-data path: the largest [N*V, E, L] over the conv ops that
-  // have to propagate a gradient to their input (every conv but the first parameterised op)
+  // scratch of the tensor-core conv paths: the unfolded input of the forward GEMM and the [N*V, E, L] buffer
+  // of the backward-data GEMM (every conv but the first parameterised op propagates a gradient)
   P.conv_scratch_off = -1;
   {
     int first_param = -1;
     for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { first_param = i; break; }
     int64_t need = 0;
-    for (int i = first_param + 1; i < n_ops; ++i)
+    for (int i = 0; i < n_ops; ++i)
       if (ops[i].kind == BNNP_OP_CONV2D) {
-        int64_t v = N * V * (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw * ops[i].out_h * ops[i].out_w;
+        const int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
+        int64_t v = N * L * ((E + 3) / 4 * 4);                    // forward: unfolded input [N*L, Epad]
+        if (i > first_param && N * V * E * L > v) v = N * V * E * L;  // backward-data: dU^T [N*V, E, L]
         need = need > v ? need : v;
       }
     if (need > 0) P.conv_scratch_off = take(need);
@@ -488,7 +518,16 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
       }
       case BNNP_OP_CONV2D: {
         const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
-        if (N <= 65535) {
+        if (plan->conv_scratch_off >= 0 && (long long)N * L * E * o.out_c >= kTcMinMacs) {
+          const int Epad = (E + 3) / 4 * 4;
+          float* U = ws + plan->conv_scratch_off;
+          im2col_fwd_kernel<<<(unsigned)ceil_div64(N * L * (int64_t)Epad, 256), 256, 0, st>>>(in, ild, N, geom_of(o), E,
+                                                                                            Epad, U);
+          BNNP_LAUNCH_CHECK();
+          int rc = tcg::gemm_tc(N * L, o.out_c, E, 1, tcg::TcRowMajor{U, Epad, 0}, tcg::TcRowMajor{o.weight, E, 0},
+                                ConvStoreOutT(out, q.act_ld, o.has_bias ? o.bias : nullptr, L), 1, st);
+          if (rc) return rc;
+        } else if (N <= 65535) {
           int rc = gemm_simt(o.out_c, L, E, (int)N, ConvWA{o.weight, E}, ConvIm2colB{in, ild, geom_of(o)},
                              ConvStoreOut{out, q.act_ld, o.has_bias ? o.bias : nullptr, L}, st);
           if (rc) return rc;

@@ -81,7 +81,8 @@ typedef struct {
   int64_t P;                         /* total #parameters */
   int32_t K;                         /* network outputs */
   int32_t reserved;
-  int64_t conv_scratch_off;          /* [N*V, E, L] buffer of the conv backward-data GEMM (or -1) */
+  int64_t conv_scratch_off;          /* scratch of the tensor-core conv GEMMs: unfolded input [N*L, E] /
+                                        backward-data [N*V, E, L] (or -1 without conv layers) */
   bnnp_op_plan_t op[BNNP_MAX_OPS];
 } bnnp_plan_t;
 
