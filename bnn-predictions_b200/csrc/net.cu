@@ -28,17 +28,19 @@ __global__ void act_fwd_kernel(float* __restrict__ x, int64_t rows, int64_t cols
   *p = v;
 }
 
-// g[(n,v), c] *= act'(out[n, c])
+// g[(n,v), c] *= act'(out[n, c])      grid: (ceil(cols/256), rows) -- no per-element index division
 __global__ void act_bwd_kernel(float* __restrict__ g, int64_t gld, const float* __restrict__ out,
-                               int64_t old, int64_t N, int V, int64_t cols, int kind) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * V * cols) return;
-  int64_t c = i % cols, r = i / cols, n = r / V;
-  float o = out[n * old + c], d;
-  if (kind == BNNP_OP_RELU) d = o > 0.f ? 1.f : 0.f;
-  else if (kind == BNNP_OP_TANH) d = 1.f - o * o;
-  else d = o * (1.f - o);
-  g[r * gld + c] *= d;
+                               int64_t old, int64_t R, int V, int64_t cols, int kind) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  for (int64_t r = blockIdx.y; r < R; r += gridDim.y) {
+    const float o = out[(r / V) * old + c];
+    float d;
+    if (kind == BNNP_OP_RELU) d = o > 0.f ? 1.f : 0.f;
+    else if (kind == BNNP_OP_TANH) d = 1.f - o * o;
+    else d = o * (1.f - o);
+    g[r * gld + c] *= d;
+  }
 }
 
 __global__ void copy2d_kernel(float* __restrict__ dst, int64_t dld, const float* __restrict__ src,
@@ -210,33 +212,41 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
   idx[n * per + r] = bi;
 }
 
+// grid: (ceil(H*W/256), C, rows): one 32-bit division per thread
 __global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
                                    float* __restrict__ gin, int64_t gild,
-                                   const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g) {
-  int64_t per = (int64_t)g.Cin * g.H * g.W;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * V * per) return;
-  int64_t r = i / per, e = i % per, n = r / V;
-  int c = (int)(e / (g.H * g.W)), ih = (int)((e / g.W) % g.H), iw = (int)(e % g.W);
-  int me = ih * g.W + iw;
-  int64_t operp = (int64_t)g.Cout * g.OH * g.OW;
-  const int32_t* id = idx + n * operp + (int64_t)c * g.OH * g.OW;
-  const float* go = gout + r * gold + (int64_t)c * g.OH * g.OW;
-  float acc = 0.f;
-  for (int a = 0; a < g.kh; ++a) {
-    int th = ih + g.pt - a;
+                                   const int32_t* __restrict__ idx, int64_t R, int V, ConvGeom g) {
+  const int me = blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = g.H * g.W;
+  if (me >= HW) return;
+  const int c = blockIdx.y;
+  const int ih = me / g.W, iw = me - ih * g.W;
+  const int OL = g.OH * g.OW;
+  const int64_t operp = (int64_t)g.Cout * OL;
+  // the (at most kh*kw) pooling windows that contain this input position
+  int cand[9];
+  int ncand = 0;
+  for (int a = 0; a < g.kh && ncand < 9; ++a) {
+    const int th = ih + g.pt - a;
     if (th < 0 || th % g.sh) continue;
-    int oh = th / g.sh;
+    const int oh = th / g.sh;
     if (oh >= g.OH) continue;
-    for (int b = 0; b < g.kw; ++b) {
-      int tw = iw + g.pl - b;
+    for (int b = 0; b < g.kw && ncand < 9; ++b) {
+      const int tw = iw + g.pl - b;
       if (tw < 0 || tw % g.sw) continue;
-      int ow = tw / g.sw;
+      const int ow = tw / g.sw;
       if (ow >= g.OW) continue;
-      if (id[oh * g.OW + ow] == me) acc += go[oh * g.OW + ow];
+      cand[ncand++] = oh * g.OW + ow;
     }
   }
-  gin[r * gild + e] = acc;
+  for (int64_t r = blockIdx.z; r < R; r += gridDim.z) {
+    const int32_t* id = idx + (r / V) * operp + (int64_t)c * OL;
+    const float* go = gout + r * gold + (int64_t)c * OL;
+    float acc = 0.f;
+    for (int t = 0; t < ncand; ++t)
+      if (id[cand[t]] == me) acc += go[cand[t]];
+    gin[r * gild + (int64_t)c * HW + me] = acc;
+  }
 }
 
 __global__ void avgpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
@@ -316,14 +326,14 @@ struct ConvStoreDUt : tcg::TcNoState {    // dUt[(r*E + e)*L + pos] = acc(m = (r
 };
 __global__ void col2im_gather_kernel(const float* __restrict__ dUt, float* __restrict__ gin, int64_t gild,
                                      int64_t R, ConvGeom g) {
-  const int64_t per = (int64_t)g.Cin * g.H * g.W;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * per) return;
-  const int64_t r = i / per, e = i % per;
-  const int ci = (int)(e / (g.H * g.W)), ih = (int)((e / g.W) % g.H), iw = (int)(e % g.W);
+  const int me = blockIdx.x * blockDim.x + threadIdx.x;      // grid: (ceil(H*W/256), Cin, rows)
+  const int HW = g.H * g.W;
+  if (me >= HW) return;
+  const int ci = blockIdx.y;
+  const int ih = me / g.W, iw = me - ih * g.W;
   const int L = g.OH * g.OW, kk = g.kh * g.kw;
-  const float* base = dUt + (r * ((int64_t)g.Cin * kk) + (int64_t)ci * kk) * L;
-  float acc = 0.f;
+  int off[25];
+  int noff = 0;
   for (int a = 0; a < g.kh; ++a) {
     const int th = ih + g.pt - a;
     if (th < 0 || th % g.sh) continue;
@@ -333,11 +343,16 @@ __global__ void col2im_gather_kernel(const float* __restrict__ dUt, float* __res
       const int tw = iw + g.pl - b;
       if (tw < 0 || tw % g.sw) continue;
       const int ow = tw / g.sw;
-      if (ow >= g.OW) continue;
-      acc += base[(int64_t)(a * g.kw + b) * L + oh * g.OW + ow];
+      if (ow >= g.OW || noff >= 25) continue;
+      off[noff++] = (a * g.kw + b) * L + oh * g.OW + ow;
     }
   }
-  gin[r * gild + e] = acc;
+  for (int64_t r = blockIdx.z; r < R; r += gridDim.z) {
+    const float* base = dUt + (r * ((int64_t)g.Cin * kk) + (int64_t)ci * kk) * L;
+    float acc = 0.f;
+    for (int t = 0; t < noff; ++t) acc += base[off[t]];
+    gin[r * gild + (int64_t)ci * HW + me] = acc;
+  }
 }
 
 // ---- convolution forward on tensor cores: out[(n,pos), co] = sum_e U[(n,pos), e] W[co, e] + bias ----
@@ -614,7 +629,15 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
           int rc = tcg::gemm_tc(R * L, E, o.out_c, 1, ConvGoutRowsA{gout, q.grad_ld, L}, tcg::TcColMajor{o.weight, E, 0},
                                 ConvStoreDUt(dUt, E, L), 1, st);
           if (rc) return rc;
-          col2im_gather_kernel<<<blocks, 256, 0, st>>>(dUt, gin, qp.grad_ld, R, geom_of(o));
+          if (o.kh * o.kw > 25) return BNNP_ERR_UNSUPPORTED;
+          {
+            // few z-blocks: the tap offsets depend on (channel, position) only and are reused across rows
+            const int64_t bxy = ceil_div64((int64_t)o.in_h * o.in_w, 256) * o.in_c;
+            int64_t gz = ceil_div64(4096, bxy);
+            gz = gz < 1 ? 1 : (gz > R ? R : gz);
+            col2im_gather_kernel<<<dim3((unsigned)ceil_div64((int64_t)o.in_h * o.in_w, 256), (unsigned)o.in_c, (unsigned)gz),
+                                   256, 0, st>>>(dUt, gin, qp.grad_ld, R, geom_of(o));
+          }
           BNNP_LAUNCH_CHECK();
         } else if (R <= 65535) {
           int rc = gemm_simt(o.in_c, (int64_t)o.in_h * o.in_w, (int64_t)o.out_c * o.kh * o.kw, (int)R,
@@ -627,8 +650,16 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
         }
         break;
       case BNNP_OP_MAXPOOL2D:
-        maxpool_bwd_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld,
-                                                   reinterpret_cast<const int32_t*>(ws) + q.idx_off, N, V, geom_of(o));
+        if (o.kh * o.kw > 9) return BNNP_ERR_UNSUPPORTED;
+        {
+          // few z-blocks: the candidate windows depend on (channel, position) only and are reused across rows
+          const int64_t bxy = ceil_div64((int64_t)o.in_h * o.in_w, 256) * o.in_c;
+          int64_t gz = ceil_div64(4096, bxy);
+          gz = gz < 1 ? 1 : (gz > R ? R : gz);
+          maxpool_bwd_kernel<<<dim3((unsigned)ceil_div64((int64_t)o.in_h * o.in_w, 256), (unsigned)o.in_c, (unsigned)gz),
+                               256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld,
+                                             reinterpret_cast<const int32_t*>(ws) + q.idx_off, R, V, geom_of(o));
+        }
         BNNP_LAUNCH_CHECK();
         break;
       case BNNP_OP_AVGPOOL2D:
@@ -636,7 +667,12 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
         BNNP_LAUNCH_CHECK();
         break;
       case BNNP_OP_RELU: case BNNP_OP_TANH: case BNNP_OP_SIGMOID:
-        act_bwd_kernel<<<blocks, 256, 0, st>>>(gout, q.grad_ld, ws + q.act_off, q.act_ld, N, V, isz, o.kind);
+        {
+          int64_t gy = ceil_div64(8192, ceil_div64(isz, 256));
+          gy = gy < 1 ? 1 : (gy > R ? R : gy);
+          act_bwd_kernel<<<dim3((unsigned)ceil_div64(isz, 256), (unsigned)gy), 256, 0, st>>>(
+              gout, q.grad_ld, ws + q.act_off, q.act_ld, R, V, isz, o.kind);
+        }
         BNNP_LAUNCH_CHECK();
         break;
       case BNNP_OP_FLATTEN:
