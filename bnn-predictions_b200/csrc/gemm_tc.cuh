@@ -43,13 +43,6 @@ struct Shape {
   int batch, wn, n_mt, n_nt, ksplit, chunks_total;
 };
 
-// generic fallback: eight scalar evaluations of f(m, k, batch)
-template <class F>
-__device__ __forceinline__ void load8_scalar(const F& f, int64_t m, int64_t k0, int64_t K, int batch, float* out) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) out[e] = (k0 + e < K) ? f(m, k0 + e, batch) : 0.f;
-}
-
 template <class LA, class LB, class EP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(Shape sh, LA la, LB lb, EP ep) {

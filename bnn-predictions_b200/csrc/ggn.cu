@@ -79,14 +79,6 @@ struct StoreJacConv {  // Js[n, offw + co*E + e, v]
     Js[(n * P + offw + co * E + e) * V + v] = acc;
   }
 };
-struct StoreBlock {    // dst[r, co*E + e]   (per-row Jacobian block of one conv weight)
-  float* dst; int64_t ld; int E;
-  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
-  __device__ void operator()(int64_t co, int64_t e, float acc, int r) const {
-    dst[(int64_t)r * ld + co * E + e] = acc;
-  }
-};
-
 // s[r, co] = sum_pos gout[r, co, pos]
 __global__ void conv_possum_kernel(const float* __restrict__ g, int64_t gld, int64_t R, int Cout,
                                    int L, float* __restrict__ s, int64_t sld) {

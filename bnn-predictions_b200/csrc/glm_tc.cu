@@ -24,7 +24,8 @@ constexpr int BK = 32, TILE_M = 128, MAX_N = 256, STAGES = 4;
 constexpr int A_TERM = TILE_M * BK * 2, A_STAGE = 2 * A_TERM;
 constexpr int B_TERM = MAX_N * BK * 2, B_STAGE = 2 * B_TERM;
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;               // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int META_BYTES = 2 * MAX_N * 12;                  // per accumulator buffer: unit id, activation column, bias value
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + META_BYTES;
 constexpr int NUM_THREADS = 256;     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
 constexpr int EPI_WARP0 = 4;
 
@@ -52,6 +53,7 @@ glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
   uint64_t* acc_full = bars + 2 * STAGES;       // [2]
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  int* meta = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + 256);     // [2][3][MAX_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -126,14 +128,27 @@ glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
     } else if (warp >= EPI_WARP0) {
       // epilogue: T[n, u(p), u'] += a~[n, c(p)] * (Y[n,p] + Sigma[p, bias(u')])
       const int q = warp - EPI_WARP0;
-      mbar_wait(&acc_full[buf], buf_phase);
-      tc_fence_after();
       const long long n = m0 + q * 32 + lane;
       const bool rowok = n < args.N;
-      const long long ncols = args.P - n0 < args.wn ? args.P - n0 : args.wn;
+      const int ncols = (int)(args.P - n0 < args.wn ? args.P - n0 : args.wn);
+      // the column metadata is the same for all 128 rows of the tile: stage it in shared memory once
+      // (unit id, activation column, bias-column value of Sigma -- row offb+u' of the symmetric matrix)
+      int* m_u = meta + buf * 3 * MAX_N;
+      int* m_c = m_u + MAX_N;
+      float* m_b = reinterpret_cast<float*>(m_c + MAX_N);
+      {
+        const float* sbias = args.Sigma + (args.offb + up) * args.P;
+        for (int e = (q * 32 + lane); e < ncols; e += 128) {
+          const long long p = n0 + e;
+          m_u[e] = __ldg(args.pu + p);
+          m_c[e] = __ldg(args.pc + p);
+          m_b[e] = args.has_bias ? __ldg(sbias + p) : 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps only
+      mbar_wait(&acc_full[buf], buf_phase);
+      tc_fence_after();
       const float* __restrict__ arow = args.A + (rowok ? n : 0) * args.ald;
-      // bias column of unit u' = row (offb + u') of the symmetric Sigma: contiguous in p
-      const float* __restrict__ sbias = args.Sigma + (args.offb + up) * args.P;
       float* trow = args.T + ((rowok ? n : 0) * args.Mtot) * (long long)args.Mtot + args.unit0p + up;
       float acc = 0.f;
       int ucur = -1;
@@ -141,26 +156,19 @@ glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
         if (rowok) {
-          // phase 1: every load of the chunk is issued before any atomic (nothing to serialise on)
           float prod[32];
-          int uu[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const bool ok = c0 + e < ncols;
-            const long long p = n0 + c0 + (ok ? e : 0);
-            uu[e] = ok ? __ldg(args.pu + p) : -2;
-            const int col = __ldg(args.pc + p);
-            float y = __uint_as_float(v[e]);
-            if (args.has_bias) y += __ldg(sbias + p);
-            prod[e] = __ldg(arow + col) * y;
+          for (int e = 0; e < 32; ++e) {                 // loads first (shared-memory broadcasts + one L1 gather)
+            const int ee = c0 + e < ncols ? c0 + e : ncols - 1;
+            prod[e] = __ldg(arow + m_c[ee]) * (__uint_as_float(v[e]) + m_b[ee]);
           }
-          // phase 2: run-length reduction over units, one atomic per run
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (uu[e] != -2) {
-              if (uu[e] != ucur) {
+          for (int e = 0; e < 32; ++e) {                 // run-length reduction over units, one atomic per run
+            if (c0 + e < ncols) {
+              const int u = m_u[c0 + e];
+              if (u != ucur) {
                 if (ucur >= 0) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
-                ucur = uu[e]; acc = 0.f;
+                ucur = u; acc = 0.f;
               }
               acc += prod[e];
             }

@@ -4,6 +4,7 @@
 No arithmetic of the hot path happens here; torch provides device memory and the stream only.
 """
 import ctypes as C
+import weakref
 
 import torch
 import torch.nn as nn
@@ -60,7 +61,7 @@ class Net:
     """Descriptor + workspace for one model on one device."""
 
     def __init__(self, model):
-        self.model = model
+        self._model = weakref.ref(model)    # the cache must not keep the model alive
         self.params = list(model.parameters())
         if not self.params:
             raise ValueError('model has no parameters')
@@ -74,7 +75,7 @@ class Net:
 
     # ------------------------------------------------------------------ descriptor
     def _build(self, in_shape):
-        model = self.model
+        model = self._model()
         sample = torch.zeros((1,) + tuple(in_shape), device=self.device)
         trace = _leaf_trace(model, sample)
         offs, off = {}, 0
@@ -267,16 +268,18 @@ class Net:
         return Js, f
 
 
-_NETS = {}
+_NETS = weakref.WeakKeyDictionary()        # model -> Net; entries die with the model
 
 
 def net_for(model):
     """One cached ``Net`` per model object (the model keeps its own parameters; we hold pointers)."""
-    key = id(model)
-    ent = _NETS.get(key)
-    if ent is None or ent.model is not model or ent.device != next(model.parameters()).device:
+    try:
+        ent = _NETS.get(model)
+    except TypeError:                       # unhashable / non-weakrefable "model" objects: no caching
+        return Net(model)
+    if ent is None or ent.device != next(model.parameters()).device:
         ent = Net(model)
-        _NETS[key] = ent
+        _NETS[model] = ent
     return ent
 
 
