@@ -2,6 +2,7 @@
 // dense helpers of the posterior code.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace bnnp {
 
@@ -63,12 +64,79 @@ struct StoreThetaVec {
   __device__ void operator()(int64_t i, int64_t s, float acc, int) const { out[s * P + off + i] = (mu ? mu[off + i] : 0.f) + acc; }
 };
 
+// theta_s = mu + (L eps)^T on the tensor cores: A = lower-triangular Cholesky factor (zeros above the diagonal are
+// generated, not read), B = eps [P, S]
+struct TcLowerTri {
+  static constexpr bool K_CONTIG = true;
+  struct Row { const float* p; long long r; };
+  const float* L; long long P;
+  __device__ __forceinline__ Row row(int64_t r, int) const { return Row{L + r * P, r}; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t, float* out) const {
+    if (k0 + 7 <= rw.r) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = __ldg(rw.p + k0 + e);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = (k0 + e <= rw.r) ? __ldg(rw.p + k0 + e) : 0.f;
+    }
+  }
+};
+struct TcStoreThetaT : tcg::TcNoState {    // theta_s[s*P + p] = (first ? mu[p] : theta_s[s*P + p]) + acc(p, s)
+  float* out; const float* mu; long long P; int first;
+  __host__ __device__ TcStoreThetaT(float* o_, const float* m_, long long P_, int f_) : out(o_), mu(m_), P(P_), first(f_) {}
+  __device__ __forceinline__ void row(State&, int64_t p, int64_t s0, const float* v, int nvalid, int, int) const {
+    const float m = mu[p];
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e < nvalid) {
+        float* q = out + (s0 + e) * P + p;
+        *q = (first ? m : *q) + v[e];
+      }
+  }
+};
+
+// batched-weights Linear layer of the BNN predictive: out[s, n, :] = act(in[s or shared, n, :] W_s^T + b_s)
+struct BnnStore {                 // SIMT epilogue
+  float* out; int64_t ld, bs; const float* theta; int64_t P, offb; int has_bias, act;
+  __device__ bool skip(int64_t, int64_t, int, int) const { return false; }
+  __device__ void operator()(int64_t n, int64_t u, float acc, int s) const {
+    float v = acc + (has_bias ? theta[(int64_t)s * P + offb + u] : 0.f);
+    if (act == BNNP_OP_RELU) v = v > 0.f ? v : 0.f;
+    else if (act == BNNP_OP_TANH) v = tanhf(v);
+    else if (act == BNNP_OP_SIGMOID) v = 1.f / (1.f + expf(-v));
+    out[(int64_t)s * bs + n * ld + u] = v;
+  }
+};
+struct TcBnnStore : tcg::TcNoState {     // tensor-core epilogue
+  float* out; long long ld, bs; const float* theta; long long P, offb; int has_bias, act;
+  __host__ __device__ TcBnnStore(float* o_, long long ld_, long long bs_, const float* t_, long long P_, long long ob_,
+                                 int hb_, int act_) : out(o_), ld(ld_), bs(bs_), theta(t_), P(P_), offb(ob_), has_bias(hb_), act(act_) {}
+  __device__ __forceinline__ void row(State&, int64_t n, int64_t u0, const float* v, int nvalid, int s, int) const {
+    float* q = out + (long long)s * bs + n * ld + u0;
+    const float* b = theta + (long long)s * P + offb + u0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (e < nvalid) {
+        float x = v[e] + (has_bias ? __ldg(b + e) : 0.f);
+        if (act == BNNP_OP_RELU) x = x > 0.f ? x : 0.f;
+        else if (act == BNNP_OP_TANH) x = tanhf(x);
+        else if (act == BNNP_OP_SIGMOID) x = 1.f / (1.f + expf(-x));
+        q[e] = x;
+      }
+    }
+  }
+};
+
 }  // namespace bnnp
 using namespace bnnp;
 
 extern "C" int bnnp_sample_theta_full(const float* L, const float* mu, const float* eps, int64_t P,
                                       int64_t S, float* theta_s, void* stream) {
   if (!L || !mu || !eps || !theta_s || P <= 0 || S <= 0) return BNNP_ERR_INVALID;
+  if ((long long)P * P * S >= (1LL << 28))
+    // K = P is long: sequential <= 4096-element segments accumulate through theta_s (TMEM adds truncate)
+    return tcg::gemm_tc_ksegments(P, S, P, 1, TcLowerTri{L, P}, tcg::TcColMajor{eps, S, 0},
+                                  [=](int seg) { return TcStoreThetaT(theta_s, mu, P, seg == 0); }, as_stream(stream));
   return gemm_simt(P, S, P, 1, LoadLowerA{L, P}, LoadRowMajorB{eps, S, 0}, StoreThetaT{theta_s, mu, P},
                    as_stream(stream));
 }
@@ -123,9 +191,20 @@ extern "C" int bnnp_kron_sample_group(const float* W1, const float* l1, const fl
 // ------------------------------------------------------------------------------------------
 // forward passes at S sampled weight vectors
 // ------------------------------------------------------------------------------------------
+static bool bnn_linear_only(const bnnp_op_t* ops, int n_ops) {
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind != BNNP_OP_LINEAR && !is_elementwise_op(ops[i]) && ops[i].kind != BNNP_OP_FLATTEN) return false;
+  return true;
+}
+// scratch: Linear-only networks keep two ping-pong activation buffers [S, N, max width]; others the
+// workspace of one forward pass (+ logits)
 extern "C" int64_t bnnp_bnn_forward_scratch_floats(const bnnp_op_t* ops, int n_ops, int64_t N, int64_t S) {
+  if (bnn_linear_only(ops, n_ops)) {
+    int64_t w = 0;
+    for (int i = 0; i < n_ops; ++i) if (ops[i].kind == BNNP_OP_LINEAR && ops[i].out_c > w) w = ops[i].out_c;
+    return 2 * S * N * w + 128;
+  }
   bnnp_plan_t plan;
-  (void)S;
   if (bnnp_net_plan(ops, n_ops, N, 1, &plan) != BNNP_OK) return -1;
   return plan.total_floats + N * plan.K + 64;
 }
@@ -134,6 +213,40 @@ extern "C" int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const 
                                 const float* theta_s, int64_t S, int64_t P, float* out, float* scratch,
                                 void* stream) {
   if (!ops || !X || !theta_s || !out || !scratch || N <= 0 || S <= 0 || n_ops > BNNP_MAX_OPS) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+  if (bnn_linear_only(ops, n_ops) && S <= 65535) {
+    // all S weight samples at once: every Linear is a batched-weights GEMM (batch index = sample), the
+    // activation that follows it is fused into the epilogue.  The model's own parameters are not touched.
+    int64_t w = 0, last = -1;
+    for (int i = 0; i < n_ops; ++i) if (ops[i].kind == BNNP_OP_LINEAR) { if (ops[i].out_c > w) w = ops[i].out_c; last = i; }
+    float* buf[2] = {scratch, scratch + S * N * w + 64};
+    const float* in = X;
+    int64_t in_ld = ops[0].in_c, in_bs = 0;       // the input batch is shared by all samples
+    int pp = 0;
+    int K = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      const bnnp_op_t& o = ops[i];
+      if (o.kind != BNNP_OP_LINEAR) continue;
+      int act = 0;
+      if (i + 1 < n_ops && is_elementwise_op(ops[i + 1])) act = ops[i + 1].kind;
+      float* dst = buf[pp];
+      const int64_t out_ld = o.out_c, out_bs = N * (int64_t)o.out_c;
+      int rc;
+      if ((long long)N * o.out_c * o.in_c >= (1LL << 22) && (long long)S * N * o.out_c * o.in_c >= (1LL << 25))
+        rc = tcg::gemm_tc(N, o.out_c, o.in_c, (int)S, tcg::TcRowMajor{in, in_ld, in_bs},
+                          tcg::TcRowMajor{theta_s + o.theta_off_w, o.in_c, P},
+                          TcBnnStore(dst, out_ld, out_bs, theta_s, P, o.theta_off_b, o.has_bias, act), 1, st);
+      else
+        rc = gemm_simt(N, o.out_c, o.in_c, (int)S, LoadRowMajorA{in, in_ld, in_bs},
+                       LoadColMajorB{theta_s + o.theta_off_w, o.in_c, P},
+                       BnnStore{dst, out_ld, out_bs, theta_s, P, o.theta_off_b, o.has_bias, act}, st);
+      if (rc) return rc;
+      in = dst; in_ld = out_ld; in_bs = out_bs; pp ^= 1;
+      K = o.out_c;
+      (void)last;
+    }
+    return bnnp_lik_inv_link(lik, in, S * N, K, out, stream);
+  }
   bnnp_plan_t plan;
   int rc = bnnp_net_plan(ops, n_ops, N, 1, &plan);
   if (rc) return rc;

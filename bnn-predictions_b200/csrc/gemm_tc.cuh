@@ -40,7 +40,7 @@ constexpr int kMaxChunksPerAccum = 128;   // 4096 K-elements per TMEM accumulati
 
 struct Shape {
   long long M, N, K;
-  int batch, wn, n_mt, n_nt, ksplit, chunks_total;
+  int batch, wn, n_mt, n_nt, ksplit, chunks_total, chunk0;   // this launch covers K-chunks [chunk0, chunk0 + chunks_total)
 };
 
 template <class LA, class LB, class EP>
@@ -77,8 +77,8 @@ gemm_tc_kernel(Shape sh, LA la, LB lb, EP ep) {
     const int mt = (int)((tile / sh.ksplit) % sh.n_mt);
     const int nt = (int)((tile / ((long long)sh.ksplit * sh.n_mt)) % sh.n_nt);
     const int b = (int)(tile / ((long long)sh.ksplit * sh.n_nt * sh.n_mt));
-    const int c_beg = (int)((long long)sh.chunks_total * ks / sh.ksplit);
-    const int c_end = (int)((long long)sh.chunks_total * (ks + 1) / sh.ksplit);
+    const int c_beg = sh.chunk0 + (int)((long long)sh.chunks_total * ks / sh.ksplit);
+    const int c_end = sh.chunk0 + (int)((long long)sh.chunks_total * (ks + 1) / sh.ksplit);
     const int n_chunks = c_end - c_beg;
     const long long m0 = (long long)mt * TILE_M, n0 = (long long)nt * sh.wn;
     const uint32_t buf = iter & 1, buf_phase = (iter >> 1) & 1;
@@ -226,16 +226,24 @@ inline int pick_wn(long long N) {
   return (int)(w < 16 ? 16 : w);
 }
 
+// chunk_lo / chunk_hi restrict the launch to K-chunks [chunk_lo, chunk_hi) (chunk_hi < 0: to the end) -- used to
+// run a long K as sequential segments that accumulate through the output (see gemm_tc_ksegments)
 template <class LA, class LB, class EP>
 inline int gemm_tc(long long M, long long N, long long K, int batch, LA la, LB lb, EP ep, int ksplit,
-                   cudaStream_t st) {
+                   cudaStream_t st, int chunk_lo = 0, int chunk_hi = -1) {
   if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return BNNP_OK;
   Shape sh;
   sh.M = M; sh.N = N; sh.K = K; sh.batch = batch;
   sh.wn = pick_wn(N);
   sh.n_mt = (int)((M + TILE_M - 1) / TILE_M);
   sh.n_nt = (int)((N + sh.wn - 1) / sh.wn);
-  sh.chunks_total = (int)((K + BK - 1) / BK);
+  {
+    const int all = (int)((K + BK - 1) / BK);
+    if (chunk_hi < 0 || chunk_hi > all) chunk_hi = all;
+    if (chunk_lo >= chunk_hi) return BNNP_OK;
+    sh.chunk0 = chunk_lo;
+    sh.chunks_total = chunk_hi - chunk_lo;
+  }
   sh.ksplit = ksplit < 1 ? 1 : (ksplit > sh.chunks_total ? sh.chunks_total : ksplit);
   static int sms = 0;
   if (!sms) {
@@ -250,6 +258,20 @@ inline int gemm_tc(long long M, long long N, long long K, int batch, LA la, LB l
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
   kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(sh, la, lb, ep);
   BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+// A long K without a split-K workspace: sequential launches over <= kMaxChunksPerAccum-chunk segments; make_ep(seg)
+// returns the epilogue of segment `seg` (segment 0 stores, later segments accumulate into the output).
+template <class LA, class LB, class MakeEP>
+inline int gemm_tc_ksegments(long long M, long long N, long long K, int batch, LA la, LB lb, MakeEP make_ep,
+                             cudaStream_t st) {
+  const int all = (int)((K + BK - 1) / BK);
+  int seg = 0;
+  for (int c0 = 0; c0 < all; c0 += kMaxChunksPerAccum, ++seg) {
+    int rc = gemm_tc(M, N, K, batch, la, lb, make_ep(seg), 1, st, c0, c0 + kMaxChunksPerAccum);
+    if (rc) return rc;
+  }
   return BNNP_OK;
 }
 

@@ -62,3 +62,20 @@ def test_cfg5_full_ggn_properties():
     Hv = (H.double() @ v) if False else torch.cat([(H[i:i + 4096].double() @ v) for i in range(0, P, 4096)])
     assert float((Hv - ref).abs().max() / ref.abs().max()) < 1e-4
     net.release()
+
+
+def test_cfg5_weight_sampling_tensor_core():
+    """theta_s = mu + L eps at P = 59 635 (tensor-core path) against torch on a row subset."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip('needs ~30 GB of free device memory')
+    from preds_b200.predictives import sample_weights
+    P, S = 59635, 24
+    g = torch.Generator(device='cuda').manual_seed(3)
+    L = torch.tril(torch.randn(P, P, device='cuda', generator=g)) / P ** 0.5
+    mu = torch.randn(P, device='cuda', generator=g)
+    eps = torch.randn(P, S, device='cuda', generator=g)
+    out = sample_weights(mu, L, S, eps=eps)                     # [S, P]
+    rows = torch.randint(0, P, (512,), device='cuda', generator=g)
+    ref = mu[rows].double().unsqueeze(0) + (L[rows].double() @ eps.double()).T
+    assert float((out[:, rows].double() - ref).abs().max() / ref.abs().max()) < 2e-5
