@@ -78,8 +78,7 @@ __global__ void lik_residual_kernel(int lik, const float* __restrict__ f, const 
   }
 }
 
-__global__ void lik_inv_link_kernel(int lik, const float* __restrict__ f, int64_t rows, int K,
-                                    float* __restrict__ out) {
+__global__ void lik_inv_link_kernel(int lik, const float* f, int64_t rows, int K, float* out) {   // out may alias f
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= rows) return;
   if (lik == BNNP_LIK_CATEGORICAL) {

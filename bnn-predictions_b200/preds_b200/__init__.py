@@ -12,6 +12,6 @@ from . import _cabi  # noqa: F401  (fails loudly if the CUDA library is missing)
 from .laplace import Laplace  # noqa: F401
 from .kron import Kron, symeig  # noqa: F401
 from .gradients import Jacobians  # noqa: F401
-from .optimizers import GGN  # noqa: F401
+from .optimizers import GGN, LaplaceGGN, get_diagonal_ggn  # noqa: F401
 from .likelihoods import CategoricalLh, GaussianLh, BernoulliLh  # noqa: F401
-from .models import MLPS, CIFAR10Net, CIFAR100Net  # noqa: F401
+from .models import MLPS, MLP, SiMLP, CIFAR10Net, CIFAR100Net  # noqa: F401

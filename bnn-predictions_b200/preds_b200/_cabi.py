@@ -88,6 +88,10 @@ _SIGS = {
     'bnnp_kron_sample_group': (_I, [_P, _P, _P, _P, _I, _I, _F, _I, _P, _L, _P, _P, _L, _L, _P, _V]),
     'bnnp_bnn_forward_scratch_floats': (_L, [_OPS, _I, _L, _L]),
     'bnnp_bnn_forward': (_I, [_OPS, _I, _I, _P, _L, _P, _L, _L, _P, _P, _V]),
+    'bnnp_jtr_scratch_floats': (_L, [_PLAN, _L]),
+    'bnnp_jtr_accum': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _V]),
+    'bnnp_glm_linear_samples_scratch_floats': (_L, [_PLAN, _L, _L]),
+    'bnnp_glm_linear_samples': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _L, _P, _P, _V]),
     'bnnp_sgemm': (_I, [_I, _I, _L, _L, _L, _F, _P, _L, _P, _L, _F, _P, _L, _V]),
     'bnnp_axpy': (_I, [_L, _F, _P, _P, _V]),
     'bnnp_sgemm_tc_scratch_floats': (_L, [_L, _L, _L]),

@@ -45,6 +45,30 @@ def _leaf_trace(model, sample):
     return trace
 
 
+_FUNCTIONAL_ACTS = {torch.relu: nn.ReLU, torch.tanh: nn.Tanh, torch.sigmoid: nn.Sigmoid}
+
+
+def _functional_mlp(model):
+    """``preds.models.MLP`` / ``SiMLP`` (preds/models.py:124-176) apply their activation as a plain function,
+    invisible to a leaf-module trace.  Recognise that layout by its attributes (``hidden_layers``,
+    ``output_layer``, ``act``) and synthesise the trace: Linear, act, ..., Linear."""
+    if not (hasattr(model, 'hidden_layers') and hasattr(model, 'output_layer') and hasattr(model, 'act')):
+        return None
+    layers = list(model.hidden_layers) + [model.output_layer]
+    if not all(isinstance(l, nn.Linear) for l in layers):
+        return None
+    if model.act not in _FUNCTIONAL_ACTS:
+        raise cabi.BnnpError('functional activation %r is outside the supported zoo (relu, tanh, sigmoid)'
+                             % (getattr(model.act, '__name__', model.act),))
+    act = _FUNCTIONAL_ACTS[model.act]
+    trace = []
+    for l in layers[:-1]:
+        trace.append((l, (l.in_features,), (l.out_features,), None))
+        trace.append((act(), (l.out_features,), (l.out_features,), None))
+    trace.append((layers[-1], (layers[-1].in_features,), (layers[-1].out_features,), None))
+    return trace
+
+
 def _pair4(p):
     return (p, p, p, p) if isinstance(p, int) else tuple(p)
 
@@ -69,6 +93,8 @@ class Net:
         cabi.require_device(self.params[0])
         self.P = sum(p.numel() for p in self.params)
         self._sig = None
+        self._verified = False
+        self.flat_output = False
         self._plans = {}
         self._ws = None
         self._scratch = None
@@ -77,7 +103,7 @@ class Net:
     def _build(self, in_shape):
         model = self._model()
         sample = torch.zeros((1,) + tuple(in_shape), device=self.device)
-        trace = _leaf_trace(model, sample)
+        trace = _functional_mlp(model) or _leaf_trace(model, sample)
         offs, off = {}, 0
         for p in self.params:
             offs[id(p)] = off
@@ -178,6 +204,35 @@ class Net:
                                for o in ops)
         self._plans = {}
         self._sig = tuple(in_shape)
+        self._verified = False
+
+    def _verify(self, in_shape):
+        """The descriptor must compute what ``model(x)`` computes: anything applied outside the traced
+        modules (functional activations, residual adds, reshapes) would otherwise give silently wrong
+        Jacobians.  Two probe inputs through both; also records whether the model flattens a single output
+        ([N] instead of [N,1], preds/models.py:165), which ``Jacobians`` / the predictives mirror."""
+        model = self._model()
+        gen = torch.Generator(device='cpu').manual_seed(1234)
+        x = (2.0 * torch.randn((2,) + tuple(in_shape), generator=gen)).to(self.device)
+        was_training = model.training
+        model.eval()
+        try:
+            with torch.no_grad():
+                want = model(x)
+        finally:
+            model.train(was_training)
+        self.flat_output = want.dim() == 1
+        _, _, got = self.forward(x.reshape(2, -1).contiguous(), 1)
+        want = want.reshape(2, -1).to(torch.float32)
+        if want.shape != got.shape:
+            raise cabi.BnnpError('model output shape %s does not match the traced network (%s)'
+                                 % (tuple(want.shape), tuple(got.shape)))
+        err = (got - want).abs().max().item()
+        if not err <= 2e-2 * max(1.0, want.abs().max().item()):     # also catches NaN
+            raise cabi.BnnpError('model(x) differs from its layer trace (max |diff| %.3g): the model applies '
+                                 'operations outside its leaf modules (functional activations, skip '
+                                 'connections, ...), which this engine cannot represent' % err)
+        self._verified = True
 
     def prepare(self, X):
         """Validate / flatten the input batch, (re)build the descriptor, refresh weight pointers."""
@@ -193,6 +248,8 @@ class Net:
                     raise cabi.BnnpError('parameters must be contiguous float32')
                 op.weight = w.data_ptr()
                 op.bias = mod.bias.data_ptr() if mod.bias is not None else None
+        if not self._verified:
+            self._verify(in_shape)
         return X.reshape(X.shape[0], -1)
 
     def plan(self, N, V):

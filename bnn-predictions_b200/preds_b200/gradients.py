@@ -9,9 +9,10 @@ from ._engine import net_for
 
 
 def Jacobians(model, data):
-    """Returns (Js [N,P,K] -- [N,P] when the model has one output -- and f [N,K]), detached."""
+    """Returns (Js [N,P,K] -- [N,P] when the model has one output -- and f as the model returns it:
+    [N,K], or [N] for a model that flattens its single output, preds/models.py:165), detached."""
     net = net_for(model)
     Js, f = net.materialise_jacobians(data)
     if net.K > 1:
         return Js, f
-    return Js.reshape(Js.shape[0], Js.shape[1]), f
+    return Js.reshape(Js.shape[0], Js.shape[1]), (f.reshape(-1) if net.flat_output else f)

@@ -139,16 +139,20 @@ class Laplace:
         net_for(self.model).release()
         self.inferred = bool(factorise)
 
-    def _accumulate_full(self, batches, H):
+    def _accumulate_full(self, batches, H, grad=None):
+        """H += sum_n J_n^T Lambda_n J_n over the batches (lower triangle, mirrored at the end).  With
+        ``grad`` ([P]) also grad += sum_n J_n^T r_n from the same factors (LaplaceGGN.post_process,
+        preds/optimizers.py:95-96); the targets are then read from the batches."""
         net = net_for(self.model)
-        pend, n_pend = [], 0
+        pend, pend_y, n_pend = [], [], 0
 
         def flush():
-            nonlocal pend, n_pend
+            nonlocal pend, pend_y, n_pend
             if not pend:
                 return
             X = torch.cat(pend) if len(pend) > 1 else pend[0]
-            pend, n_pend = [], 0
+            y = (torch.cat(pend_y) if len(pend_y) > 1 else pend_y[0]) if grad is not None else None
+            pend, pend_y, n_pend = [], [], 0
             net.prepare(X[:1])
             if not net.linear_only:
                 raise cabi.BnnpError("cov_type='full' is implemented for Linear-only networks "
@@ -159,10 +163,17 @@ class Laplace:
             sc = net.scratch(lib.bnnp_ggn_full_scratch_floats(C.byref(pl), N, self.ggn_engine))
             check(lib.bnnp_ggn_full_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H),
                                           ptr(sc), self.ggn_engine, stream()), 'bnnp_ggn_full_accum')
+            if grad is not None:
+                rs = self.likelihood.residual(y, f).reshape(N, net.K).contiguous()
+                sc = net.scratch(lib.bnnp_jtr_scratch_floats(C.byref(pl), N))
+                check(lib.bnnp_jtr_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(rs), ptr(grad),
+                                         ptr(sc), stream()), 'bnnp_jtr_accum')
 
         limit = None
-        for X, _ in batches:
+        for X, y in batches:
             X = X.to(self.device)
+            if grad is not None:
+                y = y.to(self.device)
             if limit is None:      # examples per launch from the scratch the engine needs per example
                 net.prepare(X[:1])
                 pl1 = net.plan(64, net.K)
@@ -171,6 +182,9 @@ class Laplace:
             while len(X) > 0:
                 take = min(len(X), limit - n_pend)
                 pend.append(X[:take])
+                if grad is not None:
+                    pend_y.append(y[:take])
+                    y = y[take:]
                 n_pend += take
                 X = X[take:]
                 if n_pend >= limit:

@@ -1,11 +1,14 @@
 """Model zoo the Jacobians are taken over: ``MLPS`` (preds/models.py:91-122), ``CIFAR10Net``
-(:239-285), ``CIFAR100Net`` (:182-236), with deepobs' ``tfconv2d`` / ``tfmaxpool2d`` building
+(:239-285), ``CIFAR100Net`` (:182-236), the functional-activation ``MLP`` / ``SiMLP`` (:124-176) of the
+UCI classification driver, with deepobs' ``tfconv2d`` / ``tfmaxpool2d`` building
 blocks re-created here (TF-"same" padding as a ``ZeroPad2d`` set by a forward-pre-hook) so that
 models built against the reference run unchanged.  These are plain ``nn.Module`` containers; the
 compute goes through the descriptor in ``_engine.py``.
 """
 import math
 
+import torch
+import torch.nn.functional as F
 from torch import nn
 
 
@@ -45,6 +48,40 @@ def tfmaxpool2d(kernel_size, stride=None, dilation=1, return_indices=False, ceil
     if tf_padding_type == 'same':
         seq.register_forward_pre_hook(_tf_same_hook(kernel_size, stride))
     return seq
+
+
+class MLP(nn.Module):
+    """preds/models.py:124-165: activations are plain functions (``self.act``), hidden layers live in
+    ``self.hidden_layers`` and the head in ``self.output_layer``; a single output is returned flattened
+    ([N] instead of [N,1]).  The engine reads exactly these three attributes (``_engine._functional_mlp``)."""
+    _ACTS = {'relu': torch.relu, 'tanh': torch.tanh, 'sigmoid': torch.sigmoid, 'selu': F.elu}
+
+    def __init__(self, input_size, hidden_sizes, output_size, activation='tanh', **kwargs):
+        super().__init__()
+        self.input_size = input_size
+        self.hidden_sizes = hidden_sizes
+        self.output_size = 1 if output_size is None else output_size
+        self.act = self._ACTS[activation]
+        widths = [input_size] + list(hidden_sizes)
+        if hidden_sizes:
+            self.hidden_layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        else:
+            self.hidden_layers = []
+        self.output_layer = nn.Linear(widths[-1], self.output_size)
+
+    def forward(self, x):
+        h = x.view(-1, self.input_size)
+        for layer in self.hidden_layers:
+            h = self.act(layer(h))
+        z = self.output_layer(h)
+        return z.flatten() if self.output_size == 1 else z
+
+
+class SiMLP(MLP):
+    """preds/models.py:168-176: width x depth parametrisation of ``MLP``."""
+
+    def __init__(self, input_size, output_size, n_layers, n_units, activation='tanh', **kwargs):
+        super().__init__(input_size, [n_units] * n_layers, output_size, activation, **kwargs)
 
 
 class MLPS(nn.Sequential):

@@ -174,4 +174,42 @@ def nn_sampling_predictive(X, model, likelihood, mu, Sigma_chol, mc_samples=100,
     sc = net.scratch(lib.bnnp_bnn_forward_scratch_floats(net.ops, net.n_ops, N, S))
     check(lib.bnnp_bnn_forward(net.ops, net.n_ops, lik, ptr(X2d), N, ptr(samples), S, net.P, ptr(out),
                                ptr(sc), stream()), 'bnnp_bnn_forward')
-    return out
+    return out.reshape(S, N) if net.flat_output else out
+
+
+def linear_sampling_predictive(X, model, likelihood, mu, Sigma_chol, mc_samples=100, no_link=False,
+                               eps=None):
+    """GLM predictive by weight sampling (preds/predictives.py:31-47): link(f(x) + J(x)(theta_s - theta*))
+    for theta_s = mu + Sigma_chol eps, eps [P,S]; [S, N, K] ([S, N] for a model that flattens its single
+    output).  ``Sigma_chol`` is a lower factor [P,P] (also the diagonal *matrix* of ``get_diagonal_ggn``)
+    or a vector of standard deviations [P].  All S samples go through one batched layer product per
+    layer on the Jacobian factors; J and the [S,P]x[P,N,K] product of the reference are never formed."""
+    net = net_for(model)
+    theta_star = parameters_to_vector(model.parameters()).detach()
+    mu = cabi.f32(mu, net.device)
+    dtheta = sample_weights(mu - theta_star, Sigma_chol, mc_samples, eps=eps)       # theta_s - theta* [S,P]
+    X = cabi.f32(X, net.device)
+    net.prepare(X[:1])
+    if not net.linear_only:
+        raise cabi.BnnpError('linear_sampling_predictive is implemented for Linear-only networks')
+    N, K, S = X.shape[0], net.K, dtheta.shape[0]
+    lik = cabi.LIK_GAUSSIAN if no_link else likelihood.code
+    out = torch.empty(S, N, K, dtype=torch.float32, device=net.device)
+    per = max(1, int(lib.bnnp_glm_linear_samples_scratch_floats(C.byref(net.plan(64, K)), 64, S)) // 64)
+    chunk = max(1, min(N, SCRATCH_BUDGET_FLOATS // per))
+    for s0 in range(0, N, chunk):
+        Xc = X[s0:s0 + chunk]
+        n = Xc.shape[0]
+        _, pl, ws, f = net.jacobian_factors(Xc)
+        sc = net.scratch(lib.bnnp_glm_linear_samples_scratch_floats(C.byref(pl), n, S))
+        if n == N:
+            dst = out
+        else:
+            dst = torch.empty(S, n, K, dtype=torch.float32, device=net.device)
+        check(lib.bnnp_glm_linear_samples(net.ops, net.n_ops, C.byref(pl), n, ptr(ws), ptr(f), ptr(dtheta), S,
+                                          ptr(dst), ptr(sc), stream()), 'bnnp_glm_linear_samples')
+        if lik != cabi.LIK_GAUSSIAN:
+            check(lib.bnnp_lik_inv_link(lik, ptr(dst), S * n, K, ptr(dst), stream()), 'bnnp_lik_inv_link')
+        if dst is not out:
+            out[:, s0:s0 + n] = dst
+    return out.reshape(S, N) if net.flat_output else out

@@ -238,6 +238,24 @@ int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const float* X, i
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Callers either side of the GGN kernel, Linear-only networks.  Both read the
+ * layer factors left in `ws` by bnnp_net_forward + the identity-seeded bnnp_net_backward (V = K).
+ * ---------------------------------------------------------------------------------------- */
+/* grad[P] += sum_n J_n^T r_n -- replaces `G += einsum('mpk,mk->p', Js, rs)` in
+ * LaplaceGGN.post_process (preds/optimizers.py:96).  rs [N,K]; scratch: bnnp_jtr_scratch_floats(). */
+int64_t bnnp_jtr_scratch_floats(const bnnp_plan_t* plan, int64_t N);
+int bnnp_jtr_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                   const float* ws, const float* rs, float* grad, float* scratch, void* stream);
+/* out[s,n,k] = f[n,k] + sum_p J[(n,k),p] dtheta[s,p] -- replaces `offset + Js @ samples[i]` of
+ * linear_sampling_predictive (preds/predictives.py:31-47) for all S samples at once; dtheta [S,P] =
+ * theta_s - theta*; out [S,N,K] holds logits (apply bnnp_lik_inv_link for the link).  S <= 65535.
+ * scratch: bnnp_glm_linear_samples_scratch_floats() floats. */
+int64_t bnnp_glm_linear_samples_scratch_floats(const bnnp_plan_t* plan, int64_t N, int64_t S);
+int bnnp_glm_linear_samples(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                            const float* ws, const float* f, const float* dtheta, int64_t S,
+                            float* out, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Small dense helpers used by the posterior code (preds/laplace.py:111, preds/kron.py:58-69)
  * ---------------------------------------------------------------------------------------- */
 /* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 SIMT; ta/tb: 0 = as stored, 1 = transposed. */

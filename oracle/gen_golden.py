@@ -127,6 +127,46 @@ def run_case(preds, name, model, lh, batches, Xte, prior, S, lh_desc, store_full
     print('%-12s P=%d K=%d  %.1f KB' % (name, P, K, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
 
 
+def ggn_case(preds, name, model, lh, lh_desc, X, y, Xte, prior_prec, prior_mu, S, n_steps=3):
+    """the UCI classification driver's path (experiments/classification.py:20-112):
+    a few LaplaceGGN.step()s, post_process, get_diagonal_ggn, and the linearised / BNN predictives with
+    injected draws."""
+    from preds.optimizers import LaplaceGGN, get_diagonal_ggn
+    from preds.predictives import linear_sampling_predictive, nn_sampling_predictive
+    out = {'lh': np.array(lh_desc), 'X': np_(X), 'y': np_(y), 'Xte': np_(Xte), 'theta0': np_(flat(model)),
+           'prior_prec': np_(torch.as_tensor(prior_prec)), 'prior_mu': np_(torch.as_tensor(prior_mu)),
+           'n_steps': np.array(n_steps)}
+    opt = LaplaceGGN(model, lr=1e-2, prior_prec=prior_prec, prior_mu=prior_mu)
+    losses = []
+    for _ in range(n_steps):
+        def closure():
+            model.zero_grad()
+            return lh.log_likelihood(y, model(X))
+        losses.append(opt.step(closure))
+    out['losses'], out['theta'] = np.array(losses), np_(flat(model))
+    half = len(X) // 2
+    opt.post_process(model, lh, [(X[:half], y[:half]), (X[half:], y[half:])])
+    st = opt.state
+    out['precision'], out['Sigma_chol'], out['mu'] = np_(st['precision']), np_(st['Sigma_chol']), np_(st['mu'])
+    Sigmad, Sigma_chold = get_diagonal_ggn(opt)
+    out['Sigma_d'], out['Sigma_chol_d'] = np_(Sigmad), np_(Sigma_chold)
+    P = len(out['theta'])
+    eps = randn(713, P, S)
+    out['eps'] = np_(eps)
+    theta_star = flat(model).detach()
+    for tag, mu, chol in (('full', st['mu'], st['Sigma_chol']), ('map', theta_star, st['Sigma_chol']),
+                          ('diag', theta_star, Sigma_chold), ('vec', st['mu'], torch.diag(Sigma_chold).clone())):
+        with refharness.inject_normals([eps]):
+            out['lin_' + tag] = np_(linear_sampling_predictive(Xte, model, lh, mu, chol, mc_samples=S))
+    with refharness.inject_normals([eps]):
+        out['lin_nolink'] = np_(linear_sampling_predictive(Xte, model, lh, st['mu'], st['Sigma_chol'],
+                                                           mc_samples=S, no_link=True))
+    with refharness.inject_normals([eps]):
+        out['nn_full'] = np_(nn_sampling_predictive(Xte, model, lh, theta_star, st['Sigma_chol'], mc_samples=S))
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('%-12s P=%d  %.1f KB' % (name, P, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
+
+
 def probe_case(preds, name):
     """Full-size CIFAR10Net (reference tests' own fixture: seed 71, in_channels=2, n_out=3,
     X seed 15 -- tests/test_jacobians.py:9-30): tensors too large to store, so the fixture
@@ -241,6 +281,23 @@ def main():
     y = torch.randint(3, (20,), generator=torch.Generator().manual_seed(30))
     run_case(preds, 'cnn_tiny', model, CategoricalLh(), [(X[:12], y[:12]), (X[12:], y[12:])],
              randn(31, 4, 2, 9, 9), 0.9, 5, 'categorical')
+
+    # (H) LaplaceGGN path on the driver's own model class (functional activations), K=3, vector prior
+    from preds.models import SiMLP
+    torch.manual_seed(77)
+    model = SiMLP(6, 3, 2, 8, activation='tanh')
+    X = randn(32, 44, 6)
+    y = torch.randint(3, (44,), generator=torch.Generator().manual_seed(33))
+    P = sum(p.numel() for p in model.parameters())
+    ggn_case(preds, 'ggn_simlp_cls', model, CategoricalLh(), 'categorical', X, y, randn(34, 9, 6),
+             0.5 + torch.rand(P, generator=torch.Generator().manual_seed(35)), 0.1 * randn(36, P), 6)
+
+    # (I) binary task: BernoulliLh with a single flattened output (experiments/classification.py:66-68)
+    torch.manual_seed(78)
+    model = SiMLP(4, 1, 1, 7, activation='tanh')
+    X = randn(37, 40, 4)
+    y = torch.randint(2, (40,), generator=torch.Generator().manual_seed(38)).float()
+    ggn_case(preds, 'ggn_simlp_bern', model, BernoulliLh(), 'bernoulli', X, y, randn(39, 8, 4), 0.8, 0.0, 5)
 
     # (G) the reference tests' own CIFAR10Net fixture, probed
     probe_case(preds, 'cifar10net_probe')

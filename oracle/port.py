@@ -62,6 +62,30 @@ def make_mlps(input_size, hidden_sizes, output_size, activation='tanh', flatten=
     return net
 
 
+class FunctionalMLP(nn.Module):
+    """MLP whose activation is a plain function and whose single output is flattened to [N];
+    restates preds/models.py:124-176 (``MLP`` / ``SiMLP``)."""
+
+    def __init__(self, input_size, hidden_sizes, output_size, activation='tanh'):
+        super().__init__()
+        self.input_size, self.output_size = input_size, (1 if output_size is None else output_size)
+        self.act = {'relu': torch.relu, 'tanh': torch.tanh, 'sigmoid': torch.sigmoid}[activation]
+        sizes = [input_size] + list(hidden_sizes)
+        self.hidden_layers = nn.ModuleList([nn.Linear(a, b) for a, b in zip(sizes[:-1], sizes[1:])])
+        self.output_layer = nn.Linear(sizes[-1], self.output_size)
+
+    def forward(self, x):
+        h = x.view(-1, self.input_size)
+        for layer in self.hidden_layers:
+            h = self.act(layer(h))
+        z = self.output_layer(h)
+        return z.flatten() if self.output_size == 1 else z
+
+
+def make_simlp(input_size, output_size, n_layers, n_units, activation='tanh'):
+    return FunctionalMLP(input_size, [n_units] * n_layers, output_size, activation)
+
+
 def make_cifar10net(in_channels=3, n_out=10, use_tanh=False):
     """DeepOBS 3c3d network; restates preds/models.py:239-285 (flat module list)."""
     act = nn.Tanh if use_tanh else nn.ReLU
@@ -517,3 +541,44 @@ def kron_eps_shapes(model, S):
         else:
             shapes.append((S, p.shape[0], p[0].numel()))
     return shapes
+
+
+# ------------------------------------------------------------------------------------------
+# LaplaceGGN.post_process, get_diagonal_ggn, linear_sampling_predictive
+# ------------------------------------------------------------------------------------------
+def post_process(model, lh, batches, prior_prec_matrix, prior_mu):
+    """Posterior of the linearised model; restates preds/optimizers.py:81-104.
+    Returns dict(precision, Sigma, Sigma_chol, mu, G)."""
+    theta_star = get_theta(model)
+    P = len(theta_star)
+    JLJ, G = torch.zeros(P, P), torch.zeros(P)
+    for X, y in batches:
+        Js, Hess, rs, _ = ggn_bundle(model, lh, X, y)
+        JLJ += torch.einsum('mpk,mkl,mql->pq', Js, Hess, Js)
+        G += torch.einsum('mpk,mk->p', Js, rs)
+    precision = JLJ + prior_prec_matrix
+    chol = torch.linalg.cholesky(precision)
+    Sigma = torch.cholesky_inverse(chol, upper=False)
+    b = G + JLJ @ theta_star + prior_prec_matrix @ prior_mu
+    mu = torch.cholesky_solve(b.reshape(-1, 1), chol, upper=False).flatten()
+    return {'precision': precision, 'Sigma': Sigma, 'Sigma_chol': torch.linalg.cholesky(Sigma), 'mu': mu, 'G': G}
+
+
+def diagonal_ggn(precision):
+    """(Sigma, Sigma_chol) as diagonal matrices; restates preds/optimizers.py:107-112."""
+    Sigma_diag = 1 / torch.diag(precision)
+    return torch.diag(Sigma_diag), torch.diag(torch.sqrt(Sigma_diag))
+
+
+def linear_sampling_predictive(model, lh, X, mu, Sigma_chol, eps, no_link=False):
+    """link(f + J (theta_s - theta*)) for theta_s = mu + Sigma_chol eps, eps [P,S];
+    restates preds/predictives.py:31-47 ([S,N,K]; [S,N] when the model flattens a single output)."""
+    theta_star = get_theta(model)
+    Js, f = jacobians(model, X)
+    if Js.dim() > 2:
+        Js = Js.transpose(1, 2)
+    offset = f - Js @ theta_star
+    covs = (Sigma_chol @ eps).t() if Sigma_chol.dim() == 2 else (Sigma_chol.reshape(-1, 1) * eps).t()
+    samples = mu + covs
+    link = (lambda x: x) if no_link else lh.inv_link
+    return torch.stack([link(offset + Js @ samples[i]) for i in range(samples.shape[0])])

@@ -86,3 +86,17 @@ def rel_err(a, b):
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---- LaplaceGGN path (experiments/classification.py) ---------------------------
+GGN_CASES = {
+    'ggn_simlp_cls': dict(input_size=6, output_size=3, n_layers=2, n_units=8, activation='tanh'),
+    'ggn_simlp_bern': dict(input_size=4, output_size=1, n_layers=1, n_units=7, activation='tanh'),
+}
+
+
+def ggn_prior(g, P):
+    """(prior precision as the constructor takes it, prior mean) of a LaplaceGGN golden case."""
+    pp = torch.from_numpy(g['prior_prec'])
+    pm = torch.from_numpy(g['prior_mu'])
+    return (float(pp) if pp.dim() == 0 else pp), (float(pm) if pm.dim() == 0 else pm)

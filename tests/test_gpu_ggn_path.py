@@ -1,0 +1,180 @@
+"""SURVEY.md 8f rank 1 on the GPU: LaplaceGGN (step / post_process), get_diagonal_ggn and
+linear_sampling_predictive of the product package against (a) goldens from the unmodified reference and
+(b) the CPU oracle / fp64 autograd on the same seeded inputs at sizes that take the tensor-core branches.
+Tolerance 1e-4 relative unless stated."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _product(name):
+    import preds_b200
+    from preds_b200 import models
+    g = cases.load_golden(name)
+    model = models.SiMLP(**cases.GGN_CASES[name])
+    lh = cases.make_lh(g['lh'], lib=preds_b200)
+    X, y, Xte = (torch.from_numpy(g[k]).cuda() for k in ('X', 'y', 'Xte'))
+    return g, model, lh, X, y, Xte
+
+
+@pytest.mark.parametrize('name', sorted(cases.GGN_CASES))
+def test_laplace_ggn_against_reference_golden(name):
+    from preds_b200 import LaplaceGGN, get_diagonal_ggn, Jacobians
+    from preds_b200.predictives import linear_sampling_predictive, nn_sampling_predictive
+    g, model, lh, X, y, Xte = _product(name)
+    P = len(g['theta'])
+    port.set_theta(model, torch.from_numpy(g['theta0']))
+    model = model.cuda()
+    pp, pm = cases.ggn_prior(g, P)
+    pp = pp.cuda() if torch.is_tensor(pp) else pp
+    pm = pm.cuda() if torch.is_tensor(pm) else pm
+    opt = LaplaceGGN(model, lr=1e-2, prior_prec=pp, prior_mu=pm)
+    # MAP training steps (torch autograd, as in the reference): same losses, same weights
+    losses = []
+    for _ in range(int(g['n_steps'])):
+        def closure():
+            model.zero_grad()
+            return lh.log_likelihood(y, model(X))
+        losses.append(opt.step(closure))
+    assert np.allclose(losses, g['losses'], rtol=1e-5)
+    assert cases.rel_err(port.get_theta(model).cpu(), g['theta']) < 1e-5
+    port.set_theta(model, torch.from_numpy(g['theta']).cuda())      # identical linearisation point
+
+    Js, f = Jacobians(model, X)
+    if model.output_size == 1:            # flattened single output (preds/models.py:165)
+        assert Js.dim() == 2 and f.dim() == 1
+
+    half = len(X) // 2
+    opt.post_process(model, lh, [(X[:half], y[:half]), (X[half:], y[half:])])
+    st = opt.state
+    assert cases.rel_err(st['precision'].cpu(), g['precision']) < TOL
+    assert cases.rel_err(st['mu'].cpu(), g['mu']) < TOL
+    Sref = torch.from_numpy(g['Sigma_chol'])
+    assert cases.rel_err((st['Sigma_chol'] @ st['Sigma_chol'].T).cpu(), Sref @ Sref.t()) < TOL
+    assert cases.rel_err(st['Sigma'].cpu(), Sref @ Sref.t()) < TOL
+    Sd, Scd = get_diagonal_ggn(opt)
+    assert cases.rel_err(Sd.cpu(), g['Sigma_d']) < TOL
+    assert cases.rel_err(Scd.cpu(), g['Sigma_chol_d']) < TOL
+
+    # predictives on the reference's own posterior factors, so that only this step is compared
+    eps = torch.from_numpy(g['eps']).cuda()
+    theta = port.get_theta(model)
+    mu, chol, chold = (torch.from_numpy(g[k]).cuda() for k in ('mu', 'Sigma_chol', 'Sigma_chol_d'))
+    S = eps.shape[1]
+    for tag, m, c, nl in (('full', mu, chol, False), ('map', theta, chol, False), ('diag', theta, chold, False),
+                          ('vec', mu, torch.diag(chold).contiguous(), False), ('nolink', mu, chol, True)):
+        out = linear_sampling_predictive(Xte, model, lh, m, c, mc_samples=S, no_link=nl, eps=eps)
+        assert tuple(out.shape) == g['lin_' + tag].shape
+        assert cases.rel_err(out.cpu(), g['lin_' + tag]) < TOL, tag
+    out = nn_sampling_predictive(Xte, model, lh, theta, chol, mc_samples=S, eps=eps)
+    assert tuple(out.shape) == g['nn_full'].shape
+    assert cases.rel_err(out.cpu(), g['nn_full']) < TOL
+    # the caller's weights are untouched
+    assert torch.equal(port.get_theta(model), theta)
+
+
+def test_uci_sized_driver_against_oracle():
+    """Satellite-shaped task (SURVEY.md 8 cfg 2: D=36, K=6, 2x50 tanh, P=4706): post_process and the
+    1000-sample linearised predictive vs the CPU oracle on identical inputs; sizes take the tcgen05
+    branch of bnnp_glm_linear_samples."""
+    from preds_b200 import LaplaceGGN, CategoricalLh
+    from preds_b200.models import SiMLP
+    from preds_b200.predictives import linear_sampling_predictive
+    torch.manual_seed(71)
+    ref = port.make_simlp(36, 6, 2, 50)
+    model = SiMLP(36, 6, 2, 50)
+    port.set_theta(model, port.get_theta(ref))
+    model = model.cuda()
+    g = torch.Generator().manual_seed(15)
+    X, y = torch.randn(600, 36, generator=g), torch.randint(6, (600,), generator=g)
+    Xte = torch.randn(300, 36, generator=g)
+    P = port.n_params(ref)
+    S = 64
+    eps = torch.randn(P, S, generator=g)
+    want = port.post_process(ref, port.CategoricalLh(), [(X, y)], 0.5 * torch.eye(P), torch.zeros(P))
+    opt = LaplaceGGN(model, prior_prec=0.5)
+    opt.post_process(model, CategoricalLh(), [(X[:256].cuda(), y[:256].cuda()), (X[256:].cuda(), y[256:].cuda())])
+    assert cases.rel_err(opt.state['precision'].cpu(), want['precision']) < TOL
+    # mu and Sigma come out of an fp32 Cholesky of an ill-conditioned matrix on BOTH sides (error ~ cond * 2^-24
+    # each), so fp64 linear algebra on the oracle's precision is the judge and the product must be as close to
+    # it as the reference arithmetic is (factor 2), or within the 1e-4 bound outright
+    H64, th64 = want['precision'].double(), port.get_theta(ref).double()
+    b64 = want['G'].double() + (H64 - 0.5 * torch.eye(P, dtype=torch.float64)) @ th64
+    mu64, Sigma64 = torch.linalg.solve(H64, b64), torch.linalg.inv(H64)
+    assert cases.rel_err(opt.state['mu'].cpu(), mu64) < max(TOL, 2 * cases.rel_err(want['mu'], mu64))
+    # Sigma = precision^-1 amplifies the (1e-5-level, split-bf16 tensor-core) error of the accumulated precision by
+    # the conditioning of the matrix: stated looser bound 5e-4 for this intermediate; the predictive computed from the
+    # product's own posterior is held to 1e-4 below
+    assert cases.rel_err(opt.state['Sigma'].cpu(), Sigma64) < 5e-4
+    assert cases.rel_err(H64 @ opt.state['mu'].cpu().double(), b64) < TOL        # condition-independent residual
+    out_ref = port.linear_sampling_predictive(ref, port.CategoricalLh(), Xte, want['mu'], want['Sigma_chol'], eps)
+    out = linear_sampling_predictive(Xte.cuda(), model, CategoricalLh(), want['mu'].cuda(),
+                                     want['Sigma_chol'].cuda(), mc_samples=S, eps=eps.cuda())
+    assert tuple(out.shape) == (S, 300, 6)
+    assert cases.rel_err(out.cpu(), out_ref) < TOL
+    # rows are probabilities
+    assert float((out.sum(-1) - 1).abs().max()) < 1e-5
+    # end to end: the product's own mu / Sigma_chol
+    out = linear_sampling_predictive(Xte.cuda(), model, CategoricalLh(), opt.state['mu'], opt.state['Sigma_chol'],
+                                     mc_samples=S, eps=eps.cuda())
+    assert cases.rel_err(out.cpu(), out_ref) < TOL
+
+
+@pytest.mark.parametrize('N', [700, 9000])
+def test_jtr_is_the_loglik_gradient(N):
+    """For the canonical-link likelihoods r = d log p(y|f) / df, hence sum_n J_n^T r_n is the gradient of the
+    log-likelihood (what the reference's einsum computes, preds/optimizers.py:96).  fp64 autograd on the
+    CPU is the judge; 256x256 layers with N >= 512 take the tcgen05 branch of bnnp_jtr_accum, N = 9000 also its
+    K-segmented accumulation."""
+    from preds_b200 import _cabi as cabi
+    from preds_b200._engine import net_for
+    from preds_b200 import CategoricalLh
+    from preds_b200.models import MLPS
+    torch.manual_seed(3)
+    model = MLPS(256, [256], 4, 'tanh')
+    g = torch.Generator().manual_seed(4)
+    X, y = torch.randn(N, 256, generator=g), torch.randint(4, (N,), generator=g)
+    m64 = MLPS(256, [256], 4, 'tanh').double()
+    port.set_theta(m64, port.get_theta(model).double())
+    ll = torch.distributions.Categorical(logits=m64(X.double())).log_prob(y).sum()
+    want = torch.cat([t.reshape(-1) for t in torch.autograd.grad(ll, list(m64.parameters()))])
+
+    model = model.cuda()
+    net = net_for(model)
+    lh = CategoricalLh()
+    _, pl, ws, f = net.jacobian_factors(X.cuda())
+    rs = lh.residual(y.cuda(), f).contiguous()
+    G = torch.zeros(net.P, device='cuda')
+    sc = net.scratch(cabi.lib.bnnp_jtr_scratch_floats(C.byref(pl), N))
+    cabi.check(cabi.lib.bnnp_jtr_accum(net.ops, net.n_ops, C.byref(pl), N, cabi.ptr(ws), cabi.ptr(rs), cabi.ptr(G),
+                                       cabi.ptr(sc), cabi.stream()))
+    assert cases.rel_err(G.cpu(), want) < 2e-5
+
+
+def test_engine_rejects_models_it_cannot_represent():
+    """Anything applied outside the traced leaf modules must fail loudly, never give wrong Jacobians."""
+    import torch.nn as nn
+    from preds_b200 import Jacobians, _cabi as cabi
+    from preds_b200.models import MLP
+
+    class Skip(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = nn.Linear(5, 5), nn.Linear(5, 3)
+            self.output_size = 3
+
+        def forward(self, x):
+            return self.b(torch.tanh(self.a(x)) + x)
+
+    with pytest.raises(cabi.BnnpError, match='outside its leaf modules'):
+        Jacobians(Skip().cuda(), torch.randn(4, 5).cuda())
+    with pytest.raises(cabi.BnnpError, match='functional activation'):
+        Jacobians(MLP(5, [6], 2, activation='selu').cuda(), torch.randn(4, 5).cuda())
