@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib')
 SO = os.path.join(LIB, 'libbnnp_b200.so')
-SOURCES = ['net.cu', 'lik.cu', 'ggn.cu', 'gram_tc.cu', 'gemm_tc.cu', 'glm.cu', 'glm_tc.cu', 'bnn.cu', 'linpred.cu']
+SOURCES = ['net.cu', 'lik.cu', 'ggn.cu', 'gram_tc.cu', 'gemm_tc.cu', 'glm.cu', 'glm_tc.cu', 'bnn.cu', 'linpred.cu', 'metrics.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -369,7 +369,10 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
 
 // One thread owns one input n (its K x K Cholesky factor lives in registers) and walks a slab of
 // samples; consecutive threads own consecutive n so the [S,N,K] stores of a warp are contiguous.
-template <int K>
+// MEAN: instead of storing the [S,N,K] samples, each thread sums its slab of samples in registers and adds
+// slab_sum / S to out[n, :] ([N,K], zeroed by the caller): the `.mean(0)` every driver applies
+// (experiments/imginference.py:391, classification.py:36) without the [S,N,K] round trip through HBM.
+template <int K, bool MEAN>
 __global__ void __launch_bounds__(128)
 glm_sample_kernel(int lik, const float* __restrict__ fmu, const float* __restrict__ fvar,
                   const float* __restrict__ eps, uint64_t seed, int64_t S, int64_t N,
@@ -399,6 +402,9 @@ glm_sample_kernel(int lik, const float* __restrict__ fmu, const float* __restric
   if (blockIdx.y == 0) status[n] = ok ? 0 : 1;
   int64_t s0 = (int64_t)blockIdx.y * s_per_block;
   int64_t s1 = s0 + s_per_block < S ? s0 + s_per_block : S;
+  float acc[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) acc[i] = 0.f;
   for (int64_t s = s0; s < s1; ++s) {
     float e[K], f[K];
     if (eps) {
@@ -426,21 +432,30 @@ glm_sample_kernel(int lik, const float* __restrict__ fmu, const float* __restric
       f[i] = v;
       mx = fmaxf(mx, v);
     }
-    float* o = out + (s * N + n) * K;
     if (lik == BNNP_LIK_CATEGORICAL) {
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < K; ++i) { f[i] = __expf(f[i] - mx); sum += f[i]; }
       float inv = 1.f / sum;
 #pragma unroll
-      for (int i = 0; i < K; ++i) o[i] = f[i] * inv;
+      for (int i = 0; i < K; ++i) f[i] *= inv;
     } else if (lik == BNNP_LIK_BERNOULLI) {
 #pragma unroll
-      for (int i = 0; i < K; ++i) o[i] = 1.f / (1.f + __expf(-f[i]));
+      for (int i = 0; i < K; ++i) f[i] = 1.f / (1.f + __expf(-f[i]));
+    }
+    if (MEAN) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) acc[i] += f[i];
     } else {
+      float* o = out + (s * N + n) * K;
 #pragma unroll
       for (int i = 0; i < K; ++i) o[i] = f[i];
     }
+  }
+  if (MEAN) {
+    const float invS = 1.f / (float)S;
+#pragma unroll
+    for (int i = 0; i < K; ++i) atomicAdd(out + n * K + i, acc[i] * invS);
   }
 }
 
@@ -481,7 +496,7 @@ __global__ void glm_sample_diag_kernel(int lik, const float* __restrict__ fmu, c
 
 template <int K>
 static int launch_sample(int lik, const float* fmu, const float* fvar, const float* eps, uint64_t seed,
-                         int64_t S, int64_t N, float* out, int32_t* status, cudaStream_t st) {
+                         int64_t S, int64_t N, float* out, int32_t* status, bool mean, cudaStream_t st) {
   unsigned gx = (unsigned)ceil_div64(N, 128);
   // enough y-slabs to fill the machine (148 SMs x several CTAs), at least 8 samples per slab
   int64_t want = (148 * 8 + gx - 1) / gx;
@@ -490,7 +505,13 @@ static int launch_sample(int lik, const float* fmu, const float* fvar, const flo
   int spb = (int)ceil_div64(S, slabs);
   slabs = ceil_div64(S, spb);
   if (slabs > 65535) return BNNP_ERR_UNSUPPORTED;
-  glm_sample_kernel<K><<<dim3(gx, (unsigned)slabs), 128, 0, st>>>(lik, fmu, fvar, eps, seed, S, N, out, status, spb);
+  if (mean) {
+    int rc = zero(out, N * K, st);
+    if (rc) return rc;
+    glm_sample_kernel<K, true><<<dim3(gx, (unsigned)slabs), 128, 0, st>>>(lik, fmu, fvar, eps, seed, S, N, out, status, spb);
+  } else {
+    glm_sample_kernel<K, false><<<dim3(gx, (unsigned)slabs), 128, 0, st>>>(lik, fmu, fvar, eps, seed, S, N, out, status, spb);
+  }
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
 }
@@ -780,7 +801,21 @@ extern "C" int bnnp_glm_sample(int lik, const float* f_mu, const float* f_var, c
                                void* stream) {
   if (!f_mu || !f_var || !out || !status || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
-#define BNNP_CASE(KK) case KK: return launch_sample<KK>(lik, f_mu, f_var, eps, seed, S, N, out, status, st);
+#define BNNP_CASE(KK) case KK: return launch_sample<KK>(lik, f_mu, f_var, eps, seed, S, N, out, status, false, st);
+  switch (K) {
+    BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
+    BNNP_CASE(9) BNNP_CASE(10) BNNP_CASE(11) BNNP_CASE(12) BNNP_CASE(13) BNNP_CASE(14) BNNP_CASE(15) BNNP_CASE(16)
+    default: return BNNP_ERR_UNSUPPORTED;
+  }
+#undef BNNP_CASE
+}
+
+extern "C" int bnnp_glm_sample_mean(int lik, const float* f_mu, const float* f_var, const float* eps,
+                                    uint64_t seed, int64_t S, int64_t N, int K, float* mean, int32_t* status,
+                                    void* stream) {
+  if (!f_mu || !f_var || !mean || !status || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  cudaStream_t st = as_stream(stream);
+#define BNNP_CASE(KK) case KK: return launch_sample<KK>(lik, f_mu, f_var, eps, seed, S, N, mean, status, true, st);
   switch (K) {
     BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
     BNNP_CASE(9) BNNP_CASE(10) BNNP_CASE(11) BNNP_CASE(12) BNNP_CASE(13) BNNP_CASE(14) BNNP_CASE(15) BNNP_CASE(16)

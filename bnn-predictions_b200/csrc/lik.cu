@@ -92,6 +92,50 @@ __global__ void lik_inv_link_kernel(int lik, const float* f, int64_t rows, int K
   }
 }
 
+// linear_regression_predictive epilogue (preds/predictives.py:79-94): with Lam = Hessian(f) * sigma2 (K x K,
+// symmetric), mu_star = inv_link(f) + Lam (f_mu - f), var_f = Lam f_var Lam, var_noise = Lam * sigma2.
+__global__ void lik_link_moments_kernel(int lik, const float* __restrict__ f, const float* __restrict__ fmu,
+                                        const float* __restrict__ fvar, float sigma2, int64_t N, int K,
+                                        float* __restrict__ mu_star, float* __restrict__ var_f,
+                                        float* __restrict__ var_noise) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float p[BNNP_MAX_K], lam[BNNP_MAX_K * BNNP_MAX_K], t[BNNP_MAX_K * BNNP_MAX_K];
+  if (lik == BNNP_LIK_CATEGORICAL) {
+    float pc[BNNP_MAX_K];
+    softmax_row(f + n * K, K, p);
+    for (int k = 0; k < K; ++k) pc[k] = fminf(fmaxf(p[k], kClampEps), 1.f - kClampEps);
+    for (int k = 0; k < K; ++k)
+      for (int l = 0; l < K; ++l) lam[k * K + l] = ((k == l ? pc[k] : 0.f) - pc[k] * pc[l]) * sigma2;
+  } else if (lik == BNNP_LIK_GAUSSIAN) {
+    p[0] = f[n];
+    lam[0] = (1.f / sigma2) * sigma2;
+  } else {
+    p[0] = 1.f / (1.f + expf(-f[n]));
+    const float pc = fminf(fmaxf(p[0], kClampEps), 1.f - kClampEps);
+    lam[0] = pc * (1.f - pc) * sigma2;
+  }
+  for (int l = 0; l < K; ++l) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(fmu[n * K + k] - f[n * K + k], lam[k * K + l], acc);
+    mu_star[n * K + l] = p[l] + acc;
+  }
+  const float* V = fvar + n * K * K;
+  for (int k = 0; k < K; ++k)           // t = f_var Lam
+    for (int l = 0; l < K; ++l) {
+      float acc = 0.f;
+      for (int c = 0; c < K; ++c) acc = fmaf(V[k * K + c], lam[c * K + l], acc);
+      t[k * K + l] = acc;
+    }
+  for (int k = 0; k < K; ++k)           // var_f = Lam^T t
+    for (int l = 0; l < K; ++l) {
+      float acc = 0.f;
+      for (int c = 0; c < K; ++c) acc = fmaf(lam[c * K + k], t[c * K + l], acc);
+      var_f[(n * K + k) * K + l] = acc;
+    }
+  for (int e = 0; e < K * K; ++e) var_noise[n * K * K + e] = lam[e] * sigma2;
+}
+
 }  // namespace bnnp
 using namespace bnnp;
 
@@ -136,6 +180,17 @@ extern "C" int bnnp_lik_residual(int lik, const float* f, const void* y, int64_t
 extern "C" int bnnp_lik_inv_link(int lik, const float* f, int64_t rows, int K, float* out, void* stream) {
   if (check_lik(lik, K) || !f || !out || rows <= 0) return BNNP_ERR_INVALID;
   lik_inv_link_kernel<<<(unsigned)ceil_div64(rows, 128), 128, 0, as_stream(stream)>>>(lik, f, rows, K, out);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_lik_link_moments(int lik, const float* f, const float* f_mu, const float* f_var, float sigma2,
+                                     int64_t N, int K, float* mu_star, float* var_f, float* var_noise,
+                                     void* stream) {
+  if (check_lik(lik, K) || !f || !f_mu || !f_var || !mu_star || !var_f || !var_noise || N <= 0) return BNNP_ERR_INVALID;
+  if (lik != BNNP_LIK_CATEGORICAL && K != 1) return BNNP_ERR_INVALID;
+  lik_link_moments_kernel<<<(unsigned)ceil_div64(N, 64), 64, 0, as_stream(stream)>>>(lik, f, f_mu, f_var, sigma2, N, K,
+                                                                                    mu_star, var_f, var_noise);
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
 }

@@ -92,6 +92,9 @@ _SIGS = {
     'bnnp_jtr_accum': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _V]),
     'bnnp_glm_linear_samples_scratch_floats': (_L, [_PLAN, _L, _L]),
     'bnnp_glm_linear_samples': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _L, _P, _P, _V]),
+    'bnnp_glm_sample_mean': (_I, [_I, _P, _P, _P, C.c_uint64, _L, _L, _I, _P, _P, _V]),
+    'bnnp_lik_link_moments': (_I, [_I, _P, _P, _P, _F, _L, _I, _P, _P, _P, _V]),
+    'bnnp_metric_cls': (_I, [_I, _P, _P, _L, _I, _P, _I, _P, _V]),
     'bnnp_sgemm': (_I, [_I, _I, _L, _L, _L, _F, _P, _L, _P, _L, _F, _P, _L, _V]),
     'bnnp_axpy': (_I, [_L, _F, _P, _P, _V]),
     'bnnp_sgemm_tc_scratch_floats': (_L, [_L, _L, _L]),

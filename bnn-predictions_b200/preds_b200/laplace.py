@@ -20,7 +20,7 @@ from . import _cabi as cabi
 from ._cabi import lib, check, ptr, stream
 from ._engine import net_for, ptr_array
 from .kron import Kron
-from .predictives import functional_sampling_predictive, nn_sampling_predictive
+from .predictives import functional_sampling_predictive, nn_sampling_predictive, functional_mean_predictive
 from . import parallel
 
 # Full GGN: loader batches are concatenated into super-batches of up to this many examples per
@@ -264,6 +264,14 @@ class Laplace:
         Sigma = self.Sigma if type(self.Sigma_chol) is not Kron else self.Sigma_chol
         return functional_sampling_predictive(X, self.model, self.likelihood, self.mu, Sigma, n_samples,
                                               eps=eps, seed=seed)
+
+    def predictive_mean_glm(self, X, n_samples=1000, eps=None, seed=None):
+        """``predictive_samples_glm(X, n_samples).mean(0)`` fused into the sampling kernel ([N,K]); additive."""
+        if not self.inferred:
+            raise ValueError('Need to infer first.')
+        Sigma = self.Sigma_chol if isinstance(self.Sigma_chol, Kron) else self.Sigma
+        return functional_mean_predictive(X, self.model, self.likelihood, self.mu, Sigma, mc_samples=n_samples,
+                                          eps=eps, seed=seed)
 
     def predictive_samples_bnn(self, X, n_samples=1000, eps=None):
         if not self.inferred:

@@ -52,9 +52,10 @@ def _kron_tables(net, kron):
     return ptr_array(eig), float_array(dw), float_array(db)
 
 
-def glm_moments(X, model, mu, Sigma, engine=0):
+def glm_moments(X, model, mu, Sigma, engine=0, return_f=False):
     """f_mu [N,K] and f_var [N,K,K] of the linearised model (preds/predictives.py:52-65).
-    ``Sigma`` is the full covariance [P,P], the diagonal variances [P], or a ``Kron``."""
+    ``Sigma`` is the full covariance [P,P], the diagonal variances [P], or a ``Kron``.
+    ``return_f`` also returns the network output f [N,K] at the linearisation point."""
     net = net_for(model)
     if torch.is_tensor(Sigma) and Sigma.dim() == 2 and not Sigma.is_contiguous() and Sigma.T.is_contiguous():
         Sigma = Sigma.T                # covariance is symmetric: take the contiguous view, no copy
@@ -84,12 +85,15 @@ def glm_moments(X, model, mu, Sigma, engine=0):
     chunk = max(1, min(N, cap, SCRATCH_BUDGET_FLOATS // per))
     f_mu = torch.empty(N, K, dtype=torch.float32, device=net.device)
     f_var = torch.empty(N, K, K, dtype=torch.float32, device=net.device)
+    f_all = torch.empty(N, K, dtype=torch.float32, device=net.device) if return_f else None
     tables = _kron_tables(net, Sigma) if isinstance(Sigma, Kron) else None
     for s in range(0, N, chunk):
         Xc = X[s:s + chunk]
         n = Xc.shape[0]
         X2d, pl, ws, f = net.jacobian_factors(Xc)
         fm, fv = f_mu[s:s + n], f_var[s:s + n]
+        if return_f:
+            f_all[s:s + n] = f
         check(lib.bnnp_glm_fmu(net.ops, net.n_ops, C.byref(pl), n, ptr(X2d), ptr(ws), ptr(f), delta_ptr,
                                ptr(fm), stream()), 'bnnp_glm_fmu')
         if isinstance(Sigma, Kron):
@@ -109,7 +113,7 @@ def glm_moments(X, model, mu, Sigma, engine=0):
             sc = net.scratch(lib.bnnp_glm_fvar_diag_scratch_floats(net.ops, net.n_ops, C.byref(pl), n))
             check(lib.bnnp_glm_fvar_diag(net.ops, net.n_ops, C.byref(pl), n, ptr(X2d), ptr(ws), ptr(Sigma),
                                          ptr(fv), ptr(sc), stream()), 'bnnp_glm_fvar_diag')
-    return f_mu, f_var
+    return (f_mu, f_var, f_all) if return_f else (f_mu, f_var)
 
 
 def functional_sampling_predictive(X, model, likelihood, mu, Sigma, mc_samples=1000, no_link=False,
@@ -139,6 +143,59 @@ def functional_sampling_predictive(X, model, likelihood, mu, Sigma, mc_samples=1
         check(lib.bnnp_glm_sample_diag_fallback(lik, ptr(f_mu), ptr(f_var), ptr(eps), seed, S, N, K, ptr(out),
                                                 stream()), 'bnnp_glm_sample_diag_fallback')
     return out
+
+
+def functional_mean_predictive(X, model, likelihood, mu, Sigma, mc_samples=1000, eps=None, seed=None):
+    """``functional_sampling_predictive(...).mean(0)`` -- what every driver does with the samples
+    (experiments/imginference.py:391, classification.py:36) -- with the mean over samples taken inside the
+    sampling kernel: [N,K], no [S,N,K] tensor (400 MB at config 3).  Additive API; classification only."""
+    if type(likelihood) is GaussianLh:
+        raise ValueError('the regression predictive returns moments, not samples (preds/predictives.py:66-67)')
+    if not isinstance(Sigma, Kron):
+        Sigma = cabi.f32(Sigma, mu.device)
+    f_mu, f_var = glm_moments(X, model, mu, Sigma)
+    N, K = f_mu.shape
+    S = int(mc_samples)
+    out = torch.empty(N, K, dtype=torch.float32, device=f_mu.device)
+    status = torch.empty(N, dtype=torch.int32, device=f_mu.device)
+    if eps is not None:
+        eps = cabi.f32(eps, f_mu.device)
+        assert tuple(eps.shape) == (S, N, K)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    check(lib.bnnp_glm_sample_mean(likelihood.code, ptr(f_mu), ptr(f_var), ptr(eps), seed, S, N, K, ptr(out),
+                                   ptr(status), stream()), 'bnnp_glm_sample_mean')
+    if bool(status.any()):      # indefinite f_var somewhere: the reference's whole-batch diagonal fallback (:73-76)
+        logging.warning('functional sampling covariance indefinite - use diagonal')
+        full = torch.empty(S, N, K, dtype=torch.float32, device=f_mu.device)
+        check(lib.bnnp_glm_sample_diag_fallback(likelihood.code, ptr(f_mu), ptr(f_var), ptr(eps), seed, S, N, K,
+                                                ptr(full), stream()), 'bnnp_glm_sample_diag_fallback')
+        return full.mean(0)
+    return out
+
+
+def linear_regression_predictive(X, model, likelihood, mu, Sigma_chol):
+    """preds/predictives.py:79-94: (mu_star, var_f, var_noise) of the linearised model pushed through the inverse
+    link by the delta method; ``Sigma_chol`` is a lower factor [P,P] or standard deviations [P]."""
+    Sigma_chol = cabi.f32(Sigma_chol, mu.device)
+    if Sigma_chol.dim() == 2:
+        P = Sigma_chol.shape[0]
+        Sigma = torch.empty(P, P, dtype=torch.float32, device=mu.device)
+        sc = torch.empty(max(1, int(lib.bnnp_sgemm_tc_scratch_floats(P, P, P))), dtype=torch.float32, device=mu.device)
+        check(lib.bnnp_sgemm_tc(0, 1, P, P, P, 1.0, ptr(Sigma_chol), P, ptr(Sigma_chol), P, 0.0, ptr(Sigma), P,
+                                ptr(sc), stream()), 'bnnp_sgemm_tc')
+        del sc
+    else:
+        Sigma = (Sigma_chol * Sigma_chol).contiguous()
+    f_mu, f_var, f = glm_moments(X, model, cabi.f32(mu, mu.device), Sigma, return_f=True)
+    N, K = f.shape
+    mu_star = torch.empty_like(f)
+    var_f, var_noise = torch.empty_like(f_var), torch.empty_like(f_var)
+    check(lib.bnnp_lik_link_moments(likelihood.code, ptr(f), ptr(f_mu), ptr(f_var), float(likelihood.sigma_2_dispersion),
+                                    N, K, ptr(mu_star), ptr(var_f), ptr(var_noise), stream()), 'bnnp_lik_link_moments')
+    if net_for(model).flat_output:
+        mu_star = mu_star.reshape(N)
+    return mu_star, var_f.squeeze(), var_noise.squeeze()
 
 
 def sample_weights(mu, Sigma_chol, mc_samples, eps=None):

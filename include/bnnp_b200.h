@@ -256,6 +256,25 @@ int bnnp_glm_linear_samples(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* 
                             float* out, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The steps right after the predictive in every driver
+ * ---------------------------------------------------------------------------------------- */
+/* mean over the S samples of bnnp_glm_sample without materialising them: mean [N,K] -- the `.mean(0)` of
+ * experiments/imginference.py:391 / classification.py:36 fused into the sampling epilogue.  Same eps / seed /
+ * status contract as bnnp_glm_sample (on a non-zero status redo through the materialising fallback). */
+int bnnp_glm_sample_mean(int lik, const float* f_mu, const float* f_var, const float* eps,
+                         uint64_t seed, int64_t S, int64_t N, int K, float* mean, int32_t* status,
+                         void* stream);
+/* linear_regression_predictive epilogue (preds/predictives.py:79-94): Lam = Hessian(f)*sigma2,
+ * mu_star [N,K] = inv_link(f) + Lam (f_mu - f), var_f [N,K,K] = Lam f_var Lam, var_noise [N,K,K] = Lam*sigma2. */
+int bnnp_lik_link_moments(int lik, const float* f, const float* f_mu, const float* f_var, float sigma2,
+                          int64_t N, int K, float* mu_star, float* var_f, float* var_noise, void* stream);
+/* nll_cls / acc / macc / ece (preds/utils.py:6-52) in one pass over probs ([N,K] categorical with int64 labels,
+ * [N] Bernoulli with float labels).  bounds [bins+1] = torch.linspace(0,1,bins+1); out (double[3+3*bins]):
+ * sum log p(y), #correct, N, then per bin (count, sum of confidences, #correct).  bins <= 64. */
+int bnnp_metric_cls(int lik, const float* probs, const void* y, int64_t N, int K, const float* bounds,
+                    int bins, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Small dense helpers used by the posterior code (preds/laplace.py:111, preds/kron.py:58-69)
  * ---------------------------------------------------------------------------------------- */
 /* C[M,N] = alpha * op(A) op(B) + beta * C, fp32 SIMT; ta/tb: 0 = as stored, 1 = transposed. */

@@ -167,6 +167,57 @@ def ggn_case(preds, name, model, lh, lh_desc, X, y, Xte, prior_prec, prior_mu, S
     print('%-12s P=%d  %.1f KB' % (name, P, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
 
 
+def extras_case(preds, name):
+    """metric reductions (preds/utils.py:6-52) on seeded probabilities -- including exact
+    ties, confidences on bin boundaries and near-0/1 probabilities -- and linear_regression_predictive
+    (preds/predictives.py:79-94) for a Gaussian and a categorical model."""
+    from preds.utils import acc, macc, nll_cls, ece
+    from preds.likelihoods import CategoricalLh, BernoulliLh, GaussianLh
+    from preds.models import MLPS
+    from preds.laplace import Laplace
+    from preds.predictives import linear_regression_predictive
+    out = {}
+    g = torch.Generator().manual_seed(50)
+    p = torch.softmax(3 * torch.randn(300, 5, generator=g), dim=1)
+    p[0] = torch.tensor([0.5, 0.5, 0, 0, 0])               # tie: first index wins
+    p[1] = torch.tensor([0.2, 0.2, 0.2, 0.2, 0.2])
+    p[2] = torch.tensor([0.0, 0.0, 1.0, 0.0, 0.0])         # clamped log(0)
+    p[3] = torch.tensor([0.3, 0.7, 0, 0, 0])               # confidence exactly on a bin edge (0.7 in fp32)
+    p[4] = torch.tensor([0.1, 0.9, 0, 0, 0])
+    y = torch.randint(5, (300,), generator=g)
+    y[2] = 0
+    out['cat_p'], out['cat_y'] = np_(p), np_(y)
+    lh = CategoricalLh()
+    out['cat_nll'], out['cat_acc'], out['cat_macc'] = (np.array(v) for v in (nll_cls(p, y, lh), acc(p, y, lh), macc(p, y)))
+    for b in (10, 15):
+        out['cat_ece%d' % b] = np.array(ece(p, y, lh, bins=b))
+    pb = torch.sigmoid(2.5 * torch.randn(257, generator=g))
+    pb[0], pb[1], pb[2], pb[3] = 0.5, 0.0, 1.0, 0.8
+    yb = torch.randint(2, (257,), generator=g).float()
+    out['bern_p'], out['bern_y'] = np_(pb), np_(yb)
+    lh = BernoulliLh()
+    out['bern_nll'], out['bern_acc'], out['bern_ece10'] = (np.array(v) for v in (nll_cls(pb, yb, lh), acc(pb, yb, lh),
+                                                                                   ece(pb, yb, lh, bins=10)))
+    # linear_regression_predictive
+    for tag, K, lh, sig in (('reg', 1, GaussianLh(0.6), 0.6), ('cls', 3, CategoricalLh(), None)):
+        torch.manual_seed(79)
+        model = MLPS(4, [9], K, 'tanh')
+        X = randn(51, 30, 4)
+        y = randn(52, 30, 1) if K == 1 else torch.randint(3, (30,), generator=torch.Generator().manual_seed(52))
+        lap = Laplace(model, 0.9, lh)
+        lap.infer([(X, y)], cov_type='full')
+        Xte = randn(53, 7, 4)
+        mu = lap.mu + 0.05 * randn(54, len(lap.mu))
+        out[tag + '_theta'], out[tag + '_X'], out[tag + '_mu'] = np_(flat(model)), np_(Xte), np_(mu)
+        out[tag + '_chol'] = np_(lap.Sigma_chol)
+        for ctag, chol in (('full', lap.Sigma_chol), ('diag', torch.sqrt(torch.diag(lap.Sigma)).clone())):
+            ms, vf, vn = linear_regression_predictive(Xte, model, lh, mu, chol)
+            out['%s_%s_mu_star' % (tag, ctag)], out['%s_%s_var_f' % (tag, ctag)] = np_(ms), np_(vf)
+            out['%s_%s_var_noise' % (tag, ctag)] = np_(vn)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('%-12s %.1f KB' % (name, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
+
+
 def probe_case(preds, name):
     """Full-size CIFAR10Net (reference tests' own fixture: seed 71, in_channels=2, n_out=3,
     X seed 15 -- tests/test_jacobians.py:9-30): tensors too large to store, so the fixture
@@ -298,6 +349,9 @@ def main():
     X = randn(37, 40, 4)
     y = torch.randint(2, (40,), generator=torch.Generator().manual_seed(38)).float()
     ggn_case(preds, 'ggn_simlp_bern', model, BernoulliLh(), 'bernoulli', X, y, randn(39, 8, 4), 0.8, 0.0, 5)
+
+    # (J) metric reductions and the delta-method regression predictive
+    extras_case(preds, 'extras')
 
     # (G) the reference tests' own CIFAR10Net fixture, probed
     probe_case(preds, 'cifar10net_probe')

@@ -582,3 +582,47 @@ def linear_sampling_predictive(model, lh, X, mu, Sigma_chol, eps, no_link=False)
     samples = mu + covs
     link = (lambda x: x) if no_link else lh.inv_link
     return torch.stack([link(offset + Js @ samples[i]) for i in range(samples.shape[0])])
+
+
+# ------------------------------------------------------------------------------------------
+# delta-method regression predictive and the metric reductions
+# ------------------------------------------------------------------------------------------
+def linear_regression_predictive(model, lh, X, mu, Sigma_chol):
+    """(mu_star, var_f, var_noise); restates preds/predictives.py:79-94."""
+    theta_star = get_theta(model)
+    Sigma = Sigma_chol @ Sigma_chol.t() if Sigma_chol.dim() == 2 else torch.diag(Sigma_chol ** 2)
+    Js, Hess, _, f = ggn_bundle(model, lh, X)
+    s2 = lh.sigma_noise ** 2 if lh.name == 'gaussian' else 1.0      # sigma_2_dispersion, preds/likelihoods.py:20-22,40-42
+    Lams = Hess * s2                                                # get_Lams_Vys, preds/likelihoods.py:7-12
+    Vys = Lams * s2
+    Jgs = torch.bmm(Js, Lams)
+    lin_pred = torch.einsum('mpk,p->mk', Jgs, mu - theta_star).reshape(*f.shape)
+    mu_star = lh.inv_link(f) + lin_pred
+    var_f = torch.bmm(Jgs.transpose(1, 2) @ Sigma, Jgs).squeeze()
+    return mu_star, var_f, Vys.squeeze()
+
+
+def classification_metrics(p, y, lik, bins=10):
+    """{'nll','acc','ece'}; restates preds/utils.py:6-52 (lik: 'categorical' with p [N,K], or 'bernoulli'
+    with p [N]) in plain fp32/fp64 tensor code."""
+    eps = torch.finfo(torch.float32).eps
+    N = len(y)
+    if lik == 'categorical':
+        pn = (p / p.sum(-1, keepdim=True)).clamp(eps, 1 - eps)            # Categorical(probs=p).logits
+        nll = -pn.log().gather(1, y.long().reshape(-1, 1)).mean().item()
+        acc = (p.argmax(-1) == y).sum().item() / N
+        probs = p
+    else:
+        pc = p.clamp(eps, 1 - eps)                                         # Bernoulli(probs=p).log_prob(y)
+        nll = -(y * pc.log() + (1 - y) * torch.log1p(-pc)).mean().item()
+        acc = ((p >= 0.5).float() == y).float().sum().item() / N
+        probs = torch.stack([1 - p, p]).t()
+    conf, pred = probs.max(1)
+    hit = pred.eq(y.long())
+    edges = torch.linspace(0, 1, bins + 1)
+    ece = 0.0
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        in_bin = (conf > lo) & (conf <= hi)
+        if in_bin.any():
+            ece += abs(conf[in_bin].double().mean().item() - hit[in_bin].double().mean().item()) * in_bin.double().mean().item()
+    return {'nll': nll, 'acc': acc, 'ece': ece}
