@@ -32,6 +32,43 @@ __global__ void jtr_reduce_kernel(const float* __restrict__ G, int64_t gld, cons
   for (int k = 0; k < K; ++k) acc = fmaf(G[(n * K + k) * gld + u], r[n * K + k], acc);
   gr[i] = acc;
 }
+// c[n,u] = sum_{k,l} G_cat[(n,k),u] * Lambda[n,k,l] * G_cat[(n,l),u]      (diagonal of J^T Lambda J, unit part)
+__global__ void diag_lambda_reduce_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ Lam,
+                                          int K, int64_t N, int Mtot, float* __restrict__ c) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Mtot) return;
+  const int64_t n = i / Mtot;
+  const int u = (int)(i - n * Mtot);
+  const float* L = Lam + n * K * K;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float gk = G[(n * K + k) * gld + u];
+    float t = 0.f;
+    for (int l = 0; l < K; ++l) t = fmaf(L[k * K + l], G[(n * K + l) * gld + u], t);
+    acc = fmaf(gk, t, acc);
+  }
+  c[i] = acc;
+}
+struct LoadRowMajorBSq {       // B(k,n) = p[k*ld + n]^2
+  static constexpr bool K_CONTIG = false;
+  const float* p; int64_t ld;
+  __device__ float operator()(int64_t k, int64_t n, int) const { const float v = p[k * ld + n]; return v * v; }
+};
+struct TcColMajorSqL {         // X(j, k = example) = p[k*ld + j]^2
+  static constexpr bool K_CONTIG = false;
+  using Row = const float*;
+  const float* p; long long ld;
+  __device__ __forceinline__ Row row(int64_t r, int) const { return p + r; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+    const float* q = rw + k0 * ld;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = (k0 + e < K) ? __ldg(q + (long long)e * ld) : 0.f;
+      out[e] = v * v;
+    }
+  }
+};
+
 // bias gradient: grad[offb + u] += sum_n gr[n, unit0 + u]      one warp per unit
 __global__ void jtr_bias_kernel(const float* __restrict__ gr, int Mtot, int unit0, int m, int64_t N,
                                 float* __restrict__ grad_b) {
@@ -114,6 +151,41 @@ extern "C" int bnnp_jtr_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t
     if (o.has_bias) {
       jtr_bias_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * 32, 256), 256, 0, st>>>(gr, Mtot, q.lin_unit, o.out_c, N,
                                                                                        grad + o.theta_off_b);
+      BNNP_LAUNCH_CHECK();
+    }
+  }
+  return BNNP_OK;
+}
+
+/* diag[p] += diag(sum_n J_n^T Lambda_n J_n)[p] for an arbitrary per-example Lambda [N,K,K]: the diagonal GGN of the
+ * GLM refinement loops (preds/refine.py:93-121), where Lambda is re-evaluated every iteration on fixed factors. */
+extern "C" int bnnp_ggn_diag_lambda(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                    const float* ws, const float* Lambda, float* diag, float* scratch, void* stream) {
+  if (!ops || !plan || !ws || !Lambda || !diag || !scratch || N <= 0) return BNNP_ERR_INVALID;
+  if (!linear_only_l(ops, n_ops)) return BNNP_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int K = plan->K, Mtot = plan->Mtot;
+  float* c = scratch;                                  // [N, Mtot], same size as bnnp_jtr_scratch_floats()
+  diag_lambda_reduce_kernel<<<(unsigned)ceil_div64(N * Mtot, 256), 256, 0, st>>>(ws + plan->gcat_off, Mtot, Lambda, K, N,
+                                                                                 Mtot, c);
+  BNNP_LAUNCH_CHECK();
+  const float* A = ws + plan->acat_off;
+  for (int i = 0; i < n_ops; ++i) {
+    const bnnp_op_t& o = ops[i];
+    if (o.kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_plan_t& q = plan->op[i];
+    int rc;
+    if ((long long)o.out_c * o.in_c * N >= kTcMinMacsL)
+      rc = tcg::gemm_tc_ksegments(o.out_c, o.in_c, N, 1, tcg::TcColMajor{c + q.lin_unit, Mtot, 0},
+                                  TcColMajorSqL{A + q.lin_col, plan->Dtot},
+                                  [=](int) { return tcg::TcStoreAxpby(diag + o.theta_off_w, o.in_c, 0, 1.f, 1.f); }, st);
+    else
+      rc = gemm_simt(o.out_c, o.in_c, N, 1, LoadColMajorA{c + q.lin_unit, Mtot, 0},
+                     LoadRowMajorBSq{A + q.lin_col, plan->Dtot}, StoreAxpby{diag + o.theta_off_w, o.in_c, 0, 1.f, 1.f}, st);
+    if (rc) return rc;
+    if (o.has_bias) {
+      jtr_bias_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * 32, 256), 256, 0, st>>>(c, Mtot, q.lin_unit, o.out_c, N,
+                                                                                       diag + o.theta_off_b);
       BNNP_LAUNCH_CHECK();
     }
   }

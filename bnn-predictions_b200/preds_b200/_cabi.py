@@ -90,6 +90,7 @@ _SIGS = {
     'bnnp_bnn_forward': (_I, [_OPS, _I, _I, _P, _L, _P, _L, _L, _P, _P, _V]),
     'bnnp_jtr_scratch_floats': (_L, [_PLAN, _L]),
     'bnnp_jtr_accum': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _V]),
+    'bnnp_ggn_diag_lambda': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _V]),
     'bnnp_glm_linear_samples_scratch_floats': (_L, [_PLAN, _L, _L]),
     'bnnp_glm_linear_samples': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _L, _P, _P, _V]),
     'bnnp_glm_sample_mean': (_I, [_I, _P, _P, _P, C.c_uint64, _L, _L, _I, _P, _P, _V]),

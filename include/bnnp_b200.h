@@ -246,6 +246,10 @@ int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const float* X, i
 int64_t bnnp_jtr_scratch_floats(const bnnp_plan_t* plan, int64_t N);
 int bnnp_jtr_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                    const float* ws, const float* rs, float* grad, float* scratch, void* stream);
+/* diag[P] += diag(sum_n J_n^T Lambda_n J_n) for an arbitrary per-example Lambda [N,K,K] -- the diagonal GGN that
+ * vi_diag_refine re-evaluates every iteration on a fixed J (preds/refine.py:107-112).  scratch: bnnp_jtr_scratch_floats(). */
+int bnnp_ggn_diag_lambda(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                         const float* ws, const float* Lambda, float* diag, float* scratch, void* stream);
 /* out[s,n,k] = f[n,k] + sum_p J[(n,k),p] dtheta[s,p] -- replaces `offset + Js @ samples[i]` of
  * linear_sampling_predictive (preds/predictives.py:31-47) for all S samples at once; dtheta [S,P] =
  * theta_s - theta*; out [S,N,K] holds logits (apply bnnp_lik_inv_link for the link).  S <= 65535.

@@ -163,6 +163,19 @@ def ggn_case(preds, name, model, lh, lh_desc, X, y, Xte, prior_prec, prior_mu, S
                                                            mc_samples=S, no_link=True))
     with refharness.inject_normals([eps]):
         out['nn_full'] = np_(nn_sampling_predictive(Xte, model, lh, theta_star, st['Sigma_chol'], mc_samples=S))
+    # GLM refinement on the same posterior (experiments/classification.py:137-174)
+    from preds.refine import laplace_refine, vi_refine, vi_diag_refine
+    m, S_chol, S_chold, losses = laplace_refine(model, X, y, lh, 0.7, n_epochs=6, lr=1e-2)
+    out['lapref_mu'], out['lapref_chol'], out['lapref_chold'] = np_(m), np_(S_chol), np_(S_chold)
+    out['lapref_losses'] = np.array(losses)
+    eps_vi = [randn(800 + i, P) for i in range(4)]
+    out['eps_vi'] = np_(torch.stack(eps_vi))
+    with refharness.inject_normals(eps_vi):
+        m, S_chol, losses = vi_refine(model, opt, X, y, lh, n_epochs=4, lr=0.05)
+    out['vi_mu'], out['vi_chol'], out['vi_losses'] = np_(m), np_(S_chol), np.array(losses)
+    with refharness.inject_normals(eps_vi):
+        m, S_chold, losses = vi_diag_refine(model, opt, X, y, lh, n_epochs=4, lr=0.05)
+    out['vid_mu'], out['vid_chol'], out['vid_losses'] = np_(m), np_(S_chold), np.array(losses)
     np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
     print('%-12s P=%d  %.1f KB' % (name, P, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
 

@@ -626,3 +626,97 @@ def classification_metrics(p, y, lik, bins=10):
         if in_bin.any():
             ece += abs(conf[in_bin].double().mean().item() - hit[in_bin].double().mean().item()) * in_bin.double().mean().item()
     return {'nll': nll, 'acc': acc, 'ece': ece}
+
+
+# ------------------------------------------------------------------------------------------
+# GLM refinement on a fixed Jacobian (preds/refine.py)
+# ------------------------------------------------------------------------------------------
+def _glm_parts(model, X):
+    J, f = jacobians(model, X)
+    if J.dim() == 3:
+        J = J.transpose(1, 2)                       # [N,K,P]
+    theta_star = get_theta(model)
+    return J, f - J @ theta_star, theta_star
+
+
+def _log_lik(lh, y, f):
+    """preds/likelihoods.py:31-32,44-45,64-65,81-82 (sum of log-probabilities)."""
+    if lh.name == 'categorical':
+        return torch.distributions.Categorical(logits=f).log_prob(y).sum()
+    if lh.name == 'bernoulli':
+        return torch.distributions.Bernoulli(logits=f).log_prob(y).sum()
+    return torch.distributions.Normal(f, lh.sigma_noise).log_prob(y).sum()
+
+
+def _jlj(J, Lams):
+    if J.dim() == 3:
+        return torch.einsum('mkp,mkl,mlq->pq', J, Lams, J)
+    return (J.T * Lams.reshape(1, -1)) @ J
+
+
+def _jtr(J, rs):
+    return torch.einsum('mkp,mk->p', J, rs) if J.dim() == 3 else J.T @ rs
+
+
+def laplace_refine(model, X, y, lh, prior_prec, n_epochs=1000, lr=1e-3):
+    """(mu, Sigma_chol, Sigma_chol_diag, losses); restates preds/refine.py:9-40."""
+    J, f_offset, theta_star = _glm_parts(model, X)
+    mu = theta_star.clone().requires_grad_(True)
+    opt = torch.optim.Adam([mu], lr=lr)
+    losses = []
+    for _ in range(n_epochs):
+        opt.zero_grad()
+        loss = -_log_lik(lh, y, f_offset + J @ mu) + 0.5 * mu @ mu * prior_prec
+        loss.backward()
+        losses.append(loss.item())
+        opt.step()
+    mu = mu.detach()
+    precision = _jlj(J, lh.hessian(f_offset + J @ mu)) + prior_prec * torch.eye(len(mu))
+    chol = torch.linalg.cholesky(precision)
+    Sigma_chol = torch.linalg.cholesky(torch.cholesky_inverse(chol, upper=False))
+    return mu, Sigma_chol, torch.diag(torch.sqrt(1 / torch.diag(precision))), losses
+
+
+def vi_refine(model, post, prior_prec_matrix, X, y, lh, eps, lr=1e-2):
+    """(mu, Sigma_chol, losses) after len(eps) epochs; restates preds/refine.py:42-81.
+    ``post`` = dict(precision, Sigma_chol) of the LaplaceGGN posterior; eps [n_epochs, P]."""
+    from torch.distributions import MultivariateNormal, kl_divergence
+    beta = lr
+    J, f_offset, theta_star = _glm_parts(model, X)
+    mu = theta_star.clone()
+    Sigma_chol, prec = post['Sigma_chol'].clone(), post['precision'].clone()
+    p = MultivariateNormal(torch.zeros_like(mu), scale_tril=torch.diag(torch.sqrt(1 / torch.diag(prior_prec_matrix))))
+    losses = []
+    for e in eps:
+        f_t = f_offset + J @ (mu + Sigma_chol @ e)
+        H = _jlj(J, lh.hessian(f_t))
+        g = _jtr(J, lh.residual(y, f_t)) - prior_prec_matrix @ mu
+        prec = (1 - beta) * prec + beta * (H + prior_prec_matrix)
+        pchol = torch.linalg.cholesky(prec)
+        mu = mu + beta * torch.cholesky_solve(g.reshape(-1, 1), pchol, upper=False).squeeze()
+        Sigma_chol = torch.linalg.cholesky(torch.cholesky_inverse(pchol, upper=False))
+        q = MultivariateNormal(loc=mu, scale_tril=Sigma_chol)
+        losses.append((-_log_lik(lh, y, f_t) + kl_divergence(q, p)).item())
+    return mu, Sigma_chol, losses
+
+
+def vi_diag_refine(model, post, prior_prec_matrix, X, y, lh, eps, lr=1e-3):
+    """(mu, diag-matrix Sigma_chol, losses); restates preds/refine.py:84-121."""
+    from torch.distributions import Normal, kl_divergence
+    beta = lr
+    J, f_offset, theta_star = _glm_parts(model, X)
+    mu = theta_star.clone()
+    prec = torch.diag(post['precision']).clone()
+    prior = torch.diag(prior_prec_matrix)
+    sigma_chol = torch.sqrt(1 / prec)
+    m_prior = Normal(loc=torch.zeros_like(mu), scale=1 / torch.sqrt(prior))
+    losses = []
+    for e in eps:
+        f_t = f_offset + J @ (mu + sigma_chol * e)
+        H = torch.diag(_jlj(J, lh.hessian(f_t)))
+        g = _jtr(J, lh.residual(y, f_t)) - prior * mu
+        prec = (1 - beta) * prec + beta * (H + prior)
+        mu = mu + beta * g / prec
+        sigma_chol = torch.sqrt(1 / prec)
+        losses.append((-_log_lik(lh, y, f_t) + kl_divergence(Normal(loc=mu, scale=sigma_chol), m_prior).sum()).item())
+    return mu, torch.diag(sigma_chol), losses

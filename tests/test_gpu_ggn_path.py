@@ -178,3 +178,55 @@ def test_engine_rejects_models_it_cannot_represent():
         Jacobians(Skip().cuda(), torch.randn(4, 5).cuda())
     with pytest.raises(cabi.BnnpError, match='functional activation'):
         Jacobians(MLP(5, [6], 2, activation='selu').cuda(), torch.randn(4, 5).cuda())
+
+
+@pytest.mark.parametrize('name', sorted(cases.GGN_CASES))
+def test_refinement_against_reference_golden(name):
+    """laplace_refine / vi_refine / vi_diag_refine on resident Jacobian factors vs the
+    reference's outputs for the same injected draws (few epochs; every epoch re-runs J v, J^T r, J^T Lambda J)."""
+    from preds_b200 import LaplaceGGN
+    from preds_b200.refine import laplace_refine, vi_refine, vi_diag_refine
+    g, model, lh, X, y, Xte = _product(name)
+    P = len(g['theta'])
+    port.set_theta(model, torch.from_numpy(g['theta']))
+    model = model.cuda()
+    pp, pm = cases.ggn_prior(g, P)
+    pp = pp.cuda() if torch.is_tensor(pp) else pp
+    pm = pm.cuda() if torch.is_tensor(pm) else pm
+    opt = LaplaceGGN(model, lr=1e-2, prior_prec=pp, prior_mu=pm)
+    # start the VI loops from the reference's own LaplaceGGN posterior so that only the refinement is compared
+    opt.state['precision'] = torch.from_numpy(g['precision']).cuda()
+    opt.state['Sigma_chol'] = torch.from_numpy(g['Sigma_chol']).cuda()
+
+    mu, chol, chold, losses = laplace_refine(model, X, y, lh, 0.7, n_epochs=6, lr=1e-2)
+    assert cases.rel_err(losses, g['lapref_losses']) < 1e-5
+    assert cases.rel_err(mu.cpu(), g['lapref_mu']) < 1e-5
+    assert cases.rel_err((chol @ chol.T).cpu(), g['lapref_chol'] @ g['lapref_chol'].T) < TOL
+    assert cases.rel_err(chold.cpu(), g['lapref_chold']) < TOL
+
+    eps = torch.from_numpy(g['eps_vi']).cuda()
+    mu, chol, losses = vi_refine(model, opt, X, y, lh, n_epochs=4, lr=0.05, eps=eps)
+    assert cases.rel_err(losses, g['vi_losses']) < TOL
+    assert cases.rel_err(mu.cpu(), g['vi_mu']) < TOL
+    assert cases.rel_err((chol @ chol.T).cpu(), g['vi_chol'] @ g['vi_chol'].T) < TOL
+    mu, chold, losses = vi_diag_refine(model, opt, X, y, lh, n_epochs=4, lr=0.05, eps=eps)
+    assert cases.rel_err(losses, g['vid_losses']) < TOL
+    assert cases.rel_err(mu.cpu(), g['vid_mu']) < TOL
+    assert cases.rel_err(chold.cpu(), g['vid_chol']) < TOL
+
+
+def test_ggn_diag_lambda_is_the_diagonal_of_the_full_ggn():
+    """bnnp_ggn_diag_lambda == diag(bnnp_ggn_full_accum) for the same arbitrary Lambda, at a size that takes the
+    tcgen05 branches of both (256-wide layers, N = 2000)."""
+    from preds_b200.refine import _Linearised
+    from preds_b200.models import MLPS
+    torch.manual_seed(5)
+    model = MLPS(256, [256], 3, 'tanh').cuda()
+    g = torch.Generator().manual_seed(6)
+    X = torch.randn(2000, 256, generator=g).cuda()
+    A = torch.randn(2000, 3, 3, generator=g).cuda()
+    Lam = (A @ A.transpose(1, 2)).contiguous()
+    lin = _Linearised(model, X)
+    d = lin.ggn_diag(Lam)
+    H = lin.ggn(Lam)
+    assert cases.rel_err(d.cpu(), torch.diag(H).cpu()) < 2e-5

@@ -50,3 +50,25 @@ def test_linear_sampling_predictive(name):
     post = {'mu': theta, 'Sigma_chol': chol, 'cov_type': 'full'}
     out = port.bnn_predictive(model, lh, Xte, post, eps)
     assert cases.rel_err(out.reshape(g['nn_full'].shape), g['nn_full']) < TOL
+
+
+@pytest.mark.parametrize('name', sorted(cases.GGN_CASES))
+def test_refinement(name):
+    """preds/refine.py restated, against the reference's outputs for the same draws."""
+    g, model, lh, batches, Xte, P0, mu0 = _setup(name)
+    X, y = torch.from_numpy(g['X']), torch.from_numpy(g['y'])
+    mu, chol, chold, losses = port.laplace_refine(model, X, y, lh, 0.7, n_epochs=6, lr=1e-2)
+    assert cases.rel_err(losses, g['lapref_losses']) < 1e-5
+    assert cases.rel_err(mu, g['lapref_mu']) < 1e-5
+    assert cases.rel_err(chol @ chol.t(), g['lapref_chol'] @ g['lapref_chol'].T) < TOL
+    assert cases.rel_err(chold, g['lapref_chold']) < 1e-5
+    post = {'precision': torch.from_numpy(g['precision']), 'Sigma_chol': torch.from_numpy(g['Sigma_chol'])}
+    eps = torch.from_numpy(g['eps_vi'])
+    mu, chol, losses = port.vi_refine(model, post, P0, X, y, lh, eps, lr=0.05)
+    assert cases.rel_err(losses, g['vi_losses']) < TOL
+    assert cases.rel_err(mu, g['vi_mu']) < TOL
+    assert cases.rel_err(chol @ chol.t(), g['vi_chol'] @ g['vi_chol'].T) < TOL
+    mu, chold, losses = port.vi_diag_refine(model, post, P0, X, y, lh, eps, lr=0.05)
+    assert cases.rel_err(losses, g['vid_losses']) < TOL
+    assert cases.rel_err(mu, g['vid_mu']) < TOL
+    assert cases.rel_err(chold, g['vid_chol']) < TOL
