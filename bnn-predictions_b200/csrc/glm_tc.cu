@@ -20,13 +20,17 @@ namespace glmtc {
 
 using namespace bnnp::tcp;
 
-constexpr int BK = 32, TILE_M = 128, MAX_N = 256, STAGES = 4;
+constexpr int BK = 32, TILE_M = 128, MAX_N = 256, STAGES = 3;
 constexpr int A_TERM = TILE_M * BK * 2, A_STAGE = 2 * A_TERM;
 constexpr int B_TERM = MAX_N * BK * 2, B_STAGE = 2 * B_TERM;
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;               // 48 KB
-constexpr int META_BYTES = 2 * MAX_N * 12;                  // per accumulator buffer: unit id, activation column, bias value
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + META_BYTES;
-constexpr int NUM_THREADS = 256;     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue
+constexpr int META_BYTES = 4 * MAX_N * 12;                  // per accumulator buffer x 2 (consecutive tiles of a warp group): unit id, activation column, bias value
+constexpr int EPI_STAGE_BYTES_FWD = 8 * 32 * 33 * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + META_BYTES + EPI_STAGE_BYTES_FWD;
+constexpr int NUM_THREADS = 384;     // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-11: epilogue (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;          // warps 4-7 own accumulator buffer 0 (even tiles), warps 8-11 buffer 1 (odd tiles):
+                                     // each group has two mainloop periods for its tile, which hides the exposed
+                                     // global-load latencies of the epilogue under the TMA traffic
 constexpr int EPI_WARP0 = 4;
 
 struct Args {
@@ -36,10 +40,128 @@ struct Args {
   int unit0p;                        // global index of the layer's first unit
   int unit_first, unit_step, delta;  // this launch covers units unit_first + i*unit_step (same K-start misalignment delta)
   int wn, n_mt, n_nt, n_chunks;
+  int n_mtp;                         // CTA-pair kernel: input tiles are taken two at a time
+  int dbg;                           // BNNP_GLM_DBG (measurement only): bit 0 skips the epilogue arithmetic
   long long ald; int Mtot;
   const float* Sigma; const float* A; const int32_t* pu; const int32_t* pc; float* T;
   const long long* tile_start;       // [n_units + 1] prefix of tiles per unit of this launch (lower triangle only)
 };
+
+// epilogue of one accumulator tile: T[n, u(p), u'] += a~[n, c(p)] * (Y[n,p] + Sigma[p, bias(u')]) for the 128 input
+// rows m0.. held by this CTA's TMEM; q = epilogue warp 0..3 (TMEM lane quarter).
+// Each thread owns one input row, so reading a~[n, c(p)] directly costs 32 L1 wavefronts per load instruction (32 rows
+// = 32 cache lines) -- ncu showed l1tex as the busiest unit with these gathers as ~80 % of its load, and halving the
+// operand bytes (CTA-pair kernel) changed nothing.  The 32 x 32 activation block of a column step is therefore staged
+// through a per-warp shared-memory tile: lanes run along the columns for the global reads (1-2 wavefronts per row),
+// along the rows for the (padded, conflict-free) reads back.
+constexpr int EPI_STAGE_LD = 33;
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_STAGE_LD * 4;
+__device__ __forceinline__ void glm_epilogue_tile(const Args& args, int* meta, float* stage_all, int ew, int lane,
+                                                  long long m0, long long n0, int up, uint32_t buf, uint32_t buf_phase,
+                                                  uint64_t* acc_full_bar, uint32_t tmem_base) {
+  const int q = ew & 3;                              // TMEM lane quarter (rows); ew >> 2 == buf (checked by the caller)
+  const long long n = m0 + q * 32 + lane;
+  const bool rowok = n < args.N;
+  const int ncols = (int)(args.P - n0 < args.wn ? args.P - n0 : args.wn);
+  // the column metadata is the same for all 128 rows of the tile: stage it in shared memory once
+  // (unit id, activation column, bias-column value of Sigma -- row offb+u' of the symmetric matrix)
+  // a group's consecutive tiles alternate between two copies: a fast warp staging tile i + 2 must not overwrite what a
+  // slower warp of the group still reads for tile i
+  int* m_u = meta + (buf * 2 + buf_phase) * 3 * MAX_N;
+  int* m_c = m_u + MAX_N;
+  float* m_b = reinterpret_cast<float*>(m_c + MAX_N);
+  float* sA = stage_all + ew * 32 * EPI_STAGE_LD;
+  {
+    const float* sbias = args.Sigma + (args.offb + up) * args.P;
+    for (int e = (q * 32 + lane); e < MAX_N; e += 128) {
+      const long long p = n0 + (e < ncols ? e : ncols - 1);
+      m_u[e] = e < ncols ? __ldg(args.pu + p) : -1;          // -1: padding column, contributes nothing
+      m_c[e] = __ldg(args.pc + p);
+      m_b[e] = (args.has_bias && e < ncols) ? __ldg(sbias + p) : 0.f;
+    }
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)buf) : "memory");     // the four warps of this buffer's group
+  if (args.dbg & 1) {
+    mbar_wait(acc_full_bar, buf_phase);
+    tc_fence_after();
+    return;
+  }
+  // rows of this warp: first row and how many are inside the batch
+  const long long r0 = m0 + q * 32;
+  const int nrows = (int)(args.N - r0 < 32 ? (args.N - r0 < 0 ? 0 : args.N - r0) : 32);
+  const float* __restrict__ abase = args.A + r0 * args.ald;
+  float* trow = args.T + ((rowok ? n : 0) * args.Mtot) * (long long)args.Mtot + args.unit0p + up;
+  float acc = 0.f;
+  int ucur = -1;
+  bool waited = false;
+  // a~[r0 + r, c(c0 + lane)] for the warp's 32 rows, one column step ahead: the loads of step c0 + 32 are in flight
+  // while step c0 is reduced (their latency under the TMA traffic is what bounded the epilogue)
+  const int cbeg = 0, cend = ncols;
+  float t[32];
+  if (cbeg < cend) {
+    const int cc = m_c[cbeg + lane];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t[r] = r < nrows ? __ldg(abase + (long long)r * args.ald + cc) : 0.f;
+  }
+  for (int c0 = cbeg; c0 < cend; c0 += 32) {
+    __syncwarp();                                                // previous step's reads of sA are done
+#pragma unroll
+    for (int r = 0; r < 32; ++r) sA[r * EPI_STAGE_LD + lane] = t[r];
+    __syncwarp();
+    if (c0 + 32 < cend) {
+      const int cc = m_c[c0 + 32 + lane];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = r < nrows ? __ldg(abase + (long long)r * args.ald + cc) : 0.f;
+    }
+    if (!waited) {
+      mbar_wait(acc_full_bar, buf_phase);
+      tc_fence_after();
+      waited = true;
+    }
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
+    const float* my = sA + lane * EPI_STAGE_LD;
+    const float4* b4 = reinterpret_cast<const float4*>(m_b + c0);
+    const int u_first = m_u[c0], u_last = m_u[c0 + 31];
+    if (u_first == u_last) {
+      // all 32 columns belong to one unit (runs are nin + 1 long): branch-free dot product
+      if (u_first != ucur) {
+        if (ucur >= 0 && rowok) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
+        ucur = u_first; acc = 0.f;
+      }
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 bb = b4[g];
+        s0 = fmaf(my[g * 4 + 0], __uint_as_float(v[g * 4 + 0]) + bb.x, s0);
+        s1 = fmaf(my[g * 4 + 1], __uint_as_float(v[g * 4 + 1]) + bb.y, s1);
+        s0 = fmaf(my[g * 4 + 2], __uint_as_float(v[g * 4 + 2]) + bb.z, s0);
+        s1 = fmaf(my[g * 4 + 3], __uint_as_float(v[g * 4 + 3]) + bb.w, s1);
+      }
+      acc += s0 + s1;
+    } else {
+      // a unit boundary (or the padding, unit -1) inside the step: run-length reduction, one atomic per run
+      for (int e = 0; e < 32; ++e) {
+        const int u = m_u[c0 + e];
+        if (u != ucur) {
+          if (ucur >= 0 && rowok) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
+          ucur = u; acc = 0.f;
+        }
+        float y;
+        // v[] must stay in registers: select with a fully unrolled predicated chain instead of dynamic indexing
+        y = __uint_as_float(v[0]);
+#pragma unroll
+        for (int k = 1; k < 32; ++k) y = (e == k) ? __uint_as_float(v[k]) : y;
+        acc = fmaf(my[e], y + m_b[c0 + e], acc);
+      }
+    }
+  }
+  if (!waited) {                                       // no columns for this warp: still follow the accumulator hand-over
+    mbar_wait(acc_full_bar, buf_phase);
+    tc_fence_after();
+  }
+  if (rowok && ucur >= 0) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
@@ -54,11 +176,12 @@ glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   int* meta = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + 256);     // [2][3][MAX_N]
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + META_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS / 2); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -125,57 +248,8 @@ glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
-    } else if (warp >= EPI_WARP0) {
-      // epilogue: T[n, u(p), u'] += a~[n, c(p)] * (Y[n,p] + Sigma[p, bias(u')])
-      const int q = warp - EPI_WARP0;
-      const long long n = m0 + q * 32 + lane;
-      const bool rowok = n < args.N;
-      const int ncols = (int)(args.P - n0 < args.wn ? args.P - n0 : args.wn);
-      // the column metadata is the same for all 128 rows of the tile: stage it in shared memory once
-      // (unit id, activation column, bias-column value of Sigma -- row offb+u' of the symmetric matrix)
-      int* m_u = meta + buf * 3 * MAX_N;
-      int* m_c = m_u + MAX_N;
-      float* m_b = reinterpret_cast<float*>(m_c + MAX_N);
-      {
-        const float* sbias = args.Sigma + (args.offb + up) * args.P;
-        for (int e = (q * 32 + lane); e < ncols; e += 128) {
-          const long long p = n0 + e;
-          m_u[e] = __ldg(args.pu + p);
-          m_c[e] = __ldg(args.pc + p);
-          m_b[e] = args.has_bias ? __ldg(sbias + p) : 0.f;
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps only
-      mbar_wait(&acc_full[buf], buf_phase);
-      tc_fence_after();
-      const float* __restrict__ arow = args.A + (rowok ? n : 0) * args.ald;
-      float* trow = args.T + ((rowok ? n : 0) * args.Mtot) * (long long)args.Mtot + args.unit0p + up;
-      float acc = 0.f;
-      int ucur = -1;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
-        if (rowok) {
-          float prod[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {                 // loads first (shared-memory broadcasts + one L1 gather)
-            const int ee = c0 + e < ncols ? c0 + e : ncols - 1;
-            prod[e] = __ldg(arow + m_c[ee]) * (__uint_as_float(v[e]) + m_b[ee]);
-          }
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {                 // run-length reduction over units, one atomic per run
-            if (c0 + e < ncols) {
-              const int u = m_u[c0 + e];
-              if (u != ucur) {
-                if (ucur >= 0) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
-                ucur = u; acc = 0.f;
-              }
-              acc += prod[e];
-            }
-          }
-        }
-      }
-      if (rowok && ucur >= 0) atomicAdd(trow + (long long)ucur * args.Mtot, acc);
+    } else if (warp >= EPI_WARP0 && (uint32_t)((warp - EPI_WARP0) >> 2) == buf) {
+      glm_epilogue_tile(args, meta, epi_stage, warp - EPI_WARP0, lane, m0, n0, up, buf, buf_phase, &acc_full[buf], tmem_base);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -187,6 +261,121 @@ glm_fvar_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- CTA-pair version ------------------------------------------------------------------------------------
+// The single-CTA kernel above is bound by the bytes each SM has to pull from L2: 48 KB per K-chunk against 786 tensor
+// cycles (ncu: 6.7 TB/s L2->SM, tensor pipe 30 %).  Here two CTAs of a cluster (one TPC) run ONE M = 256
+// `tcgen05.mma.cta_group::2`: each CTA stages its own 128 input rows and only HALF of the Sigma tile (wn/2 rows), the
+// tensor core reads both halves -- 32 KB per chunk per SM for the same work.  Rank 0 issues the MMAs and commits to the
+// barriers of both CTAs; every TMA load credits rank 0's `full` barrier; both CTAs run the epilogue on their own TMEM
+// rows and release the accumulator buffer on rank 0's `acc_empty` barrier.
+constexpr int P_STAGES = 5;
+constexpr int P_B_TERM = (MAX_N / 2) * BK * 2, P_STAGE_BYTES = A_STAGE + 2 * P_B_TERM;      // 32 KB
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256 + META_BYTES + EPI_STAGE_BYTES;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+glm_fvar_pair_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                     const __grid_constant__ CUtensorMap map_sh, const __grid_constant__ CUtensorMap map_sl,
+                     Args args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);
+  uint64_t* full = bars;                          // [P_STAGES] used in rank 0 only: all TMA bytes of the pair
+  uint64_t* empty = bars + P_STAGES;              // [P_STAGES] in both CTAs: multicast commit of rank 0
+  uint64_t* acc_full = bars + 2 * P_STAGES;       // [2] in both CTAs
+  uint64_t* acc_empty = bars + 2 * P_STAGES + 2;  // [2] used in rank 0 only: 8 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 4);
+  int* meta = reinterpret_cast<int*>(smem + P_STAGES * P_STAGE_BYTES + 256);
+  float* epi_stage = reinterpret_cast<float*>(smem + P_STAGES * P_STAGE_BYTES + 256 + META_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
+    fence_barrier_init();
+  }
+  cluster_sync_all();                             // barriers of both CTAs exist before anything remote touches them
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_tiles = args.tile_start[args.n_units];
+  const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int half = args.wn / 2;
+  uint32_t stage = 0, phase = 0, iter = 0;
+  int ui = 0;
+  for (long long tile = pair; tile < n_tiles; tile += n_pairs, ++iter) {
+    while (args.tile_start[ui + 1] <= tile) ++ui;
+    const int up = args.unit_first + args.unit_step * ui;
+    const int nt0 = (int)((args.offw + (long long)up * args.nin) / args.wn);
+    const long long local = tile - args.tile_start[ui];
+    const int mtp = (int)(local % args.n_mtp);
+    const int nt = nt0 + (int)(local / args.n_mtp);
+    const long long m0 = ((long long)mtp * 2 + rank) * TILE_M, n0 = (long long)nt * args.wn;
+    const uint32_t buf = iter & 1, buf_phase = (iter >> 1) & 1;
+
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t s = stage, ph = phase;
+        const uint32_t bytes = 2u * (uint32_t)(A_STAGE + 2 * half * BK * 2);
+        const int kcol0 = (int)(args.offw + (long long)up * args.nin) - args.delta;
+        for (int c = 0; c < args.n_chunks; ++c) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* base = smem + s * P_STAGE_BYTES;
+          const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+          // Only rank 0 arrives, expecting the bytes of BOTH CTAs.  Rank 1's loads may complete first (the transaction
+          // count goes negative, the phase cannot end before rank 0's arrival) but never a phase early: its own `empty`
+          // wait orders them after the MMA that consumed the previous use of the stage.  (A per-chunk remote
+          // mbarrier.arrive.release.cluster here costs a GPU-scope MEMBAR per chunk and throttled the whole pipeline.)
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], bytes);
+          tma_load_2d_pair(&map_ah, lead_full, base, c * BK, (int)m0);
+          tma_load_2d_pair(&map_al, lead_full, base + A_TERM, c * BK, (int)m0);
+          tma_load_2d_pair(&map_sh, lead_full, base + A_STAGE, kcol0 + c * BK, (int)(n0 + rank * half));
+          tma_load_2d_pair(&map_sl, lead_full, base + A_STAGE + P_B_TERM, kcol0 + c * BK, (int)(n0 + rank * half));
+          if (++s == P_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && rank == 0) {
+        mbar_wait(&acc_empty[buf], buf_phase ^ 1);
+        tc_fence_after();
+        uint32_t s = stage, ph = phase;
+        const uint32_t idesc = umma_idesc_bf16_pair(args.wn);
+        const uint32_t d = tmem_base + buf * MAX_N;
+        for (int c = 0; c < args.n_chunks; ++c) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + s * P_STAGE_BYTES), b0 = a0 + A_STAGE;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t dah = umma_desc_sw64(a0 + kk * 32), dal = umma_desc_sw64(a0 + A_TERM + kk * 32);
+            const uint64_t dbh = umma_desc_sw64(b0 + kk * 32), dbl = umma_desc_sw64(b0 + P_B_TERM + kk * 32);
+            umma_bf16_pair(d, dah, dbh, idesc, (c | kk) ? 1u : 0u);
+            umma_bf16_pair(d, dah, dbl, idesc, 1u);
+            umma_bf16_pair(d, dal, dbh, idesc, 1u);
+          }
+          umma_commit_pair(&empty[s]);
+          if (c == args.n_chunks - 1) umma_commit_pair(&acc_full[buf]);
+          if (++s == P_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp >= EPI_WARP0 && (uint32_t)((warp - EPI_WARP0) >> 2) == buf) {
+      glm_epilogue_tile(args, meta, epi_stage, warp - EPI_WARP0, lane, m0, n0, up, buf, buf_phase, &acc_full[buf], tmem_base);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+    }
+    const uint32_t tot = stage + (uint32_t)args.n_chunks;
+    phase ^= (tot / P_STAGES) & 1;
+    stage = tot % P_STAGES;
+  }
+  tc_fence_before();
+  cluster_sync_all();                             // nobody leaves while the peer may still signal its barriers / read its smem
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // dst_hi/lo[r, c] = bf16 split of src[r*lds + c] for c < cols, 0 for cols <= c < cpad
@@ -345,10 +534,16 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
     a.n_nt = (int)((P + a.wn - 1) / a.wn);
     a.n_mt = (int)((N + TILE_M - 1) / TILE_M);
   }
-  int rc = make_map(&msh, Sh, P, P, Ppitch, a.wn);
+  // CTA-pair kernel (two input tiles per M = 256 MMA, each CTA stages half of the Sigma tile) whenever there are at
+  // least two input tiles; BNNP_GLM_SINGLE=1 forces the single-CTA kernel (A/B measurements)
+  const bool pair = a.n_mt >= 2 && !getenv("BNNP_GLM_SINGLE");
+  a.n_mtp = (a.n_mt + 1) / 2;
+  a.dbg = getenv("BNNP_GLM_DBG") ? atoi(getenv("BNNP_GLM_DBG")) : 0;
+  int rc = make_map(&msh, Sh, P, P, Ppitch, pair ? a.wn / 2 : a.wn);
   if (rc) return rc;
-  rc = make_map(&msl, Sl, P, P, Ppitch, a.wn);
+  rc = make_map(&msl, Sl, P, P, Ppitch, pair ? a.wn / 2 : a.wn);
   if (rc) return rc;
+  if (pair) BNNP_CUDA_CHECK(cudaFuncSetAttribute(glm_fvar_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
   for (int i = 0; i < n_ops; ++i) {
     const bnnp_op_t& o = ops[i];
     if (o.kind != BNNP_OP_LINEAR) continue;
@@ -378,12 +573,13 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
       a.nin = o.in_c; a.has_bias = o.has_bias;
       a.offw = o.theta_off_w; a.offb = o.has_bias ? o.theta_off_b : 0; a.unit0p = q.lin_unit;
       a.n_chunks = (o.in_c + delta + BK - 1) / BK;
+      if (a.dbg & 2) a.n_chunks = 1;          // measurement only: epilogue-bound run (wrong results)
       // per-unit tile counts (lower triangle): n-tiles from the one holding the unit's first weight row
       std::vector<long long> prefix(a.n_units + 1, 0);
       for (int ui = 0; ui < a.n_units; ++ui) {
         const long long up = grp + (long long)period * ui;
         const long long nt0 = (o.theta_off_w + up * o.in_c) / a.wn;
-        prefix[ui + 1] = prefix[ui] + (a.n_nt - nt0) * a.n_mt;
+        prefix[ui + 1] = prefix[ui] + (a.n_nt - nt0) * (pair ? a.n_mtp : a.n_mt);
       }
       if (prefix_used + a.n_units + 1 > (long long)(M + 64) * 8) return BNNP_ERR_UNSUPPORTED;
       BNNP_CUDA_CHECK(cudaMemcpyAsync(prefix_dev + prefix_used, prefix.data(), sizeof(long long) * (a.n_units + 1),
@@ -391,8 +587,14 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
       a.tile_start = prefix_dev + prefix_used;
       prefix_used += a.n_units + 1;
       const long long n_tiles = prefix[a.n_units];
-      const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-      glm_fvar_tma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, msh, msl, a);
+      if (pair) {
+        const long long pairs = sms / 2;
+        const int grid = 2 * (int)(n_tiles < pairs ? n_tiles : pairs);
+        glm_fvar_pair_kernel<<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(mah, mal, msh, msl, a);
+      } else {
+        const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+        glm_fvar_tma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, msh, msl, a);
+      }
       BNNP_LAUNCH_CHECK();
       if (getenv("BNNP_DEBUG_SYNC")) {
         cudaError_t e = cudaStreamSynchronize(st);
