@@ -258,10 +258,17 @@ def run_ours(args):
         pmean = out.mean(0).cpu()                                           # what the drivers keep (imginference.py:45)
         e2e_glm_s = time.perf_counter() - t0
         glm_ms = ev[2].elapsed_time(ev[3])
+        del out
+        # the same quantity with the mean over samples taken inside the sampling kernel (no [S,N,K] tensor)
+        lap.predictive_mean_glm(Xte[:256], n_samples=8, seed=1)
+        barrier()
+        t0 = time.perf_counter()
+        pmean_fused = lap.predictive_mean_glm(Xte_host, n_samples=S, seed=3).cpu()
+        e2e_fused_s = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([glm_ms, e2e_glm_s], device=dev, dtype=torch.float64)
+            t = torch.tensor([glm_ms, e2e_glm_s, e2e_fused_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            glm_ms, e2e_glm_s = float(t[0]), float(t[1])
+            glm_ms, e2e_glm_s, e2e_fused_s = float(t[0]), float(t[1]), float(t[2])
         secondary = {
             'factorise_full_ms': ev[0].elapsed_time(ev[1]),
             'factorise_note': 'one-off chol(H), cholesky_inverse, chol(Sigma) via cuSOLVER (torch.linalg), P=59635',
@@ -270,6 +277,9 @@ def run_ours(args):
                 'unit': '(inputs x samples)/s', 'inputs_per_gpu': nte, 'samples': S, 'ms': glm_ms,
                 'e2e_value': nte * S * world / e2e_glm_s,
                 'e2e_note': 'pinned host inputs -> predictive_samples_glm -> .mean(0) read back',
+                'e2e_fused_mean_value': nte * S * world / e2e_fused_s,
+                'e2e_fused_mean_note': 'pinned host inputs -> predictive_mean_glm (mean over samples inside the sampler) read back',
+                'fused_vs_materialised_max_abs_diff': float((pmean_fused - pmean).abs().max()),
                 'prob_rows_sum_to_one': float((pmean.sum(1) - 1).abs().max()),
                 'scaling': 'test inputs sharded across ranks, no collective',
             },

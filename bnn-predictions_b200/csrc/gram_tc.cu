@@ -17,6 +17,7 @@
 //   D += Ah*Bh + Ah*Bl + Al*Bh   (3 tcgen05.mma kind::f16 per 16-wide K-step; products exact, fp32
 //        accumulation in TMEM => ~2^-17 relative per term, "fp32-grade" after summation).
 // Epilogue: tcgen05.ld -> registers -> H[p,q] += acc (tiles on/below the diagonal only).
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "gram_tc.cuh"
 
@@ -49,6 +50,7 @@ struct BlockArgs {
   int diag_block;                      // 1 when l == l' (skip tiles strictly above the diagonal)
   int n_chunks, chunk0, Mtot;          // K-chunks of this accumulation segment: [chunk0, chunk0 + n_chunks)
   long long Npad, P;
+  int dbg;                             // BNNP_GRAM_DBG (measurement only): 1 skips the H read-modify-write, 2 skips the A generation
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -220,7 +222,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
         uint8_t* abase = smem + s * STAGE_BYTES;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          if (a < nacc) {
+          if (a < nacc && !(args.dbg & 2)) {
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
               float v[8];
@@ -248,7 +250,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
       mbar_wait(acc_full, acc_phase);
       tc_fence_after();
       const int a = gw >> 2, quarter = gw & 3;
-      if (a < nacc) {
+      if (a < nacc && !(args.dbg & 1)) {
         float* sc = reinterpret_cast<float*>(smem + gw * (32 * 33 * 4 + 128));     // [32][33]
         const int ip = a == 0 ? ipa : ipb;
         const int ncols = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
@@ -528,6 +530,7 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
       const bnnp_op_t& Cc = ops[j];
       if (R.has_bias && R.theta_off_b != R.theta_off_w + (long long)R.out_c * R.in_c) return BNNP_ERR_UNSUPPORTED;
       BlockArgs a;
+      a.dbg = getenv("BNNP_GRAM_DBG") ? atoi(getenv("BNNP_GRAM_DBG")) : 0;
       a.m = R.out_c; a.n = R.in_c; a.has_bias = R.has_bias;
       a.unit0 = plan->op[i].lin_unit; a.col0 = plan->op[i].lin_col; a.row_theta0 = R.theta_off_w;
       a.mp = Cc.out_c; a.np = Cc.in_c; a.unit0p = plan->op[j].lin_unit; a.col_theta0 = Cc.theta_off_w;
