@@ -233,12 +233,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
               uint4 hi, lo;
               split8(v, hi, lo);
               uint8_t* dst = abase + a * 2 * A_TERM_BYTES + soff[it];
-              *reinterpret_cast<uint4*>(dst) = hi;
-              *reinterpret_cast<uint4*>(dst + A_TERM_BYTES) = lo;
+              if (!(args.dbg & 8)) {
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + A_TERM_BYTES) = lo;
+              } else if (hi.x == 0x7fc07fc0u && lo.x == 0x12345678u) {   // keeps the arithmetic alive (never true in practice)
+                *reinterpret_cast<uint4*>(dst) = hi;
+              }
             }
           }
         }
-        fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core (async proxy)
+        if (!(args.dbg & 16)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_a[s]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -266,14 +270,21 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
           for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
           __syncwarp();
           const bool colok = c0 + lane < ncols;
-          {
-            float h[32];                       // all 32 rows of this warp in flight before the first add
+          if (args.dbg & 4) {
+            float h[32];                       // (measurement only) the load-add-store form: pays the read latency
 #pragma unroll
             for (int u = 0; u < 32; ++u)
               h[u] = (colok && u < nrows) ? hbase[(long long)u * args.P + c0 + lane] : 0.f;
 #pragma unroll
             for (int u = 0; u < 32; ++u)
               if (colok && u < nrows) hbase[(long long)u * args.P + c0 + lane] = h[u] + sc[u * 33 + lane];
+          } else {
+            // fire-and-forget reductions (RED.ADD.F32, 128 B per warp request): the add happens in L2, the epilogue
+            // never waits for H.  Every element of H receives exactly one add per launch, so the result does not
+            // depend on the order in which the reductions land.
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (colok && u < nrows) atomicAdd(hbase + (long long)u * args.P + c0 + lane, sc[u * 33 + lane]);
           }
         }
       }
@@ -294,6 +305,263 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
 
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- CTA-pair version -------------------------------------------------------------------------------------------
+// gram_tc_kernel is bound by shared-memory traffic: per 32-example chunk the generators store 32 KB of A, TMA stores
+// 32 KB of B and the tensor core reads 144 KB of operands (measured: 43 ms per launch, 36 without the A stores, 32
+// with neither stores nor H epilogue).  Here two CTAs of a cluster (one TPC) run ONE M = 256 `tcgen05.mma.cta_group::2`
+// over two consecutive 128-row tiles: each CTA generates the A rows of its own tile and stages only HALF of the B tile
+// (the instruction reads the other half from the peer), which also leaves room for a fourth pipeline stage.
+// Rank 0 fetches the tile index for both CTAs, issues the MMAs and commits to the barriers of both; the generators of
+// rank 1 arrive on rank 0's `full_a` barrier, every TMA load credits rank 0's `full_b`.
+constexpr int P_STAGES = 4;
+constexpr int P_B_TERM_BYTES = (MAX_WC / 2) * BK * 2;                      // 8 KB
+constexpr int P_STAGE_BYTES = A_STAGE_BYTES + 2 * P_B_TERM_BYTES;          // 48 KB
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gram_pair_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                 const float* __restrict__ XT32, const float* __restrict__ Ct, float* __restrict__ H,
+                 int* __restrict__ tile_counter, BlockArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_STAGES * P_STAGE_BYTES);
+  uint64_t* full_a = bars;                      // [P_STAGES] rank 0 only: generator warps of both CTAs
+  uint64_t* full_b = bars + P_STAGES;           // [P_STAGES] rank 0 only: TMA bytes of both CTAs
+  uint64_t* empty = bars + 2 * P_STAGES;        // [P_STAGES] both CTAs (multicast commit)
+  uint64_t* acc_full = bars + 3 * P_STAGES;     // both CTAs (multicast commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * P_STAGES + 1);
+  int* tile_slot = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_a[s], 16); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_rtp = (args.n_rt + 1) / 2;
+  const int n_tiles = args.n_pairs * args.n_jt * n_rtp;
+  const int rows_total = args.m * args.n + (args.has_bias ? args.m : 0);
+  uint32_t stage = 0, phase = 0;
+  uint32_t acc_phase = 0;
+
+  for (;;) {
+    if (threadIdx.x == 0 && rank == 0) {
+      const int t = atomicAdd(tile_counter, 1);
+      *tile_slot = t;
+      st_shared_cluster_u32(mapa_shared(smem_u32(tile_slot), 1), (uint32_t)t);
+    }
+    cluster_sync_all();                         // release/acquire at cluster scope: the slot is visible in both CTAs
+    const int tile = *tile_slot;
+    if (tile >= n_tiles) break;
+    const int rtp = tile % n_rtp;
+    const int jt = (tile / n_rtp) % args.n_jt;
+    const int pair = tile / (n_rtp * args.n_jt);
+    const int ipa = 2 * pair, ipb = 2 * pair + 1;
+    const int nacc = ipb < args.mp ? 2 : 1;
+    const int jc0 = jt * args.wc;
+    const int row0 = (2 * rtp + (int)rank) * TILE_M;
+    bool own_needed = row0 < rows_total;
+    bool pair_needed = true;
+    if (args.diag_block) {
+      const long long min_col = args.col_theta0 + (long long)ipa * args.np + jc0;
+      const int prow_last = 2 * rtp * TILE_M + 2 * TILE_M - 1;
+      const long long pair_max_row = args.row_theta0 + (prow_last < rows_total - 1 ? prow_last : rows_total - 1);
+      pair_needed = pair_max_row >= min_col;
+      const long long own_max_row = args.row_theta0 + (row0 + TILE_M - 1 < rows_total - 1 ? row0 + TILE_M - 1 : rows_total - 1);
+      own_needed = own_needed && own_max_row >= min_col;
+    }
+    if (pair_needed) {
+      const int wvalid = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
+      const int nmma = (wvalid + 15) / 16 * 16;                 // instruction N; each CTA supplies nmma/2 rows of B
+      if (warp == 0) {
+        // ===================== TMA producer: this CTA's half of B =====================
+        if (lane == 0) {
+          uint32_t s = stage, ph = phase;
+          const uint32_t bytes = 2u * 2u * (uint32_t)(args.wc / 2) * BK * 2u;        // both CTAs, hi + lo
+          const int brow = jc0 + (int)rank * (nmma / 2);
+          for (int c = 0; c < args.n_chunks; ++c) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* bdst = smem + s * P_STAGE_BYTES + A_STAGE_BYTES;
+            const uint32_t lead_full = mapa_shared(smem_u32(&full_b[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_b[s], bytes);
+            tma_load_2d_pair(&map_bh, lead_full, bdst, (args.chunk0 + c) * BK, brow);
+            tma_load_2d_pair(&map_bl, lead_full, bdst + P_B_TERM_BYTES, (args.chunk0 + c) * BK, brow);
+            if (++s == P_STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      } else if (warp == 1) {
+        // ===================== MMA issuer (rank 0) =====================
+        if (lane == 0 && rank == 0) {
+          uint32_t s = stage, ph = phase;
+          const uint32_t idesc = umma_idesc_bf16_pair(nmma);
+          for (int c = 0; c < args.n_chunks; ++c) {
+            mbar_wait_cluster(&full_a[s], ph);
+            mbar_wait(&full_b[s], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(smem + s * P_STAGE_BYTES);
+            const uint32_t b0 = a0 + A_STAGE_BYTES;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              if (a < nacc) {
+                const uint32_t ah = a0 + a * 2 * A_TERM_BYTES, al = ah + A_TERM_BYTES;
+                const uint32_t d = tmem_base + a * MAX_WC;
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ++ks) {
+                  const uint64_t dah = umma_desc_sw64(ah + ks * 32), dal = umma_desc_sw64(al + ks * 32);
+                  const uint64_t dbh = umma_desc_sw64(b0 + ks * 32), dbl = umma_desc_sw64(b0 + P_B_TERM_BYTES + ks * 32);
+                  umma_bf16_pair(d, dah, dbh, idesc, (c | ks) ? 1u : 0u);
+                  umma_bf16_pair(d, dah, dbl, idesc, 1u);
+                  umma_bf16_pair(d, dal, dbh, idesc, 1u);
+                }
+              }
+            }
+            umma_commit_pair(&empty[s]);
+            if (c == args.n_chunks - 1) umma_commit_pair(acc_full);
+            if (++s == P_STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      } else if (warp >= GEN_WARP0) {
+        // ===================== A generators (then epilogue), rows of this CTA's own tile =====================
+        const int gw = warp - GEN_WARP0;
+        const int g = lane & 3;
+        const float* xsrc[2];
+        const float* csrc[2][2];
+        bool rvalid[2];
+        uint32_t soff[2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int rl = gw * 16 + it * 8 + (lane >> 2);
+          const int r = row0 + rl;
+          rvalid[it] = r < rows_total;
+          int u = args.unit0, src = args.col0;
+          if (rvalid[it]) {
+            if (r < args.m * args.n) { u += r / args.n; src += r % args.n; }
+            else { u += r - args.m * args.n; src += args.n; }
+          }
+          xsrc[it] = XT32 + (long long)src * args.Npad + (long long)args.chunk0 * BK + g * 8;
+          csrc[0][it] = Ct + ((long long)(args.unit0p + ipa) * args.Mtot + u) * args.Npad + (long long)args.chunk0 * BK + g * 8;
+          csrc[1][it] = Ct + ((long long)(args.unit0p + (nacc > 1 ? ipb : ipa)) * args.Mtot + u) * args.Npad + (long long)args.chunk0 * BK + g * 8;
+          soff[it] = (uint32_t)((rl >> 3) * 512 + (rl & 7) * 64 + ((g ^ ((rl >> 1) & 3)) << 4));
+        }
+        uint32_t s = stage, ph = phase;
+        const int pf_chunk = args.n_chunks > 48 ? args.n_chunks - 40 : 0;
+        float4 xv[2][2], cv[2][2][2];
+        auto load_chunk = [&](int c) {
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const float4* xp = reinterpret_cast<const float4*>(xsrc[it] + c * BK);
+            xv[it][0] = __ldg(xp); xv[it][1] = __ldg(xp + 1);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              const float4* cp = reinterpret_cast<const float4*>(csrc[a][it] + c * BK);
+              cv[a][it][0] = __ldg(cp); cv[a][it][1] = __ldg(cp + 1);
+            }
+          }
+        };
+        load_chunk(0);
+        for (int c = 0; c < args.n_chunks; ++c) {
+          float4 x[2][2], cc[2][2][2];
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            x[it][0] = xv[it][0]; x[it][1] = xv[it][1];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) { cc[a][it][0] = cv[a][it][0]; cc[a][it][1] = cv[a][it][1]; }
+          }
+          if (c + 1 < args.n_chunks) load_chunk(c + 1);
+          if (c == pf_chunk && own_needed) {
+            const int lines = (wvalid * 4 + 127) / 128 + 1;
+            for (int a = 0; a < nacc; ++a) {
+              const int ip = a == 0 ? ipa : ipb;
+              for (int w = (warp - GEN_WARP0) * 32 + lane; w < TILE_M * lines; w += 256) {
+                const int rr = w / lines, ln = w % lines;
+                if (row0 + rr < rows_total) {
+                  const float* ptr = H + (args.row_theta0 + row0 + rr) * args.P + args.col_theta0 +
+                                     (long long)ip * args.np + jc0 + ln * 32;
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                }
+              }
+            }
+          }
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* abase = smem + s * P_STAGE_BYTES;
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            if (a < nacc) {
+#pragma unroll
+              for (int it = 0; it < 2; ++it) {
+                float v[8];
+                const float* xf = reinterpret_cast<const float*>(&x[it][0]);
+                const float* cf = reinterpret_cast<const float*>(&cc[a][it][0]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = rvalid[it] ? xf[e] * cf[e] : 0.f;
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                uint8_t* dst = abase + a * 2 * A_TERM_BYTES + soff[it];
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + A_TERM_BYTES) = lo;
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&full_a[s]);
+            else mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&full_a[s]), 0));
+          }
+          if (++s == P_STAGES) { s = 0; ph ^= 1; }
+        }
+        // ---------------- epilogue: H[p, q] += D for this CTA's rows ----------------
+        mbar_wait(acc_full, acc_phase);
+        tc_fence_after();
+        const int a = gw >> 2, quarter = gw & 3;
+        if (a < nacc && own_needed) {
+          float* sc = reinterpret_cast<float*>(smem + gw * (32 * 33 * 4 + 128));
+          const int ip = a == 0 ? ipa : ipb;
+          const int rbase = row0 + quarter * 32;
+          float* hbase = H + (args.row_theta0 + rbase) * args.P + args.col_theta0 + (long long)ip * args.np + jc0;
+          int nrows = rows_total - rbase;
+          nrows = nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows);
+          for (int c0 = 0; c0 < wvalid; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * MAX_WC + c0), v);
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
+            __syncwarp();
+            const bool colok = c0 + lane < wvalid;
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (colok && u < nrows) atomicAdd(hbase + (long long)u * args.P + c0 + lane, sc[u * 33 + lane]);
+          }
+        }
+        tc_fence_before();
+      }
+      {
+        const uint32_t tot = stage + (uint32_t)args.n_chunks;
+        phase ^= (tot / P_STAGES) & 1;
+        stage = tot % P_STAGES;
+        acc_phase ^= 1;
+      }
+    }
+    tc_fence_before();
+    cluster_sync_all();         // both CTAs drained their TMEM rows (and read the tile slot) before the next tile
+    tc_fence_after();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------- pre-kernels
@@ -517,6 +785,7 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
     if (rc) return rc;
   }
   BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -555,13 +824,16 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
       a.n_rt = (rows_total + TILE_M - 1) / TILE_M;
       a.diag_block = (i == j);
       a.Mtot = M; a.Npad = L.Npad; a.P = plan->P;
+      // CTA-pair kernel (two row tiles per M = 256 MMA, half of the B tile per SM) whenever the block has at least two
+      // row tiles; BNNP_GRAM_SINGLE=1 forces the single-CTA kernel (A/B measurements)
+      const bool use_pair = a.n_rt >= 2 && !getenv("BNNP_GRAM_SINGLE");
       CUtensorMap mh, ml;
-      int rc = make_b_map(&mh, XTh + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, a.wc);
+      int rc = make_b_map(&mh, XTh + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, use_pair ? a.wc / 2 : a.wc);
       if (rc) return rc;
-      rc = make_b_map(&ml, XTl + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, a.wc);
+      rc = make_b_map(&ml, XTl + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, use_pair ? a.wc / 2 : a.wc);
       if (rc) return rc;
-      const long long n_tiles = (long long)a.n_pairs * a.n_jt * a.n_rt;
-      int grid = (int)(n_tiles < sms ? n_tiles : sms);
+      const long long n_tiles = (long long)a.n_pairs * a.n_jt * (use_pair ? (a.n_rt + 1) / 2 : a.n_rt);
+      int grid = use_pair ? 2 * (int)(n_tiles < sms / 2 ? n_tiles : sms / 2) : (int)(n_tiles < sms ? n_tiles : sms);
       // The TMEM accumulators truncate on every update, so one accumulation never spans more than
       // kMaxAccumExamples examples; the segments are combined in fp32 (round-to-nearest) through H.
       const int total_chunks = (int)(L.Npad / BK), seg_chunks = kMaxAccumExamples / BK;
@@ -578,7 +850,8 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
           gram_flops(a, &g_prof.executed[g_prof.n], &g_prof.useful[g_prof.n]);
           cudaEventRecord(g_prof.beg[g_prof.n], st);
         }
-        gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+        if (use_pair) gram_pair_kernel<<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+        else gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
         if (prof) { cudaEventRecord(g_prof.end[g_prof.n], st); ++g_prof.n; }
         BNNP_LAUNCH_CHECK();
         ++pair_idx;
