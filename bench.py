@@ -307,7 +307,7 @@ def run_ours(args):
         except Exception:
             pass
         roofline = {
-            'bound': 'tensor', 'kernel': 'gram_tc_kernel', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+            'bound': 'tensor', 'kernel': 'gram_pair_kernel (CTA-pair tcgen05.mma; gram_tc_kernel when a block has one row tile)', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': ach / peak, 'traffic': traffic, 'peak_source': pk_kind + ' bf16 dense (sustained)',
             'kernel_ms_per_launch': avg_ms, 'kernel_share_of_step': sum(r[0] for r in recs) / ms,
             'flops_note': 'achieved = useful bf16 MMA flops (3 split passes x 2*N*rows*cols of the computed '
