@@ -212,10 +212,15 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
   idx[n * per + r] = bi;
 }
 
-// grid: (ceil(H*W/256), C, rows): one 32-bit division per thread
+// grid: (ceil(H*W/256), C, z): the candidate windows of a position are found once and reused for all rows.
+// FUSE != 0: the op in front of the pool is an elementwise activation whose (in-place) output `act` is the pool's
+// input; its backward  g *= act'(out)  is applied to the value before the single store, which removes one full
+// read-modify-write pass over the [R, C*H*W] gradient (the K-column backward of a conv net is HBM-bound).
+template <int FUSE>
 __global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
                                    float* __restrict__ gin, int64_t gild,
-                                   const int32_t* __restrict__ idx, int64_t R, int V, ConvGeom g) {
+                                   const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g,
+                                   const float* __restrict__ act, int64_t actld, int act_kind) {
   const int me = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = g.H * g.W;
   if (me >= HW) return;
@@ -223,29 +228,48 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
   const int ih = me / g.W, iw = me - ih * g.W;
   const int OL = g.OH * g.OW;
   const int64_t operp = (int64_t)g.Cout * OL;
-  // the (at most kh*kw) pooling windows that contain this input position
-  int cand[9];
-  int ncand = 0;
-  for (int a = 0; a < g.kh && ncand < 9; ++a) {
-    const int th = ih + g.pt - a;
-    if (th < 0 || th % g.sh) continue;
-    const int oh = th / g.sh;
-    if (oh >= g.OH) continue;
-    for (int b = 0; b < g.kw && ncand < 9; ++b) {
-      const int tw = iw + g.pl - b;
-      if (tw < 0 || tw % g.sw) continue;
-      const int ow = tw / g.sw;
-      if (ow >= g.OW) continue;
-      cand[ncand++] = oh * g.OW + ow;
-    }
+  // the (at most 3 x 3) pooling windows that contain this input position: up to three output rows and three output
+  // columns, kept in registers (compile-time indexed) -- a dynamically indexed candidate list lives in local memory and
+  // costs a load per use in the row loop
+  int ohs[3], ows[3];
+  bool vh[3], vw[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int th = ih + g.pt - a, tw = iw + g.pl - a;
+    vh[a] = a < g.kh && th >= 0 && th % g.sh == 0 && th / g.sh < g.OH;
+    vw[a] = a < g.kw && tw >= 0 && tw % g.sw == 0 && tw / g.sw < g.OW;
+    ohs[a] = vh[a] ? th / g.sh : 0;
+    ows[a] = vw[a] ? tw / g.sw : 0;
   }
-  for (int64_t r = blockIdx.z; r < R; r += gridDim.z) {
-    const int32_t* id = idx + (r / V) * operp + (int64_t)c * OL;
-    const float* go = gout + r * gold + (int64_t)c * OL;
-    float acc = 0.f;
-    for (int t = 0; t < ncand; ++t)
-      if (id[cand[t]] == me) acc += go[cand[t]];
-    gin[r * gild + (int64_t)c * HW + me] = acc;
+  // examples in the outer loop: the arg-max indices (and the activation derivative) are per example, shared by its V rows
+  for (int64_t n = blockIdx.z; n < N; n += gridDim.z) {
+    const int32_t* id = idx + n * operp + (int64_t)c * OL;
+    unsigned hit = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        if (vh[a] && vw[b] && id[ohs[a] * g.OW + ows[b]] == me) hit |= 1u << (a * 3 + b);
+    float d = 1.f;
+    if (FUSE) {
+      const float o = act[n * actld + (int64_t)c * HW + me];
+      d = act_kind == BNNP_OP_RELU ? (o > 0.f ? 1.f : 0.f) : (act_kind == BNNP_OP_TANH ? 1.f - o * o : o * (1.f - o));
+    }
+    if (hit == 0) {                         // not the arg-max of any window (most positions): the V rows are zeros
+      for (int v = 0; v < V; ++v) gin[(n * V + v) * gild + (int64_t)c * HW + me] = 0.f;
+      continue;
+    }
+    for (int v = 0; v < V; ++v) {
+      const int64_t r = n * V + v;
+      const float* go = gout + r * gold + (int64_t)c * OL;
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+          if (hit & (1u << (a * 3 + b))) acc += go[ohs[a] * g.OW + ows[b]];
+      gin[r * gild + (int64_t)c * HW + me] = FUSE ? acc * d : acc;
+    }
   }
 }
 
@@ -600,7 +624,9 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
     int rc = copy2d(ws + q.grad_off, q.grad_ld, seed, K, R, K, st);
     if (rc) return rc;
   }
+  bool fused_prev = false;
   for (int i = n_ops - 1; i > first_param; --i) {
+    if (fused_prev) { fused_prev = false; continue; }      // this activation's backward was folded into the op after it
     const bnnp_op_t& o = ops[i];
     const bnnp_op_plan_t& q = plan->op[i];
     const bnnp_op_plan_t& qp = plan->op[i - 1];
@@ -650,15 +676,24 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
         }
         break;
       case BNNP_OP_MAXPOOL2D:
-        if (o.kh * o.kw > 9) return BNNP_ERR_UNSUPPORTED;
+        if (o.kh > 3 || o.kw > 3) return BNNP_ERR_UNSUPPORTED;
         {
-          // few z-blocks: the candidate windows depend on (channel, position) only and are reused across rows
+          // few z-blocks: the candidate windows depend on (channel, position) only and are reused across examples
           const int64_t bxy = ceil_div64((int64_t)o.in_h * o.in_w, 256) * o.in_c;
           int64_t gz = ceil_div64(4096, bxy);
-          gz = gz < 1 ? 1 : (gz > R ? R : gz);
-          maxpool_bwd_kernel<<<dim3((unsigned)ceil_div64((int64_t)o.in_h * o.in_w, 256), (unsigned)o.in_c, (unsigned)gz),
-                               256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld,
-                                             reinterpret_cast<const int32_t*>(ws) + q.idx_off, R, V, geom_of(o));
+          gz = gz < 1 ? 1 : (gz > N ? N : gz);
+          const dim3 grid((unsigned)ceil_div64((int64_t)o.in_h * o.in_w, 256), (unsigned)o.in_c, (unsigned)gz);
+          const int32_t* idxp = reinterpret_cast<const int32_t*>(ws) + q.idx_off;
+          // an elementwise activation right in front of the pool (conv -> relu -> pool): its backward is folded into
+          // this kernel's store and the op is skipped below
+          if (i - 1 > first_param && is_elementwise_op(ops[i - 1])) {
+            maxpool_bwd_kernel<1><<<grid, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o),
+                                                        ws + qp.act_off, qp.act_ld, ops[i - 1].kind);
+            fused_prev = true;
+          } else {
+            maxpool_bwd_kernel<0><<<grid, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o),
+                                                        nullptr, 0, 0);
+          }
         }
         BNNP_LAUNCH_CHECK();
         break;
