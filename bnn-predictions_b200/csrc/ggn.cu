@@ -577,6 +577,9 @@ extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, con
       int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
       int64_t v = N * L * ((E + 3) / 4 * 4) + 64 + (int64_t)tcg::pick_ksplit(E, E, N * L, 1) * E * E;
       part = part > v ? part : v;
+      int64_t m = ops[i].out_c;
+      int64_t gsplit = (int64_t)(tcg::pick_ksplit(m, m, N * V, 1) + (N * V + 4095) / 4096 + 1) * m * m;
+      part = part > gsplit ? part : gsplit;
     }
   }
   return kfac_conv_floats(ops, n_ops, N, V) + part + 128;
@@ -622,8 +625,16 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
       conv_possum_kernel<<<(unsigned)ceil_div64(R * o.out_c * 32, 256), 256, 0, st>>>(G, q.grad_ld, R, o.out_c, L,
                                                                                        scratch, o.out_c);
       BNNP_LAUNCH_CHECK();
-      int rc = gemm_simt(o.out_c, o.out_c, R, 1, LoadTA{scratch, o.out_c, 0}, LoadNB{scratch, o.out_c, 0},
-                         AccumScaled{Gf, o.out_c, factor}, st);
+      int rc;
+      // G += factor * S^T S over the R position-summed rows: a 64..128-wide Gram is one to four SIMT blocks walking
+      // all R rows -- the split-K tensor-core Gram spreads it over the machine
+      if ((long long)o.out_c * o.out_c * R >= (1LL << 22))
+        rc = tcg::gemm_tc_splitk(o.out_c, o.out_c, R, 1, tcg::TcColMajor{scratch, o.out_c, 0}, tcg::TcColMajor{scratch, o.out_c, 0},
+                                 factor, 1.f, Gf, o.out_c, 0, scratch + kfac_conv_floats(ops, n_ops, N, V),
+                                 tcg::pick_ksplit(o.out_c, o.out_c, R, 1), st);
+      else
+        rc = gemm_simt(o.out_c, o.out_c, R, 1, LoadTA{scratch, o.out_c, 0}, LoadNB{scratch, o.out_c, 0},
+                       AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       Im2col u = make_im2col(o, in, ild, 1);
       if ((long long)E * E * N * L >= kTcMinMacsG) {
