@@ -231,7 +231,47 @@ __global__ void im2col_kernel(Im2col u, int64_t N, int L, int E, int Epad, float
   U[i] = e < E ? u.at(rp / L, (int)(rp % L), e) : 0.f;
 }
 
-// conv weight diag: d[co, e] += factor * sum_r ( sum_pos gout[r,co,pos] U[r/V, e, pos] )^2
+// ---- conv weight diag on the tensor cores: one [Cout x L]·[L x E] product per row r = (n,v) as a batched gemm_tc whose
+// epilogue squares the accumulator and adds it to the partial sum of the CTA that ran the tile (tiles are assigned
+// statically, so every partial has a fixed summation order; the partials are reduced afterwards).
+struct TcUnfoldT {         // X(e, k = pos) of batch r: U[((r / V) * L + pos) * Epad + e]
+  static constexpr bool K_CONTIG = false;
+  using Row = const float*;
+  const float* U; long long Epad; int L, V;
+  __device__ __forceinline__ Row row(int64_t e, int b) const { return U + (long long)(b / V) * L * Epad + e; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = (k0 + j < K) ? __ldg(rw + (k0 + j) * Epad) : 0.f;
+  }
+};
+struct TcSqAccumPart : tcg::TcNoState {     // part[cta][e][co] += acc^2
+  // The epilogue thread owns one accumulator row (co) and 32 consecutive columns (e): with the partials stored
+  // column-major (co contiguous) the 32 lanes of a warp touch 128 contiguous bytes per access; row-major partials
+  // cost 32 L1 wavefronts per instruction (ncu: generators idle on `empty`, tensor pipe 1.4 %, 52 us per tile).
+  float* part; long long stride; int MP;
+  __host__ __device__ TcSqAccumPart(float* p_, long long s_, int MP_) : part(p_), stride(s_), MP(MP_) {}
+  __device__ __forceinline__ void row(State&, int64_t m, int64_t n0, const float* v, int nvalid, int, int) const {
+    float* __restrict__ q = part + (long long)blockIdx.x * stride + n0 * MP + m;
+    float h[32];                             // all 32 loads in flight before the first dependent store
+#pragma unroll
+    for (int e = 0; e < 32; ++e) h[e] = e < nvalid ? q[(long long)e * MP] : 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (e < nvalid) q[(long long)e * MP] = fmaf(v[e], v[e], h[e]);
+  }
+};
+// d[co*E + e] += factor * sum_cta part[cta][e*MP + co]   (fixed summation order)
+__global__ void reduce_partials_t_kernel(const float* __restrict__ part, int ncta, long long stride, int Cout, int E,
+                                         int MP, float factor, float* __restrict__ d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // over [E][Cout], co fastest (coalesced reads)
+  if (i >= (int64_t)E * Cout) return;
+  const int co = (int)(i % Cout), e = (int)(i / Cout);
+  float acc = 0.f;
+  for (int z = 0; z < ncta; ++z) acc += part[(long long)z * stride + (long long)e * MP + co];
+  d[(long long)co * E + e] += factor * acc;
+}
+
+// conv weight diag (SIMT, small problems): d[co, e] += factor * sum_r ( sum_pos gout[r,co,pos] U[r/V, e, pos] )^2
 // one block per 64x64 output tile, looping over all rows r (the per-sample Jacobian tile is
 // formed in registers, squared and accumulated -- never stored).
 __global__ void __launch_bounds__(G_THREADS)
@@ -475,7 +515,9 @@ extern "C" int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops,
   int64_t lin = 0;
   for (int i = 0; i < n_ops; ++i) {
     if (ops[i].kind == BNNP_OP_CONV2D) {
-      int64_t v = N * V * ops[i].out_c + 64 + 64LL * ops[i].out_c * ops[i].in_c * ops[i].kh * ops[i].kw + 64;
+      // position sums + per-CTA partials (<= 256 CTAs) + the unfolded input of the tensor-core path
+      int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
+      int64_t v = N * V * ops[i].out_c + 64 + 256LL * ((ops[i].out_c + 31) / 32 * 32) * E + 64 + N * L * ((E + 3) / 4 * 4) + 64;
       need = need > v ? need : v;
     }
     if (ops[i].kind == BNNP_OP_LINEAR) {
@@ -531,16 +573,36 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     if (!in) return BNNP_ERR_INVALID;
     int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
     const float* G = ws + q.grad_off;
-    const int nz = conv_diag_splits(o, N * V);
     float* partial = scratch + N * V * (int64_t)o.out_c + 64;
-    dim3 grid((unsigned)ceil_div64(E, G_BN), (unsigned)ceil_div64(o.out_c, G_BM), (unsigned)nz);
-    conv_diag_kernel<<<grid, G_THREADS, 0, st>>>(ConvGradA{G, q.grad_ld, L},
-                                                 ConvUnfoldB{make_im2col(o, in, ild, V)}, N * V, o.out_c, E,
-                                                 L, partial);
-    BNNP_LAUNCH_CHECK();
-    reduce_partials_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * E, 256), 256, 0, st>>>(
-        partial, nz, (int64_t)o.out_c * E, factor, diag + o.theta_off_w);
-    BNNP_LAUNCH_CHECK();
+    if ((long long)N * V * o.out_c * L * E >= kTcMinMacsG && N * V <= 0x7fffffff) {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int Epad = (E + 3) / 4 * 4;
+      const int MP = (o.out_c + 31) / 32 * 32;
+      const long long stride = (long long)MP * E;
+      float* U = partial + sms * stride + 64;
+      BNNP_CUDA_CHECK(cudaMemsetAsync(partial, 0, sizeof(float) * sms * stride, st));
+      im2col_kernel<<<(unsigned)ceil_div64(N * L * (int64_t)Epad, 256), 256, 0, st>>>(make_im2col(o, in, ild, 1), N, L, E,
+                                                                                     Epad, U);
+      BNNP_LAUNCH_CHECK();
+      int rc = tcg::gemm_tc(o.out_c, E, L, (int)(N * V), tcg::TcRowMajor{G, L, q.grad_ld}, TcUnfoldT{U, Epad, L, V},
+                            TcSqAccumPart(partial, stride, MP), 1, st);
+      if (rc) return rc;
+      reduce_partials_t_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * E, 256), 256, 0, st>>>(
+          partial, sms, stride, o.out_c, E, MP, factor, diag + o.theta_off_w);
+      BNNP_LAUNCH_CHECK();
+    } else {
+      const int nz = conv_diag_splits(o, N * V);
+      dim3 grid((unsigned)ceil_div64(E, G_BN), (unsigned)ceil_div64(o.out_c, G_BM), (unsigned)nz);
+      conv_diag_kernel<<<grid, G_THREADS, 0, st>>>(ConvGradA{G, q.grad_ld, L},
+                                                   ConvUnfoldB{make_im2col(o, in, ild, V)}, N * V, o.out_c, E,
+                                                   L, partial);
+      BNNP_LAUNCH_CHECK();
+      reduce_partials_kernel<<<(unsigned)ceil_div64((int64_t)o.out_c * E, 256), 256, 0, st>>>(
+          partial, nz, (int64_t)o.out_c * E, factor, diag + o.theta_off_w);
+      BNNP_LAUNCH_CHECK();
+    }
     if (o.has_bias) {
       int64_t R = N * V;
       conv_possum_kernel<<<(unsigned)ceil_div64(R * o.out_c * 32, 256), 256, 0, st>>>(G, q.grad_ld, R, o.out_c, L,
