@@ -341,6 +341,66 @@ __global__ void fvar_gg_const_kernel(const float* __restrict__ Gh, int64_t gld, 
   fvar[i] += acc;
 }
 
+// fvar[n,k,l] += sum_u Gh[(n,k),u] Gh[(n,l),u] (T[n,u] + wb[u])   -- weight and bias terms of a Linear layer in ONE pass.
+// One warp per input: the K rows of Gh[n] are read once (coalesced along u), the K(K+1)/2 products live in registers
+// (the thread-per-(n,k,l) kernels above re-read every row K times with stride-m access).
+template <int KK>
+__global__ void __launch_bounds__(128)
+fvar_gg_fused_kernel(const float* __restrict__ Gh, int64_t gld, const float* __restrict__ T, int64_t tld,
+                     const float* __restrict__ wb, int64_t N, int m, float* __restrict__ fvar) {
+  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float acc[KK * (KK + 1) / 2];
+#pragma unroll
+  for (int i = 0; i < KK * (KK + 1) / 2; ++i) acc[i] = 0.f;
+  const float* g = Gh + n * KK * gld;
+  const float* t = T + n * tld;
+  for (int u = lane; u < m; u += 32) {
+    const float w = t[u] + (wb ? wb[u] : 0.f);
+    float gv[KK];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) gv[k] = g[k * gld + u];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      const float gw = gv[k] * w;
+#pragma unroll
+      for (int l = 0; l <= k; ++l) acc[k * (k + 1) / 2 + l] = fmaf(gw, gv[l], acc[k * (k + 1) / 2 + l]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KK; ++k)
+#pragma unroll
+    for (int l = 0; l <= k; ++l) {
+      const float v = warp_sum(acc[k * (k + 1) / 2 + l]);
+      if (lane == 0) {
+        fvar[(n * KK + k) * KK + l] += v;
+        if (l != k) fvar[(n * KK + l) * KK + k] += v;
+      }
+    }
+}
+template <int KK>
+static int launch_gg_fused(const float* Gh, int64_t gld, const float* T, int64_t tld, const float* wb, int64_t N, int m,
+                           float* fvar, cudaStream_t st) {
+  fvar_gg_fused_kernel<KK><<<(unsigned)ceil_div64(N * 32, 128), 128, 0, st>>>(Gh, gld, T, tld, wb, N, m, fvar);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+struct TcRowMajorSq {      // X(r, k) = p[r*ld + k]^2
+  static constexpr bool K_CONTIG = true;
+  using Row = const float*;
+  const float* p; long long ld;
+  __device__ __forceinline__ Row row(int64_t r, int) const { return p + r * ld; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = (k0 + e < K) ? __ldg(rw + k0 + e) : 0.f;
+      out[e] = v * v;
+    }
+  }
+};
+constexpr long long kTcMinMacsK = 1LL << 25;
+
 // ---- sampling epilogue ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
   *hi = __umulhi(a, b);
@@ -752,23 +812,48 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       float* T = Gh + R * m;               // [N, m]    Dinv (Ah^2)
       float* D = T + N * m;                // [m, n]
       float* db = D + (int64_t)m * n;      // [m]
-      rc = gemm_simt(N, n, n, 1, LoadRowMajorA{ws + plan->acat_off + q.lin_col, plan->Dtot, 0},
-                     LoadRowMajorB{W2, n, 0}, StoreAxpby{Ah, n, 0, 1.f, 0.f}, st);
+      // the three contractions go to the tensor cores (split-bf16, fp32-grade) once they are large enough
+      const float* Ain = ws + plan->acat_off + q.lin_col;
+      if ((long long)N * n * n >= kTcMinMacsK)
+        rc = tcg::gemm_tc(N, n, n, 1, tcg::TcRowMajor{Ain, plan->Dtot, 0}, tcg::TcColMajor{W2, n, 0},
+                          tcg::TcStoreAxpby(Ah, n, 0, 1.f, 0.f), 1, st);
+      else
+        rc = gemm_simt(N, n, n, 1, LoadRowMajorA{Ain, plan->Dtot, 0}, LoadRowMajorB{W2, n, 0}, StoreAxpby{Ah, n, 0, 1.f, 0.f}, st);
       if (rc) return rc;
-      rc = gemm_simt(R, m, m, 1, LoadRowMajorA{G, q.grad_ld, 0}, LoadRowMajorB{W1, m, 0},
-                     StoreAxpby{Gh, m, 0, 1.f, 0.f}, st);
+      if ((long long)R * m * m >= kTcMinMacsK)
+        rc = tcg::gemm_tc(R, m, m, 1, tcg::TcRowMajor{G, q.grad_ld, 0}, tcg::TcColMajor{W1, m, 0},
+                          tcg::TcStoreAxpby(Gh, m, 0, 1.f, 0.f), 1, st);
+      else
+        rc = gemm_simt(R, m, m, 1, LoadRowMajorA{G, q.grad_ld, 0}, LoadRowMajorB{W1, m, 0}, StoreAxpby{Gh, m, 0, 1.f, 0.f}, st);
       if (rc) return rc;
       kron_dinv_kernel<<<(unsigned)ceil_div64((int64_t)m * n, 256), 256, 0, st>>>(l1, l2, m, n, delta_w[i], dampen, 0, D);
       BNNP_LAUNCH_CHECK();
-      rc = gemm_simt(N, m, n, 1, LoadSqRows{Ah, n}, LoadDinvT{D, n}, StoreAxpby{T, m, 0, 1.f, 0.f}, st);
+      if ((long long)N * m * n >= kTcMinMacsK)
+        rc = tcg::gemm_tc(N, m, n, 1, TcRowMajorSq{Ah, n}, tcg::TcRowMajor{D, n, 0}, tcg::TcStoreAxpby(T, m, 0, 1.f, 0.f), 1, st);
+      else
+        rc = gemm_simt(N, m, n, 1, LoadSqRows{Ah, n}, LoadDinvT{D, n}, StoreAxpby{T, m, 0, 1.f, 0.f}, st);
       if (rc) return rc;
-      fvar_weighted_gg_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(Gh, m, T, m, N, K, m, f_var);
-      BNNP_LAUNCH_CHECK();
       if (o.has_bias) {
         inv_shift_kernel<<<(unsigned)ceil_div64(m, 128), 128, 0, st>>>(l1, m, delta_b[i], 0, db);
         BNNP_LAUNCH_CHECK();
-        fvar_gg_const_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(Gh, m, db, N, K, m, f_var);
-        BNNP_LAUNCH_CHECK();
+      }
+      {
+        const float* wb = o.has_bias ? db : nullptr;
+#define BNNP_CASE(KK) case KK: rc = launch_gg_fused<KK>(Gh, m, T, m, wb, N, m, f_var, st); break;
+        switch (K) {
+          BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
+          BNNP_CASE(9) BNNP_CASE(10) BNNP_CASE(11) BNNP_CASE(12) BNNP_CASE(13) BNNP_CASE(14) BNNP_CASE(15) BNNP_CASE(16)
+          default:
+            fvar_weighted_gg_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(Gh, m, T, m, N, K, m, f_var);
+            BNNP_LAUNCH_CHECK();
+            if (o.has_bias) {
+              fvar_gg_const_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(Gh, m, db, N, K, m, f_var);
+              BNNP_LAUNCH_CHECK();
+            }
+            rc = BNNP_OK;
+        }
+#undef BNNP_CASE
+        if (rc) return rc;
       }
     } else {
       int64_t ild; const float* in = op_input_g(ops, plan, i, X, ws, &ild);
