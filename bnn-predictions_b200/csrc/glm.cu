@@ -1,5 +1,6 @@
 // GLM predictive: f_mu = f + J (mu - theta*), f_var = J Sigma J^T, then the fused
 // Cholesky + sampling + inverse-link epilogue.  preds/predictives.py:50-76, preds/kron.py:112-143.
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -400,6 +401,8 @@ struct TcRowMajorSq {      // X(r, k) = p[r*ld + k]^2
   }
 };
 constexpr long long kTcMinMacsK = 1LL << 25;
+// BNNP_GLM_SIMT=1 (tests): keep the kron / diag GLM contractions on the fp32 SIMT kernels and the unfused reductions
+static bool glm_force_simt() { const char* e = getenv("BNNP_GLM_SIMT"); return e && e[0] == '1'; }
 
 // ---- sampling epilogue ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
@@ -692,13 +695,33 @@ extern "C" int bnnp_glm_fvar_diag(const bnnp_op_t* ops, int n_ops, const bnnp_pl
     const float* G = ws + q.grad_off;
     if (o.kind == BNNP_OP_LINEAR) {
       // T[n,u] = sum_j sigma2[u,j] a[n,j]^2 (+ sigma2_b[u])
-      rc = gemm_simt(N, o.out_c, o.in_c + 1, 1, LoadSqA{ws + plan->acat_off, plan->Dtot, q.lin_col},
-                     LoadSigma2B{sigma2, o.theta_off_w, o.theta_off_b, o.in_c, o.has_bias},
-                     StoreAxpby{scratch, o.out_c, 0, 1.f, 0.f}, st);
+      // (the bias variance is the constant term wb[u] of the fused reduction when the tensor-core path is taken)
+      const bool simt = glm_force_simt();
+      const bool tcpath = !simt && (long long)N * o.out_c * o.in_c >= kTcMinMacsK && K <= 16;
+      if (tcpath)
+        rc = tcg::gemm_tc(N, o.out_c, o.in_c, 1, TcRowMajorSq{ws + plan->acat_off + q.lin_col, plan->Dtot},
+                          tcg::TcRowMajor{sigma2 + o.theta_off_w, o.in_c, 0}, tcg::TcStoreAxpby(scratch, o.out_c, 0, 1.f, 0.f),
+                          1, st);
+      else
+        rc = gemm_simt(N, o.out_c, o.in_c + 1, 1, LoadSqA{ws + plan->acat_off, plan->Dtot, q.lin_col},
+                       LoadSigma2B{sigma2, o.theta_off_w, o.theta_off_b, o.in_c, o.has_bias},
+                       StoreAxpby{scratch, o.out_c, 0, 1.f, 0.f}, st);
       if (rc) return rc;
-      fvar_weighted_gg_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(G, q.grad_ld, scratch, o.out_c,
-                                                                                  N, K, o.out_c, f_var);
-      BNNP_LAUNCH_CHECK();
+      {
+        const float* wb = (tcpath && o.has_bias) ? sigma2 + o.theta_off_b : nullptr;
+#define BNNP_CASE(KK) case KK: rc = launch_gg_fused<KK>(G, q.grad_ld, scratch, o.out_c, wb, N, o.out_c, f_var, st); break;
+        switch (simt ? 0 : K) {
+          BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
+          BNNP_CASE(9) BNNP_CASE(10) BNNP_CASE(11) BNNP_CASE(12) BNNP_CASE(13) BNNP_CASE(14) BNNP_CASE(15) BNNP_CASE(16)
+          default:
+            fvar_weighted_gg_kernel<<<(unsigned)ceil_div64(N * K * K, 128), 128, 0, st>>>(G, q.grad_ld, scratch, o.out_c,
+                                                                                        N, K, o.out_c, f_var);
+            BNNP_LAUNCH_CHECK();
+            rc = BNNP_OK;
+        }
+#undef BNNP_CASE
+        if (rc) return rc;
+      }
     } else {
       int64_t ild; const float* in = op_input_g(ops, plan, i, X, ws, &ild);
       if (!in) return BNNP_ERR_INVALID;
@@ -814,13 +837,14 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       float* db = D + (int64_t)m * n;      // [m]
       // the three contractions go to the tensor cores (split-bf16, fp32-grade) once they are large enough
       const float* Ain = ws + plan->acat_off + q.lin_col;
-      if ((long long)N * n * n >= kTcMinMacsK)
+      const bool simt = glm_force_simt();
+      if (!simt && (long long)N * n * n >= kTcMinMacsK)
         rc = tcg::gemm_tc(N, n, n, 1, tcg::TcRowMajor{Ain, plan->Dtot, 0}, tcg::TcColMajor{W2, n, 0},
                           tcg::TcStoreAxpby(Ah, n, 0, 1.f, 0.f), 1, st);
       else
         rc = gemm_simt(N, n, n, 1, LoadRowMajorA{Ain, plan->Dtot, 0}, LoadRowMajorB{W2, n, 0}, StoreAxpby{Ah, n, 0, 1.f, 0.f}, st);
       if (rc) return rc;
-      if ((long long)R * m * m >= kTcMinMacsK)
+      if (!simt && (long long)R * m * m >= kTcMinMacsK)
         rc = tcg::gemm_tc(R, m, m, 1, tcg::TcRowMajor{G, q.grad_ld, 0}, tcg::TcColMajor{W1, m, 0},
                           tcg::TcStoreAxpby(Gh, m, 0, 1.f, 0.f), 1, st);
       else
@@ -828,7 +852,7 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       if (rc) return rc;
       kron_dinv_kernel<<<(unsigned)ceil_div64((int64_t)m * n, 256), 256, 0, st>>>(l1, l2, m, n, delta_w[i], dampen, 0, D);
       BNNP_LAUNCH_CHECK();
-      if ((long long)N * m * n >= kTcMinMacsK)
+      if (!simt && (long long)N * m * n >= kTcMinMacsK)
         rc = tcg::gemm_tc(N, m, n, 1, TcRowMajorSq{Ah, n}, tcg::TcRowMajor{D, n, 0}, tcg::TcStoreAxpby(T, m, 0, 1.f, 0.f), 1, st);
       else
         rc = gemm_simt(N, m, n, 1, LoadSqRows{Ah, n}, LoadDinvT{D, n}, StoreAxpby{T, m, 0, 1.f, 0.f}, st);
@@ -840,7 +864,7 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       {
         const float* wb = o.has_bias ? db : nullptr;
 #define BNNP_CASE(KK) case KK: rc = launch_gg_fused<KK>(Gh, m, T, m, wb, N, m, f_var, st); break;
-        switch (K) {
+        switch (simt ? 0 : K) {
           BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
           BNNP_CASE(9) BNNP_CASE(10) BNNP_CASE(11) BNNP_CASE(12) BNNP_CASE(13) BNNP_CASE(14) BNNP_CASE(15) BNNP_CASE(16)
           default:

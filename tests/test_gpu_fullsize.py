@@ -7,6 +7,8 @@ import ctypes as C
 import pytest
 import torch
 
+from tests import cases
+
 pytestmark = pytest.mark.gpu
 
 
@@ -79,3 +81,30 @@ def test_cfg5_weight_sampling_tensor_core():
     rows = torch.randint(0, P, (512,), device='cuda', generator=g)
     ref = mu[rows].double().unsqueeze(0) + (L[rows].double() @ eps.double()).T
     assert float((out[:, rows].double() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize('cov', ['kron', 'diag'])
+def test_glm_kron_diag_tensor_core_paths(cov, monkeypatch):
+    """Kron / diag GLM moments at a size where every contraction takes the tcgen05 branch (and the fused
+    warp-per-input reduction) against the fp32 SIMT kernels with the unfused reductions on the same inputs
+    (BNNP_GLM_SIMT=1; the SIMT path is the one pinned against the reference goldens at small sizes), plus the K x K
+    symmetry and positive diagonal that f_var = J Sigma J^T must have."""
+    from preds_b200 import MLPS, CategoricalLh, Laplace
+    from preds_b200.predictives import glm_moments
+    from preds_b200.kron import Kron
+    torch.manual_seed(71)
+    model = MLPS(784, [256, 128], 10, 'tanh', flatten=True).cuda()
+    g = torch.Generator().manual_seed(15)
+    X, y = torch.randn(512, 1, 28, 28, generator=g).cuda(), torch.randint(10, (512,), generator=g).cuda()
+    Xte = torch.randn(384, 1, 28, 28, generator=g).cuda()
+    lap = Laplace(model, 1.0, CategoricalLh())
+    lap.infer([(X, y)], cov_type=cov)
+    Sigma = lap.Sigma_chol if isinstance(lap.Sigma_chol, Kron) else lap.Sigma
+    fmu, fvar = glm_moments(Xte, model, lap.mu, Sigma)
+    monkeypatch.setenv('BNNP_GLM_SIMT', '1')
+    fmu_ref, fvar_ref = glm_moments(Xte, model, lap.mu, Sigma)
+    monkeypatch.delenv('BNNP_GLM_SIMT')
+    assert torch.equal(fmu, fmu_ref)
+    assert cases.rel_err(fvar.cpu(), fvar_ref.cpu()) < 3e-5
+    assert cases.rel_err(fvar.cpu(), fvar.transpose(1, 2).cpu()) < 1e-6
+    assert bool((fvar.diagonal(dim1=1, dim2=2) > 0).all())
