@@ -108,3 +108,31 @@ def test_glm_kron_diag_tensor_core_paths(cov, monkeypatch):
     assert cases.rel_err(fvar.cpu(), fvar_ref.cpu()) < 3e-5
     assert cases.rel_err(fvar.cpu(), fvar.transpose(1, 2).cpu()) < 1e-6
     assert bool((fvar.diagonal(dim1=1, dim2=2) > 0).all())
+
+
+@pytest.mark.parametrize('arch', [(784, [75], 10, 2500), (300, [40, 24], 7, 1100)])
+def test_gram_pair_kernel_is_bitwise_the_single_cta_kernel(arch, monkeypatch):
+    """The CTA-pair full-GGN kernel (tcgen05.mma.cta_group::2 over two row tiles, cross-CTA barriers with a relaxed remote
+    arrive) must reproduce the single-CTA kernel bit for bit: same MMA sequence per accumulator, and every element of H
+    receives exactly one add per launch.  Run twice to catch a rare ordering problem; odd tile counts and a ragged last
+    K-segment (N not a multiple of 64) included."""
+    from preds_b200 import MLPS, CategoricalLh, Laplace
+    din, hid, K, N = arch
+    torch.manual_seed(11)
+    model = MLPS(din, hid, K, 'tanh').cuda()
+    g = torch.Generator().manual_seed(12)
+    X, y = torch.randn(N, din, generator=g).cuda(), torch.randint(K, (N,), generator=g).cuda()
+
+    def run():
+        lap = Laplace(model, 1.0, CategoricalLh())
+        lap.ggn_engine = 2
+        lap.infer([(X, y)], cov_type='full', factorise=False)
+        return lap.precision
+
+    pair = [run() for _ in range(2)]
+    monkeypatch.setenv('BNNP_GRAM_SINGLE', '1')
+    single = run()
+    monkeypatch.delenv('BNNP_GRAM_SINGLE')
+    assert torch.equal(pair[0], pair[1])
+    assert torch.equal(pair[0], single)
+    assert torch.equal(single, single.T)
