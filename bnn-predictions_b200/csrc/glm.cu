@@ -752,6 +752,32 @@ extern "C" int bnnp_glm_fvar_diag(const bnnp_op_t* ops, int n_ops, const bnnp_pl
 // One parameter group of Kron.functional_variance on a materialised Jacobian block
 // Jb[R, m*n] (row r = (b,k), row stride ldj):  f_var[b,k,l] += sum_ij M_k M_l Dinv,  M = W1^T J W2
 // (equal to bmm(J, (W1 ((W1^T J W2) * Dinv) W2^T)^T) of preds/kron.py:135-141).
+// ---- conv layers on the tensor cores: the per-row weight-Jacobian block and its two rotations as gemm_tc launches ----
+// U[(n,pos), e] = unfold(in[n])[e, pos]   (row pitch Epad = roundup4(E), zero padded)
+__global__ void im2col_g_kernel(Im2colG u, int64_t N, int L, int E, int Epad, float* __restrict__ U) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * L * Epad) return;
+  const int e = (int)(i % Epad);
+  const int64_t rp = i / Epad;
+  U[i] = e < E ? u.at(rp / L, (int)(rp % L), e) : 0.f;
+}
+struct TcUnfoldTG {        // X(e, k = pos) of batch r: U[((r / V) * L + pos) * Epad + e]
+  static constexpr bool K_CONTIG = false;
+  using Row = const float*;
+  const float* U; long long Epad; int L, V;
+  __device__ __forceinline__ Row row(int64_t e, int b) const { return U + (long long)(b / V) * L * Epad + e; }
+  __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t K, float* out) const {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = (k0 + j < K) ? __ldg(rw + (k0 + j) * Epad) : 0.f;
+  }
+};
+// Jb[r, co, e] = sum_pos gout[r, co, pos] * U[n(r), pos, e]     (one [m x L]·[L x E] product per row r = (n,k))
+static int conv_jac_blocks_tc(const float* G, int64_t gld, const float* U, int Epad, int64_t R, int V, int m, int E, int L,
+                              float* Jb, cudaStream_t st) {
+  return tcg::gemm_tc(m, E, L, (int)R, tcg::TcRowMajor{G, L, gld}, TcUnfoldTG{U, Epad, L, V},
+                      tcg::TcStoreAxpby(Jb, E, (long long)m * E, 1.f, 0.f), 1, st);
+}
+
 static int kron_fvar_block(const float* Jb, int64_t ldj, int64_t R, int K, int m, int n, const float* W1,
                            const float* l1, const float* W2, const float* l2, float delta, int dampen,
                            float* f_var, float* scratch, cudaStream_t st) {
@@ -773,12 +799,22 @@ static int kron_fvar_block(const float* Jb, int64_t ldj, int64_t R, int K, int m
   float* T1 = scratch;                   // [R, m, n]
   float* T2 = T1 + R * bw;               // [R, m, n]
   float* D = T2 + R * bw;                // [m, n]
-  rc = gemm_simt(m, n, n, (int)R, LoadRowMajorA{Jb, n, ldj}, LoadRowMajorB{W2, n, 0},
-                 StoreAxpby{T1, n, bw, 1.f, 0.f}, st);
-  if (rc) return rc;
-  rc = gemm_simt(m, n, m, (int)R, LoadColMajorA{W1, m, 0}, LoadRowMajorB{T1, n, bw},
-                 StoreAxpby{T2, n, bw, 1.f, 0.f}, st);
-  if (rc) return rc;
+  if (!glm_force_simt() && ldj == bw && (long long)R * m * n * n >= kTcMinMacsK) {
+    // T1 = Jb W2 for all rows at once ([R*m, n] x [n, n]); T2[r] = W1^T T1[r] batched over the rows
+    rc = tcg::gemm_tc(R * m, n, n, 1, tcg::TcRowMajor{Jb, n, 0}, tcg::TcColMajor{W2, n, 0},
+                      tcg::TcStoreAxpby(T1, n, 0, 1.f, 0.f), 1, st);
+    if (rc) return rc;
+    rc = tcg::gemm_tc(m, n, m, (int)R, tcg::TcColMajor{W1, m, 0}, tcg::TcColMajor{T1, n, bw},
+                      tcg::TcStoreAxpby(T2, n, bw, 1.f, 0.f), 1, st);
+    if (rc) return rc;
+  } else {
+    rc = gemm_simt(m, n, n, (int)R, LoadRowMajorA{Jb, n, ldj}, LoadRowMajorB{W2, n, 0},
+                   StoreAxpby{T1, n, bw, 1.f, 0.f}, st);
+    if (rc) return rc;
+    rc = gemm_simt(m, n, m, (int)R, LoadColMajorA{W1, m, 0}, LoadRowMajorB{T1, n, bw},
+                   StoreAxpby{T2, n, bw, 1.f, 0.f}, st);
+    if (rc) return rc;
+  }
   kron_dinv_kernel<<<(unsigned)ceil_div64(bw, 256), 256, 0, st>>>(l1, l2, m, n, delta, dampen, 0, D);
   BNNP_LAUNCH_CHECK();
   fvar_weighted_block_kernel<<<(unsigned)(N * K * K), 256, 0, st>>>(T2, bw, D, bw, K, f_var);
@@ -804,7 +840,8 @@ extern "C" int64_t bnnp_glm_fvar_kron_scratch_floats(const bnnp_op_t* ops, int n
     if (!is_param_op(o)) continue;
     int64_t m = o.out_c, n = (int64_t)o.in_c * o.kh * o.kw, v;
     if (o.kind == BNNP_OP_LINEAR) v = N * n + N * K * m + N * m + m * n + m;
-    else v = 3 * N * K * m * n + 2 * N * K * m + m * n + m;
+    else v = 3 * N * K * m * n + 2 * N * K * m + m * n + m + 128 +
+             N * (int64_t)o.out_h * o.out_w * ((n + 3) / 4 * 4);      // + unfolded input of the tensor-core path
     mx = v > mx ? v : mx;
   }
   return mx + 256;
@@ -888,8 +925,17 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       float* Jb = scratch;                 // [R, m, n]
       float* sb = Jb + R * bw;             // [R, m]
       float* rest = sb + R * m;
-      rc = gemm_simt(m, n, L, (int)R, ConvGradA2{G, q.grad_ld, L}, ConvUnfoldB2{make_im2col_g(o, in, ild, K)},
-                     StoreBlock2{Jb, bw, n}, st);
+      if (!glm_force_simt() && (long long)R * m * n * L >= kTcMinMacsK) {
+        const int Epad = (n + 3) / 4 * 4;
+        float* U = rest + 2 * R * bw + bw + 64;            // behind kron_fvar_block's T1, T2, D
+        im2col_g_kernel<<<(unsigned)ceil_div64(N * L * (int64_t)Epad, 256), 256, 0, st>>>(make_im2col_g(o, in, ild, 1), N, L, n,
+                                                                                       Epad, U);
+        BNNP_LAUNCH_CHECK();
+        rc = conv_jac_blocks_tc(G, q.grad_ld, U, Epad, R, K, m, n, L, Jb, st);
+      } else {
+        rc = gemm_simt(m, n, L, (int)R, ConvGradA2{G, q.grad_ld, L}, ConvUnfoldB2{make_im2col_g(o, in, ild, K)},
+                       StoreBlock2{Jb, bw, n}, st);
+      }
       if (rc) return rc;
       rc = kron_fvar_block(Jb, bw, R, K, m, n, W1, l1, W2, l2, delta_w[i], dampen, f_var, rest, st);
       if (rc) return rc;
