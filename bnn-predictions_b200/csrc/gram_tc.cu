@@ -50,6 +50,7 @@ struct BlockArgs {
   int diag_block;                      // 1 when l == l' (skip tiles strictly above the diagonal)
   int n_chunks, chunk0, Mtot;          // K-chunks of this accumulation segment: [chunk0, chunk0 + n_chunks)
   long long Npad, P;
+  int ts_stride, ts_bufs;              // TMEM-A kernel: accumulator column stride, number of K=16 A buffers behind them
   int dbg;                             // BNNP_GRAM_DBG (measurement only): 1 skips the H read-modify-write, 2 skips the A generation
 };
 
@@ -564,6 +565,288 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_consta
   if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
 }
 
+// ---- CTA-pair version with the A operand in TMEM --------------------------------------------------------------------
+// What still separates gram_pair_kernel from the tensor peak is the generators' shared-memory traffic: 32 KB of A stores
+// per chunk that the tensor core reads back three times.  `tcgen05.mma` can take A from tensor memory: the generator
+// warps write their bf16 hi/lo products with `tcgen05.st` (16x256b: four lanes per row, the same coalesced global-load
+// pattern as before) into a 3-deep ring of K = 16 steps that lives in the 96 TMEM columns left by two <= 208-wide
+// accumulators; shared memory then carries only the TMA-fed half B tiles (8 stages).  Hand-offs are per K = 16 step:
+// a_full (generators of both CTAs -> rank 0's MMA thread), a_empty (multicast commit -> generators of both CTAs).
+constexpr int TS_ACC_STRIDE = 208;                 // widest accumulator of this kernel: a at TMEM column a * args.ts_stride
+constexpr int TS_A_BUFS = 8;                       // upper bound of args.ts_bufs = (512 - 2 * ts_stride) / 32
+#define TS_A_COL0 (2 * args.ts_stride)             // [buf][acc][hi 8 | lo 8] columns behind the accumulators
+constexpr int TS_B_STAGES = 8;
+constexpr int TS_B_STAGE_BYTES = 2 * P_B_TERM_BYTES;                                 // 16 KB (hi + lo half tiles)
+constexpr int TS_SCRATCH_BYTES = 8 * (32 * 33 * 4 + 128);                           // epilogue transposes
+constexpr int TS_SMEM_BYTES = TS_B_STAGES * TS_B_STAGE_BYTES + TS_SCRATCH_BYTES + 1024 + 512;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gram_pair_ts_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                    const float* __restrict__ XT32, const float* __restrict__ Ct, float* __restrict__ H,
+                    int* __restrict__ tile_counter, BlockArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* scratch = smem + TS_B_STAGES * TS_B_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + TS_SCRATCH_BYTES);
+  uint64_t* full_b = bars;                            // [TS_B_STAGES] rank 0: TMA bytes of both CTAs
+  uint64_t* empty_b = bars + TS_B_STAGES;             // [TS_B_STAGES] both CTAs (multicast commit)
+  uint64_t* a_full = bars + 2 * TS_B_STAGES;          // [TS_A_BUFS] rank 0: generator warps of both CTAs
+  uint64_t* a_empty = a_full + TS_A_BUFS;             // [TS_A_BUFS] both CTAs (multicast commit)
+  uint64_t* acc_full = a_empty + TS_A_BUFS;           // both CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  int* tile_slot = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TS_B_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+    for (int s = 0; s < TS_A_BUFS; ++s) { mbar_init(&a_full[s], 16); mbar_init(&a_empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_rtp = (args.n_rt + 1) / 2;
+  const int n_tiles = args.n_pairs * args.n_jt * n_rtp;
+  const int rows_total = args.m * args.n + (args.has_bias ? args.m : 0);
+  uint32_t bstage = 0, bphase = 0;       // B ring (per 32-example chunk)
+  uint32_t abuf = 0, aphase = 0;         // A ring (per 16-example step)
+  uint32_t acc_phase = 0;
+
+  for (;;) {
+    if (threadIdx.x == 0 && rank == 0) {
+      const int t = atomicAdd(tile_counter, 1);
+      *tile_slot = t;
+      st_shared_cluster_u32(mapa_shared(smem_u32(tile_slot), 1), (uint32_t)t);
+    }
+    cluster_sync_all();
+    const int tile = *tile_slot;
+    if (tile >= n_tiles) break;
+    const int rtp = tile % n_rtp;
+    const int jt = (tile / n_rtp) % args.n_jt;
+    const int pair = tile / (n_rtp * args.n_jt);
+    const int ipa = 2 * pair, ipb = 2 * pair + 1;
+    const int nacc = ipb < args.mp ? 2 : 1;
+    const int jc0 = jt * args.wc;
+    const int row0 = (2 * rtp + (int)rank) * TILE_M;
+    bool own_needed = row0 < rows_total;
+    bool pair_needed = true;
+    if (args.diag_block) {
+      const long long min_col = args.col_theta0 + (long long)ipa * args.np + jc0;
+      const int prow_last = 2 * rtp * TILE_M + 2 * TILE_M - 1;
+      const long long pair_max_row = args.row_theta0 + (prow_last < rows_total - 1 ? prow_last : rows_total - 1);
+      pair_needed = pair_max_row >= min_col;
+      const long long own_max_row = args.row_theta0 + (row0 + TILE_M - 1 < rows_total - 1 ? row0 + TILE_M - 1 : rows_total - 1);
+      own_needed = own_needed && own_max_row >= min_col;
+    }
+    if (pair_needed) {
+      const int wvalid = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
+      const int nmma = (wvalid + 15) / 16 * 16;
+      if (warp == 0) {
+        // ===================== TMA producer: this CTA's half of B =====================
+        if (lane == 0) {
+          uint32_t s = bstage, ph = bphase;
+          const uint32_t bytes = 2u * 2u * (uint32_t)(args.wc / 2) * BK * 2u;
+          const int brow = jc0 + (int)rank * (nmma / 2);
+          for (int c = 0; c < args.n_chunks; ++c) {
+            mbar_wait(&empty_b[s], ph ^ 1);
+            uint8_t* bdst = smem + s * TS_B_STAGE_BYTES;
+            const uint32_t lead_full = mapa_shared(smem_u32(&full_b[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_b[s], bytes);
+            tma_load_2d_pair(&map_bh, lead_full, bdst, (args.chunk0 + c) * BK, brow);
+            tma_load_2d_pair(&map_bl, lead_full, bdst + P_B_TERM_BYTES, (args.chunk0 + c) * BK, brow);
+            if (++s == TS_B_STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      } else if (warp == 1) {
+        // ===================== MMA issuer (rank 0) =====================
+        if (lane == 0 && rank == 0) {
+          uint32_t s = bstage, ph = bphase, ab = abuf, aph = aphase;
+          const uint32_t idesc = umma_idesc_bf16_pair(nmma);
+          for (int c = 0; c < args.n_chunks; ++c) {
+            mbar_wait(&full_b[s], ph);
+            const uint32_t b0 = smem_u32(smem + s * TS_B_STAGE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              mbar_wait_cluster(&a_full[ab], aph);
+              tc_fence_after();
+              const uint64_t dbh = umma_desc_sw64(b0 + ks * 32), dbl = umma_desc_sw64(b0 + P_B_TERM_BYTES + ks * 32);
+#pragma unroll
+              for (int a = 0; a < 2; ++a) {
+                if (a < nacc) {
+                  const uint32_t d = tmem_base + a * args.ts_stride;
+                  const uint32_t ah = tmem_base + TS_A_COL0 + ab * 32 + a * 16, al = ah + 8;
+                  umma_bf16_pair_ts(d, ah, dbh, idesc, (c | ks) ? 1u : 0u);
+                  umma_bf16_pair_ts(d, ah, dbl, idesc, 1u);
+                  umma_bf16_pair_ts(d, al, dbh, idesc, 1u);
+                }
+              }
+              umma_commit_pair(&a_empty[ab]);
+              if (++ab == (uint32_t)args.ts_bufs) { ab = 0; aph ^= 1; }
+            }
+            umma_commit_pair(&empty_b[s]);
+            if (c == args.n_chunks - 1) umma_commit_pair(acc_full);
+            if (++s == TS_B_STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      } else if (warp >= GEN_WARP0) {
+        // ===================== A generators (then epilogue) =====================
+        // warp gw: TMEM lane quarter q = gw & 3 (the only lanes this warp may access), 16-row half h2 = gw >> 2;
+        // thread: rows rl0 = q*32 + h2*16 + lane/4 and rl0 + 8, examples 4*(lane&3) .. +3 of each 16-example step
+        const int gw = warp - GEN_WARP0;
+        const int q = gw & 3, h2 = gw >> 2;
+        const int g = lane & 3;
+        const float* xsrc[2];
+        const float* csrc[2][2];
+        bool rvalid[2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int rl = q * 32 + h2 * 16 + it * 8 + (lane >> 2);
+          const int r = row0 + rl;
+          rvalid[it] = r < rows_total;
+          int u = args.unit0, src = args.col0;
+          if (rvalid[it]) {
+            if (r < args.m * args.n) { u += r / args.n; src += r % args.n; }
+            else { u += r - args.m * args.n; src += args.n; }
+          }
+          xsrc[it] = XT32 + (long long)src * args.Npad + (long long)args.chunk0 * BK + g * 4;
+          csrc[0][it] = Ct + ((long long)(args.unit0p + ipa) * args.Mtot + u) * args.Npad + (long long)args.chunk0 * BK + g * 4;
+          csrc[1][it] = Ct + ((long long)(args.unit0p + (nacc > 1 ? ipb : ipa)) * args.Mtot + u) * args.Npad + (long long)args.chunk0 * BK + g * 4;
+        }
+        const uint32_t a_lane = (uint32_t)(q * 32 + h2 * 16) << 16;
+        uint32_t ab = abuf, aph = aphase;
+        const int pf_chunk = args.n_chunks > 48 ? args.n_chunks - 40 : 0;
+        float4 xv[2][2], cv[2][2][2];            // [row][step], [acc][row][step]
+        auto load_chunk = [&](int c) {
+#pragma unroll
+          for (int it = 0; it < 2; ++it)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              xv[it][ks] = __ldg(reinterpret_cast<const float4*>(xsrc[it] + c * BK + ks * 16));
+#pragma unroll
+              for (int a = 0; a < 2; ++a) cv[a][it][ks] = __ldg(reinterpret_cast<const float4*>(csrc[a][it] + c * BK + ks * 16));
+            }
+        };
+        load_chunk(0);
+        for (int c = 0; c < args.n_chunks; ++c) {
+          float4 x[2][2], cc[2][2][2];
+#pragma unroll
+          for (int it = 0; it < 2; ++it)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              x[it][ks] = xv[it][ks];
+#pragma unroll
+              for (int a = 0; a < 2; ++a) cc[a][it][ks] = cv[a][it][ks];
+            }
+          if (c + 1 < args.n_chunks) load_chunk(c + 1);
+          if (c == pf_chunk && own_needed) {
+            const int lines = (wvalid * 4 + 127) / 128 + 1;
+            for (int a = 0; a < nacc; ++a) {
+              const int ip = a == 0 ? ipa : ipb;
+              for (int w = (warp - GEN_WARP0) * 32 + lane; w < TILE_M * lines; w += 256) {
+                const int rr = w / lines, ln = w % lines;
+                if (row0 + rr < rows_total) {
+                  const float* ptr = H + (args.row_theta0 + row0 + rr) * args.P + args.col_theta0 +
+                                     (long long)ip * args.np + jc0 + ln * 32;
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            // bf16 hi/lo of the 2 rows x 4 examples x 2 accumulators of this step
+            uint32_t hi[2][2][2], lo[2][2][2];     // [acc][row][pair]
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int it = 0; it < 2; ++it) {
+                const float* xf = reinterpret_cast<const float*>(&x[it][ks]);
+                const float* cf = reinterpret_cast<const float*>(&cc[a][it][ks]);
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[e] = rvalid[it] ? xf[e] * cf[e] : 0.f;
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * pp], v[2 * pp + 1]);
+                  const float2 hf = __bfloat1622float2(h);
+                  const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * pp] - hf.x, v[2 * pp + 1] - hf.y);
+                  hi[a][it][pp] = *reinterpret_cast<const uint32_t*>(&h);
+                  lo[a][it][pp] = *reinterpret_cast<const uint32_t*>(&l);
+                }
+              }
+            mbar_wait(&a_empty[ab], aph ^ 1);
+            tc_fence_after();
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              if (a < nacc && !(args.dbg & 2)) {
+                const uint32_t col = (uint32_t)(TS_A_COL0 + ab * 32 + a * 16);
+                tmem_st_16x256b(tmem_base + a_lane + col, hi[a][0][0], hi[a][0][1], hi[a][1][0], hi[a][1][1]);
+                tmem_st_16x256b(tmem_base + a_lane + col + 8, lo[a][0][0], lo[a][0][1], lo[a][1][0], lo[a][1][1]);
+              }
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(&a_full[ab]);
+              else mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&a_full[ab]), 0));
+            }
+            if (++ab == (uint32_t)args.ts_bufs) { ab = 0; aph ^= 1; }
+          }
+        }
+        // ---------------- epilogue: H[p, q] += D for this CTA's rows ----------------
+        mbar_wait(acc_full, acc_phase);
+        tc_fence_after();
+        const int a = gw >> 2, quarter = gw & 3;
+        if (a < nacc && own_needed) {
+          float* sc = reinterpret_cast<float*>(scratch + gw * (32 * 33 * 4 + 128));
+          const int ip = a == 0 ? ipa : ipb;
+          const int rbase = row0 + quarter * 32;
+          float* hbase = H + (args.row_theta0 + rbase) * args.P + args.col_theta0 + (long long)ip * args.np + jc0;
+          int nrows = rows_total - rbase;
+          nrows = nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows);
+          for (int c0 = 0; c0 < wvalid; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * args.ts_stride + c0), v);
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
+            __syncwarp();
+            const bool colok = c0 + lane < wvalid;
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (colok && u < nrows) atomicAdd(hbase + (long long)u * args.P + c0 + lane, sc[u * 33 + lane]);
+          }
+        }
+        tc_fence_before();
+      }
+      {
+        const uint32_t tb = bstage + (uint32_t)args.n_chunks;
+        bphase ^= (tb / TS_B_STAGES) & 1;
+        bstage = tb % TS_B_STAGES;
+        const uint32_t ta = abuf + 2u * (uint32_t)args.n_chunks;
+        aphase ^= (ta / (uint32_t)args.ts_bufs) & 1;
+        abuf = ta % (uint32_t)args.ts_bufs;
+        acc_phase ^= 1;
+      }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------- pre-kernels
 // XT32[c, n] = A[n, c];  XTh/XTl = bf16 hi/lo split;  zero for n >= N   (32x32 smem transpose)
 __global__ void transpose_split_kernel(const float* __restrict__ A, long long ald, long long N, int D,
@@ -786,6 +1069,7 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
   }
   BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+  BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_pair_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -807,7 +1091,9 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
       // when the last tile issues a narrower instruction (e.g. 784 = 3 x 224 + 112 instead of 4 x 208)
       {
         int best_w = 16; long long best_cost = -1;
-        for (int w = 256; w >= 64; w -= 16) {
+        // TMEM-A kernel (BNNP_GRAM_TS=<widest accumulator, <= 208>): narrower accumulators leave more K=16 A buffers
+        const int ts_cap = getenv("BNNP_GRAM_TS") ? atoi(getenv("BNNP_GRAM_TS")) : 0;
+        for (int w = ts_cap >= 64 && ts_cap <= TS_ACC_STRIDE ? ts_cap / 16 * 16 : 256; w >= 64; w -= 16) {
           const int nj = (a.np + w - 1) / w;
           const int last = a.np - (nj - 1) * w;
           const int last16 = (last + 15) / 16 * 16;
@@ -850,7 +1136,11 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
           gram_flops(a, &g_prof.executed[g_prof.n], &g_prof.useful[g_prof.n]);
           cudaEventRecord(g_prof.beg[g_prof.n], st);
         }
-        if (use_pair) gram_pair_kernel<<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+        a.ts_stride = (a.wc + 15) / 16 * 16;
+        a.ts_bufs = (512 - 2 * a.ts_stride) / 32 < TS_A_BUFS ? (512 - 2 * a.ts_stride) / 32 : TS_A_BUFS;
+        if (use_pair && getenv("BNNP_GRAM_TS") && a.wc <= TS_ACC_STRIDE && a.ts_bufs >= 3)
+          gram_pair_ts_kernel<<<grid, NUM_THREADS, TS_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+        else if (use_pair) gram_pair_kernel<<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
         else gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
         if (prof) { cudaEventRecord(g_prof.end[g_prof.n], st); ++g_prof.n; }
         BNNP_LAUNCH_CHECK();

@@ -136,3 +136,26 @@ def test_gram_pair_kernel_is_bitwise_the_single_cta_kernel(arch, monkeypatch):
     assert torch.equal(pair[0], pair[1])
     assert torch.equal(pair[0], single)
     assert torch.equal(single, single.T)
+
+
+def test_gram_tmem_a_kernel_is_bitwise_the_pair_kernel(monkeypatch):
+    """Experimental (opt-in, BNNP_GRAM_TS=<accumulator width>): the A operand written to tensor memory with tcgen05.st
+    and consumed by tcgen05.mma from TMEM, K = 16 step ring.  Same bf16 operands and accumulation order as the default
+    kernels, so H must be bit-identical for every ring depth."""
+    from preds_b200 import MLPS, CategoricalLh, Laplace
+    torch.manual_seed(11)
+    model = MLPS(300, [40, 24], 7, 'tanh').cuda()
+    g = torch.Generator().manual_seed(12)
+    X, y = torch.randn(1100, 300, generator=g).cuda(), torch.randint(7, (1100,), generator=g).cuda()
+
+    def run():
+        lap = Laplace(model, 1.0, CategoricalLh())
+        lap.ggn_engine = 2
+        lap.infer([(X, y)], cov_type='full', factorise=False)
+        return lap.precision
+
+    ref = run()
+    for width in ('208', '160', '96'):
+        monkeypatch.setenv('BNNP_GRAM_TS', width)
+        assert torch.equal(run(), ref), width
+    monkeypatch.delenv('BNNP_GRAM_TS')
