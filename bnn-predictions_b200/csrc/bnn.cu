@@ -64,13 +64,15 @@ struct StoreThetaVec {
   __device__ void operator()(int64_t i, int64_t s, float acc, int) const { out[s * P + off + i] = (mu ? mu[off + i] : 0.f) + acc; }
 };
 
-// theta_s = mu + (L eps)^T on the tensor cores: A = lower-triangular Cholesky factor (zeros above the diagonal are
-// generated, not read), B = eps [P, S]
-struct TcLowerTri {
+// theta_s = mu + (L eps)^T on the tensor cores (zeros above the diagonal of the factor are generated, not read).
+// The factor is the wide (N) operand: 256 of its rows per tile stream 32 KB per K-chunk through the generators (16 KB
+// when it was the 128-row A operand), eps -- the S <= 128 samples -- is the A operand, and the output is written in its
+// own [S, P] layout.  p_off: a K-segment [k0, k1) only concerns the rows p >= k0 of a lower-triangular factor.
+struct TcLowerTriOff {
   static constexpr bool K_CONTIG = true;
   struct Row { const float* p; long long r; };
-  const float* L; long long P;
-  __device__ __forceinline__ Row row(int64_t r, int) const { return Row{L + r * P, r}; }
+  const float* L; long long P, p_off;
+  __device__ __forceinline__ Row row(int64_t r, int) const { return Row{L + (r + p_off) * P, r + p_off}; }
   __device__ __forceinline__ void load8(const Row& rw, int64_t k0, int64_t, float* out) const {
     if (k0 + 7 <= rw.r) {
 #pragma unroll
@@ -81,17 +83,23 @@ struct TcLowerTri {
     }
   }
 };
-struct TcStoreThetaT : tcg::TcNoState {    // theta_s[s*P + p] = (first ? mu[p] : theta_s[s*P + p]) + acc(p, s)
-  float* out; const float* mu; long long P; int first;
-  __host__ __device__ TcStoreThetaT(float* o_, const float* m_, long long P_, int f_) : out(o_), mu(m_), P(P_), first(f_) {}
-  __device__ __forceinline__ void row(State&, int64_t p, int64_t s0, const float* v, int nvalid, int, int) const {
-    const float m = mu[p];
+struct TcStoreTheta : tcg::TcNoState {     // theta_s[s*P + p] = (first ? mu[p] : theta_s[s*P + p]) + acc(s, p - p_off)
+  float* out; const float* mu; long long P, p_off; int first;
+  __host__ __device__ TcStoreTheta(float* o_, const float* m_, long long P_, long long off_, int f_)
+      : out(o_), mu(m_), P(P_), p_off(off_), first(f_) {}
+  __device__ __forceinline__ void row(State&, int64_t s_, int64_t n0, const float* v, int nvalid, int, int) const {
+    float* q = out + s_ * P + p_off + n0;
+    const float* m = mu + p_off + n0;
+    if (first) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e)
-      if (e < nvalid) {
-        float* q = out + (s0 + e) * P + p;
-        *q = (first ? m : *q) + v[e];
-      }
+      for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = __ldg(m + e) + v[e];
+    } else {
+      float h[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) h[e] = e < nvalid ? q[e] : 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = h[e] + v[e];
+    }
   }
 };
 
@@ -135,8 +143,18 @@ extern "C" int bnnp_sample_theta_full(const float* L, const float* mu, const flo
   if (!L || !mu || !eps || !theta_s || P <= 0 || S <= 0) return BNNP_ERR_INVALID;
   if ((long long)P * P * S >= (1LL << 28))
     // K = P is long: sequential <= 4096-element segments accumulate through theta_s (TMEM adds truncate)
-    return tcg::gemm_tc_ksegments(P, S, P, 1, TcLowerTri{L, P}, tcg::TcColMajor{eps, S, 0},
-                                  [=](int seg) { return TcStoreThetaT(theta_s, mu, P, seg == 0); }, as_stream(stream));
+  {
+    const int all = (int)((P + tcg::BK - 1) / tcg::BK);
+    int seg = 0;
+    for (int c0 = 0; c0 < all; c0 += tcg::kMaxChunksPerAccum, ++seg) {
+      const long long p_off = (long long)c0 * tcg::BK;          // rows above the segment's first column are all zero there
+      int rc = tcg::gemm_tc(S, P - p_off, P, 1, tcg::TcColMajor{eps, S, 0}, TcLowerTriOff{L, P, p_off},
+                            TcStoreTheta(theta_s, mu, P, p_off, seg == 0), 1, as_stream(stream), c0,
+                            c0 + tcg::kMaxChunksPerAccum);
+      if (rc) return rc;
+    }
+    return BNNP_OK;
+  }
   return gemm_simt(P, S, P, 1, LoadLowerA{L, P}, LoadRowMajorB{eps, S, 0}, StoreThetaT{theta_s, mu, P},
                    as_stream(stream));
 }
