@@ -545,7 +545,7 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     const bnnp_op_plan_t& q = plan->op[i];
     if (o.kind == BNNP_OP_LINEAR) {
       int rc;
-      if ((long long)o.out_c * (o.in_c + 1) * N >= kTcMinMacsG) {
+      if ((long long)o.out_c * (o.in_c + 1) * N >= kTcMinMacsG || N >= 2048) {
         // T[i, j] = sum_n Q[n, i] a[n, j]^2 on the tensor cores (split-K partials -> T), then scatter into d
         const long long mm = o.out_c, nn = o.in_c + 1;
         float* T = scratch + N * (int64_t)M + 64;
@@ -664,7 +664,9 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
     if (o.kind == BNNP_OP_LINEAR) {
       int rc;
       float* wsk = scratch + kfac_conv_floats(ops, n_ops, N, V);
-      if ((long long)o.out_c * o.out_c * R >= kTcMinMacsG)
+      // (a narrow Gram over many rows -- the 10 x 10 factor of the output layer over N*K rows -- is ONE SIMT block
+      // walking all rows: 3.5 ms of a 6.2 ms pass; split-K on the tensor cores spreads it over the machine)
+      if ((long long)o.out_c * o.out_c * R >= kTcMinMacsG || R >= 2048)
         rc = tcg::gemm_tc_splitk(o.out_c, o.out_c, R, 1, tcg::TcColMajor{G, q.grad_ld, 0}, tcg::TcColMajor{G, q.grad_ld, 0},
                                  factor, 1.f, Gf, o.out_c, 0, wsk, tcg::pick_ksplit(o.out_c, o.out_c, R, 1), st);
       else
@@ -672,7 +674,7 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
                        AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       const float* A = ws + plan->acat_off;
-      if ((long long)o.in_c * o.in_c * N >= kTcMinMacsG)
+      if ((long long)o.in_c * o.in_c * N >= kTcMinMacsG || N >= 2048)
         rc = tcg::gemm_tc_splitk(o.in_c, o.in_c, N, 1, tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0},
                                  tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0}, batch_factor / (float)N, 1.f, Af, o.in_c,
                                  0, wsk, tcg::pick_ksplit(o.in_c, o.in_c, N, 1), st);
