@@ -69,7 +69,7 @@ def glm_moments(X, model, mu, Sigma, engine=0, return_f=False):
     # chunk size from the scratch the chosen structure needs per input
     if isinstance(Sigma, Kron):
         per = max(1, int(lib.bnnp_glm_fvar_kron_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(1, K)), 1)))
-        cap = 65535 // K
+        cap = 65535 // K if not net.linear_only else 1 << 30      # the batched conv kernels index rows with 16 bits
     elif Sigma.dim() == 2:
         if engine == 0:
             engine = 3 if P >= FULL_TMA_MIN_P else 1
