@@ -20,11 +20,11 @@ def run(name, model, in_shape, N, bs, covs, nte, S):
     for cov in covs:
         lap = Laplace(model, 1.0, CategoricalLh())
         lap.infer(batches[:1], cov_type=cov, factorise=False)
-        ms = timed(lambda: lap.infer(batches, cov_type=cov, factorise=False))
+        ms = min(timed(lambda: lap.infer(batches, cov_type=cov, factorise=False)) for _ in range(4))
         lap.infer(batches, cov_type=cov)
         fact = lap.timings['factorise_ms']
         lap.predictive_samples_glm(Xte[:4], n_samples=S)
-        gms = timed(lambda: lap.predictive_samples_glm(Xte, n_samples=S))
+        gms = min(timed(lambda: lap.predictive_samples_glm(Xte, n_samples=S)) for _ in range(3))
         bms = timed(lambda: lap.predictive_samples_bnn(Xte[:64], n_samples=32))
         print(json.dumps({'cfg': name, 'cov': cov, 'N': N, 'accum_ex_per_s': round(N / ms * 1e3), 'accum_ms': round(ms, 1),
                           'factorise_ms': round(fact, 1), 'glm_units_per_s': round(nte * S / gms * 1e3), 'glm_ms': round(gms, 1),
