@@ -16,7 +16,7 @@ from .likelihoods import GaussianLh
 # upper bound for per-call scratch; inputs are processed in chunks that respect it
 SCRATCH_BUDGET_FLOATS = 1 << 30
 # full-covariance GLM engines: 1 SIMT (as written), 2 tcgen05 with generated operands, 3 tcgen05 + TMA
-FULL_TMA_MIN_P = 4096
+FULL_TMA_MIN_P = 1024
 _SPLIT_CACHE = {}
 
 
