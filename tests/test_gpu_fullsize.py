@@ -159,3 +159,25 @@ def test_gram_tmem_a_kernel_is_bitwise_the_pair_kernel(monkeypatch):
         monkeypatch.setenv('BNNP_GRAM_TS', width)
         assert torch.equal(run(), ref), width
     monkeypatch.delenv('BNNP_GRAM_TS')
+
+
+@pytest.mark.parametrize('engine,tol', [('trsm', 3e-5), ('cublas', 3e-5), ('tc', 5e-4)])
+def test_blocked_spd_inverse_matches_potri(engine, tol, monkeypatch):
+    """dense.spd_inverse_from_chol (blocked triangular inverse + blocked Gram, used for the one-off factorisation above
+    dense.MIN_P) against torch.cholesky_inverse on a moderately conditioned SPD matrix; odd size so that the recursion
+    and the block loops see ragged tails.  Stated bounds: fp32-library engines 3e-5 relative, split-bf16 engine 5e-4."""
+    from preds_b200 import dense
+    P = 9001
+    g = torch.Generator(device='cuda').manual_seed(0)
+    A = torch.randn(P, 1500, device='cuda', generator=g)
+    H = A @ A.T
+    H.diagonal().add_(float(H.diagonal().mean()) * 0.02)
+    L = torch.linalg.cholesky(H)
+    want = torch.cholesky_inverse(L, upper=False)
+    monkeypatch.setattr(dense, 'ENGINE', engine)
+    got = dense.spd_inverse_from_chol(L)
+    assert torch.equal(got, got.T)
+    assert cases.rel_err(got.cpu(), want.cpu()) < tol
+    # below MIN_P the library call is used unchanged
+    small = torch.linalg.cholesky(H[:300, :300].contiguous())
+    assert cases.rel_err(dense.spd_inverse_from_chol(small).cpu(), torch.cholesky_inverse(small, upper=False).cpu()) < 1e-6
