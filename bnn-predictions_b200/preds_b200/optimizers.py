@@ -8,6 +8,7 @@ import torch
 from torch.nn.utils import parameters_to_vector
 from torch.optim import Adam
 
+from . import dense
 from .gradients import Jacobians
 
 
@@ -99,10 +100,8 @@ class LaplaceGGN(Adam):
         self.state['precision'] = precision
         Chol = torch.linalg.cholesky(precision)
         self.state['mu'] = torch.cholesky_solve(b.reshape(-1, 1), Chol, upper=False).flatten()
-        Sigma = torch.cholesky_inverse(Chol, upper=False)
+        Sigma = dense.spd_inverse_from_chol(Chol)      # potri below dense.MIN_P, blocked inverse above
         del Chol
-        if not Sigma.is_contiguous() and Sigma.T.is_contiguous():
-            Sigma = Sigma.T
         self.state['Sigma'] = Sigma
         self.state['Sigma_chol'] = torch.linalg.cholesky(Sigma)
         return self

@@ -18,6 +18,7 @@ from torch.nn.utils import parameters_to_vector
 from torch.optim import Adam
 
 from . import _cabi as cabi
+from . import dense
 from ._cabi import lib, check, ptr, stream
 from ._engine import net_for
 
@@ -76,10 +77,7 @@ class _Linearised:
 def _chol_inverse_chol(prec):
     """(chol(prec), chol(prec^-1)) -- preds/refine.py:36-38,72,75."""
     pchol = torch.linalg.cholesky(prec)
-    Sigma = torch.cholesky_inverse(pchol, upper=False)
-    if not Sigma.is_contiguous() and Sigma.T.is_contiguous():
-        Sigma = Sigma.T
-    return pchol, torch.linalg.cholesky(Sigma)
+    return pchol, torch.linalg.cholesky(dense.spd_inverse_from_chol(pchol))
 
 
 def laplace_refine(model, X, y, likelihood, prior_prec, n_epochs=1000, lr=1e-3):
