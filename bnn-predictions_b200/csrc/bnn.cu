@@ -103,6 +103,29 @@ struct TcStoreTheta : tcg::TcNoState {     // theta_s[s*P + p] = (first ? mu[p] 
   }
 };
 
+// Kron weight sampling on the tensor cores (preds/kron.py:94-109): epilogues of the four contractions
+struct TcStoreScaledBy : tcg::TcNoState {      // T2[s][i, j] = acc * D[i, j]
+  float* out; long long ld, bs; const float* D;
+  __host__ __device__ TcStoreScaledBy(float* o_, long long ld_, long long bs_, const float* D_) : out(o_), ld(ld_), bs(bs_), D(D_) {}
+  __device__ __forceinline__ void row(State&, int64_t i, int64_t j0, const float* v, int nvalid, int s, int) const {
+    float* q = out + (long long)s * bs + i * ld + j0;
+    const float* d = D + i * ld + j0;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = v[e] * __ldg(d + e);
+  }
+};
+struct TcStoreThetaGroup : tcg::TcNoState {    // theta_s[s, off + i*n + j] = mu[...] + acc
+  float* out; const float* mu; long long P, off; int n;
+  __host__ __device__ TcStoreThetaGroup(float* o_, const float* m_, long long P_, long long off_, int n_)
+      : out(o_), mu(m_), P(P_), off(off_), n(n_) {}
+  __device__ __forceinline__ void row(State&, int64_t i, int64_t j0, const float* v, int nvalid, int s, int) const {
+    const long long p = off + i * n + j0;
+    float* q = out + (long long)s * P + p;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = (mu ? __ldg(mu + p + e) : 0.f) + v[e];
+  }
+};
+
 // batched-weights Linear layer of the BNN predictive: out[s, n, :] = act(in[s or shared, n, :] W_s^T + b_s)
 struct BnnStore {                 // SIMT epilogue
   float* out; int64_t ld, bs; const float* theta; int64_t P, offb; int has_bias, act;
@@ -191,6 +214,21 @@ extern "C" int bnnp_kron_sample_group(const float* W1, const float* l1, const fl
   kron_d_kernel<<<(unsigned)ceil_div64(per, 256), 256, 0, st>>>(l1, l2, m, n, delta, dampen, D);
   BNNP_LAUNCH_CHECK();
   // T1 = eps W2 ; T2 = W1^T T1 ; T2 *= D ; T1 = T2 W2^T ; out = W1 T1
+  if ((long long)S * m * n * (m < n ? m : n) >= (1LL << 27)) {
+    // tensor cores: the W2 products for all samples at once ([S*m, n] x [n, n]), the W1 products batched over samples;
+    // the D scaling rides in the epilogue of the second one
+    int rc = tcg::gemm_tc(S * m, n, n, 1, tcg::TcRowMajor{eps, n, 0}, tcg::TcColMajor{W2, n, 0},
+                          tcg::TcStoreAxpby(T1, n, 0, 1.f, 0.f), 1, st);
+    if (rc) return rc;
+    rc = tcg::gemm_tc(m, n, m, (int)S, tcg::TcColMajor{W1, m, 0}, tcg::TcColMajor{T1, n, per},
+                      TcStoreScaledBy(T2, n, per, D), 1, st);
+    if (rc) return rc;
+    rc = tcg::gemm_tc(S * m, n, n, 1, tcg::TcRowMajor{T2, n, 0}, tcg::TcRowMajor{W2, n, 0},
+                      tcg::TcStoreAxpby(T1, n, 0, 1.f, 0.f), 1, st);
+    if (rc) return rc;
+    return tcg::gemm_tc(m, n, m, (int)S, tcg::TcRowMajor{W1, m, 0}, tcg::TcColMajor{T1, n, per},
+                        TcStoreThetaGroup(theta_s, mu, P, off, n), 1, st);
+  }
   int rc = gemm_simt(m, n, n, (int)S, LoadRowMajorA{eps, n, per}, LoadRowMajorB{W2, n, 0},
                      StoreAxpby{T1, n, per, 1.f, 0.f}, st);
   if (rc) return rc;

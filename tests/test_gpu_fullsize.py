@@ -181,3 +181,35 @@ def test_blocked_spd_inverse_matches_potri(engine, tol, monkeypatch):
     # below MIN_P the library call is used unchanged
     small = torch.linalg.cholesky(H[:300, :300].contiguous())
     assert cases.rel_err(dense.spd_inverse_from_chol(small).cpu(), torch.cholesky_inverse(small, upper=False).cpu()) < 1e-6
+
+
+@pytest.mark.parametrize('dampen', [0, 1])
+def test_kron_weight_sampling_tensor_core(dampen):
+    """bnnp_kron_sample_group at a size that takes the tcgen05 branch (S*m*n*min(m,n) >= 2^27) against an fp64
+    evaluation of preds/kron.py:94-109:  W1 ((W1^T eps W2) * D) W2^T  with D = sqrt(1/(l1 l2^T + delta)) (or the dampened
+    form), written behind an offset into theta_s [S, P]."""
+    from preds_b200 import _cabi as cabi
+    m, n, S, off, delta = 192, 160, 40, 37, 0.7
+    P = off + m * n + 11
+    g = torch.Generator().manual_seed(21)
+    W1 = torch.linalg.qr(torch.randn(m, m, generator=g, dtype=torch.float64))[0]
+    W2 = torch.linalg.qr(torch.randn(n, n, generator=g, dtype=torch.float64))[0]
+    l1, l2 = torch.rand(m, generator=g, dtype=torch.float64) * 5, torch.rand(n, generator=g, dtype=torch.float64) * 3
+    eps = torch.randn(S, m, n, generator=g, dtype=torch.float64)
+    mu = torch.randn(P, generator=g, dtype=torch.float64)
+    if dampen:
+        D = torch.sqrt(1 / ((l1 + delta ** 0.5).unsqueeze(1) * (l2 + delta ** 0.5).unsqueeze(0)))
+    else:
+        D = torch.sqrt(1 / (l1.unsqueeze(1) * l2.unsqueeze(0) + delta))
+    want = W1 @ ((W1.T @ eps @ W2) * D) @ W2.T + mu[off:off + m * n].reshape(m, n)
+    dev = 'cuda'
+    f = lambda t: t.to(dev, torch.float32).contiguous()
+    out = torch.zeros(S, P, device=dev)
+    scratch = torch.empty(2 * S * m * n + m * n + 64, device=dev)
+    dW1, dl1, dW2, dl2, deps, dmu = (f(t) for t in (W1, l1, W2, l2, eps, mu))      # keep the device copies alive
+    cabi.check(cabi.lib.bnnp_kron_sample_group(cabi.ptr(dW1), cabi.ptr(dl1), cabi.ptr(dW2), cabi.ptr(dl2), m, n, delta,
+                                               dampen, cabi.ptr(deps), S, cabi.ptr(dmu), cabi.ptr(out), P, off,
+                                               cabi.ptr(scratch), cabi.stream()))
+    got = out[:, off:off + m * n].reshape(S, m, n)
+    assert cases.rel_err(got.cpu(), want) < 2e-5
+    assert float(out[:, :off].abs().max()) == 0 and float(out[:, off + m * n:].abs().max()) == 0     # nothing else touched
