@@ -228,7 +228,8 @@ class Net:
             raise cabi.BnnpError('model output shape %s does not match the traced network (%s)'
                                  % (tuple(want.shape), tuple(got.shape)))
         err = (got - want).abs().max().item()
-        if not err <= 2e-2 * max(1.0, want.abs().max().item()):     # also catches NaN
+        scale = max(want.abs().max().item(), got.abs().max().item())
+        if not err <= 2e-2 * scale + 1e-6:                          # relative to the outputs' own scale; also catches NaN
             raise cabi.BnnpError('model(x) differs from its layer trace (max |diff| %.3g): the model applies '
                                  'operations outside its leaf modules (functional activations, skip '
                                  'connections, ...), which this engine cannot represent' % err)
