@@ -12,9 +12,9 @@ def timed(fn, reps=1):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
-def run(name, model, in_shape, N, bs, covs, nte, S):
+def run(name, model, in_shape, N, bs, covs, nte, S, K=10):
     g = torch.Generator().manual_seed(15)
-    X = torch.randn(N, *in_shape, generator=g); y = torch.randint(10, (N,), generator=g)
+    X = torch.randn(N, *in_shape, generator=g); y = torch.randint(K, (N,), generator=g)
     batches = [(X[i:i + bs].cuda(), y[i:i + bs].cuda()) for i in range(0, N, bs)]
     Xte = torch.randn(nte, *in_shape, generator=g).cuda()
     for cov in covs:
@@ -31,9 +31,12 @@ def run(name, model, in_shape, N, bs, covs, nte, S):
                           'nte': nte, 'S': S, 'bnn_fwd_per_s(64x32)': round(64 * 32 / bms * 1e3)}), flush=True)
 
 torch.manual_seed(71)
-which = sys.argv[1:] or ['cfg1', 'cfg3', 'cfg4']
+which = sys.argv[1:] or ['cfg1', 'cfg2', 'cfg3', 'cfg4']
 if 'cfg1' in which:
-    run('cfg1 banana MLPS(2,[50,50],2)', MLPS(2, [50, 50], 2).cuda(), (2,), 5300, 5300, ['full', 'kron', 'diag'], 5300, 1000)
+    run('cfg1 banana MLPS(2,[50,50],2)', MLPS(2, [50, 50], 2).cuda(), (2,), 5300, 5300, ['full', 'kron', 'diag'], 5300, 1000, K=2)
+if 'cfg2' in which:
+    run('cfg2 satellite MLPS(36,[50,50],6)', MLPS(36, [50, 50], 6).cuda(), (36,), 4504, 4504, ['full', 'kron', 'diag'], 965, 1000, K=6)
+    run('cfg2 waveform MLPS(21,[50,50],3)', MLPS(21, [50, 50], 3).cuda(), (21,), 700, 700, ['full', 'kron', 'diag'], 150, 1000, K=3)
 if 'cfg3' in which:
     run('cfg3 MNIST MLP 784-1024-512-256-128-10', MLPS(784, [1024, 512, 256, 128], 10, flatten=True).cuda(), (1, 28, 28), 2048, 256, ['kron', 'diag'], 512, 1000)
 if 'cfg4' in which:
