@@ -291,6 +291,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    if secondary is not None and world == 1 and not args.no_other_configs:
+        lap = None
+        torch.cuda.empty_cache()
+        secondary['configs'] = other_configs(dev)
+
     pk, pk_kind = peaks()
     recs = [(pms[i], pex[i], pus[i]) for i in range(max(nrec, 0))]
     roofline = None
@@ -342,6 +347,62 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def other_configs(dev):
+    """Device-timed rates of the other BASELINE.json configurations (3: MNIST-shape MLP kron/diag + GLM predictive on
+    10 000 inputs x 1000 samples; 4: CIFAR10Net KFAC accumulation), reported under `secondary.configs`.  Never fatal for
+    the headline line."""
+    from preds_b200 import Laplace, CategoricalLh, MLPS, CIFAR10Net
+    out = []
+
+    def timed(fn, reps=3):
+        best = None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        return best
+
+    g = torch.Generator().manual_seed(15)
+    try:
+        torch.manual_seed(71)
+        model = MLPS(784, [1024, 512, 256, 128], 10, flatten=True).to(dev)
+        N, bs, nte, S = 4096, 256, 10000, 1000
+        X = torch.randn(N, 1, 28, 28, generator=g)
+        y = torch.randint(10, (N,), generator=g)
+        batches = [(X[i:i + bs].to(dev), y[i:i + bs].to(dev)) for i in range(0, N, bs)]
+        Xte = torch.randn(nte, 1, 28, 28, generator=g).to(dev)
+        for cov in ('kron', 'diag'):
+            lap = Laplace(model, 1.0, CategoricalLh())
+            lap.infer(batches[:2], cov_type=cov, factorise=False)
+            acc_ms = timed(lambda: lap.infer(batches, cov_type=cov, factorise=False))
+            lap.infer(batches, cov_type=cov)
+            lap.predictive_samples_glm(Xte[:64], n_samples=8, seed=1)
+            glm_ms = timed(lambda: lap.predictive_samples_glm(Xte, n_samples=S, seed=2), reps=2)
+            out.append({'config': 'cfg3 MLP 784-1024-512-256-128-10 (P=1494154), loader batch 256', 'cov_type': cov,
+                        'accum_examples_per_s': N / acc_ms * 1e3, 'glm_input_samples_per_s': nte * S / glm_ms * 1e3,
+                        'glm_inputs': nte, 'glm_samples': S})
+        del model, lap, batches, Xte
+        torch.manual_seed(71)
+        model = CIFAR10Net(3, 10, use_tanh=True).to(dev)
+        N = 2048
+        X = torch.randn(N, 3, 32, 32, generator=g)
+        y = torch.randint(10, (N,), generator=g)
+        batches = [(X[i:i + 256].to(dev), y[i:i + 256].to(dev)) for i in range(0, N, 256)]
+        lap = Laplace(model, 1.0, CategoricalLh())
+        lap.infer(batches[:2], cov_type='kron', factorise=False)
+        acc_ms = timed(lambda: lap.infer(batches, cov_type='kron', factorise=False))
+        out.append({'config': 'cfg4 CIFAR10Net(3,10) (P=895210), loader batch 256', 'cov_type': 'kron',
+                    'accum_examples_per_s': N / acc_ms * 1e3})
+    except Exception as exc:       # secondary numbers must not cost the headline
+        out.append({'error': repr(exc)[:200]})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -354,6 +415,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=24)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-glm', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--glm-inputs', type=int, default=10000)
     ap.add_argument('--glm-samples', type=int, default=1000)
     args = ap.parse_args()
