@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, 'lib')
 SO = os.path.join(LIB, 'libbnnp_b200.so')
 SOURCES = ['net.cu', 'lik.cu', 'ggn.cu', 'gram_tc.cu', 'gemm_tc.cu', 'glm.cu', 'glm_tc.cu', 'bnn.cu', 'linpred.cu', 'metrics.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Wno-deprecated-gpu-targets']
 
 
 def _stale(obj, src):

@@ -273,8 +273,8 @@ extern "C" int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const 
   if (bnn_linear_only(ops, n_ops) && S <= 65535) {
     // all S weight samples at once: every Linear is a batched-weights GEMM (batch index = sample), the
     // activation that follows it is fused into the epilogue.  The model's own parameters are not touched.
-    int64_t w = 0, last = -1;
-    for (int i = 0; i < n_ops; ++i) if (ops[i].kind == BNNP_OP_LINEAR) { if (ops[i].out_c > w) w = ops[i].out_c; last = i; }
+    int64_t w = 0;
+    for (int i = 0; i < n_ops; ++i) if (ops[i].kind == BNNP_OP_LINEAR && ops[i].out_c > w) w = ops[i].out_c;
     float* buf[2] = {scratch, scratch + S * N * w + 64};
     const float* in = X;
     int64_t in_ld = ops[0].in_c, in_bs = 0;       // the input batch is shared by all samples
