@@ -299,7 +299,6 @@ extern "C" int bnnp_bnn_forward(const bnnp_op_t* ops, int n_ops, int lik, const 
       if (rc) return rc;
       in = dst; in_ld = out_ld; in_bs = out_bs; pp ^= 1;
       K = o.out_c;
-      (void)last;
     }
     return bnnp_lik_inv_link(lik, in, S * N, K, out, stream);
   }
