@@ -40,7 +40,7 @@ def build(verbose=False, force=False):
     if failed:
         raise RuntimeError('nvcc failed')
     if procs or not os.path.exists(SO):
-        subprocess.check_call(['nvcc', '-shared', '-o', SO] + objs + ['-lcudart'])
+        subprocess.check_call(['nvcc', '-shared', '-Wno-deprecated-gpu-targets', '-o', SO] + objs + ['-lcudart'])
     return SO
 
 
