@@ -240,7 +240,11 @@ def linear_sampling_predictive(X, model, likelihood, mu, Sigma_chol, mc_samples=
     for theta_s = mu + Sigma_chol eps, eps [P,S]; [S, N, K] ([S, N] for a model that flattens its single
     output).  ``Sigma_chol`` is a lower factor [P,P] (also the diagonal *matrix* of ``get_diagonal_ggn``)
     or a vector of standard deviations [P].  All S samples go through one batched layer product per
-    layer on the Jacobian factors; J and the [S,P]x[P,N,K] product of the reference are never formed."""
+    layer on the Jacobian factors; J and the [S,P]x[P,N,K] product of the reference are never formed.
+
+    Deviation: for a single-output model that does NOT flatten (``MLPS(..., 1)``: f is [N,1], Js is [N,P]) the
+    reference's ``f - Js @ theta`` broadcasts [N,1] - [N] to [N,N] (preds/predictives.py:36); here that case returns
+    the intended [S, N, 1]."""
     net = net_for(model)
     theta_star = parameters_to_vector(model.parameters()).detach()
     mu = cabi.f32(mu, net.device)
