@@ -90,6 +90,14 @@ class Laplace:
         t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         t0.record()
         if cov_type == 'full':
+            # [P,P] fp32 accumulator (+ the factor, the inverse and one temporary while factorising): say so before
+            # the allocator does, the reference would simply run out of memory inside einsum / cholesky
+            need = 4 * self.P * self.P * (4 if factorise else 1)
+            free = torch.cuda.mem_get_info(self.device)[0] + torch.cuda.memory_reserved(self.device) \
+                - torch.cuda.memory_allocated(self.device)
+            if need > free:
+                raise cabi.BnnpError("cov_type='full' with P = %d needs about %.1f GB of device memory (%.1f GB available); "
+                                     "use cov_type='kron' or 'diag'" % (self.P, need / 1e9, free / 1e9))
             prior = self.expand_prior_precision(cov_type)
             if dist:
                 acc = torch.zeros(self.P, self.P, device=self.device)

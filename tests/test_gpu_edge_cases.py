@@ -158,3 +158,13 @@ def test_unsupported_layers_fail_loudly():
     net.output_size = 2
     with pytest.raises(BnnpError, match='outside the supported zoo'):
         Jacobians(net, torch.randn(3, 4))
+
+
+def test_full_covariance_too_large_fails_with_a_clear_message():
+    """[P,P] for the cfg-3 MLP (P = 1.49M) is 8.9 TB: refuse up front instead of dying inside an allocation."""
+    from preds_b200 import MLPS, CategoricalLh, Laplace, _cabi as cabi
+    model = MLPS(784, [1024, 512, 256, 128], 10, flatten=True).cuda()
+    lap = Laplace(model, 1.0, CategoricalLh())
+    X, y = torch.randn(4, 1, 28, 28).cuda(), torch.randint(10, (4,)).cuda()
+    with pytest.raises(cabi.BnnpError, match="needs about"):
+        lap.infer([(X, y)], cov_type='full')
