@@ -16,6 +16,12 @@ reference's arithmetic that lives in an absent third-party dependency is BackPAC
 ``G (x) A == exact block``.  Conv-weight KFLR values (spatial pre-sum in G) follow the published
 BackPACK ``HBPConv2d`` definition and are *unpinned by any reference test* (SURVEY.md 8c).
 
+The callers either side of the path (``post_process``, ``diagonal_ggn``,
+``linear_sampling_predictive``, ``laplace_refine`` / ``vi_refine`` / ``vi_diag_refine``, ``linear_regression_predictive``,
+``classification_metrics``) are restated at the end of the file and PINNED the same way
+(``tests/golden/ggn_simlp_{cls,bern}.npz``, ``extras.npz``; ``tests/test_oracle_ggn_golden.py``,
+``tests/test_oracle_extras_golden.py``).
+
 Everything is float32 torch on the CPU, written as plain functions with explicit
 standard-normal draws (``eps``) so the CUDA path can be fed identical numbers.
 """
