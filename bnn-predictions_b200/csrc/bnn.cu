@@ -1,5 +1,6 @@
 // BNN predictive (preds/predictives.py:12-28), Kron.sample (preds/kron.py:85-110) and the small
 // dense helpers of the posterior code.
+#include <string.h>
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -357,6 +358,25 @@ extern "C" const char* bnnp_strerror(int code) {
   }
 }
 unsigned long long g_bnnp_launches = 0;
+BnnpOptions g_bnnp_opt = {0, 0, 0, 0};
+static int* option_slot(const char* name) {
+  if (!name) return nullptr;
+  if (!strcmp(name, "gram_kernel")) return &g_bnnp_opt.gram_kernel;
+  if (!strcmp(name, "glm_single")) return &g_bnnp_opt.glm_single;
+  if (!strcmp(name, "glm_simt")) return &g_bnnp_opt.glm_simt;
+  if (!strcmp(name, "debug_sync")) return &g_bnnp_opt.debug_sync;
+  return nullptr;
+}
+extern "C" int bnnp_set_option(const char* name, int value) {
+  int* slot = option_slot(name);
+  if (!slot) return BNNP_ERR_INVALID;
+  *slot = value;
+  return BNNP_OK;
+}
+extern "C" int bnnp_get_option(const char* name) {
+  int* slot = option_slot(name);
+  return slot ? *slot : BNNP_ERR_INVALID;
+}
 extern "C" uint64_t bnnp_launch_count(void) { return g_bnnp_launches; }
 extern "C" int bnnp_version(void) { return 100; }
 extern "C" int bnnp_device_ok(void) {

@@ -23,6 +23,16 @@ extern unsigned long long g_bnnp_launches;
     BNNP_CUDA_CHECK(cudaGetLastError());    \
   } while (0)
 
+// Engine-selection options (bnnp_set_option): process-wide, default 0, set explicitly by tests / A-B scripts -- never
+// read from the environment, and none of them makes a kernel skip work.
+struct BnnpOptions {
+  int gram_kernel;     // full GGN on tensor cores: 0 auto (wide CTA-pair kernel), 1 single-CTA kernel, 2 two-unit CTA-pair kernel (BNNP_EXPERIMENTS builds)
+  int glm_single;      // full-covariance GLM: 1 forces the single-CTA TMA kernel
+  int glm_simt;        // kron / diag GLM contractions on the fp32 SIMT kernels with the unfused reductions
+  int debug_sync;      // synchronise and report after every GLM TMA launch
+};
+extern BnnpOptions g_bnnp_opt;
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

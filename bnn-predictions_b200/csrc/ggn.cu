@@ -462,11 +462,26 @@ extern "C" int64_t bnnp_ggn_full_scratch_floats(const bnnp_plan_t* plan, int64_t
 extern "C" int bnnp_ggn_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                                    const float* ws, const float* Lambda, float* H, float* scratch,
                                    int engine, void* stream) {
+  return bnnp_ggn_full_accum_rows(ops, n_ops, plan, N, ws, Lambda, H, scratch, engine, 0, -1, 0, stream);
+}
+
+extern "C" int bnnp_ggn_full_row_chunks(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int engine,
+                                        int n_chunks, int64_t* bounds) {
+  if (!ops || !plan || !bounds || n_chunks < 1 || N <= 0) return BNNP_ERR_INVALID;
+  if (engine == 0) engine = gram_tc_preferred(ops, n_ops, plan, N) ? 2 : 1;
+  if (engine != 2) { bounds[0] = 0; bounds[1] = plan->P; return 1; }       // the SIMT engine is not row-chunked
+  return gram_row_chunks(ops, n_ops, plan, n_chunks, bounds);
+}
+
+extern "C" int bnnp_ggn_full_accum_rows(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                        const float* ws, const float* Lambda, float* H, float* scratch, int engine,
+                                        int64_t row_begin, int64_t row_end, int prepared, void* stream) {
   if (!ops || !plan || !ws || !Lambda || !H || !scratch || N <= 0) return BNNP_ERR_INVALID;
   if (!linear_only(ops, n_ops)) return BNNP_ERR_UNSUPPORTED;
   cudaStream_t st = as_stream(stream);
   if (engine == 0) engine = gram_tc_preferred(ops, n_ops, plan, N) ? 2 : 1;
-  if (engine == 2) return gram_tc_full_accum(ops, n_ops, plan, N, ws, Lambda, H, scratch, st);
+  if (engine == 2) return gram_tc_full_accum(ops, n_ops, plan, N, ws, Lambda, H, scratch, row_begin, row_end, prepared, st);
+  if (!(row_end < 0 || (row_begin == 0 && row_end == plan->P))) return BNNP_ERR_UNSUPPORTED;   // SIMT engine: whole matrix only
   const int K = plan->K, M = plan->Mtot;
   const int64_t P = plan->P, Ppad = (P + 31) / 32 * 32;
   int32_t* pu = reinterpret_cast<int32_t*>(scratch);

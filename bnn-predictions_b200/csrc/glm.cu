@@ -401,8 +401,8 @@ struct TcRowMajorSq {      // X(r, k) = p[r*ld + k]^2
   }
 };
 constexpr long long kTcMinMacsK = 1LL << 25;
-// BNNP_GLM_SIMT=1 (tests): keep the kron / diag GLM contractions on the fp32 SIMT kernels and the unfused reductions
-static bool glm_force_simt() { const char* e = getenv("BNNP_GLM_SIMT"); return e && e[0] == '1'; }
+// option glm_simt (tests): keep the kron / diag GLM contractions on the fp32 SIMT kernels and the unfused reductions
+static bool glm_force_simt() { return g_bnnp_opt.glm_simt != 0; }
 
 // ---- sampling epilogue ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {

@@ -41,7 +41,6 @@ struct Args {
   int unit_first, unit_step, delta;  // this launch covers units unit_first + i*unit_step (same K-start misalignment delta)
   int wn, n_mt, n_nt, n_chunks;
   int n_mtp;                         // CTA-pair kernel: input tiles are taken two at a time
-  int dbg;                           // BNNP_GLM_DBG (measurement only): bit 0 skips the epilogue arithmetic
   long long ald; int Mtot;
   const float* Sigma; const float* A; const int32_t* pu; const int32_t* pc; float* T;
   const long long* tile_start;       // [n_units + 1] prefix of tiles per unit of this launch (lower triangle only)
@@ -81,11 +80,6 @@ __device__ __forceinline__ void glm_epilogue_tile(const Args& args, int* meta, f
     }
   }
   asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)buf) : "memory");     // the four warps of this buffer's group
-  if (args.dbg & 1) {
-    mbar_wait(acc_full_bar, buf_phase);
-    tc_fence_after();
-    return;
-  }
   // rows of this warp: first row and how many are inside the batch
   const long long r0 = m0 + q * 32;
   const int nrows = (int)(args.N - r0 < 32 ? (args.N - r0 < 0 ? 0 : args.N - r0) : 32);
@@ -535,10 +529,9 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
     a.n_mt = (int)((N + TILE_M - 1) / TILE_M);
   }
   // CTA-pair kernel (two input tiles per M = 256 MMA, each CTA stages half of the Sigma tile) whenever there are at
-  // least two input tiles; BNNP_GLM_SINGLE=1 forces the single-CTA kernel (A/B measurements)
-  const bool pair = a.n_mt >= 2 && !getenv("BNNP_GLM_SINGLE");
+  // least two input tiles; option glm_single forces the single-CTA kernel (A/B measurements)
+  const bool pair = a.n_mt >= 2 && !g_bnnp_opt.glm_single;
   a.n_mtp = (a.n_mt + 1) / 2;
-  a.dbg = getenv("BNNP_GLM_DBG") ? atoi(getenv("BNNP_GLM_DBG")) : 0;
   int rc = make_map(&msh, Sh, P, P, Ppitch, pair ? a.wn / 2 : a.wn);
   if (rc) return rc;
   rc = make_map(&msl, Sl, P, P, Ppitch, pair ? a.wn / 2 : a.wn);
@@ -573,7 +566,6 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
       a.nin = o.in_c; a.has_bias = o.has_bias;
       a.offw = o.theta_off_w; a.offb = o.has_bias ? o.theta_off_b : 0; a.unit0p = q.lin_unit;
       a.n_chunks = (o.in_c + delta + BK - 1) / BK;
-      if (a.dbg & 2) a.n_chunks = 1;          // measurement only: epilogue-bound run (wrong results)
       // per-unit tile counts (lower triangle): n-tiles from the one holding the unit's first weight row
       std::vector<long long> prefix(a.n_units + 1, 0);
       for (int ui = 0; ui < a.n_units; ++ui) {
@@ -596,7 +588,7 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
         glm_fvar_tma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, msh, msl, a);
       }
       BNNP_LAUNCH_CHECK();
-      if (getenv("BNNP_DEBUG_SYNC")) {
+      if (g_bnnp_opt.debug_sync) {
         cudaError_t e = cudaStreamSynchronize(st);
         fprintf(stderr, "[bnnp debug] glm_fvar_tma op %d grp %d delta %d: units %d nin %d wn %d n_nt %d n_mt %d chunks %d -> %s\n",
                 i, grp, delta, a.n_units, a.nin, a.wn, a.n_nt, a.n_mt, a.n_chunks, cudaGetErrorString(e));

@@ -17,6 +17,7 @@
 //   D += Ah*Bh + Ah*Bl + Al*Bh   (3 tcgen05.mma kind::f16 per 16-wide K-step; products exact, fp32
 //        accumulation in TMEM => ~2^-17 relative per term, "fp32-grade" after summation).
 // Epilogue: tcgen05.ld -> registers -> H[p,q] += acc (tiles on/below the diagonal only).
+#include <math.h>
 #include <stdlib.h>
 #include "tc_common.cuh"
 #include "gram_tc.cuh"
@@ -46,12 +47,12 @@ struct BlockArgs {
   // column side (layer l')
   int mp, np, unit0p;                  // column tiles: unit i' in [0,mp), j' in [0,np)
   long long col_theta0;
-  int wc, n_jt, n_pairs, n_rt;         // column tile width, #j' tiles, #unit pairs, #row tiles
+  int wc, n_jt, n_pairs;               // column tile width, #j' tiles, #unit pairs
+  int rt0, n_rt;                       // row tiles [rt0, rt0 + n_rt) of this launch (single-CTA kernel)
+  int rtp0, n_rtp;                     // row-tile pairs [rtp0, rtp0 + n_rtp) of this launch (CTA-pair kernels)
   int diag_block;                      // 1 when l == l' (skip tiles strictly above the diagonal)
   int n_chunks, chunk0, Mtot;          // K-chunks of this accumulation segment: [chunk0, chunk0 + n_chunks)
   long long Npad, P;
-  int ts_stride, ts_bufs;              // TMEM-A kernel: accumulator column stride, number of K=16 A buffers behind them
-  int dbg;                             // BNNP_GRAM_DBG (measurement only): 1 skips the H read-modify-write, 2 skips the A generation
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -92,7 +93,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
     const int tile = *tile_slot;
     __syncthreads();
     if (tile >= n_tiles) break;
-    const int rt = tile % args.n_rt;
+    const int rt = args.rt0 + tile % args.n_rt;
     const int jt = (tile / args.n_rt) % args.n_jt;
     const int pair = tile / (args.n_rt * args.n_jt);
     const int ipa = 2 * pair, ipb = 2 * pair + 1;
@@ -223,7 +224,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
         uint8_t* abase = smem + s * STAGE_BYTES;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
-          if (a < nacc && !(args.dbg & 2)) {
+          if (a < nacc) {
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
               float v[8];
@@ -234,16 +235,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
               uint4 hi, lo;
               split8(v, hi, lo);
               uint8_t* dst = abase + a * 2 * A_TERM_BYTES + soff[it];
-              if (!(args.dbg & 8)) {
-                *reinterpret_cast<uint4*>(dst) = hi;
-                *reinterpret_cast<uint4*>(dst + A_TERM_BYTES) = lo;
-              } else if (hi.x == 0x7fc07fc0u && lo.x == 0x12345678u) {   // keeps the arithmetic alive (never true in practice)
-                *reinterpret_cast<uint4*>(dst) = hi;
-              }
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + A_TERM_BYTES) = lo;
             }
           }
         }
-        if (!(args.dbg & 16)) fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
+        fence_proxy_async();   // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_a[s]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -255,7 +252,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
       mbar_wait(acc_full, acc_phase);
       tc_fence_after();
       const int a = gw >> 2, quarter = gw & 3;
-      if (a < nacc && !(args.dbg & 1)) {
+      if (a < nacc) {
         float* sc = reinterpret_cast<float*>(smem + gw * (32 * 33 * 4 + 128));     // [32][33]
         const int ip = a == 0 ? ipa : ipb;
         const int ncols = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
@@ -271,15 +268,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
           for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
           __syncwarp();
           const bool colok = c0 + lane < ncols;
-          if (args.dbg & 4) {
-            float h[32];                       // (measurement only) the load-add-store form: pays the read latency
-#pragma unroll
-            for (int u = 0; u < 32; ++u)
-              h[u] = (colok && u < nrows) ? hbase[(long long)u * args.P + c0 + lane] : 0.f;
-#pragma unroll
-            for (int u = 0; u < 32; ++u)
-              if (colok && u < nrows) hbase[(long long)u * args.P + c0 + lane] = h[u] + sc[u * 33 + lane];
-          } else {
+          {
             // fire-and-forget reductions (RED.ADD.F32, 128 B per warp request): the add happens in L2, the epilogue
             // never waits for H.  Every element of H receives exactly one add per launch, so the result does not
             // depend on the order in which the reductions land.
@@ -316,6 +305,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant
 // (the instruction reads the other half from the peer), which also leaves room for a fourth pipeline stage.
 // Rank 0 fetches the tile index for both CTAs, issues the MMAs and commits to the barriers of both; the generators of
 // rank 1 arrive on rank 0's `full_a` barrier, every TMA load credits rank 0's `full_b`.
+#ifdef BNNP_EXPERIMENTS      // kept for A/B timing against gram_wide_kernel (build with BNNP_EXPERIMENTS=1)
 constexpr int P_STAGES = 4;
 constexpr int P_B_TERM_BYTES = (MAX_WC / 2) * BK * 2;                      // 8 KB
 constexpr int P_STAGE_BYTES = A_STAGE_BYTES + 2 * P_B_TERM_BYTES;          // 48 KB
@@ -350,7 +340,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_rtp = (args.n_rt + 1) / 2;
+  const int n_rtp = args.n_rtp;
   const int n_tiles = args.n_pairs * args.n_jt * n_rtp;
   const int rows_total = args.m * args.n + (args.has_bias ? args.m : 0);
   uint32_t stage = 0, phase = 0;
@@ -365,7 +355,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_consta
     cluster_sync_all();                         // release/acquire at cluster scope: the slot is visible in both CTAs
     const int tile = *tile_slot;
     if (tile >= n_tiles) break;
-    const int rtp = tile % n_rtp;
+    const int rtp = args.rtp0 + tile % n_rtp;
     const int jt = (tile / n_rtp) % args.n_jt;
     const int pair = tile / (n_rtp * args.n_jt);
     const int ipa = 2 * pair, ipb = 2 * pair + 1;
@@ -564,44 +554,44 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_consta
   cluster_sync_all();
   if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
 }
+#endif  // BNNP_EXPERIMENTS
 
-// ---- CTA-pair version with the A operand in TMEM --------------------------------------------------------------------
-// What still separates gram_pair_kernel from the tensor peak is the generators' shared-memory traffic: 32 KB of A stores
-// per chunk that the tensor core reads back three times.  `tcgen05.mma` can take A from tensor memory: the generator
-// warps write their bf16 hi/lo products with `tcgen05.st` (16x256b: four lanes per row, the same coalesced global-load
-// pattern as before) into a 3-deep ring of K = 16 steps that lives in the 96 TMEM columns left by two <= 208-wide
-// accumulators; shared memory then carries only the TMA-fed half B tiles (8 stages).  Hand-offs are per K = 16 step:
-// a_full (generators of both CTAs -> rank 0's MMA thread), a_empty (multicast commit -> generators of both CTAs).
-constexpr int TS_ACC_STRIDE = 208;                 // widest accumulator of this kernel: a at TMEM column a * args.ts_stride
-constexpr int TS_A_BUFS = 8;                       // upper bound of args.ts_bufs = (512 - 2 * ts_stride) / 32
-#define TS_A_COL0 (2 * args.ts_stride)             // [buf][acc][hi 8 | lo 8] columns behind the accumulators
-constexpr int TS_B_STAGES = 8;
-constexpr int TS_B_STAGE_BYTES = 2 * P_B_TERM_BYTES;                                 // 16 KB (hi + lo half tiles)
-constexpr int TS_SCRATCH_BYTES = 8 * (32 * 33 * 4 + 128);                           // epilogue transposes
-constexpr int TS_SMEM_BYTES = TS_B_STAGES * TS_B_STAGE_BYTES + TS_SCRATCH_BYTES + 1024 + 512;
+// ---- CTA-pair version, ONE column unit x TWO column tiles ("wide") -------------------------------------------------
+// In gram_pair_kernel the two accumulators belong to two column units i'_a, i'_b: they share the TMA-fed B tile but each
+// needs its own generated A = c_n[i(p), i'] * x_n[j(p)] (32 KB of generator stores per 32-example chunk).  Here both
+// accumulators belong to the SAME unit i' and cover two adjacent j' ranges [jc0, jc0+wc), [jc0+wc, jc0+2wc): they share
+// the generated A (16 KB per chunk: half the generator loads, multiplies, bf16 splits and shared-memory stores, each
+// generated element now feeds up to 448 output columns) and take two B tiles, which the TMA engine delivers without any
+// thread work.  The MMA sequence per accumulator is unchanged, so H stays bit-identical to the other kernels.  A second
+// column tile that lies entirely above the diagonal of H is skipped on its own (finer than whole-tile skipping).
+// `args.rtp0 / args.n_rtp` restrict a launch to a range of row-tile pairs (row-chunked accumulation, so that finished
+// row chunks of H can be exchanged between GPUs while later chunks still accumulate).
+constexpr int W_STAGES = 4;
+constexpr int W_A_STAGE_BYTES = 2 * A_TERM_BYTES;                     // hi + lo: 16 KB
+constexpr int W_B_TERM_BYTES = (MAX_WC / 2) * BK * 2;                 // this CTA's half of one column tile, one term: 8 KB
+constexpr int W_B_STAGE_BYTES = 2 * 2 * W_B_TERM_BYTES;               // 2 column tiles x (hi, lo): 32 KB
+constexpr int W_STAGE_BYTES = W_A_STAGE_BYTES + W_B_STAGE_BYTES;      // 48 KB
+constexpr int W_SMEM_BYTES = W_STAGES * W_STAGE_BYTES + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gram_pair_ts_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                    const float* __restrict__ XT32, const float* __restrict__ Ct, float* __restrict__ H,
-                    int* __restrict__ tile_counter, BlockArgs args) {
+gram_wide_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                 const float* __restrict__ XT32, const float* __restrict__ Ct, float* __restrict__ H,
+                 int* __restrict__ tile_counter, BlockArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* scratch = smem + TS_B_STAGES * TS_B_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + TS_SCRATCH_BYTES);
-  uint64_t* full_b = bars;                            // [TS_B_STAGES] rank 0: TMA bytes of both CTAs
-  uint64_t* empty_b = bars + TS_B_STAGES;             // [TS_B_STAGES] both CTAs (multicast commit)
-  uint64_t* a_full = bars + 2 * TS_B_STAGES;          // [TS_A_BUFS] rank 0: generator warps of both CTAs
-  uint64_t* a_empty = a_full + TS_A_BUFS;             // [TS_A_BUFS] both CTAs (multicast commit)
-  uint64_t* acc_full = a_empty + TS_A_BUFS;           // both CTAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W_STAGES * W_STAGE_BYTES);
+  uint64_t* full_a = bars;                      // [W_STAGES] rank 0 only: generator warps of both CTAs
+  uint64_t* full_b = bars + W_STAGES;           // [W_STAGES] rank 0 only: TMA bytes of both CTAs
+  uint64_t* empty = bars + 2 * W_STAGES;        // [W_STAGES] both CTAs (multicast commit)
+  uint64_t* acc_full = bars + 3 * W_STAGES;     // both CTAs (multicast commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * W_STAGES + 1);
   int* tile_slot = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TS_B_STAGES; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < TS_A_BUFS; ++s) { mbar_init(&a_full[s], 16); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(&full_a[s], 16); mbar_init(&full_b[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -612,11 +602,11 @@ gram_pair_ts_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_rtp = (args.n_rt + 1) / 2;
-  const int n_tiles = args.n_pairs * args.n_jt * n_rtp;
+  const int n_rtp = args.n_rtp;
+  const int n_jtp = (args.n_jt + 1) / 2;
+  const int n_tiles = args.mp * n_jtp * n_rtp;
   const int rows_total = args.m * args.n + (args.has_bias ? args.m : 0);
-  uint32_t bstage = 0, bphase = 0;       // B ring (per 32-example chunk)
-  uint32_t abuf = 0, aphase = 0;         // A ring (per 16-example step)
+  uint32_t stage = 0, phase = 0;
   uint32_t acc_phase = 0;
 
   for (;;) {
@@ -625,89 +615,97 @@ gram_pair_ts_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_con
       *tile_slot = t;
       st_shared_cluster_u32(mapa_shared(smem_u32(tile_slot), 1), (uint32_t)t);
     }
-    cluster_sync_all();
+    cluster_sync_all();                         // release/acquire at cluster scope: the slot is visible in both CTAs
     const int tile = *tile_slot;
     if (tile >= n_tiles) break;
-    const int rtp = tile % n_rtp;
-    const int jt = (tile / n_rtp) % args.n_jt;
-    const int pair = tile / (n_rtp * args.n_jt);
-    const int ipa = 2 * pair, ipb = 2 * pair + 1;
-    const int nacc = ipb < args.mp ? 2 : 1;
-    const int jc0 = jt * args.wc;
+    const int rtp = args.rtp0 + tile % n_rtp;   // row-tile pair fastest: concurrent CTAs share c_n rows and B tiles in L2
+    const int jtp = (tile / n_rtp) % n_jtp;
+    const int ip = tile / (n_rtp * n_jtp);
+    const int jc0 = jtp * 2 * args.wc;
+    int nacc = jc0 + args.wc < args.np ? 2 : 1;
     const int row0 = (2 * rtp + (int)rank) * TILE_M;
     bool own_needed = row0 < rows_total;
     bool pair_needed = true;
+    bool own_acc1 = true;                        // this CTA's rows reach the second column tile
     if (args.diag_block) {
-      const long long min_col = args.col_theta0 + (long long)ipa * args.np + jc0;
+      const long long min_col = args.col_theta0 + (long long)ip * args.np + jc0;
       const int prow_last = 2 * rtp * TILE_M + 2 * TILE_M - 1;
       const long long pair_max_row = args.row_theta0 + (prow_last < rows_total - 1 ? prow_last : rows_total - 1);
       pair_needed = pair_max_row >= min_col;
+      if (nacc == 2 && pair_max_row < min_col + args.wc) nacc = 1;
       const long long own_max_row = args.row_theta0 + (row0 + TILE_M - 1 < rows_total - 1 ? row0 + TILE_M - 1 : rows_total - 1);
       own_needed = own_needed && own_max_row >= min_col;
+      own_acc1 = own_max_row >= min_col + args.wc;
     }
     if (pair_needed) {
-      const int wvalid = args.np - jc0 < args.wc ? args.np - jc0 : args.wc;
-      const int nmma = (wvalid + 15) / 16 * 16;
+      int wvalid[2], nmma[2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int left = args.np - (jc0 + a * args.wc);
+        wvalid[a] = left < args.wc ? (left > 0 ? left : 0) : args.wc;
+        nmma[a] = (wvalid[a] + 15) / 16 * 16;                  // instruction N; each CTA supplies nmma/2 rows of B
+      }
       if (warp == 0) {
-        // ===================== TMA producer: this CTA's half of B =====================
+        // ===================== TMA producer: this CTA's half of each column tile, hi and lo =====================
         if (lane == 0) {
-          uint32_t s = bstage, ph = bphase;
-          const uint32_t bytes = 2u * 2u * (uint32_t)(args.wc / 2) * BK * 2u;
-          const int brow = jc0 + (int)rank * (nmma / 2);
+          uint32_t s = stage, ph = phase;
+          const uint32_t bytes = 2u * (uint32_t)nacc * 2u * (uint32_t)(args.wc / 2) * BK * 2u;    // both CTAs
           for (int c = 0; c < args.n_chunks; ++c) {
-            mbar_wait(&empty_b[s], ph ^ 1);
-            uint8_t* bdst = smem + s * TS_B_STAGE_BYTES;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* bdst = smem + s * W_STAGE_BYTES + W_A_STAGE_BYTES;
             const uint32_t lead_full = mapa_shared(smem_u32(&full_b[s]), 0);
             if (rank == 0) mbar_arrive_expect_tx(&full_b[s], bytes);
-            tma_load_2d_pair(&map_bh, lead_full, bdst, (args.chunk0 + c) * BK, brow);
-            tma_load_2d_pair(&map_bl, lead_full, bdst + P_B_TERM_BYTES, (args.chunk0 + c) * BK, brow);
-            if (++s == TS_B_STAGES) { s = 0; ph ^= 1; }
+            for (int a = 0; a < nacc; ++a) {
+              const int brow = jc0 + a * args.wc + (int)rank * (nmma[a] / 2);
+              tma_load_2d_pair(&map_bh, lead_full, bdst + a * 2 * W_B_TERM_BYTES, (args.chunk0 + c) * BK, brow);
+              tma_load_2d_pair(&map_bl, lead_full, bdst + a * 2 * W_B_TERM_BYTES + W_B_TERM_BYTES, (args.chunk0 + c) * BK, brow);
+            }
+            if (++s == W_STAGES) { s = 0; ph ^= 1; }
           }
         }
       } else if (warp == 1) {
         // ===================== MMA issuer (rank 0) =====================
         if (lane == 0 && rank == 0) {
-          uint32_t s = bstage, ph = bphase, ab = abuf, aph = aphase;
-          const uint32_t idesc = umma_idesc_bf16_pair(nmma);
+          uint32_t s = stage, ph = phase;
+          const uint32_t idesc0 = umma_idesc_bf16_pair(nmma[0]), idesc1 = umma_idesc_bf16_pair(nmma[1] ? nmma[1] : 16);
           for (int c = 0; c < args.n_chunks; ++c) {
+            mbar_wait_cluster(&full_a[s], ph);
             mbar_wait(&full_b[s], ph);
-            const uint32_t b0 = smem_u32(smem + s * TS_B_STAGE_BYTES);
+            tc_fence_after();
+            const uint32_t ah = smem_u32(smem + s * W_STAGE_BYTES), al = ah + A_TERM_BYTES;
+            const uint32_t b0 = ah + W_A_STAGE_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < BK / 16; ++ks) {
-              mbar_wait_cluster(&a_full[ab], aph);
-              tc_fence_after();
-              const uint64_t dbh = umma_desc_sw64(b0 + ks * 32), dbl = umma_desc_sw64(b0 + P_B_TERM_BYTES + ks * 32);
+            for (int a = 0; a < 2; ++a) {
+              if (a < nacc) {
+                const uint32_t bh = b0 + a * 2 * W_B_TERM_BYTES, bl = bh + W_B_TERM_BYTES;
+                const uint32_t d = tmem_base + a * MAX_WC;
+                const uint32_t idesc = a ? idesc1 : idesc0;
 #pragma unroll
-              for (int a = 0; a < 2; ++a) {
-                if (a < nacc) {
-                  const uint32_t d = tmem_base + a * args.ts_stride;
-                  const uint32_t ah = tmem_base + TS_A_COL0 + ab * 32 + a * 16, al = ah + 8;
-                  umma_bf16_pair_ts(d, ah, dbh, idesc, (c | ks) ? 1u : 0u);
-                  umma_bf16_pair_ts(d, ah, dbl, idesc, 1u);
-                  umma_bf16_pair_ts(d, al, dbh, idesc, 1u);
+                for (int ks = 0; ks < BK / 16; ++ks) {
+                  const uint64_t dah = umma_desc_sw64(ah + ks * 32), dal = umma_desc_sw64(al + ks * 32);
+                  const uint64_t dbh = umma_desc_sw64(bh + ks * 32), dbl = umma_desc_sw64(bl + ks * 32);
+                  umma_bf16_pair(d, dah, dbh, idesc, (c | ks) ? 1u : 0u);
+                  umma_bf16_pair(d, dah, dbl, idesc, 1u);
+                  umma_bf16_pair(d, dal, dbh, idesc, 1u);
                 }
               }
-              umma_commit_pair(&a_empty[ab]);
-              if (++ab == (uint32_t)args.ts_bufs) { ab = 0; aph ^= 1; }
             }
-            umma_commit_pair(&empty_b[s]);
+            umma_commit_pair(&empty[s]);
             if (c == args.n_chunks - 1) umma_commit_pair(acc_full);
-            if (++s == TS_B_STAGES) { s = 0; ph ^= 1; }
+            if (++s == W_STAGES) { s = 0; ph ^= 1; }
           }
         }
       } else if (warp >= GEN_WARP0) {
-        // ===================== A generators (then epilogue) =====================
-        // warp gw: TMEM lane quarter q = gw & 3 (the only lanes this warp may access), 16-row half h2 = gw >> 2;
-        // thread: rows rl0 = q*32 + h2*16 + lane/4 and rl0 + 8, examples 4*(lane&3) .. +3 of each 16-example step
+        // ===================== A generators (then epilogue), rows of this CTA's own tile =====================
         const int gw = warp - GEN_WARP0;
-        const int q = gw & 3, h2 = gw >> 2;
         const int g = lane & 3;
         const float* xsrc[2];
-        const float* csrc[2][2];
+        const float* csrc[2];
         bool rvalid[2];
+        uint32_t soff[2];
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-          const int rl = q * 32 + h2 * 16 + it * 8 + (lane >> 2);
+          const int rl = gw * 16 + it * 8 + (lane >> 2);
           const int r = row0 + rl;
           rvalid[it] = r < rows_total;
           int u = args.unit0, src = args.col0;
@@ -715,130 +713,114 @@ gram_pair_ts_kernel(const __grid_constant__ CUtensorMap map_bh, const __grid_con
             if (r < args.m * args.n) { u += r / args.n; src += r % args.n; }
             else { u += r - args.m * args.n; src += args.n; }
           }
-          xsrc[it] = XT32 + (long long)src * args.Npad + (long long)args.chunk0 * BK + g * 4;
-          csrc[0][it] = Ct + ((long long)(args.unit0p + ipa) * args.Mtot + u) * args.Npad + (long long)args.chunk0 * BK + g * 4;
-          csrc[1][it] = Ct + ((long long)(args.unit0p + (nacc > 1 ? ipb : ipa)) * args.Mtot + u) * args.Npad + (long long)args.chunk0 * BK + g * 4;
+          xsrc[it] = XT32 + (long long)src * args.Npad + (long long)args.chunk0 * BK + g * 8;
+          csrc[it] = Ct + ((long long)(args.unit0p + ip) * args.Mtot + u) * args.Npad + (long long)args.chunk0 * BK + g * 8;
+          soff[it] = (uint32_t)((rl >> 3) * 512 + (rl & 7) * 64 + ((g ^ ((rl >> 1) & 3)) << 4));
         }
-        const uint32_t a_lane = (uint32_t)(q * 32 + h2 * 16) << 16;
-        uint32_t ab = abuf, aph = aphase;
+        uint32_t s = stage, ph = phase;
         const int pf_chunk = args.n_chunks > 48 ? args.n_chunks - 40 : 0;
-        float4 xv[2][2], cv[2][2][2];            // [row][step], [acc][row][step]
+        float4 xv[2][2], cv[2][2];
         auto load_chunk = [&](int c) {
 #pragma unroll
-          for (int it = 0; it < 2; ++it)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              xv[it][ks] = __ldg(reinterpret_cast<const float4*>(xsrc[it] + c * BK + ks * 16));
-#pragma unroll
-              for (int a = 0; a < 2; ++a) cv[a][it][ks] = __ldg(reinterpret_cast<const float4*>(csrc[a][it] + c * BK + ks * 16));
-            }
+          for (int it = 0; it < 2; ++it) {
+            const float4* xp = reinterpret_cast<const float4*>(xsrc[it] + c * BK);
+            xv[it][0] = __ldg(xp); xv[it][1] = __ldg(xp + 1);
+            const float4* cp = reinterpret_cast<const float4*>(csrc[it] + c * BK);
+            cv[it][0] = __ldg(cp); cv[it][1] = __ldg(cp + 1);
+          }
         };
         load_chunk(0);
         for (int c = 0; c < args.n_chunks; ++c) {
-          float4 x[2][2], cc[2][2][2];
+          float4 x[2][2], cc[2][2];
 #pragma unroll
-          for (int it = 0; it < 2; ++it)
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              x[it][ks] = xv[it][ks];
-#pragma unroll
-              for (int a = 0; a < 2; ++a) cc[a][it][ks] = cv[a][it][ks];
-            }
+          for (int it = 0; it < 2; ++it) {
+            x[it][0] = xv[it][0]; x[it][1] = xv[it][1];
+            cc[it][0] = cv[it][0]; cc[it][1] = cv[it][1];
+          }
           if (c + 1 < args.n_chunks) load_chunk(c + 1);
           if (c == pf_chunk && own_needed) {
-            const int lines = (wvalid * 4 + 127) / 128 + 1;
+            // pull this tile of H towards L2 so that the reductions of the epilogue do not pay DRAM latency
             for (int a = 0; a < nacc; ++a) {
-              const int ip = a == 0 ? ipa : ipb;
+              if (a == 1 && !own_acc1) break;
+              const int lines = (wvalid[a] * 4 + 127) / 128 + 1;
               for (int w = (warp - GEN_WARP0) * 32 + lane; w < TILE_M * lines; w += 256) {
                 const int rr = w / lines, ln = w % lines;
                 if (row0 + rr < rows_total) {
                   const float* ptr = H + (args.row_theta0 + row0 + rr) * args.P + args.col_theta0 +
-                                     (long long)ip * args.np + jc0 + ln * 32;
+                                     (long long)ip * args.np + jc0 + a * args.wc + ln * 32;
                   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
                 }
               }
             }
           }
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* abase = smem + s * W_STAGE_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            // bf16 hi/lo of the 2 rows x 4 examples x 2 accumulators of this step
-            uint32_t hi[2][2][2], lo[2][2][2];     // [acc][row][pair]
+          for (int it = 0; it < 2; ++it) {
+            float v[8];
+            const float* xf = reinterpret_cast<const float*>(&x[it][0]);
+            const float* cf = reinterpret_cast<const float*>(&cc[it][0]);
 #pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-              for (int it = 0; it < 2; ++it) {
-                const float* xf = reinterpret_cast<const float*>(&x[it][ks]);
-                const float* cf = reinterpret_cast<const float*>(&cc[a][it][ks]);
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = rvalid[it] ? xf[e] * cf[e] : 0.f;
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                  const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * pp], v[2 * pp + 1]);
-                  const float2 hf = __bfloat1622float2(h);
-                  const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * pp] - hf.x, v[2 * pp + 1] - hf.y);
-                  hi[a][it][pp] = *reinterpret_cast<const uint32_t*>(&h);
-                  lo[a][it][pp] = *reinterpret_cast<const uint32_t*>(&l);
-                }
-              }
-            mbar_wait(&a_empty[ab], aph ^ 1);
-            tc_fence_after();
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-              if (a < nacc && !(args.dbg & 2)) {
-                const uint32_t col = (uint32_t)(TS_A_COL0 + ab * 32 + a * 16);
-                tmem_st_16x256b(tmem_base + a_lane + col, hi[a][0][0], hi[a][0][1], hi[a][1][0], hi[a][1][1]);
-                tmem_st_16x256b(tmem_base + a_lane + col + 8, lo[a][0][0], lo[a][0][1], lo[a][1][0], lo[a][1][1]);
-              }
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (rank == 0) mbar_arrive(&a_full[ab]);
-              else mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&a_full[ab]), 0));
-            }
-            if (++ab == (uint32_t)args.ts_bufs) { ab = 0; aph ^= 1; }
+            for (int e = 0; e < 8; ++e) v[e] = rvalid[it] ? xf[e] * cf[e] : 0.f;
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            uint8_t* dst = abase + soff[it];
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + A_TERM_BYTES) = lo;
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&full_a[s]);
+            else mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&full_a[s]), 0));
+          }
+          if (++s == W_STAGES) { s = 0; ph ^= 1; }
         }
         // ---------------- epilogue: H[p, q] += D for this CTA's rows ----------------
+        // two groups of four warps (one warp per 32-lane TMEM quarter): with two column tiles each group drains one
+        // accumulator, with one they split its 32-column steps
         mbar_wait(acc_full, acc_phase);
         tc_fence_after();
-        const int a = gw >> 2, quarter = gw & 3;
-        if (a < nacc && own_needed) {
-          float* sc = reinterpret_cast<float*>(scratch + gw * (32 * 33 * 4 + 128));
-          const int ip = a == 0 ? ipa : ipb;
+        const int grp = gw >> 2, quarter = gw & 3;
+        if (own_needed) {
+          float* sc = reinterpret_cast<float*>(smem + gw * (32 * 33 * 4 + 128));
+          const int a = nacc == 2 ? grp : 0;
+          const int nsteps = (wvalid[a] + 31) / 32;
+          const int s_beg = nacc == 2 ? 0 : (grp == 0 ? 0 : (nsteps + 1) / 2);
+          const int s_end = nacc == 2 ? nsteps : (grp == 0 ? (nsteps + 1) / 2 : nsteps);
           const int rbase = row0 + quarter * 32;
-          float* hbase = H + (args.row_theta0 + rbase) * args.P + args.col_theta0 + (long long)ip * args.np + jc0;
+          float* hbase = H + (args.row_theta0 + rbase) * args.P + args.col_theta0 + (long long)ip * args.np + jc0 + a * args.wc;
           int nrows = rows_total - rbase;
           nrows = nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows);
-          for (int c0 = 0; c0 < wvalid; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * args.ts_stride + c0), v);
-            __syncwarp();
+          if (!(a == 1 && !own_acc1)) {
+            for (int st = s_beg; st < s_end; ++st) {
+              const int c0 = st * 32;
+              uint32_t v[32];
+              tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * MAX_WC + c0), v);
+              __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
-            __syncwarp();
-            const bool colok = c0 + lane < wvalid;
+              for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
+              __syncwarp();
+              const bool colok = c0 + lane < wvalid[a];
+              // fire-and-forget reductions (RED.ADD.F32, 128 B per warp request): the add happens in L2; every element
+              // of H receives exactly one add per launch, so the result does not depend on the order they land in
 #pragma unroll
-            for (int u = 0; u < 32; ++u)
-              if (colok && u < nrows) atomicAdd(hbase + (long long)u * args.P + c0 + lane, sc[u * 33 + lane]);
+              for (int u = 0; u < 32; ++u)
+                if (colok && u < nrows) atomicAdd(hbase + (long long)u * args.P + c0 + lane, sc[u * 33 + lane]);
+            }
           }
         }
         tc_fence_before();
       }
       {
-        const uint32_t tb = bstage + (uint32_t)args.n_chunks;
-        bphase ^= (tb / TS_B_STAGES) & 1;
-        bstage = tb % TS_B_STAGES;
-        const uint32_t ta = abuf + 2u * (uint32_t)args.n_chunks;
-        aphase ^= (ta / (uint32_t)args.ts_bufs) & 1;
-        abuf = ta % (uint32_t)args.ts_bufs;
+        const uint32_t tot = stage + (uint32_t)args.n_chunks;
+        phase ^= (tot / W_STAGES) & 1;
+        stage = tot % W_STAGES;
         acc_phase ^= 1;
       }
     }
     tc_fence_before();
-    cluster_sync_all();
+    cluster_sync_all();         // both CTAs drained their TMEM rows (and read the tile slot) before the next tile
     tc_fence_after();
   }
 
@@ -921,11 +903,10 @@ static int launch_ct(const float* GL, const float* G, long long N, int K, int M,
 // Bias columns (SIMT): H[row_theta0 + r, bias_theta0p + i'] += sum_n Ct[(u'_i' * M + u(r)), n] * XT32[src(r), n]
 // one warp per (r, i').
 __global__ void bias_cols_kernel(const float* __restrict__ XT32, const float* __restrict__ Ct,
-                                 float* __restrict__ H, BlockArgs a, long long bias_theta0p, int r_begin) {
+                                 float* __restrict__ H, BlockArgs a, long long bias_theta0p, int r_begin, int r_end) {
   long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const int rows_total = a.m * a.n + (a.has_bias ? a.m : 0);
-  const long long nwork = (long long)(rows_total - r_begin) * a.mp;
+  const long long nwork = (long long)(r_end - r_begin) * a.mp;
   if (w >= nwork) return;
   const int r = r_begin + (int)(w / a.mp), ip = (int)(w % a.mp);
   int u = a.unit0, src = a.col0;
@@ -989,24 +970,47 @@ struct GramProf {
 };
 static GramProf g_prof;
 
-// MMA flops of one launch: executed (padded 128 x wc tiles, 3 split passes) and useful (valid rows/cols only)
-static void gram_flops(const tc::BlockArgs& a, double* executed, double* useful) {
+// MMA flops of one launch: executed (padded tiles as issued, 3 split passes) and useful (elements of H on or below
+// its diagonal only, valid rows / columns only -- the strict count the roofline fraction is quoted on).
+// mode: 0 single-CTA kernel, 1 CTA-pair kernel (two units), 2 wide kernel (one unit, two column tiles)
+static void gram_flops(const tc::BlockArgs& a, int mode, double* executed, double* useful) {
   const long long rows_total = (long long)a.m * a.n + (a.has_bias ? a.m : 0);
+  const double kflops = 3.0 * 2.0 * (double)a.n_chunks * tc::BK;
   double ex = 0, us = 0;
-  for (int pair = 0; pair < a.n_pairs; ++pair)
-    for (int jt = 0; jt < a.n_jt; ++jt)
-      for (int rt = 0; rt < a.n_rt; ++rt) {
-        const int ipa = 2 * pair, nacc = (2 * pair + 1 < a.mp) ? 2 : 1;
-        const long long row0 = (long long)rt * tc::TILE_M, jc0 = (long long)jt * a.wc;
+  // lower-triangle element count of rows [r0, r1) x cols [c0, c1) (global indices)
+  auto lower = [](long long r0, long long r1, long long c0, long long c1) {
+    double n = 0;
+    for (long long r = r0; r < r1; ++r) { long long k = r - c0 + 1; n += (double)(k < 0 ? 0 : (k > c1 - c0 ? c1 - c0 : k)); }
+    return n;
+  };
+  const int tile_rows = mode == 0 ? tc::TILE_M : 2 * tc::TILE_M;
+  const int t0 = mode == 0 ? a.rt0 : a.rtp0, nt = mode == 0 ? a.n_rt : a.n_rtp;
+  for (int t = t0; t < t0 + nt; ++t) {
+    const long long row0 = (long long)t * tile_rows;
+    const long long row1 = row0 + tile_rows < rows_total ? row0 + tile_rows : rows_total;
+    const long long gr0 = a.row_theta0 + row0, gr1 = a.row_theta0 + row1;
+    for (int ip = 0; ip < a.mp; ++ip)
+      for (int jt = 0; jt < a.n_jt; ++jt) {
+        const long long jc0 = (long long)jt * a.wc;
+        const long long vc = a.np - jc0 < a.wc ? a.np - jc0 : a.wc;
+        const long long gc0 = a.col_theta0 + (long long)ip * a.np + jc0;
         if (a.diag_block) {
-          long long last = row0 + tc::TILE_M - 1 < rows_total - 1 ? row0 + tc::TILE_M - 1 : rows_total - 1;
-          if (a.row_theta0 + last < a.col_theta0 + (long long)ipa * a.np + jc0) continue;
+          // tile-skipping granularity of each kernel: unit pair x column tile (0, 1) / unit x column tile, decided
+          // on the first column of the group the accumulator belongs to (second tile of a wide pair: its own)
+          long long group_c0 = gc0;
+          if (mode != 2) group_c0 = a.col_theta0 + (long long)(ip & ~1) * a.np + jc0;
+          else if (jt & 1) {
+            const long long first = a.col_theta0 + (long long)ip * a.np + (long long)(jt - 1) * a.wc;
+            group_c0 = (gr1 - 1 >= first + a.wc) ? first : gr1;      // skipped on its own when entirely above the diagonal
+          }
+          if (gr1 - 1 < group_c0) continue;
+          us += kflops * lower(gr0, gr1, gc0, gc0 + vc);
+        } else {
+          us += kflops * (double)(row1 - row0) * (double)vc;
         }
-        long long vr = rows_total - row0 < tc::TILE_M ? rows_total - row0 : tc::TILE_M;
-        long long vc = a.np - jc0 < a.wc ? a.np - jc0 : a.wc;
-        ex += 3.0 * 2.0 * tc::TILE_M * ((vc + 15) / 16 * 16) * (double)a.n_chunks * tc::BK * nacc;
-        us += 3.0 * 2.0 * vr * vc * (double)a.n_chunks * tc::BK * nacc;
+        ex += kflops * tile_rows * (double)((vc + 15) / 16 * 16);
       }
+  }
   *executed = ex; *useful = us;
 }
 
@@ -1036,11 +1040,18 @@ bool gram_tc_preferred(const bnnp_op_t*, int, const bnnp_plan_t* plan, int64_t N
   return plan->P >= 2048 && N >= 256 && 8LL * plan->K * plan->Mtot * 2 * 4 <= 200 * 1024;
 }
 
+// rows [row_begin, row_end) of H only (row_end < 0: all rows).  A boundary that falls inside a layer's row block must
+// sit on a multiple of 256 rows of that block (one CTA-pair row tile) -- gram_row_chunks() produces such boundaries.
+// prepared != 0: the per-batch operands in `scratch` (transposed activations, C_n) were already built by an earlier call
+// for the same batch and are reused.
 int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, const float* ws,
-                       const float* Lambda, float* H, float* scratch, cudaStream_t st) {
+                       const float* Lambda, float* H, float* scratch, int64_t row_begin, int64_t row_end, int prepared,
+                       cudaStream_t st) {
   using namespace tc;
   const int K = plan->K, M = plan->Mtot, D = plan->Dtot;
   if ((long long)8 * K * M * 2 * 4 > 200 * 1024) return BNNP_ERR_UNSUPPORTED;
+  if (row_end < 0) { row_begin = 0; row_end = plan->P; }
+  if (row_begin < 0 || row_end > plan->P || row_begin > row_end) return BNNP_ERR_INVALID;
   // scratch must be 1 KB aligned for the tensor maps / vector loads
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 1023) & ~uintptr_t(1023));
   const TcLayout L = tc_layout(plan, N);
@@ -1054,7 +1065,7 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
   const float* G = ws + plan->gcat_off;
 
   BNNP_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4096 * sizeof(int), st));
-  {
+  if (!prepared) {
     dim3 grid((unsigned)(L.Npad / 32), (unsigned)((D + 31) / 32));
     transpose_split_kernel<<<grid, dim3(32, 8), 0, st>>>(A, D, N, D, L.Npad, XT32, XTh, XTl);
     BNNP_LAUNCH_CHECK();
@@ -1067,9 +1078,15 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
     else rc = launch_ct<8>(GL, G, N, K, M, L.Npad, Ct, st);
     if (rc) return rc;
   }
-  BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-  BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_pair_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+  static bool attrs_set = false;
+  if (!attrs_set) {
+    BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
+#ifdef BNNP_EXPERIMENTS
+    BNNP_CUDA_CHECK(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+#endif
+    attrs_set = true;
+  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1077,49 +1094,64 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
   int pair_idx = 0;
   for (int i = 0; i < n_ops; ++i) {
     if (ops[i].kind != BNNP_OP_LINEAR) continue;
+    const bnnp_op_t& R = ops[i];
+    if (R.has_bias && R.theta_off_b != R.theta_off_w + (long long)R.out_c * R.in_c) return BNNP_ERR_UNSUPPORTED;
+    const long long rows_total = (long long)R.out_c * R.in_c + (R.has_bias ? R.out_c : 0);
+    // rows of this layer's block inside [row_begin, row_end)
+    long long lr0 = row_begin - R.theta_off_w, lr1 = row_end - R.theta_off_w;
+    lr0 = lr0 < 0 ? 0 : (lr0 > rows_total ? rows_total : lr0);
+    lr1 = lr1 < 0 ? 0 : (lr1 > rows_total ? rows_total : lr1);
+    if (lr0 >= lr1) continue;
+    if (lr0 % (2 * TILE_M) != 0 || (lr1 % (2 * TILE_M) != 0 && lr1 != rows_total)) return BNNP_ERR_INVALID;
     for (int j = 0; j <= i; ++j) {
       if (ops[j].kind != BNNP_OP_LINEAR) continue;
-      const bnnp_op_t& R = ops[i];
       const bnnp_op_t& Cc = ops[j];
-      if (R.has_bias && R.theta_off_b != R.theta_off_w + (long long)R.out_c * R.in_c) return BNNP_ERR_UNSUPPORTED;
       BlockArgs a;
-      a.dbg = getenv("BNNP_GRAM_DBG") ? atoi(getenv("BNNP_GRAM_DBG")) : 0;
       a.m = R.out_c; a.n = R.in_c; a.has_bias = R.has_bias;
       a.unit0 = plan->op[i].lin_unit; a.col0 = plan->op[i].lin_col; a.row_theta0 = R.theta_off_w;
       a.mp = Cc.out_c; a.np = Cc.in_c; a.unit0p = plan->op[j].lin_unit; a.col_theta0 = Cc.theta_off_w;
+      a.rt0 = (int)(lr0 / TILE_M);
+      a.n_rt = (int)((lr1 + TILE_M - 1) / TILE_M) - a.rt0;
+      a.rtp0 = a.rt0 / 2;
+      a.n_rtp = (int)((lr1 + 2 * TILE_M - 1) / (2 * TILE_M)) - a.rtp0;
+      // kernel: wide CTA-pair kernel (one unit, two column tiles sharing the generated A operand, M = 256 over two row
+      // tiles) whenever the block has at least two row tiles; the single-CTA kernel otherwise (or by option)
+      int mode = (rows_total + TILE_M - 1) / TILE_M >= 2 ? 2 : 0;
+      if (g_bnnp_opt.gram_kernel == 1) mode = 0;
+#ifdef BNNP_EXPERIMENTS
+      if (g_bnnp_opt.gram_kernel == 2 && mode == 2) mode = 1;
+#endif
       // column tile width: widest box (<= 256, multiple of 16) whose tiling of np wastes the least MMA work
-      // when the last tile issues a narrower instruction (e.g. 784 = 3 x 224 + 112 instead of 4 x 208)
+      // when the last tile issues a narrower instruction (e.g. 784 = 3 x 224 + 112 instead of 4 x 208); the wide
+      // kernel pays the per-tile generator / epilogue overhead once per PAIR of column tiles
       {
         int best_w = 16; long long best_cost = -1;
-        // TMEM-A kernel (BNNP_GRAM_TS=<widest accumulator, <= 208>): narrower accumulators leave more K=16 A buffers
-        const int ts_cap = getenv("BNNP_GRAM_TS") ? atoi(getenv("BNNP_GRAM_TS")) : 0;
-        for (int w = ts_cap >= 64 && ts_cap <= TS_ACC_STRIDE ? ts_cap / 16 * 16 : 256; w >= 64; w -= 16) {
+        for (int w = 256; w >= 64; w -= 16) {
           const int nj = (a.np + w - 1) / w;
           const int last = a.np - (nj - 1) * w;
           const int last16 = (last + 15) / 16 * 16;
           // executed MMA columns (a very narrow last tile is smem-bound: count it as >= 64) + ~64 columns worth of
           // per-tile generator / epilogue work
-          const long long cost = (long long)(nj - 1) * w + (last16 < 64 ? 64 : last16) + 64LL * nj;
+          const long long groups = mode == 2 ? (nj + 1) / 2 : nj;
+          const long long cost = (long long)(nj - 1) * w + (last16 < 64 ? 64 : last16) + 64LL * groups;
           if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_w = w; }
         }
         a.wc = a.np < 64 ? (a.np + 15) / 16 * 16 : best_w;
       }
       a.n_jt = (a.np + a.wc - 1) / a.wc;
       a.n_pairs = (a.mp + 1) / 2;
-      const int rows_total = a.m * a.n + (a.has_bias ? a.m : 0);
-      a.n_rt = (rows_total + TILE_M - 1) / TILE_M;
       a.diag_block = (i == j);
       a.Mtot = M; a.Npad = L.Npad; a.P = plan->P;
-      // CTA-pair kernel (two row tiles per M = 256 MMA, half of the B tile per SM) whenever the block has at least two
-      // row tiles; BNNP_GRAM_SINGLE=1 forces the single-CTA kernel (A/B measurements)
-      const bool use_pair = a.n_rt >= 2 && !getenv("BNNP_GRAM_SINGLE");
       CUtensorMap mh, ml;
-      int rc = make_b_map(&mh, XTh + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, use_pair ? a.wc / 2 : a.wc);
+      int rc = make_b_map(&mh, XTh + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, mode ? a.wc / 2 : a.wc);
       if (rc) return rc;
-      rc = make_b_map(&ml, XTl + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, use_pair ? a.wc / 2 : a.wc);
+      rc = make_b_map(&ml, XTl + (long long)plan->op[j].lin_col * L.Npad, a.np, L.Npad, mode ? a.wc / 2 : a.wc);
       if (rc) return rc;
-      const long long n_tiles = (long long)a.n_pairs * a.n_jt * (use_pair ? (a.n_rt + 1) / 2 : a.n_rt);
-      int grid = use_pair ? 2 * (int)(n_tiles < sms / 2 ? n_tiles : sms / 2) : (int)(n_tiles < sms ? n_tiles : sms);
+      long long n_tiles;
+      if (mode == 0) n_tiles = (long long)a.n_pairs * a.n_jt * a.n_rt;
+      else if (mode == 1) n_tiles = (long long)a.n_pairs * a.n_jt * a.n_rtp;
+      else n_tiles = (long long)a.mp * ((a.n_jt + 1) / 2) * a.n_rtp;
+      const int grid = mode ? 2 * (int)(n_tiles < sms / 2 ? n_tiles : sms / 2) : (int)(n_tiles < sms ? n_tiles : sms);
       // The TMEM accumulators truncate on every update, so one accumulation never spans more than
       // kMaxAccumExamples examples; the segments are combined in fp32 (round-to-nearest) through H.
       const int total_chunks = (int)(L.Npad / BK), seg_chunks = kMaxAccumExamples / BK;
@@ -1133,14 +1165,13 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
             for (int e = 0; e < GramProf::CAP; ++e) { cudaEventCreate(&g_prof.beg[e]); cudaEventCreate(&g_prof.end[e]); }
             g_prof.created = true;
           }
-          gram_flops(a, &g_prof.executed[g_prof.n], &g_prof.useful[g_prof.n]);
+          gram_flops(a, mode, &g_prof.executed[g_prof.n], &g_prof.useful[g_prof.n]);
           cudaEventRecord(g_prof.beg[g_prof.n], st);
         }
-        a.ts_stride = (a.wc + 15) / 16 * 16;
-        a.ts_bufs = (512 - 2 * a.ts_stride) / 32 < TS_A_BUFS ? (512 - 2 * a.ts_stride) / 32 : TS_A_BUFS;
-        if (use_pair && getenv("BNNP_GRAM_TS") && a.wc <= TS_ACC_STRIDE && a.ts_bufs >= 3)
-          gram_pair_ts_kernel<<<grid, NUM_THREADS, TS_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
-        else if (use_pair) gram_pair_kernel<<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+        if (mode == 2) gram_wide_kernel<<<grid, NUM_THREADS, W_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+#ifdef BNNP_EXPERIMENTS
+        else if (mode == 1) gram_pair_kernel<<<grid, NUM_THREADS, P_SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
+#endif
         else gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mh, ml, XT32, Ct, H, counters + pair_idx, a);
         if (prof) { cudaEventRecord(g_prof.end[g_prof.n], st); ++g_prof.n; }
         BNNP_LAUNCH_CHECK();
@@ -1150,16 +1181,40 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
       a.n_chunks = total_chunks;
       // bias columns of layer l' (SIMT): all rows for l' < l, bias rows only on the diagonal block
       if (Cc.has_bias) {
-        int r_begin = (i == j) ? a.m * a.n : 0;
-        long long nwork = (long long)(rows_total - r_begin) * a.mp;
+        long long r_begin = (i == j) ? (long long)a.m * a.n : 0;
+        if (r_begin < lr0) r_begin = lr0;
+        const long long nwork = (lr1 - r_begin) * a.mp;
         if (nwork > 0) {
-          bias_cols_kernel<<<(unsigned)ceil_div64(nwork * 32, 256), 256, 0, st>>>(XT32, Ct, H, a, Cc.theta_off_b, r_begin);
+          bias_cols_kernel<<<(unsigned)ceil_div64(nwork * 32, 256), 256, 0, st>>>(XT32, Ct, H, a, Cc.theta_off_b, (int)r_begin,
+                                                                                  (int)lr1);
           BNNP_LAUNCH_CHECK();
         }
       }
     }
   }
   return BNNP_OK;
+}
+
+// Row boundaries b[0] = 0 < b[1] < ... < b[n] = P that split the lower triangle of H into n_chunks chunks of roughly equal
+// area, each boundary legal for gram_tc_full_accum (a multiple of 256 rows inside its layer block, or a block edge).
+// Returns the number of chunks actually produced (<= n_chunks; boundaries that collapse are dropped).
+int gram_row_chunks(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int n_chunks, int64_t* bounds) {
+  const long long P = plan->P;
+  int n = 0;
+  bounds[n++] = 0;
+  for (int c = 1; c < n_chunks; ++c) {
+    long long want = (long long)((double)P * sqrt((double)c / n_chunks));
+    long long snapped = want;
+    for (int i = 0; i < n_ops; ++i) {
+      if (ops[i].kind != BNNP_OP_LINEAR) continue;
+      const long long b0 = ops[i].theta_off_w;
+      const long long rows = (long long)ops[i].out_c * ops[i].in_c + (ops[i].has_bias ? ops[i].out_c : 0);
+      if (want >= b0 && want < b0 + rows) { snapped = b0 + (want - b0) / (2 * tc::TILE_M) * (2 * tc::TILE_M); break; }
+    }
+    if (snapped > bounds[n - 1] && snapped < P) bounds[n++] = snapped;
+  }
+  bounds[n] = P;
+  return n;
 }
 
 }  // namespace bnnp

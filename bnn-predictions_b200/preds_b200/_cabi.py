@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libbnnp_b200.so')
 
 MAX_OPS = 64
-MAX_K = 16            # sampling epilogue is instantiated for K <= 16
+MAX_K = 32            # BNNP_MAX_K of include/bnnp_b200.h (register-resident K x K code)
 OP_LINEAR, OP_CONV2D, OP_RELU, OP_TANH, OP_MAXPOOL2D, OP_AVGPOOL2D, OP_FLATTEN, OP_SIGMOID = range(1, 9)
 LIK_CATEGORICAL, LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1, 2
 ERR_INVALID = -1
@@ -64,7 +64,13 @@ _SIGS = {
     'bnnp_jacobians': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _V]),
     'bnnp_ggn_full_scratch_floats': (_L, [_PLAN, _L, _I]),
     'bnnp_ggn_full_accum': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _I, _V]),
+    'bnnp_ggn_full_row_chunks': (_I, [_OPS, _I, _PLAN, _L, _I, _I, C.POINTER(C.c_int64)]),
+    'bnnp_ggn_full_accum_rows': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _I, _L, _L, _I, _V]),
     'bnnp_symmetrize_lower': (_I, [_P, _L, _V]),
+    'bnnp_exchange_lower_allreduce': (_I, [C.POINTER(_P), _P, _I, _I, _L, _L, _L, _P, _F, _I, _V]),
+    'bnnp_packed_lower_floats': (_L, [_L, _L]),
+    'bnnp_pack_lower': (_I, [_P, _L, _L, _L, _P, _V]),
+    'bnnp_unpack_lower': (_I, [_P, _L, _L, _L, _P, _P, _F, _V]),
     'bnnp_ggn_diag_accum': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _P, _P, _V]),
     'bnnp_ggn_diag_scratch_floats': (_L, [_OPS, _I, _PLAN, _L, _I]),
     'bnnp_kfac_accum': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _F, C.POINTER(_P), _P, _V]),
@@ -101,6 +107,8 @@ _SIGS = {
     'bnnp_sgemm_tc_scratch_floats': (_L, [_L, _L, _L]),
     'bnnp_sgemm_tc': (_I, [_I, _I, _L, _L, _L, _F, _P, _L, _P, _L, _F, _P, _L, _P, _V]),
     'bnnp_launch_count': (C.c_uint64, []),
+    'bnnp_set_option': (_I, [C.c_char_p, _I]),
+    'bnnp_get_option': (_I, [C.c_char_p]),
     'bnnp_prof_enable': (_I, [_I]),
     'bnnp_prof_read': (_I, [C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), _I]),
 }

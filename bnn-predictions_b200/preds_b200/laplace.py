@@ -57,17 +57,21 @@ class Laplace:
         self._Sigma = None
         self.precision = None
         self.timings = {}
+        self.exchange_stats = None   # parallel.LowerExchange of the last sharded full-covariance infer
         self.ggn_engine = 0          # 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16
 
     # ------------------------------------------------------------------------------ infer
-    def infer(self, train_loader, cov_type='full', dampen_kron=False, shard=None, factorise=True):
+    def infer(self, train_loader, cov_type='full', dampen_kron=False, shard=None, factorise=True, exchange='auto'):
         """Compute the posterior (preds/laplace.py:30-82).
 
         shard: None   -- single process, exactly the reference's semantics;
                'batches'    -- under torch.distributed, rank r takes loader batches r, r+W, ...;
                'presharded' -- the loader already yields this rank's examples only.
-        In both sharded modes the accumulated factors are summed with ONE all-reduce and the
-        prior is added once afterwards, so every rank ends with the same posterior.
+        In both sharded modes the accumulated factors are summed with ONE exchange step and the
+        prior is added once, so every rank ends with the same posterior.  For the full covariance the exchange is
+        the library's own kernel over NVLink peer memory (lower triangle only, row chunks overlapped with the
+        accumulation of the last super-batch; ``exchange`` = 'auto' | 'nvls' | 'p2p' | 'nccl', see
+        ``parallel.LowerExchange``); kron / diag exchange a few MB through NCCL.
 
         factorise=False stops after the accumulation (``self.precision`` / the ``Kron`` factors
         are set, ``Sigma_chol`` is not): the one-off factorisation is timed separately.
@@ -76,6 +80,7 @@ class Laplace:
         self.mu = parameters_to_vector(self.model.parameters()).detach()
         self.model.eval()
         self._Sigma = None
+        self.exchange_stats = None
         dist = _dist() if shard else None
         if shard and shard not in ('batches', 'presharded'):
             raise ValueError("shard must be None, 'batches' or 'presharded'")
@@ -90,23 +95,42 @@ class Laplace:
         t0, t1, t2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         t0.record()
         if cov_type == 'full':
-            # [P,P] fp32 accumulator (+ the factor, the inverse and one temporary while factorising): say so before
-            # the allocator does, the reference would simply run out of memory inside einsum / cholesky
-            need = 4 * self.P * self.P * (4 if factorise else 1)
+            # [P,P] fp32 accumulator (+ the factor, the inverse, one temporary while factorising, and the bf16 hi/lo copies
+            # of Sigma the GLM predictive keeps): say so before the allocator does, the reference would simply run out of
+            # memory inside einsum / cholesky
+            need = 4 * self.P * self.P * (5 if factorise else 1)
             free = torch.cuda.mem_get_info(self.device)[0] + torch.cuda.memory_reserved(self.device) \
                 - torch.cuda.memory_allocated(self.device)
             if need > free:
                 raise cabi.BnnpError("cov_type='full' with P = %d needs about %.1f GB of device memory (%.1f GB available); "
                                      "use cov_type='kron' or 'diag'" % (self.P, need / 1e9, free / 1e9))
-            prior = self.expand_prior_precision(cov_type)
+            # a scalar / [P] prior only ever touches the diagonal: it is added there in place (the reference builds a dense
+            # [P,P] diag matrix, preds/laplace.py:115-135 -- 14 GB at config 5 to hold P numbers)
+            prior = self.prior_prec
+            dense_prior = torch.is_tensor(prior) and prior.ndim == 2
+            if torch.is_tensor(prior) and prior.ndim > 2:
+                raise ValueError('Invalid shape for prior precision')
+            if torch.is_tensor(prior) and prior.ndim == 0:
+                prior = float(prior)
+            diag_prior = None if dense_prior else prior
+            ex = None
             if dist:
+                acc, hdl = (None, None) if exchange == 'nccl' else parallel.symmetric_zeros(self.P, self.device)
+                if acc is None:
+                    acc = torch.zeros(self.P, self.P, device=self.device)
+                ex = parallel.LowerExchange(acc, hdl, diag_prior, mode=exchange)
+            elif dense_prior:           # accumulate on top of the prior; never mutate a caller-owned prior matrix
+                acc = prior.to(device=self.device, dtype=torch.float32).clone().contiguous()
+            else:
                 acc = torch.zeros(self.P, self.P, device=self.device)
-            else:       # accumulate on top of the prior; never mutate a caller-owned prior matrix
-                acc = prior.clone() if torch.is_tensor(self.prior_prec) else prior
-                acc = acc.to(torch.float32).contiguous()
-            self._accumulate_full(my_batches(), acc)
-            if dist:
-                parallel.reduce_sum_(acc, prior)
+            self._accumulate_full(my_batches(), acc, exchange=ex)
+            if ex is not None:
+                self.exchange_stats = ex
+                if dense_prior:
+                    acc += prior.to(device=self.device, dtype=torch.float32)
+            elif not dense_prior:
+                pv = diag_prior if not torch.is_tensor(diag_prior) else diag_prior.to(device=self.device, dtype=torch.float32)
+                acc.diagonal().add_(pv)
             self.precision = acc
             t1.record()
             if factorise:
@@ -148,20 +172,46 @@ class Laplace:
         net_for(self.model).release()
         self.inferred = bool(factorise)
 
-    def _accumulate_full(self, batches, H, grad=None):
+    def _accumulate_full(self, batches, H, grad=None, exchange=None):
         """H += sum_n J_n^T Lambda_n J_n over the batches (lower triangle, mirrored at the end).  With
         ``grad`` ([P]) also grad += sum_n J_n^T r_n from the same factors (LaplaceGGN.post_process,
-        preds/optimizers.py:95-96); the targets are then read from the batches."""
-        net = net_for(self.model)
-        pend, pend_y, n_pend = [], [], 0
+        preds/optimizers.py:95-96); the targets are then read from the batches.
 
-        def flush():
-            nonlocal pend, pend_y, n_pend
-            if not pend:
-                return
-            X = torch.cat(pend) if len(pend) > 1 else pend[0]
-            y = (torch.cat(pend_y) if len(pend_y) > 1 else pend_y[0]) if grad is not None else None
-            pend, pend_y, n_pend = [], [], 0
+        ``exchange`` (a ``parallel.LowerExchange``, data-parallel mode): the LAST super-batch is accumulated row chunk
+        by row chunk of H, and every finished chunk is handed to the exchange (own kernel over NVLink on a side stream)
+        while the tensor-core kernel works on the next chunk; H is mirrored after the exchange has joined."""
+        net = net_for(self.model)
+
+        def superbatches():
+            """Loader batches concatenated into super-batches of up to `limit` examples (examples per launch from the
+            scratch the engine needs per example)."""
+            pend, pend_y, n_pend, limit = [], [], 0, None
+            for X, y in batches:
+                X = X.to(self.device, non_blocking=True)
+                if grad is not None:
+                    y = y.to(self.device)
+                if limit is None:
+                    net.prepare(X[:1])
+                    pl1 = net.plan(64, net.K)
+                    per = max(1, int(lib.bnnp_ggn_full_scratch_floats(C.byref(pl1), 64, self.ggn_engine)) // 64)
+                    limit = max(64, min(FULL_SUPERBATCH, FULL_SCRATCH_FLOATS // per))
+                while len(X) > 0:
+                    take = min(len(X), limit - n_pend)
+                    pend.append(X[:take])
+                    if grad is not None:
+                        pend_y.append(y[:take])
+                        y = y[take:]
+                    n_pend += take
+                    X = X[take:]
+                    if n_pend >= limit:
+                        yield (torch.cat(pend) if len(pend) > 1 else pend[0]), \
+                            ((torch.cat(pend_y) if len(pend_y) > 1 else pend_y[0]) if grad is not None else None)
+                        pend, pend_y, n_pend = [], [], 0
+            if pend:
+                yield (torch.cat(pend) if len(pend) > 1 else pend[0]), \
+                    ((torch.cat(pend_y) if len(pend_y) > 1 else pend_y[0]) if grad is not None else None)
+
+        def run(X, y, last):
             net.prepare(X[:1])
             if not net.linear_only:
                 raise cabi.BnnpError("cov_type='full' is implemented for Linear-only networks "
@@ -170,35 +220,39 @@ class Laplace:
             N = X2d.shape[0]
             Lam = self.likelihood._hessian_nkk(f)
             sc = net.scratch(lib.bnnp_ggn_full_scratch_floats(C.byref(pl), N, self.ggn_engine))
-            check(lib.bnnp_ggn_full_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H),
-                                          ptr(sc), self.ggn_engine, stream()), 'bnnp_ggn_full_accum')
+            if last and exchange is not None:
+                bounds = (C.c_int64 * (parallel.EXCHANGE_CHUNKS + 1))()
+                n = lib.bnnp_ggn_full_row_chunks(net.ops, net.n_ops, C.byref(pl), N, self.ggn_engine,
+                                                 parallel.EXCHANGE_CHUNKS, bounds)
+                check(min(n, 0), 'bnnp_ggn_full_row_chunks')
+                if not exchange.agree(n > 1):        # some rank cannot chunk (no examples / SIMT engine): one exchange at the end
+                    n, bounds[1] = 1, self.P
+                for c in range(n):
+                    check(lib.bnnp_ggn_full_accum_rows(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H),
+                                                       ptr(sc), self.ggn_engine, bounds[c], bounds[c + 1], int(c > 0),
+                                                       stream()), 'bnnp_ggn_full_accum_rows')
+                    exchange.rows_done(int(bounds[c]), int(bounds[c + 1]))
+            else:
+                check(lib.bnnp_ggn_full_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H),
+                                              ptr(sc), self.ggn_engine, stream()), 'bnnp_ggn_full_accum')
             if grad is not None:
                 rs = self.likelihood.residual(y, f).reshape(N, net.K).contiguous()
                 sc = net.scratch(lib.bnnp_jtr_scratch_floats(C.byref(pl), N))
                 check(lib.bnnp_jtr_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(rs), ptr(grad),
                                          ptr(sc), stream()), 'bnnp_jtr_accum')
 
-        limit = None
-        for X, y in batches:
-            X = X.to(self.device)
-            if grad is not None:
-                y = y.to(self.device)
-            if limit is None:      # examples per launch from the scratch the engine needs per example
-                net.prepare(X[:1])
-                pl1 = net.plan(64, net.K)
-                per = max(1, int(lib.bnnp_ggn_full_scratch_floats(C.byref(pl1), 64, self.ggn_engine)) // 64)
-                limit = max(64, min(FULL_SUPERBATCH, FULL_SCRATCH_FLOATS // per))
-            while len(X) > 0:
-                take = min(len(X), limit - n_pend)
-                pend.append(X[:take])
-                if grad is not None:
-                    pend_y.append(y[:take])
-                    y = y[take:]
-                n_pend += take
-                X = X[take:]
-                if n_pend >= limit:
-                    flush()
-        flush()
+        prev = None
+        for sb in superbatches():            # one super-batch of look-ahead: the last one is exchanged chunk by chunk
+            if prev is not None:
+                run(prev[0], prev[1], False)
+            prev = sb
+        if prev is not None:
+            run(prev[0], prev[1], True)
+        elif exchange is not None:
+            exchange.agree(False)            # a rank without examples still takes part in the exchange (H_r = 0)
+            exchange.rows_done(0, self.P)
+        if exchange is not None:
+            exchange.finish()
         check(lib.bnnp_symmetrize_lower(ptr(H), self.P, stream()), 'bnnp_symmetrize_lower')
 
     def _factorise_full(self, H):

@@ -21,10 +21,14 @@ def get_Lams_Vys(lh, Hess):
     return scaled, scaled * lh.sigma_2_dispersion
 
 
-def _rows(f):
-    """[rows, K] float32 contiguous device view of network outputs ([N] counts as K = 1)."""
+def _rows(f, scalar=False):
+    """[rows, K] float32 contiguous device view of network outputs ([N] counts as K = 1).  ``scalar``: the likelihood
+    acts elementwise on a single output (Bernoulli / Gaussian: the reference's sigmoid, p(1-p), identity work on any
+    shape, e.g. the [S, N] samples of a model that flattens its output), so every element is its own row."""
     cabi.require_device(f)
     f = f.detach().to(torch.float32).contiguous()
+    if scalar:
+        return f.reshape(-1, 1)
     return f.reshape(-1, f.shape[-1]) if f.dim() > 1 else f.reshape(-1, 1)
 
 
@@ -32,6 +36,7 @@ class Likelihood:
     """Common machinery: subclasses set ``code`` (the library's likelihood id) and ``_distribution``."""
     code = None
     sigma_2_dispersion = 1.0
+    _scalar = False         # True: one output, elementwise on any shape
 
     def _distribution(self, f):
         raise NotImplementedError
@@ -40,7 +45,7 @@ class Likelihood:
         return self._distribution(f).log_prob(y).sum()
 
     def _hessian_nkk(self, f):
-        f2 = _rows(f)
+        f2 = _rows(f, self._scalar)
         n, k = f2.shape
         out = torch.empty(n, k, k, dtype=torch.float32, device=f2.device)
         check(lib.bnnp_lik_hessian(self.code, ptr(f2), n, k, float(self.sigma_2_dispersion), ptr(out), stream()),
@@ -51,7 +56,7 @@ class Likelihood:
         return self._hessian_nkk(f)
 
     def residual(self, y, f):
-        f2 = _rows(f)
+        f2 = _rows(f, self._scalar)
         n, k = f2.shape
         if self.code == cabi.LIK_CATEGORICAL:           # integer labels index the softmax (:84-88)
             target = y.to(device=f2.device).long().contiguous()
@@ -63,7 +68,7 @@ class Likelihood:
         return out.reshape(f.shape)
 
     def inv_link(self, f):
-        f2 = _rows(f)
+        f2 = _rows(f, self._scalar)
         out = torch.empty_like(f2)
         check(lib.bnnp_lik_inv_link(self.code, ptr(f2), f2.shape[0], f2.shape[1], ptr(out), stream()),
               'bnnp_lik_inv_link')
@@ -87,6 +92,7 @@ class CategoricalLh(Likelihood):
 class BernoulliLh(Likelihood):
     """Binary classification on one logit (preds/likelihoods.py:61-75): Hessian p(1-p), returned in the shape of f."""
     code = cabi.LIK_BERNOULLI
+    _scalar = True
 
     def _distribution(self, f):
         return D.Bernoulli(logits=f)
@@ -101,6 +107,7 @@ class BernoulliLh(Likelihood):
 class GaussianLh(Likelihood):
     """Regression with fixed noise (preds/likelihoods.py:34-58): Hessian 1/sigma^2, residual (y - f)/sigma^2."""
     code = cabi.LIK_GAUSSIAN
+    _scalar = True
 
     def __init__(self, sigma_noise=1):
         self.sigma_noise = sigma_noise

@@ -1,9 +1,15 @@
 """One-process-per-GPU helpers (torch.distributed / NCCL is plumbing only).
 
-Accumulation shards examples and needs exactly one all-reduce of the factors (done inside
+Accumulation shards examples and needs exactly one exchange of the factors (done inside
 ``Laplace.infer(shard=...)``).  The predictive shards TEST INPUTS: the posterior is replicated,
 each rank evaluates a contiguous block, and the only exchange is the gather of the outputs.
+
+The full-covariance exchange (``LowerExchange``) is the library's own kernel over NVLink peer memory
+(``csrc/exchange.cu``): the accumulator lives in a symmetric allocation, only its lower triangle is exchanged, row
+chunk by row chunk on a side stream while the tensor-core kernel still accumulates later chunks.
 """
+import ctypes as C
+
 import torch
 
 
@@ -84,3 +90,121 @@ def reduce_factors_(qhs):
             m.copy_(flat[off:off + m.numel()].reshape(m.shape))
             off += m.numel()
     return qhs
+
+
+# ----------------------------------------------------------------------------------------------
+# full covariance: exchange of the lower triangle of H over peer memory (csrc/exchange.cu)
+# ----------------------------------------------------------------------------------------------
+EXCHANGE_CHUNKS = 6          # row chunks of the last super-batch (equal triangle area); the last one is not overlapped
+EXCHANGE_CTAS = 32
+
+
+def symmetric_zeros(P, device):
+    """([P,P] fp32 zeros in symmetric memory, rendezvous handle) over the default group, or (None, None) when this
+    torch / system cannot provide peer mappings (then the packed NCCL exchange is used)."""
+    import torch.distributed as dist
+    try:
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        t = symm.empty((P, P), dtype=torch.float32, device=device)
+        hdl = symm.rendezvous(t, group.group_name)
+        t.zero_()
+        return t, hdl
+    except Exception as exc:                       # no peer access / no VMM export in this environment
+        import logging
+        logging.warning('symmetric memory unavailable (%s): full-covariance exchange falls back to packed NCCL', exc)
+        return None, None
+
+
+class LowerExchange:
+    """Sum the lower triangle of the rank-local accumulators ``H`` ([P,P], row-major) in place, chunk of rows by chunk
+    of rows, and add the prior precision (scalar or [P]) to the diagonal once.
+
+    mode 'nvls'  own kernel, sum formed inside NVSwitch (multimem.ld_reduce / multimem.st) -- needs ``hdl`` with a
+                 multicast mapping;
+         'p2p'   own kernel over the peer mappings of ``hdl`` (loads from every peer in rank order, stores to every peer);
+         'nccl'  pack the rows' triangle -> ``dist.all_reduce`` -> unpack (half the bytes of the square).
+    ``rows_done(r0, r1)`` is called on the accumulation stream as soon as rows [r0, r1) are final on this rank; the
+    exchange of those rows runs on a side stream.  ``finish()`` joins the side stream.  ``stats`` holds CUDA events
+    around every chunk's exchange (bench.py reports allreduce_ms and the bus bandwidth from them)."""
+
+    def __init__(self, H, hdl, prior, mode='auto'):
+        import torch.distributed as dist
+        from ._cabi import BnnpError
+        self.H, self.hdl, self.P = H, hdl, H.shape[0]
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if mode == 'auto':
+            mode = 'nccl' if hdl is None else ('nvls' if int(hdl.multicast_ptr) != 0 else 'p2p')
+        if mode in ('nvls', 'p2p') and hdl is None:
+            raise BnnpError("exchange mode '%s' needs the accumulator in symmetric memory" % mode)
+        if mode == 'nvls' and int(hdl.multicast_ptr) == 0:
+            raise BnnpError("exchange mode 'nvls' needs a multicast mapping (NVSwitch multicast is unavailable here)")
+        if mode not in ('nvls', 'p2p', 'nccl'):
+            raise ValueError("exchange must be 'auto', 'nvls', 'p2p' or 'nccl'")
+        self.mode = mode
+        self.prior_vec, self.prior_scalar = None, 0.0
+        if torch.is_tensor(prior) and prior.dim() == 1:
+            self.prior_vec = prior.to(device=H.device, dtype=torch.float32).contiguous()
+        elif prior is not None:
+            self.prior_scalar = float(prior)
+        self.comm = torch.cuda.Stream(device=H.device)
+        self.events = []
+        self._first = True
+        if hdl is not None:
+            off = H.data_ptr() - int(hdl.buffer_ptrs[self.rank])
+            self.peers = (C.c_void_p * self.world)(*[int(b) + off for b in hdl.buffer_ptrs])
+            self.mc = int(hdl.multicast_ptr) + off if int(hdl.multicast_ptr) else None
+
+    def agree(self, can_chunk):
+        """True iff EVERY rank can exchange row chunk by row chunk (the chunk boundaries depend on the model only, but a
+        rank without examples, or one whose last super-batch runs on the SIMT engine, accumulates H in one piece).  The
+        number of ``rows_done`` calls must be the same on every rank: each one contains a cross-rank barrier."""
+        import torch.distributed as dist
+        flag = torch.tensor([1 if can_chunk else 0], device=self.H.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
+    def rows_done(self, r0, r1):
+        import torch.distributed as dist
+        from ._cabi import lib, check, ptr
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if self.mode == 'nccl':
+                n = int(lib.bnnp_packed_lower_floats(r0, r1))
+                buf = torch.empty(max(n, 1), dtype=torch.float32, device=self.H.device)
+                check(lib.bnnp_pack_lower(ptr(self.H), self.P, r0, r1, ptr(buf), self.comm.cuda_stream), 'bnnp_pack_lower')
+                e0.record()
+                dist.all_reduce(buf)
+                e1.record()
+                check(lib.bnnp_unpack_lower(ptr(buf), self.P, r0, r1, ptr(self.H), ptr(self.prior_vec),
+                                            self.prior_scalar, self.comm.cuda_stream), 'bnnp_unpack_lower')
+                buf.record_stream(self.comm)
+            else:
+                # every rank has finished accumulating these rows (and the previous chunk's broadcasts have landed)
+                self.hdl.barrier(channel=0)
+                e0.record()
+                check(lib.bnnp_exchange_lower_allreduce(self.peers, self.mc if self.mode == 'nvls' else None, self.rank,
+                                                        self.world, self.P, r0, r1, ptr(self.prior_vec),
+                                                        self.prior_scalar, EXCHANGE_CTAS, self.comm.cuda_stream),
+                      'bnnp_exchange_lower_allreduce')
+                e1.record()
+            self.events.append((r0, r1, e0, e1))
+
+    def finish(self):
+        with torch.cuda.stream(self.comm):
+            if self.mode != 'nccl':
+                self.hdl.barrier(channel=0)          # every owner's broadcasts have landed in this rank's H
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+    def stats(self):
+        """(total exchange ms summed over the chunks, bytes of the triangle exchanged)."""
+        ms = sum(e0.elapsed_time(e1) for _, _, e0, e1 in self.events)
+        nbytes = 4 * sum(r1 * (r1 + 1) // 2 - r0 * (r0 + 1) // 2 for r0, r1, _, _ in self.events)
+        return ms, nbytes

@@ -12,27 +12,31 @@ from ._cabi import lib, check, ptr, stream
 from ._engine import net_for, ptr_array, float_array
 from .kron import Kron
 from .likelihoods import GaussianLh
+from . import dense
 
 # upper bound for per-call scratch; inputs are processed in chunks that respect it
 SCRATCH_BUDGET_FLOATS = 1 << 30
 # full-covariance GLM engines: 1 SIMT (as written), 2 tcgen05 with generated operands, 3 tcgen05 + TMA
 FULL_TMA_MIN_P = 1024
-_SPLIT_CACHE = {}
 
 
 def sigma_split(Sigma):
-    """bf16 hi/lo copies of the covariance (row pitch roundup8(P)) for the TMA-fed GLM kernel,
-    made once per posterior and cached (keyed on the tensor's storage and version)."""
-    key = (Sigma.data_ptr(), Sigma._version, tuple(Sigma.shape))
-    if _SPLIT_CACHE.get('key') != key:
-        _SPLIT_CACHE.clear()
+    """bf16 hi/lo copies of the covariance (row pitch roundup8(P)) for the TMA-fed GLM kernel, made once per
+    posterior.  The copies live ON the covariance tensor object (attribute ``_bnnp_split``) together with the tensor
+    version they were made from: they die with the posterior (``Laplace.infer`` drops ``_Sigma``), an in-place update of
+    Sigma invalidates them, and a NEW covariance that the caching allocator places at a freed one's address can never
+    pick up the old split (a cache keyed on ``data_ptr`` could)."""
+    ent = getattr(Sigma, '_bnnp_split', None)
+    if ent is None or ent[0] != Sigma._version:
+        Sigma._bnnp_split = None
         P = Sigma.shape[0]
         pitch = (P + 7) // 8 * 8
         hi = torch.empty(P, pitch, dtype=torch.bfloat16, device=Sigma.device)
         lo = torch.empty(P, pitch, dtype=torch.bfloat16, device=Sigma.device)
         check(lib.bnnp_split_bf16(ptr(Sigma), P, P, P, ptr(hi), ptr(lo), stream()), 'bnnp_split_bf16')
-        _SPLIT_CACHE.update(key=key, hi=hi, lo=lo)
-    return _SPLIT_CACHE['hi'], _SPLIT_CACHE['lo']
+        ent = (Sigma._version, hi, lo)
+        Sigma._bnnp_split = ent
+    return ent[1], ent[2]
 
 
 def _kron_tables(net, kron):
@@ -180,11 +184,10 @@ def linear_regression_predictive(X, model, likelihood, mu, Sigma_chol):
     Sigma_chol = cabi.f32(Sigma_chol, mu.device)
     if Sigma_chol.dim() == 2:
         P = Sigma_chol.shape[0]
+        # Sigma = L L^T with the K range walked in 4096-wide segments accumulated through C (no split-K workspace:
+        # that would be several extra [P,P] buffers where the reference needs one)
         Sigma = torch.empty(P, P, dtype=torch.float32, device=mu.device)
-        sc = torch.empty(max(1, int(lib.bnnp_sgemm_tc_scratch_floats(P, P, P))), dtype=torch.float32, device=mu.device)
-        check(lib.bnnp_sgemm_tc(0, 1, P, P, P, 1.0, ptr(Sigma_chol), P, ptr(Sigma_chol), P, 0.0, ptr(Sigma), P,
-                                ptr(sc), stream()), 'bnnp_sgemm_tc')
-        del sc
+        dense._gemm(0, 1, P, P, P, 1.0, Sigma_chol.data_ptr(), P, Sigma_chol.data_ptr(), P, 0.0, Sigma.data_ptr(), P)
     else:
         Sigma = (Sigma_chol * Sigma_chol).contiguous()
     f_mu, f_var, f = glm_moments(X, model, cabi.f32(mu, mu.device), Sigma, return_f=True)

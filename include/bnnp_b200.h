@@ -11,7 +11,8 @@
  * Conventions
  *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless marked [host];
  *   - the caller allocates and owns every buffer (torch does, in our glue); nothing here
- *     allocates or frees device memory and there is no global state;
+ *     allocates or frees device memory; the only process-wide state is the launch counter, the
+ *     profiling hooks and the engine-selection options at the end of this header;
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call is
  *     asynchronous on that stream;
  *   - float32 everywhere; matrices are row-major;
@@ -136,8 +137,38 @@ int64_t bnnp_ggn_full_scratch_floats(const bnnp_plan_t* plan, int64_t N, int eng
 int bnnp_ggn_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                         const float* ws, const float* Lambda, float* H, float* scratch,
                         int engine, void* stream);
+/* The same restricted to rows [row_begin, row_end) of H (row_end < 0: all rows), so that finished row chunks can be
+ * exchanged between GPUs while later chunks still accumulate (data-parallel mode).  Chunk boundaries come from
+ * bnnp_ggn_full_row_chunks(): bounds[0..n] with bounds[0] = 0, bounds[n] = P, chunks of roughly equal triangle
+ * area; returns n (<= n_chunks; 1 when the engine that would run is not row-chunked).  prepared != 0: the per-batch
+ * operands in `scratch` were built by an earlier call for the same batch (same ws / Lambda / N) and are reused. */
+int bnnp_ggn_full_row_chunks(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int engine,
+                             int n_chunks, int64_t* bounds /* [host], n_chunks + 1 */);
+int bnnp_ggn_full_accum_rows(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                             const float* ws, const float* Lambda, float* H, float* scratch, int engine,
+                             int64_t row_begin, int64_t row_end, int prepared, void* stream);
 /* H[p,q] = H[q,p] for p < q. */
 int bnnp_symmetrize_lower(float* H, int64_t P, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The one exchange step of the data-parallel full-covariance path (the reference loop
+ * preds/laplace.py:39-42 sharded over examples): in-place all-reduce(sum) of rows [row0,row1) of the LOWER TRIANGLE
+ * of H over peer memory, with the prior precision added to the diagonal by the owner of each row.  H must live at
+ * the same offset of a symmetric allocation on every rank: peers[w] = rank w's H mapped into this process [host
+ * array of `world` device pointers]; multicast = NVLS multicast mapping of H or NULL.  With a multicast mapping the
+ * sum is formed inside NVSwitch (multimem.ld_reduce) and broadcast with multimem.st; without, the owner of a row
+ * loads it from every peer in rank order and stores the sum to every peer.  Every rank ends with identical bits.
+ * The caller orders the launch against the other ranks (a cross-rank barrier on the stream before and after).
+ * prior_vec [P] (device) or NULL -> prior_scalar.  n_ctas <= 0: default. */
+int bnnp_exchange_lower_allreduce(float* const* peers /* [host] */, float* multicast, int rank, int world, int64_t P,
+                                  int64_t row0, int64_t row1, const float* prior_vec, float prior_scalar,
+                                  int n_ctas, void* stream);
+/* Packed lower triangle of rows [row0,row1) (row p contributes p+1 floats) for a library all-reduce of half the bytes:
+ * pack -> collective -> unpack (+ prior on the diagonal). */
+int64_t bnnp_packed_lower_floats(int64_t row0, int64_t row1);
+int bnnp_pack_lower(const float* H, int64_t P, int64_t row0, int64_t row1, float* packed, void* stream);
+int bnnp_unpack_lower(const float* packed, int64_t P, int64_t row0, int64_t row1, float* H,
+                      const float* prior_vec, float prior_scalar, void* stream);
 
 /* diag[P] += factor * diag(sum_n J_n^T Lambda_n J_n) from a sqrt-seeded backward
  * (BackPACK DiagGGNExact as read by preds/laplace.py:52-59). */
@@ -299,6 +330,12 @@ int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream);
  * CUDA-event timing of the tensor-core gram launches (recorded on the launching stream).
  * ---------------------------------------------------------------------------------------- */
 uint64_t bnnp_launch_count(void);
+/* Engine-selection options for tests and A/B measurements (process-wide, default 0; never read from the
+ * environment; none of them makes a kernel skip work):  "gram_kernel" 0 auto / 1 single-CTA kernel,
+ * "glm_single" 1 = single-CTA full-covariance GLM kernel, "glm_simt" 1 = kron / diag GLM contractions on the fp32
+ * SIMT kernels, "debug_sync" 1 = synchronise after every GLM TMA launch.  Unknown name: BNNP_ERR_INVALID. */
+int bnnp_set_option(const char* name, int value);
+int bnnp_get_option(const char* name);
 int bnnp_prof_enable(int on);
 int bnnp_prof_read(float* ms, double* executed_flops, double* useful_flops, int cap);
 

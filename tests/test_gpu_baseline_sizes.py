@@ -1,0 +1,216 @@
+"""Parity at the sizes BASELINE.json names, directly against the CPU oracle (``oracle/port.py``), asserted PER BLOCK
+(layer pair / parameter group) so that a small cross-layer or bias block cannot hide behind the large first-layer block
+of a global max-norm:
+
+  cfg5  full-covariance GGN of MLPS(784,[75],10) at P = 59 635 (reference loop preds/laplace.py:39-42) and the
+        full-covariance GLM moments (preds/predictives.py:52-65) with a random SPD covariance;
+  cfg4  CIFAR10Net(3,10,use_tanh=True) on 32x32 inputs, one loader batch of 256 (preds/laplace.py:47-80): KFLR factors,
+        diagonal GGN and Kron GLM moments -- every tensor-core conv branch against the oracle rather than against SIMT;
+  cfg3  MLP 784-1024-512-256-128-10, 512 examples: KFLR factors, diagonal GGN, Kron / diag GLM moments
+        (preds/kron.py:112-143).
+
+Tolerance: 1e-4 relative to the block's own largest reference entry (the north-star fp32 bound).
+"""
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import port
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _blocks(model):
+    """[(name, lo, hi)] of the flat parameter vector, one entry per parameter tensor."""
+    out, off = [], 0
+    for name, p in model.named_parameters():
+        out.append((name, off, off + p.numel()))
+        off += p.numel()
+    return out
+
+
+def _block_err(a, b):
+    scale = float(b.abs().max())
+    return float((a - b).abs().max()) / max(scale, 1e-30), scale
+
+
+def test_cfg5_full_ggn_against_oracle_per_block():
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip('needs ~30 GB of free device memory')
+    from preds_b200 import Laplace, CategoricalLh, MLPS
+    torch.manual_seed(71)
+    model = MLPS(784, [75], 10, 'tanh', flatten=True)
+    omodel = port.make_mlps(784, [75], 10, 'tanh', flatten=True)
+    port.set_theta(omodel, port.get_theta(model))
+    P = port.n_params(omodel)
+    assert P == 59635
+    g = torch.Generator().manual_seed(15)
+    N = 48
+    X = torch.randn(N, 1, 28, 28, generator=g)
+    y = torch.randint(10, (N,), generator=g)
+    batches = [(X[:30], y[:30]), (X[30:], y[30:])]
+    Href = port.ggn_full_accumulate(omodel, port.CategoricalLh(), batches, torch.zeros(P, P))
+    model = model.cuda()
+    worst = {}
+    for engine in (2, 1):                   # tcgen05 CTA-pair kernel (the bench path) and the fp32 SIMT engine
+        lap = Laplace(model, 0.0, CategoricalLh())
+        lap.ggn_engine = engine
+        lap.infer(batches, cov_type='full', factorise=False)
+        H = lap.precision.cpu()
+        lap.precision = None
+        blocks = _blocks(model)
+        for (na, a0, a1) in blocks:
+            for (nb, b0, b1) in blocks:
+                err, scale = _block_err(H[a0:a1, b0:b1], Href[a0:a1, b0:b1])
+                assert scale > 0, (na, nb)
+                worst[(engine, na, nb)] = err
+                assert err < TOL, (engine, na, nb, err)
+        del H
+    print('cfg5 per-block max rel err:', max(worst.values()))
+
+
+def test_cfg5_full_glm_moments_against_oracle():
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip('needs ~45 GB of free device memory')
+    from preds_b200 import MLPS
+    from preds_b200.predictives import glm_moments
+    torch.manual_seed(71)
+    model = MLPS(784, [75], 10, 'tanh', flatten=True)
+    omodel = port.make_mlps(784, [75], 10, 'tanh', flatten=True)
+    port.set_theta(omodel, port.get_theta(model))
+    P = port.n_params(omodel)
+    model = model.cuda()
+    gg = torch.Generator(device='cuda').manual_seed(9)
+    # random SPD covariance (symmetric, strictly diagonally dominant), built on the device, checked on the host
+    R = torch.randn(P, P, device='cuda', generator=gg) * (0.02 / P ** 0.5)
+    Sigma = (R + R.T) * 0.5
+    del R
+    Sigma.diagonal().add_(torch.rand(P, device='cuda', generator=gg) * 0.5 + 0.5)
+    g = torch.Generator().manual_seed(16)
+    Xte = torch.randn(8, 1, 28, 28, generator=g)
+    mu = port.get_theta(omodel) + 0.01 * torch.randn(P, generator=g)
+    f_mu, f_var = glm_moments(Xte.cuda(), model, mu.cuda(), Sigma)
+    Js, f = port.jacobians(omodel, Xte)                        # [8, P, K]
+    Jt = Js.transpose(1, 2)                                    # [8, K, P]
+    Sig = Sigma.cpu()
+    fmu_ref = f + Jt @ (mu - port.get_theta(omodel))
+    fvar_ref = torch.einsum('nkp,pq,ncq->nkc', Jt, Sig, Jt)    # preds/predictives.py:63
+    assert cases.rel_err(f_mu.cpu(), fmu_ref) < 1e-5
+    for n in range(8):                                         # per input: no input hides behind another
+        assert cases.rel_err(f_var[n].cpu(), fvar_ref[n]) < TOL, n
+    # per layer-pair block of Sigma: zero all but one block pair and compare again (cross-layer terms are small)
+    blocks = _blocks(model)
+    (_, a0, a1), (_, b0, b1) = blocks[0], blocks[2]            # layer-1 weights x layer-2 weights
+    Sx = torch.zeros_like(Sigma)
+    Sx[a0:a1, b0:b1] = Sigma[a0:a1, b0:b1]
+    Sx[b0:b1, a0:a1] = Sigma[b0:b1, a0:a1]
+    del Sigma
+    _, f_var_x = glm_moments(Xte.cuda(), model, mu.cuda(), Sx)
+    ref_x = torch.einsum('nkp,pq,ncq->nkc', Jt[:, :, a0:a1], Sig[a0:a1, b0:b1], Jt[:, :, b0:b1])
+    ref_x = ref_x + ref_x.transpose(1, 2)
+    assert cases.rel_err(f_var_x.cpu(), ref_x) < TOL
+
+
+def _port_cifar10(in_ch, n_out):
+    from preds_b200 import CIFAR10Net
+    torch.manual_seed(71)
+    model = CIFAR10Net(in_ch, n_out, use_tanh=True)
+    omodel = port.make_cifar10net(in_ch, n_out, use_tanh=True)
+    port.set_theta(omodel, port.get_theta(model))
+    return model, omodel
+
+
+def _check_kron_factors(kron, qref, names):
+    for pi, (qh, qr) in enumerate(zip(kron.qhs, qref)):
+        for fi, (m, r) in enumerate(zip(qh, qr)):
+            err, scale = _block_err(m.cpu(), r)
+            assert err < TOL, (names[pi], fi, err)
+
+
+def test_cfg4_cifar10net_batch256_against_oracle():
+    """cfg4 as BASELINE.json states it: CIFAR10Net(3,10), 3x32x32 inputs, loader batch 256.  At this size every conv
+    contraction (forward, K-column backward-data, im2col Grams, per-row diagonal) is above the 2^25-MAC threshold and
+    runs on the tensor-core kernels."""
+    from preds_b200 import Laplace, CategoricalLh, Kron
+    from preds_b200.predictives import glm_moments
+    model, omodel = _port_cifar10(3, 10)
+    names = [n for n, _ in model.named_parameters()]
+    g = torch.Generator().manual_seed(15)
+    X = torch.randn(256, 3, 32, 32, generator=g)
+    y = torch.randint(10, (256,), generator=g)
+    Xte = torch.randn(8, 3, 32, 32, generator=g)
+    olh = port.CategoricalLh()
+    model = model.cuda()
+    # logits first: a wrong activation / pooling index would show up here before any second-order quantity
+    from preds_b200._engine import net_for
+    net = net_for(model)
+    _, _, f = net.forward(net.prepare(X.cuda()), 1)
+    with torch.no_grad():
+        fref = omodel(X)
+    assert cases.rel_err(f.cpu(), fref) < 5e-5            # nine layers of fp32-grade (split-bf16) products vs MKL fp32
+    # --- diagonal GGN, per parameter tensor
+    dref = port.diag_ggn_batch(omodel, olh, X)
+    lap = Laplace(model, 0.0, CategoricalLh())
+    lap.infer([(X, y)], cov_type='diag', factorise=False)
+    d = lap.precision.cpu()
+    for name, lo, hi in _blocks(model):
+        err, scale = _block_err(d[lo:hi], dref[lo:hi])
+        assert err < TOL, ('diag', name, err)
+    # --- KFLR factors, per factor
+    post = port.infer(omodel, 1.0, olh, [(X, y)], 'kron')
+    lap = Laplace(model, 1.0, CategoricalLh())
+    lap.infer([(X, y)], cov_type='kron')
+    assert type(lap.Sigma_chol) is Kron
+    _check_kron_factors(lap.Sigma_chol, post['kron'].qhs, names)
+    # --- Kron GLM moments on 8 inputs (as-written oracle: materialised Jacobians rotated per parameter group)
+    fmu_ref, fvar_ref = port.glm_moments(omodel, Xte, post)
+    fmu, fvar = glm_moments(Xte.cuda(), model, lap.mu, lap.Sigma_chol)
+    assert cases.rel_err(fmu.cpu(), fmu_ref) < 1e-5
+    for n in range(8):
+        assert cases.rel_err(fvar[n].cpu(), fvar_ref[n]) < TOL, n
+
+
+def test_cfg3_mlp_512_against_oracle():
+    """cfg3: MLPS(784,[1024,512,256,128],10,'tanh',flatten=True), P = 1 494 154, two loader batches of 256."""
+    from preds_b200 import Laplace, CategoricalLh, MLPS, Kron
+    from preds_b200.predictives import glm_moments
+    torch.manual_seed(71)
+    model = MLPS(784, [1024, 512, 256, 128], 10, 'tanh', flatten=True)
+    omodel = port.make_mlps(784, [1024, 512, 256, 128], 10, 'tanh', flatten=True)
+    port.set_theta(omodel, port.get_theta(model))
+    names = [n for n, _ in model.named_parameters()]
+    g = torch.Generator().manual_seed(15)
+    X = torch.randn(512, 1, 28, 28, generator=g)
+    y = torch.randint(10, (512,), generator=g)
+    Xte = torch.randn(6, 1, 28, 28, generator=g)
+    batches = [(X[:256], y[:256]), (X[256:], y[256:])]
+    olh = port.CategoricalLh()
+    model = model.cuda()
+    # diag
+    post_d = port.infer(omodel, 1.0, olh, batches, 'diag')
+    lap = Laplace(model, 1.0, CategoricalLh())
+    lap.infer(batches, cov_type='diag')
+    d, dref = lap.precision.cpu(), post_d['precision']
+    for name, lo, hi in _blocks(model):
+        err, scale = _block_err(d[lo:hi], dref[lo:hi])
+        assert err < TOL, ('diag', name, err)
+    fmu_ref, fvar_ref = port.glm_moments(omodel, Xte, post_d)
+    fmu, fvar = glm_moments(Xte.cuda(), model, lap.mu, lap.Sigma)
+    assert cases.rel_err(fmu.cpu(), fmu_ref) < 1e-5
+    for n in range(len(Xte)):
+        assert cases.rel_err(fvar[n].cpu(), fvar_ref[n]) < TOL, ('diag glm', n)
+    # kron
+    post_k = port.infer(omodel, 1.0, olh, batches, 'kron')
+    lap = Laplace(model, 1.0, CategoricalLh())
+    lap.infer(batches, cov_type='kron')
+    assert type(lap.Sigma_chol) is Kron
+    _check_kron_factors(lap.Sigma_chol, post_k['kron'].qhs, names)
+    fmu_ref, fvar_ref = port.glm_moments(omodel, Xte, post_k)
+    fmu, fvar = glm_moments(Xte.cuda(), model, lap.mu, lap.Sigma_chol)
+    assert cases.rel_err(fmu.cpu(), fmu_ref) < 1e-5
+    for n in range(len(Xte)):
+        assert cases.rel_err(fvar[n].cpu(), fvar_ref[n]) < TOL, ('kron glm', n)

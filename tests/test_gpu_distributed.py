@@ -81,3 +81,81 @@ def test_two_gpu_sharded_infer_and_predictive(tmp_path):
             assert torch.allclose(r['glm_' + cov], ref_glm, rtol=1e-3, atol=1e-5)
         if cov != 'kron':
             assert torch.equal(res[0][cov], res[1][cov])      # identical sums on every rank
+
+
+def _exchange_worker(rank, world, port_no, out_dir):
+    for p in (ROOT, os.path.join(ROOT, 'bnn-predictions_b200')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from preds_b200 import Laplace, CategoricalLh, MLPS, parallel
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port_no))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    torch.manual_seed(11)
+    model = MLPS(300, [40, 24], 7, 'tanh').cuda()           # P = 13 199: tensor-core engine, several row chunks
+    g = torch.Generator().manual_seed(12)
+    X, y = torch.randn(1500, 300, generator=g), torch.randint(7, (1500,), generator=g)
+    batches = [(X[i:i + 250], y[i:i + 250]) for i in range(0, 1500, 250)]
+    prior_vec = torch.rand(13199, generator=g) + 0.5
+    res = {}
+    _, hdl = parallel.symmetric_zeros(8, torch.device('cuda', rank))
+    modes = ['nccl'] + (['p2p'] if hdl is not None else []) + (['nvls'] if hdl is not None and int(hdl.multicast_ptr) else [])
+    res['modes'] = modes
+    for mode in modes:
+        for pname, prior in (('scalar', 0.6), ('vector', prior_vec)):
+            lap = Laplace(model, prior, CategoricalLh())
+            lap.infer(batches, cov_type='full', shard='batches', factorise=False, exchange=mode)
+            res[mode + '_' + pname] = lap.precision.cpu()
+            res[mode + '_chunks'] = len(lap.exchange_stats.events)
+            lap.precision = None
+    # a rank without examples still takes part (rank 1 owns nothing when there is one batch)
+    lap = Laplace(model, 0.6, CategoricalLh())
+    lap.infer(batches[:1], cov_type='full', shard='batches', factorise=False)
+    res['one_batch'] = lap.precision.cpu()
+    lap = Laplace(model, 0.6, CategoricalLh())
+    lap.infer(batches[:1], cov_type='kron', shard='batches', factorise=False)
+    res['one_batch_kron'] = [[m.cpu() for m in qh] for qh in lap.Sigma_chol.qhs]
+    torch.save(res, os.path.join(out_dir, 'x%d.pt' % rank))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_lower_triangle_exchange(tmp_path):
+    """The full-covariance exchange (own kernel over peer memory: NVLS multimem / P2P, and the packed NCCL path), row
+    chunks overlapped with the accumulation: every mode must give the single-process H (1e-4), identical bits on both
+    ranks, the prior exactly once on the diagonal; a rank without examples must not hang the others."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from preds_b200 import Laplace, CategoricalLh, MLPS
+    mp.spawn(_exchange_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), 'x%d.pt' % r), weights_only=False) for r in range(2)]
+    torch.manual_seed(11)
+    model = MLPS(300, [40, 24], 7, 'tanh').cuda()
+    g = torch.Generator().manual_seed(12)
+    X, y = torch.randn(1500, 300, generator=g), torch.randint(7, (1500,), generator=g)
+    batches = [(X[i:i + 250], y[i:i + 250]) for i in range(0, 1500, 250)]
+    prior_vec = torch.rand(13199, generator=g) + 0.5
+    print('exchange modes available:', res[0]['modes'])
+    for pname, prior in (('scalar', 0.6), ('vector', prior_vec)):
+        lap = Laplace(model, prior, CategoricalLh())
+        lap.infer(batches, cov_type='full', factorise=False)
+        ref = lap.precision.cpu()
+        for mode in res[0]['modes']:
+            a, b = res[0][mode + '_' + pname], res[1][mode + '_' + pname]
+            assert torch.equal(a, b), (mode, pname)
+            assert torch.equal(a, a.T), (mode, pname)
+            assert float((a - ref).abs().max() / ref.abs().max()) < 1e-4, (mode, pname)
+            # the prior entered exactly once: compare the diagonal on its own scale
+            assert float((a.diagonal() - ref.diagonal()).abs().max() / ref.diagonal().abs().max()) < 1e-4, (mode, pname)
+            assert res[0][mode + '_chunks'] > 1
+    lap = Laplace(model, 0.6, CategoricalLh())
+    lap.infer(batches[:1], cov_type='full', factorise=False)
+    ref = lap.precision.cpu()
+    for r in res:
+        assert float((r['one_batch'] - ref).abs().max() / ref.abs().max()) < 1e-4
+    lap = Laplace(model, 0.6, CategoricalLh())
+    lap.infer(batches[:1], cov_type='kron', factorise=False)
+    for r in res:
+        for qa, qb in zip(r['one_batch_kron'], lap.Sigma_chol.qhs):
+            for a, b in zip(qa, qb):
+                assert torch.allclose(a, b.cpu(), rtol=1e-4, atol=1e-6)

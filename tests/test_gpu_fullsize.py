@@ -84,10 +84,10 @@ def test_cfg5_weight_sampling_tensor_core():
 
 
 @pytest.mark.parametrize('cov', ['kron', 'diag'])
-def test_glm_kron_diag_tensor_core_paths(cov, monkeypatch):
+def test_glm_kron_diag_tensor_core_paths(cov):
     """Kron / diag GLM moments at a size where every contraction takes the tcgen05 branch (and the fused
     warp-per-input reduction) against the fp32 SIMT kernels with the unfused reductions on the same inputs
-    (BNNP_GLM_SIMT=1; the SIMT path is the one pinned against the reference goldens at small sizes), plus the K x K
+    (library option glm_simt; the SIMT path is the one pinned against the reference goldens at small sizes), plus the K x K
     symmetry and positive diagonal that f_var = J Sigma J^T must have."""
     from preds_b200 import MLPS, CategoricalLh, Laplace
     from preds_b200.predictives import glm_moments
@@ -101,22 +101,27 @@ def test_glm_kron_diag_tensor_core_paths(cov, monkeypatch):
     lap.infer([(X, y)], cov_type=cov)
     Sigma = lap.Sigma_chol if isinstance(lap.Sigma_chol, Kron) else lap.Sigma
     fmu, fvar = glm_moments(Xte, model, lap.mu, Sigma)
-    monkeypatch.setenv('BNNP_GLM_SIMT', '1')
-    fmu_ref, fvar_ref = glm_moments(Xte, model, lap.mu, Sigma)
-    monkeypatch.delenv('BNNP_GLM_SIMT')
+    from preds_b200._cabi import lib
+    lib.bnnp_set_option(b'glm_simt', 1)
+    try:
+        fmu_ref, fvar_ref = glm_moments(Xte, model, lap.mu, Sigma)
+    finally:
+        lib.bnnp_set_option(b'glm_simt', 0)
     assert torch.equal(fmu, fmu_ref)
     assert cases.rel_err(fvar.cpu(), fvar_ref.cpu()) < 3e-5
     assert cases.rel_err(fvar.cpu(), fvar.transpose(1, 2).cpu()) < 1e-6
     assert bool((fvar.diagonal(dim1=1, dim2=2) > 0).all())
 
 
-@pytest.mark.parametrize('arch', [(784, [75], 10, 2500), (300, [40, 24], 7, 1100)])
-def test_gram_pair_kernel_is_bitwise_the_single_cta_kernel(arch, monkeypatch):
-    """The CTA-pair full-GGN kernel (tcgen05.mma.cta_group::2 over two row tiles, cross-CTA barriers with a relaxed remote
-    arrive) must reproduce the single-CTA kernel bit for bit: same MMA sequence per accumulator, and every element of H
-    receives exactly one add per launch.  Run twice to catch a rare ordering problem; odd tile counts and a ragged last
-    K-segment (N not a multiple of 64) included."""
+@pytest.mark.parametrize('arch', [(784, [75], 10, 2500), (300, [40, 24], 7, 1100), (500, [33], 4, 700)])
+def test_gram_wide_kernel_is_bitwise_the_single_cta_kernel(arch):
+    """The default full-GGN kernel (CTA pair, tcgen05.mma.cta_group::2 over two row tiles, ONE column unit x two column
+    tiles sharing the generated A operand, cross-CTA barriers with a relaxed remote arrive) must reproduce the single-CTA
+    kernel (two units sharing the B tile) bit for bit: same MMA sequence per accumulator, and every element of H
+    receives exactly one add per launch.  Run twice to catch a rare ordering problem; odd tile counts, a single
+    (unpaired) column tile and a ragged last K-segment (N not a multiple of 64) included."""
     from preds_b200 import MLPS, CategoricalLh, Laplace
+    from preds_b200._cabi import lib
     din, hid, K, N = arch
     torch.manual_seed(11)
     model = MLPS(din, hid, K, 'tanh').cuda()
@@ -129,36 +134,53 @@ def test_gram_pair_kernel_is_bitwise_the_single_cta_kernel(arch, monkeypatch):
         lap.infer([(X, y)], cov_type='full', factorise=False)
         return lap.precision
 
-    pair = [run() for _ in range(2)]
-    monkeypatch.setenv('BNNP_GRAM_SINGLE', '1')
-    single = run()
-    monkeypatch.delenv('BNNP_GRAM_SINGLE')
-    assert torch.equal(pair[0], pair[1])
-    assert torch.equal(pair[0], single)
+    wide = [run() for _ in range(2)]
+    lib.bnnp_set_option(b'gram_kernel', 1)
+    try:
+        single = run()
+    finally:
+        lib.bnnp_set_option(b'gram_kernel', 0)
+    assert torch.equal(wide[0], wide[1])
+    assert torch.equal(wide[0], single)
     assert torch.equal(single, single.T)
 
 
-def test_gram_tmem_a_kernel_is_bitwise_the_pair_kernel(monkeypatch):
-    """Experimental (opt-in, BNNP_GRAM_TS=<accumulator width>): the A operand written to tensor memory with tcgen05.st
-    and consumed by tcgen05.mma from TMEM, K = 16 step ring.  Same bf16 operands and accumulation order as the default
-    kernels, so H must be bit-identical for every ring depth."""
-    from preds_b200 import MLPS, CategoricalLh, Laplace
+def test_row_chunked_accumulation_is_bitwise_the_whole_matrix():
+    """bnnp_ggn_full_accum_rows over the chunks of bnnp_ggn_full_row_chunks (the data-parallel mode accumulates the last
+    super-batch this way so that finished row chunks can be exchanged early) == one call over all rows, bit for bit."""
+    import ctypes as C
+    from preds_b200 import MLPS, CategoricalLh
+    from preds_b200._cabi import lib, check, ptr, stream
+    from preds_b200._engine import net_for
     torch.manual_seed(11)
     model = MLPS(300, [40, 24], 7, 'tanh').cuda()
     g = torch.Generator().manual_seed(12)
-    X, y = torch.randn(1100, 300, generator=g).cuda(), torch.randint(7, (1100,), generator=g).cuda()
-
-    def run():
-        lap = Laplace(model, 1.0, CategoricalLh())
-        lap.ggn_engine = 2
-        lap.infer([(X, y)], cov_type='full', factorise=False)
-        return lap.precision
-
-    ref = run()
-    for width in ('208', '160', '96'):
-        monkeypatch.setenv('BNNP_GRAM_TS', width)
-        assert torch.equal(run(), ref), width
-    monkeypatch.delenv('BNNP_GRAM_TS')
+    X = torch.randn(1100, 300, generator=g).cuda()
+    net = net_for(model)
+    X2d, pl, ws, f = net.jacobian_factors(X)
+    N, P = X2d.shape[0], net.P
+    Lam = CategoricalLh()._hessian_nkk(f)
+    sc = net.scratch(lib.bnnp_ggn_full_scratch_floats(C.byref(pl), N, 2))
+    H0 = torch.zeros(P, P, device='cuda')
+    check(lib.bnnp_ggn_full_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H0), ptr(sc), 2, stream()))
+    for want_chunks in (2, 5):
+        bounds = (C.c_int64 * (want_chunks + 1))()
+        n = lib.bnnp_ggn_full_row_chunks(net.ops, net.n_ops, C.byref(pl), N, 2, want_chunks, bounds)
+        assert 1 < n <= want_chunks and bounds[0] == 0 and bounds[n] == P
+        assert all(bounds[i] < bounds[i + 1] for i in range(n))
+        H1 = torch.zeros(P, P, device='cuda')
+        for c in range(n):
+            check(lib.bnnp_ggn_full_accum_rows(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H1), ptr(sc), 2,
+                                               bounds[c], bounds[c + 1], int(c > 0), stream()))
+            # rows of later chunks are untouched so far (what the early exchange relies on)
+            if c + 1 < n:
+                assert float(H1[bounds[c + 1]:].abs().max()) == 0
+        assert torch.equal(torch.tril(H1), torch.tril(H0))
+    # an illegal boundary is refused, not rounded
+    with pytest.raises(ValueError):
+        check(lib.bnnp_ggn_full_accum_rows(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H1), ptr(sc), 2,
+                                           0, 100, 1, stream()))
+    net.release()
 
 
 @pytest.mark.parametrize('engine,tol', [('trsm', 3e-5), ('cublas', 3e-5), ('tc', 5e-4)])
