@@ -136,9 +136,121 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+def cpu_glm_rate(Sigma_dev, n_inputs, n_samples):
+    """(inputs x samples)/s of the reference's GLM predictive at cfg5 on the host cores (oracle/port.py: Jacobians,
+    einsum('nkp,pq,ncq->nkc') with the full covariance, K x K Cholesky, sampling + softmax; preds/predictives.py:50-76)
+    on `n_inputs` inputs x `n_samples` samples, as experiments/imginference.py:45,391 batches it.  The reference also
+    recomputes Sigma = L L^T (2 P^3 flops) on EVERY call (preds/laplace.py:111); that is left out here (it would
+    take minutes at P = 59 635), so the figure flatters the CPU path."""
+    from oracle import port
+    torch.manual_seed(71)
+    model = port.make_mlps(**MODEL)
+    Sigma = Sigma_dev.cpu()
+    g = torch.Generator().manual_seed(16)
+    X = torch.randn(n_inputs, 1, 28, 28, generator=g)
+    eps = torch.randn(n_samples, n_inputs, K_OUT, generator=g)
+    t0 = time.perf_counter()
+    Js, f = port.jacobians(model, X)
+    Jt = Js.transpose(1, 2)
+    f_var = torch.einsum('nkp,pq,ncq->nkc', Jt, Sigma, Jt)
+    L = torch.linalg.cholesky(f_var)
+    out = torch.softmax(f.unsqueeze(0) + torch.einsum('nkl,snl->snk', L, eps), dim=-1)
+    float(out.mean())
+    sec = time.perf_counter() - t0
+    return n_inputs * n_samples / sec, sec
+
+
+def strong_scaling(dev, rank, world, args):
+    """Strong-scaling records of the configurations as BASELINE.json states them: the TOTAL work is fixed and sharded
+    over the ranks, through the public API with pinned host batches (H2D inside), the exchange step included:
+      cfg5  60 000 examples, full covariance  -> Laplace.infer(shard='presharded'), own lower-triangle exchange kernel
+      cfg4  50 000 examples, CIFAR10Net KFAC  -> Laplace.infer(cov_type='kron', shard='presharded'), NCCL bucket
+    Each is run twice (the first run warms allocator / communicator); the second is timed by wall clock between
+    barriers, max over ranks.  N = 1 gives the baseline the driver's per-N files are compared with."""
+    import torch.distributed as dist
+    from preds_b200 import Laplace, CategoricalLh, MLPS, CIFAR10Net, parallel
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def my_batches(total, bs, shape, classes, seed):
+        lo, hi = parallel.shard_bounds(total, rank, world)
+        g = torch.Generator().manual_seed(seed + rank)
+        X = torch.randn((hi - lo,) + shape, generator=g).pin_memory()
+        y = torch.randint(classes, (hi - lo,), generator=g).pin_memory()
+        return [(X[i:i + bs], y[i:i + bs]) for i in range(0, hi - lo, bs)], hi - lo
+
+    shard = 'presharded' if world > 1 else None
+    try:
+        torch.manual_seed(71)
+        model = MLPS(**MODEL).to(dev)
+        batches, n_mine = my_batches(60000, 2500, (1, 28, 28), K_OUT, 1500)
+        lap = Laplace(model, 1.0, CategoricalLh())
+        lap.ggn_engine = args.engine
+        rec = None
+        for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            lap.infer(batches, cov_type='full', shard=shard, factorise=False)
+            trace = float(lap.precision.diagonal().sum())
+            barrier()
+            sec = maxr(time.perf_counter() - t0)
+            rec = {'examples_total': 60000, 'examples_this_rank': n_mine, 'loader_batch': 2500, 'seconds': sec,
+                   'examples_per_s': 60000 / sec, 'accumulate_ms_device': maxr(lap.timings['accumulate_ms']),
+                   'trace_H': trace}
+            if world > 1 and lap.exchange_stats is not None:
+                ms, nbytes = lap.exchange_stats.stats()
+                ms = maxr(ms)
+                rec.update({'exchange_mode': lap.exchange_stats.mode, 'exchange_chunks': len(lap.exchange_stats.events),
+                            'allreduce_ms': ms, 'allreduce_bytes': nbytes,
+                            'allreduce_busbw_GBs': 2 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9,
+                            'allreduce_note': 'sum over the row chunks of the CUDA-event time of the own exchange kernel '
+                                              '(lower triangle only); all but the last chunk overlap the accumulation'})
+            lap.release_posterior()
+        out['cfg5_full'] = rec
+        del lap, batches, model
+    except Exception as exc:
+        out['cfg5_full'] = {'error': repr(exc)[:300]}
+    try:
+        torch.manual_seed(71)
+        model = CIFAR10Net(3, 10, use_tanh=True).to(dev)
+        batches, n_mine = my_batches(50000, 250, (3, 32, 32), 10, 2500)
+        lap = Laplace(model, 1.0, CategoricalLh())
+        rec = None
+        for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            lap.infer(batches, cov_type='kron', shard=shard, factorise=False)
+            chk = float(sum(m.double().sum() for qh in lap.Sigma_chol.qhs for m in qh))
+            barrier()
+            sec = maxr(time.perf_counter() - t0)
+            rec = {'examples_total': 50000, 'examples_this_rank': n_mine, 'loader_batch': 250, 'seconds': sec,
+                   'examples_per_s': 50000 / sec, 'accumulate_ms_device': maxr(lap.timings['accumulate_ms']),
+                   'checksum_factors': chk}
+            if world > 1 and lap.exchange_stats:
+                xt = lap.exchange_stats
+                ms = maxr(xt['e0'].elapsed_time(xt['e1']))
+                rec.update({'allreduce_ms': ms, 'allreduce_bytes': xt['bytes'],
+                            'allreduce_note': 'one NCCL all-reduce of the flat bucket of all Kronecker factors'})
+        out['cfg4_kron'] = rec
+    except Exception as exc:
+        out['cfg4_kron'] = {'error': repr(exc)[:300]}
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from preds_b200 import Laplace, CategoricalLh, MLPS
+    from preds_b200 import Laplace, CategoricalLh, MLPS, parallel
     from preds_b200._cabi import lib, check, ptr, stream
     from preds_b200._engine import net_for
 
@@ -160,23 +272,27 @@ def run_ours(args):
     for i in range(n_distinct):        # different examples on every rank (sharded data set)
         host[i][0].add_(0.01 * rank)
     resident = [(X.to(dev), y.to(dev)) for X, y in host]
-    H = torch.zeros(P_PARAMS, P_PARAMS, device=dev)
+    lap = Laplace(model, 1.0, lh)
+    lap.ggn_engine = args.engine
+    hdl = None
+    if world > 1:
+        H, hdl = parallel.symmetric_zeros(P_PARAMS, dev)
+    if world == 1 or H is None:
+        H = torch.zeros(P_PARAMS, P_PARAMS, device=dev)
 
-    def step(X):
-        X2d, pl, ws, f = net.jacobian_factors(X)
-        N = X2d.shape[0]
-        Lam = lh._hessian_nkk(f)
-        sc = net.scratch(lib.bnnp_ggn_full_scratch_floats(C.byref(pl), N, args.engine))
-        check(lib.bnnp_ggn_full_accum(net.ops, net.n_ops, C.byref(pl), N, ptr(ws), ptr(Lam), ptr(H), ptr(sc),
-                                      args.engine, stream()), 'bnnp_ggn_full_accum')
+    def job(n_steps, exchange):
+        """The hot path over n_steps resident batches through the product's own accumulation routine; with N > 1 the
+        path's one exchange step (own kernel over NVLink, row chunks overlapped with the last batch) and the mirror."""
+        ex = parallel.LowerExchange(H, hdl, 1.0) if exchange else None
+        lap._accumulate_full(((resident[i % n_distinct][0], None) for i in range(n_steps)), H, exchange=ex)
+        return ex
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(W):
-        step(resident[i % n_distinct][0])
+    job(W, world > 1)                  # warm-up: kernels, allocator, and (N > 1) communicator + exchange kernel
     barrier()
     H.zero_()
     lib.bnnp_prof_enable(1)
@@ -187,41 +303,44 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(K):
-        step(resident[i % n_distinct][0])
-    if world > 1:
-        dist.all_reduce(H)              # the path's one exchange step: sum of the local GGNs
-    check(lib.bnnp_symmetrize_lower(ptr(H), P_PARAMS, stream()), 'bnnp_symmetrize_lower')
+    ex = job(K, world > 1)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.bnnp_launch_count() - launches0)
-    # dominant kernel: CUDA-event records of every gram_tc launch (recorded on the launching stream)
+    # dominant kernel: CUDA-event records of every gram launch (recorded on the launching stream)
     cap = 4096
     pms, pex, pus = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
     nrec = lib.bnnp_prof_read(pms, pex, pus, cap)
     lib.bnnp_prof_enable(0)
+    exchange = None
+    if ex is not None:
+        xms, xbytes = ex.stats()
+        exchange = {'mode': ex.mode, 'chunks': len(ex.events), 'allreduce_ms': xms, 'allreduce_bytes': xbytes,
+                    'busbw_GBs': 2 * (world - 1) / world * xbytes / (xms * 1e-3) / 1e9,
+                    'note': 'own kernel over NVLink peer memory, lower triangle of H only, prior fused; all but the last '
+                            'row chunk overlap the accumulation of the last batch'}
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = K * B * world / (ms * 1e-3)
     checksum = float(H.diagonal().double().sum())
-    lap = None
 
     # ---- e2e through the public API with pinned host batches (H2D inside, D2H read per step) ----
-    lap = Laplace(model, 1.0, lh)
-    lap.ggn_engine = args.engine
     e2e_steps = max(1, min(K, args.e2e_steps))
+    shard = 'presharded' if world > 1 else None     # N > 1: every rank infers on its own examples, exchange included
     for _ in range(2):      # warm-up: the second call makes the allocator hold both 14.2 GB blocks (old + new precision)
-        lap.infer([host[0]], cov_type='full', factorise=False)
+        lap.infer([host[0]], cov_type='full', factorise=False, shard=shard)
         float(lap.precision.diagonal().sum())
+        lap.release_posterior()
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        lap.infer([host[i % n_distinct]], cov_type='full', factorise=False)
+        lap.infer([host[i % n_distinct]], cov_type='full', factorise=False, shard=shard)
         float(lap.precision.diagonal().sum())                  # device -> host read of the step's result
+        lap.release_posterior()
     if world > 1:
         dist.barrier()
     e2e_s = time.perf_counter() - t0
@@ -230,13 +349,17 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = e2e_steps * B * world / e2e_s
-    lap.precision = None
+
+    # ---- strong scaling of the configurations as stated (total work fixed) ----
+    strong = None
+    if not args.no_strong:
+        strong = strong_scaling(dev, rank, world, args)
 
     # ---- secondary: the one-off factorisation (timed separately) and the GLM predictive ----------
     secondary = None
+    Sigma_for_cpu = None
     if not args.no_glm:
-        from preds_b200.predictives import glm_moments
-        H.diagonal().add_(1.0)                       # prior precision (added once, after the reduce)
+        H.diagonal().add_(1.0 if world == 1 else 0.0)   # prior precision (N > 1: the exchange kernel already added it)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         barrier()
         ev[0].record()
@@ -250,9 +373,14 @@ def run_ours(args):
         Xte = Xte_host.to(dev)
         lap.predictive_samples_glm(Xte[:256], n_samples=8, seed=1)          # warm-up (also builds the Sigma split)
         barrier()
+        lib.bnnp_prof_enable(1)
         ev[2].record()
         out = lap.predictive_samples_glm(Xte, n_samples=S, seed=2)
         ev[3].record()
+        torch.cuda.synchronize()
+        gms, gus = (C.c_float * 1024)(), (C.c_double * 1024)()
+        gn = lib.bnnp_glm_prof_read(gms, gus, 1024)
+        lib.bnnp_prof_enable(0)
         out.mean(0).cpu()                                                   # warm-up of the reduction kernels (first call: ~19 ms)
         barrier()
         t0 = time.perf_counter()
@@ -271,12 +399,25 @@ def run_ours(args):
             t = torch.tensor([glm_ms, e2e_glm_s, e2e_fused_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             glm_ms, e2e_glm_s, e2e_fused_s = float(t[0]), float(t[1]), float(t[2])
+        pk, _ = peaks()
+        glm_roof = None
+        if gn > 0:
+            kms = sum(gms[i] for i in range(gn))
+            kflops = sum(gus[i] for i in range(gn))
+            peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+            glm_roof = {'bound': 'tensor', 'kernel': 'glm_fvar_pair_kernel (TMA-fed CTA-pair tcgen05.mma)', 'achieved': kflops / (kms * 1e-3) / 1e12,
+                        'peak': peak, 'unit': 'TFLOP/s', 'frac': kflops / (kms * 1e-3) / 1e12 / peak, 'traffic': None,
+                        'kernel_ms': kms, 'kernel_launches': gn, 'kernel_share_of_call': kms / glm_ms,
+                        'flops_note': 'useful = 3 split-bf16 passes x 2 x inputs x elements of Sigma on/below the block diagonal '
+                                      '(f_var = J Sigma J^T evaluated as T[n,u,u\'] = a^T Sigma_uu\' a\' for u\' <= u); '
+                                      'as written the reference einsum costs 2 K P^2 + 2 K^2 P per input'}
         secondary = {
             'factorise_full_ms': ev[0].elapsed_time(ev[1]),
-            'factorise_note': 'one-off chol(H), cholesky_inverse, chol(Sigma) via cuSOLVER (torch.linalg), P=59635',
+            'factorise_note': 'one-off chol(H), inverse, chol(Sigma), P=59635 (timed separately, north star (3))',
             'glm_predictive': {
                 'metric': 'glm_predictive_input_samples_per_s', 'value': nte * S * world / (glm_ms * 1e-3),
                 'unit': '(inputs x samples)/s', 'inputs_per_gpu': nte, 'samples': S, 'ms': glm_ms,
+                'roofline': glm_roof,
                 'e2e_value': nte * S * world / e2e_glm_s,
                 'e2e_note': 'pinned host inputs -> predictive_samples_glm -> .mean(0) read back',
                 'e2e_fused_mean_value': nte * S * world / e2e_fused_s,
@@ -286,39 +427,61 @@ def run_ours(args):
                 'scaling': 'test inputs sharded across ranks, no collective',
             },
         }
+        if world == 1 and rank == 0 and not args.no_cpu_baseline:
+            Sigma_for_cpu = Sigma
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    if Sigma_for_cpu is not None:
+        try:
+            torch.set_num_threads(os.cpu_count())
+            rate, sec = cpu_glm_rate(Sigma_for_cpu, 20, 100)
+            secondary['glm_predictive']['cpu_baseline'] = {
+                'value': rate, 'unit': '(inputs x samples)/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                'sample': '20 inputs x 100 samples (experiments/imginference.py:45,391), Jacobians + einsum with the full '
+                          '[P,P] covariance + sampling, oracle/port.py, %.1f s; the reference\'s per-call Sigma = L L^T '
+                          '(2 P^3 flops) excluded' % sec}
+        except Exception as exc:
+            secondary['glm_predictive']['cpu_baseline'] = {'error': repr(exc)[:200]}
+        Sigma_for_cpu = None
+
     if secondary is not None and world == 1 and not args.no_other_configs:
         lap = None
         torch.cuda.empty_cache()
         secondary['configs'] = other_configs(dev)
+    if secondary is None:
+        secondary = {}
+    secondary['strong_scaling'] = strong
+    secondary['exchange'] = exchange
 
     pk, pk_kind = peaks()
     recs = [(pms[i], pex[i], pus[i]) for i in range(max(nrec, 0))]
     roofline = None
     if recs:
         top = max(r[2] for r in recs)
-        dom = [r for r in recs if r[2] >= 0.5 * top]           # the (layer1, layer1) block launches
+        dom = [r for r in recs if r[2] >= 0.5 * top]           # the whole (layer1, layer1) block launches
         avg_ms = statistics.mean(r[0] for r in dom)
         useful = statistics.mean(r[2] for r in dom)
         executed = statistics.mean(r[1] for r in dom)
         peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
         ach = useful / (avg_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'gram_tc_traffic.json')))['dram_bytes_per_launch']
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'gram_wide_traffic.json')))
+            traffic, traffic_src = tj['dram_bytes_per_launch'], tj.get('source')
         except Exception:
             pass
         roofline = {
-            'bound': 'tensor', 'kernel': 'gram_pair_kernel (CTA-pair tcgen05.mma; gram_tc_kernel when a block has one row tile)', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-            'frac': ach / peak, 'traffic': traffic, 'peak_source': pk_kind + ' bf16 dense (sustained)',
+            'bound': 'tensor', 'kernel': 'gram_wide_kernel (CTA-pair tcgen05.mma.cta_group::2, one unit x two column tiles)',
+            'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk_kind + ' bf16 dense (sustained)',
             'kernel_ms_per_launch': avg_ms, 'kernel_share_of_step': sum(r[0] for r in recs) / ms,
-            'flops_note': 'achieved = useful bf16 MMA flops (3 split passes x 2*N*rows*cols of the computed '
-                          'lower-triangle tiles, padding excluded) / CUDA-event kernel time',
+            'flops_note': 'achieved = useful bf16 MMA flops (3 split passes x 2 x examples x elements of H on or below its '
+                          'diagonal in the launch\'s rows, padding and the above-diagonal part of crossing tiles excluded) '
+                          '/ CUDA-event kernel time',
             'executed_tflops_incl_padding': executed / (avg_ms * 1e-3) / 1e12,
             'einsum_as_written_tflops': (2.0 * K_OUT * P_PARAMS ** 2 + 2.0 * P_PARAMS * K_OUT ** 2) * B / (ms / K * 1e-3) / 1e12,
         }
@@ -336,11 +499,12 @@ def run_ours(args):
         'dtype': 'bf16x2-split (fp32-grade) tensor cores, f32 accumulate', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'engine': 'tcgen05' if args.engine != 1 else 'simt',
                    'l2': 'working set >> L2: the 14.2 GB H is read-modify-written every step',
-                   'timed_region': 'K steps + all-reduce of H (N>1) + symmetrise'},
+                   'timed_region': 'K steps + exchange of the lower triangle of H (N>1, own NVLink kernel, overlapped with the last step) + symmetrise'},
         'roofline': roofline, 'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * 784 * 4 + B * 8,
                 'd2h_bytes_per_step': 4, 'steps': e2e_steps,
-                'call': "Laplace.infer([(X_pinned_host, y)], cov_type='full', factorise=False) + float(precision.trace)"},
+                'call': "Laplace.infer([(X_pinned_host, y)], cov_type='full', factorise=False%s) + float(precision.trace)"
+                        % (", shard='presharded'" if world > 1 else '')},
         'gpu_launches': launches, 'clocks': clocks, 'checksum_trace_H': checksum, 'secondary': secondary,
     }
     print(json.dumps(line))
@@ -417,6 +581,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-glm', action='store_true')
     ap.add_argument('--no-other-configs', action='store_true')
+    ap.add_argument('--no-strong', action='store_true')
     ap.add_argument('--glm-inputs', type=int, default=10000)
     ap.add_argument('--glm-samples', type=int, default=1000)
     args = ap.parse_args()

@@ -30,8 +30,11 @@ struct BnnpOptions {
   int glm_single;      // full-covariance GLM: 1 forces the single-CTA TMA kernel
   int glm_simt;        // kron / diag GLM contractions on the fp32 SIMT kernels with the unfused reductions
   int debug_sync;      // synchronise and report after every GLM TMA launch
+  int net_simt;        // forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size (parity bisection)
 };
 extern BnnpOptions g_bnnp_opt;
+
+namespace bnnp { void glm_prof_set(bool on); }
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

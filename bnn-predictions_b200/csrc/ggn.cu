@@ -560,7 +560,7 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     const bnnp_op_plan_t& q = plan->op[i];
     if (o.kind == BNNP_OP_LINEAR) {
       int rc;
-      if ((long long)o.out_c * (o.in_c + 1) * N >= kTcMinMacsG || N >= 2048) {
+      if (!g_bnnp_opt.net_simt && ((long long)o.out_c * (o.in_c + 1) * N >= kTcMinMacsG || N >= 2048)) {
         // T[i, j] = sum_n Q[n, i] a[n, j]^2 on the tensor cores (split-K partials -> T), then scatter into d
         const long long mm = o.out_c, nn = o.in_c + 1;
         float* T = scratch + N * (int64_t)M + 64;
@@ -589,7 +589,7 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
     const float* G = ws + q.grad_off;
     float* partial = scratch + N * V * (int64_t)o.out_c + 64;
-    if ((long long)N * V * o.out_c * L * E >= kTcMinMacsG && N * V <= 0x7fffffff) {
+    if (!g_bnnp_opt.net_simt && (long long)N * V * o.out_c * L * E >= kTcMinMacsG && N * V <= 0x7fffffff) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -681,7 +681,7 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
       float* wsk = scratch + kfac_conv_floats(ops, n_ops, N, V);
       // (a narrow Gram over many rows -- the 10 x 10 factor of the output layer over N*K rows -- is ONE SIMT block
       // walking all rows: 3.5 ms of a 6.2 ms pass; split-K on the tensor cores spreads it over the machine)
-      if ((long long)o.out_c * o.out_c * R >= kTcMinMacsG || R >= 2048)
+      if (!g_bnnp_opt.net_simt && ((long long)o.out_c * o.out_c * R >= kTcMinMacsG || R >= 2048))
         rc = tcg::gemm_tc_splitk(o.out_c, o.out_c, R, 1, tcg::TcColMajor{G, q.grad_ld, 0}, tcg::TcColMajor{G, q.grad_ld, 0},
                                  factor, 1.f, Gf, o.out_c, 0, wsk, tcg::pick_ksplit(o.out_c, o.out_c, R, 1), st);
       else
@@ -689,7 +689,7 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
                        AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       const float* A = ws + plan->acat_off;
-      if ((long long)o.in_c * o.in_c * N >= kTcMinMacsG || N >= 2048)
+      if (!g_bnnp_opt.net_simt && ((long long)o.in_c * o.in_c * N >= kTcMinMacsG || N >= 2048))
         rc = tcg::gemm_tc_splitk(o.in_c, o.in_c, N, 1, tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0},
                                  tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0}, batch_factor / (float)N, 1.f, Af, o.in_c,
                                  0, wsk, tcg::pick_ksplit(o.in_c, o.in_c, N, 1), st);
@@ -707,7 +707,7 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
       int rc;
       // G += factor * S^T S over the R position-summed rows: a 64..128-wide Gram is one to four SIMT blocks walking
       // all R rows -- the split-K tensor-core Gram spreads it over the machine
-      if ((long long)o.out_c * o.out_c * R >= (1LL << 22))
+      if (!g_bnnp_opt.net_simt && (long long)o.out_c * o.out_c * R >= (1LL << 22))
         rc = tcg::gemm_tc_splitk(o.out_c, o.out_c, R, 1, tcg::TcColMajor{scratch, o.out_c, 0}, tcg::TcColMajor{scratch, o.out_c, 0},
                                  factor, 1.f, Gf, o.out_c, 0, scratch + kfac_conv_floats(ops, n_ops, N, V),
                                  tcg::pick_ksplit(o.out_c, o.out_c, R, 1), st);
@@ -716,7 +716,7 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
                        AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       Im2col u = make_im2col(o, in, ild, 1);
-      if ((long long)E * E * N * L >= kTcMinMacsG) {
+      if (!g_bnnp_opt.net_simt && (long long)E * E * N * L >= kTcMinMacsG) {
         // materialise the unfolded input once, then A += (bf/N) U^T U as a tensor-core Gram (split-K)
         const int Epad = (E + 3) / 4 * 4;
         float* U = scratch + kfac_conv_floats(ops, n_ops, N, V);

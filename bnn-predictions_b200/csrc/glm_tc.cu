@@ -480,6 +480,28 @@ __global__ void glmtc_fvar_from_units_kernel(const float* __restrict__ G, int64_
   }
 }
 
+// Optional CUDA-event timing of the f_var kernel launches of every call (bench.py's live roofline of the GLM
+// predictive); one record per (layer, alignment group) launch, useful flops = 3 split passes x 2 x inputs x the
+// elements of Sigma on/below the block diagonal that the launch contracts.
+struct GlmProf {
+  bool on = false, created = false;
+  int n = 0;
+  static constexpr int CAP = 1024;
+  cudaEvent_t beg[CAP], end[CAP];
+  double useful[CAP];
+};
+static GlmProf g_glm_prof;
+namespace bnnp { void glm_prof_set(bool on) { g_glm_prof.on = on; g_glm_prof.n = 0; } }
+extern "C" int bnnp_glm_prof_read(float* ms, double* useful, int cap) {
+  int n = g_glm_prof.n < cap ? g_glm_prof.n : cap;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_glm_prof.end[i]) != cudaSuccess) return BNNP_ERR_CUDA;
+    if (cudaEventElapsedTime(&ms[i], g_glm_prof.beg[i], g_glm_prof.end[i]) != cudaSuccess) return BNNP_ERR_CUDA;
+    useful[i] = g_glm_prof.useful[i];
+  }
+  return n;
+}
+
 // Sigma: fp32 [P,P]; Sh/Sl: its bf16 hi/lo split with row pitch roundup8(P) (bnnp_split_bf16).
 extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                                       const float* ws, const float* Sigma, const void* Sh, const void* Sl,
@@ -579,6 +601,21 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
       a.tile_start = prefix_dev + prefix_used;
       prefix_used += a.n_units + 1;
       const long long n_tiles = prefix[a.n_units];
+      const bool prof = g_glm_prof.on && g_glm_prof.n < GlmProf::CAP;
+      if (prof) {
+        if (!g_glm_prof.created) {
+          for (int e = 0; e < GlmProf::CAP; ++e) { cudaEventCreate(&g_glm_prof.beg[e]); cudaEventCreate(&g_glm_prof.end[e]); }
+          g_glm_prof.created = true;
+        }
+        // unit u' contracts its fan-in (+ bias handled in the epilogue) with the Sigma rows from its first weight row on
+        double us = 0;
+        for (int ui = 0; ui < a.n_units; ++ui) {
+          const long long up = grp + (long long)period * ui;
+          us += (double)o.in_c * (double)(P - (o.theta_off_w + up * o.in_c));
+        }
+        g_glm_prof.useful[g_glm_prof.n] = 3.0 * 2.0 * (double)N * us;
+        cudaEventRecord(g_glm_prof.beg[g_glm_prof.n], st);
+      }
       if (pair) {
         const long long pairs = sms / 2;
         const int grid = 2 * (int)(n_tiles < pairs ? n_tiles : pairs);
@@ -587,6 +624,7 @@ extern "C" int bnnp_glm_fvar_full_tma(const bnnp_op_t* ops, int n_ops, const bnn
         const int grid = (int)(n_tiles < sms ? n_tiles : sms);
         glm_fvar_tma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mah, mal, msh, msl, a);
       }
+      if (prof) { cudaEventRecord(g_glm_prof.end[g_glm_prof.n], st); ++g_glm_prof.n; }
       BNNP_LAUNCH_CHECK();
       if (g_bnnp_opt.debug_sync) {
         cudaError_t e = cudaStreamSynchronize(st);

@@ -1222,6 +1222,7 @@ int gram_row_chunks(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, in
 extern "C" int bnnp_prof_enable(int on) {
   bnnp::g_prof.on = on != 0;
   bnnp::g_prof.n = 0;
+  bnnp::glm_prof_set(on != 0);
   return BNNP_OK;
 }
 // Copies up to cap records {ms, executed flops, useful flops} of the gram launches since enable;

@@ -544,7 +544,7 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
         fill_col_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(slice + o.in_c, plan->Dtot, N, 1.f);
         BNNP_LAUNCH_CHECK();
         int rc;
-        if ((long long)N * o.out_c * o.in_c >= kTcMinMacs)
+        if (!g_bnnp_opt.net_simt && (long long)N * o.out_c * o.in_c >= kTcMinMacs)
           rc = tcg::gemm_tc(N, o.out_c, o.in_c, 1, tcg::TcRowMajor{slice, plan->Dtot, 0},
                             tcg::TcRowMajor{o.weight, o.in_c, 0},
                             TcStoreBias(out, q.act_ld, o.has_bias ? o.bias : nullptr), 1, st);
@@ -557,7 +557,7 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
       }
       case BNNP_OP_CONV2D: {
         const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
-        if (plan->conv_scratch_off >= 0 && (long long)N * L * E * o.out_c >= kTcMinMacs) {
+        if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)N * L * E * o.out_c >= kTcMinMacs) {
           const int Epad = (E + 3) / 4 * 4;
           float* U = ws + plan->conv_scratch_off;
           im2col_fwd_kernel<<<(unsigned)ceil_div64(N * L * (int64_t)Epad, 256), 256, 0, st>>>(in, ild, N, geom_of(o), E,
@@ -637,7 +637,7 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
     switch (o.kind) {
       case BNNP_OP_LINEAR: {
         int rc;
-        if ((long long)R * o.in_c * o.out_c >= kTcMinMacs)
+        if (!g_bnnp_opt.net_simt && (long long)R * o.in_c * o.out_c >= kTcMinMacs)
           rc = tcg::gemm_tc(R, o.in_c, o.out_c, 1, tcg::TcRowMajor{gout, q.grad_ld, 0},
                             tcg::TcColMajor{o.weight, o.in_c, 0},
                             tcg::TcStoreAxpby(gin, qp.grad_ld, 0, 1.f, 0.f), 1, st);
@@ -649,7 +649,7 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
         break;
       }
       case BNNP_OP_CONV2D:
-        if (plan->conv_scratch_off >= 0 && (long long)R * o.out_c * o.out_h * o.out_w * o.in_c * o.kh * o.kw >= kTcMinMacs) {
+        if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)R * o.out_c * o.out_h * o.out_w * o.in_c * o.kh * o.kw >= kTcMinMacs) {
           const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
           float* dUt = ws + plan->conv_scratch_off;
           int rc = tcg::gemm_tc(R * L, E, o.out_c, 1, ConvGoutRowsA{gout, q.grad_ld, L}, tcg::TcColMajor{o.weight, E, 0},

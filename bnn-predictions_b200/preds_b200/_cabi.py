@@ -111,6 +111,7 @@ _SIGS = {
     'bnnp_get_option': (_I, [C.c_char_p]),
     'bnnp_prof_enable': (_I, [_I]),
     'bnnp_prof_read': (_I, [C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double), _I]),
+    'bnnp_glm_prof_read': (_I, [C.POINTER(C.c_float), C.POINTER(C.c_double), _I]),
 }
 EXPORTED = sorted(_SIGS)
 for _name, (_res, _args) in _SIGS.items():

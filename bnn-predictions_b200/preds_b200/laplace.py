@@ -58,6 +58,7 @@ class Laplace:
         self.precision = None
         self.timings = {}
         self.exchange_stats = None   # parallel.LowerExchange of the last sharded full-covariance infer
+        self._symmetric = None       # (accumulator, handle) when the precision lives in symmetric memory
         self.ggn_engine = 0          # 0 auto, 1 SIMT fp32, 2 tcgen05 split-bf16
 
     # ------------------------------------------------------------------------------ infer
@@ -81,6 +82,7 @@ class Laplace:
         self.model.eval()
         self._Sigma = None
         self.exchange_stats = None
+        self._symmetric = None
         dist = _dist() if shard else None
         if shard and shard not in ('batches', 'presharded'):
             raise ValueError("shard must be None, 'batches' or 'presharded'")
@@ -116,6 +118,7 @@ class Laplace:
             ex = None
             if dist:
                 acc, hdl = (None, None) if exchange == 'nccl' else parallel.symmetric_zeros(self.P, self.device)
+                self._symmetric = (acc, hdl) if acc is not None else None
                 if acc is None:
                     acc = torch.zeros(self.P, self.P, device=self.device)
                 ex = parallel.LowerExchange(acc, hdl, diag_prior, mode=exchange)
@@ -159,7 +162,9 @@ class Laplace:
                 N = parallel.global_count(N, self.device, enabled=bool(dist) and shard == 'presharded')
             self._accumulate_kron(my_batches(), precision, float(hess_factor), N)
             if dist:
-                parallel.reduce_factors_(precision.qhs)
+                xt = {}
+                parallel.reduce_factors_(precision.qhs, timing=xt)
+                self.exchange_stats = xt
             t1.record()
             if factorise:
                 precision.decompose()
@@ -171,6 +176,17 @@ class Laplace:
         self.timings = {'accumulate_ms': t0.elapsed_time(t1), 'factorise_ms': t1.elapsed_time(t2)}
         net_for(self.model).release()
         self.inferred = bool(factorise)
+
+    def release_posterior(self):
+        """Drop the posterior and hand a symmetric-memory accumulator back to ``parallel`` for the next sharded
+        ``infer`` of the same size (e.g. a prior-precision sweep).  The caller must not use ``precision`` afterwards.
+        Collective in the sharded mode: every rank calls it."""
+        if self._symmetric is not None:
+            parallel.symmetric_release(*self._symmetric)
+        self._symmetric = None
+        self.precision = self.Sigma_chol = self._Sigma = None
+        self.exchange_stats = None
+        self.inferred = False
 
     def _accumulate_full(self, batches, H, grad=None, exchange=None):
         """H += sum_n J_n^T Lambda_n J_n over the batches (lower triangle, mirrored at the end).  With

@@ -77,13 +77,20 @@ def reduce_sum_(acc, prior=None):
     return acc
 
 
-def reduce_factors_(qhs):
-    """All Kronecker factors of all parameters in ONE flat bucket (one launch, one all-reduce)."""
+def reduce_factors_(qhs, timing=None):
+    """All Kronecker factors of all parameters in ONE flat bucket (one launch, one all-reduce).  ``timing``: optional
+    dict that receives CUDA events around the collective ('e0', 'e1') and the bucket size in bytes."""
     import torch.distributed as dist
     if world()[1] == 1:
         return qhs
     flat = torch.cat([m.reshape(-1) for qh in qhs for m in qh])
+    if timing is not None:
+        timing['e0'], timing['e1'] = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        timing['bytes'] = flat.numel() * 4
+        timing['e0'].record()
     dist.all_reduce(flat)
+    if timing is not None:
+        timing['e1'].record()
     off = 0
     for qh in qhs:
         for m in qh:
@@ -99,15 +106,34 @@ EXCHANGE_CHUNKS = 6          # row chunks of the last super-batch (equal triangl
 EXCHANGE_CTAS = 32
 
 
+_SYMMETRIC_POOL = {}         # (P, device index) -> [(tensor, handle)] handed back by Laplace.release_posterior()
+
+
+def symmetric_release(t, hdl):
+    """Hand a symmetric accumulator back for the next sharded infer of the same size (allocation + rendezvous of a
+    14 GB symmetric buffer costs far more than zeroing it).  Only the owner may call this, once it holds no other
+    reference to ``t``."""
+    _SYMMETRIC_POOL.setdefault((t.shape[0], t.device.index), []).append((t, hdl))
+
+
 def symmetric_zeros(P, device):
     """([P,P] fp32 zeros in symmetric memory, rendezvous handle) over the default group, or (None, None) when this
-    torch / system cannot provide peer mappings (then the packed NCCL exchange is used)."""
+    torch / system cannot provide peer mappings (then the packed NCCL exchange is used).  Collective: every rank must
+    call it (and ``symmetric_release``) in the same order."""
     import torch.distributed as dist
+    pool = _SYMMETRIC_POOL.get((P, torch.device(device).index))
+    if pool:
+        t, hdl = pool.pop()
+        t.zero_()
+        return t, hdl
     try:
+        import warnings
         import torch.distributed._symmetric_memory as symm
         group = dist.group.WORLD
         try:
-            symm.enable_symm_mem_for_group(group.group_name)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                symm.enable_symm_mem_for_group(group.group_name)
         except Exception:
             pass
         t = symm.empty((P, P), dtype=torch.float32, device=device)
@@ -138,7 +164,10 @@ class LowerExchange:
         self.H, self.hdl, self.P = H, hdl, H.shape[0]
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         if mode == 'auto':
-            mode = 'nccl' if hdl is None else ('nvls' if int(hdl.multicast_ptr) != 0 else 'p2p')
+            # bytes per GPU and link direction: NVLS (1 + 1/W) x triangle (every copy is read through the switch, own copy
+            # included), P2P 2 (W-1)/W x triangle -> NVLS from W = 4 (measured at W = 2: NVLS 20.3 ms, P2P 11.8 ms)
+            nvls = hdl is not None and int(hdl.multicast_ptr) != 0 and self.world >= 4
+            mode = 'nccl' if hdl is None else ('nvls' if nvls else 'p2p')
         if mode in ('nvls', 'p2p') and hdl is None:
             raise BnnpError("exchange mode '%s' needs the accumulator in symmetric memory" % mode)
         if mode == 'nvls' and int(hdl.multicast_ptr) == 0:

@@ -333,11 +333,14 @@ uint64_t bnnp_launch_count(void);
 /* Engine-selection options for tests and A/B measurements (process-wide, default 0; never read from the
  * environment; none of them makes a kernel skip work):  "gram_kernel" 0 auto / 1 single-CTA kernel,
  * "glm_single" 1 = single-CTA full-covariance GLM kernel, "glm_simt" 1 = kron / diag GLM contractions on the fp32
- * SIMT kernels, "debug_sync" 1 = synchronise after every GLM TMA launch.  Unknown name: BNNP_ERR_INVALID. */
+ * SIMT kernels, "debug_sync" 1 = synchronise after every GLM TMA launch,
+ * "net_simt" 1 = forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size.  Unknown name: BNNP_ERR_INVALID. */
 int bnnp_set_option(const char* name, int value);
 int bnnp_get_option(const char* name);
 int bnnp_prof_enable(int on);
 int bnnp_prof_read(float* ms, double* executed_flops, double* useful_flops, int cap);
+/* the same for the full-covariance GLM f_var launches (bnnp_glm_fvar_full_tma) since bnnp_prof_enable(1) */
+int bnnp_glm_prof_read(float* ms, double* useful_flops, int cap);
 
 #ifdef __cplusplus
 }
