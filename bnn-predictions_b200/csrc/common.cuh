@@ -34,7 +34,15 @@ struct BnnpOptions {
 };
 extern BnnpOptions g_bnnp_opt;
 
-namespace bnnp { void glm_prof_set(bool on); }
+namespace bnnp {
+void glm_prof_set(bool on);
+// wide-K variants (wide_k.cu): BNNP_MAX_K < K <= BNNP_MAX_K_WIDE
+int lik_wide(int mode, const float* f, const void* y, int64_t N, int K, float* out, cudaStream_t st);
+int link_moments_wide(const float* f, const float* fmu, const float* fvar, float sigma2, int64_t N, int K, float* mu_star,
+                      float* var_f, float* var_noise, cudaStream_t st);
+int glm_sample_wide(int lik, const float* fmu, const float* fvar, const float* eps, uint64_t seed, int64_t S, int64_t N,
+                    int K, float* out, int32_t* status, int mean, int diag, cudaStream_t st);
+}
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

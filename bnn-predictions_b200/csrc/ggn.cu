@@ -148,20 +148,21 @@ struct AccumLower {
   __device__ void operator()(int64_t m, int64_t n, float acc, int) const { H[m * P + n] += acc; }
 };
 
-__global__ void symmetrize_kernel(float* __restrict__ H, int64_t P) {
+// mirror of source rows [row0, row1): H[c, r] = H[r, c] for r in [row0, row1), c < r.
+// grid: x = 32-column tiles 0 .. (row1-1)/32, y = 32-row tiles of the range (source tile = rows by, cols bx)
+__global__ void symmetrize_kernel(float* __restrict__ H, int64_t P, int64_t row0, int64_t row1) {
   __shared__ float tile[32][33];
-  int64_t bi = blockIdx.y, bj = blockIdx.x;     // destination tile (rows bi, cols bj), bi <= bj
-  if (bi > bj) return;
+  const int64_t bx = blockIdx.x, by = row0 / 32 + blockIdx.y;     // source tile: rows by*32.., cols bx*32..
+  if (bx > by) return;
   int tx = threadIdx.x, ty = threadIdx.y;
-  // load source tile (rows bj*32.., cols bi*32..)
   for (int r = ty; r < 32; r += 8) {
-    int64_t sr = bj * 32 + r, sc = bi * 32 + tx;
-    tile[r][tx] = (sr < P && sc < P) ? H[sr * P + sc] : 0.f;
+    int64_t sr = by * 32 + r, sc = bx * 32 + tx;
+    tile[r][tx] = (sr >= row0 && sr < row1 && sc < P) ? H[sr * P + sc] : 0.f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
-    int64_t dr = bi * 32 + r, dc = bj * 32 + tx;
-    if (dr < P && dc < P && dr < dc) H[dr * P + dc] = tile[tx][r];
+    int64_t dr = bx * 32 + r, dc = by * 32 + tx;                  // destination: row = source col, col = source row
+    if (dc >= row0 && dc < row1 && dr < dc) H[dr * P + dc] = tile[tx][r];
   }
 }
 
@@ -505,13 +506,17 @@ extern "C" int bnnp_ggn_full_accum_rows(const bnnp_op_t* ops, int n_ops, const b
   return BNNP_OK;
 }
 
-extern "C" int bnnp_symmetrize_lower(float* H, int64_t P, void* stream) {
-  if (!H || P <= 0) return BNNP_ERR_INVALID;
-  unsigned nb = (unsigned)ceil_div64(P, 32);
-  if (nb > 65535u) return BNNP_ERR_UNSUPPORTED;
-  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, as_stream(stream)>>>(H, P);
+extern "C" int bnnp_symmetrize_lower_rows(float* H, int64_t P, int64_t row0, int64_t row1, void* stream) {
+  if (!H || P <= 0 || row0 < 0 || row1 > P || row0 > row1) return BNNP_ERR_INVALID;
+  if (row0 == row1) return BNNP_OK;
+  const unsigned nx = (unsigned)ceil_div64(row1, 32), ny = (unsigned)(ceil_div64(row1, 32) - row0 / 32);
+  if (ny > 65535u) return BNNP_ERR_UNSUPPORTED;
+  symmetrize_kernel<<<dim3(nx, ny), dim3(32, 8), 0, as_stream(stream)>>>(H, P, row0, row1);
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
+}
+extern "C" int bnnp_symmetrize_lower(float* H, int64_t P, void* stream) {
+  return bnnp_symmetrize_lower_rows(H, P, 0, P, stream);
 }
 
 // ---------------------------------------------------------------------------- diag

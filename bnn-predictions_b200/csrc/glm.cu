@@ -970,8 +970,9 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
 extern "C" int bnnp_glm_sample(int lik, const float* f_mu, const float* f_var, const float* eps,
                                uint64_t seed, int64_t S, int64_t N, int K, float* out, int32_t* status,
                                void* stream) {
-  if (!f_mu || !f_var || !out || !status || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  if (!f_mu || !f_var || !out || !status || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K_WIDE) return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
+  if (K > 16) return glm_sample_wide(lik, f_mu, f_var, eps, seed, S, N, K, out, status, 0, 0, st);
 #define BNNP_CASE(KK) case KK: return launch_sample<KK>(lik, f_mu, f_var, eps, seed, S, N, out, status, false, st);
   switch (K) {
     BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
@@ -984,8 +985,9 @@ extern "C" int bnnp_glm_sample(int lik, const float* f_mu, const float* f_var, c
 extern "C" int bnnp_glm_sample_mean(int lik, const float* f_mu, const float* f_var, const float* eps,
                                     uint64_t seed, int64_t S, int64_t N, int K, float* mean, int32_t* status,
                                     void* stream) {
-  if (!f_mu || !f_var || !mean || !status || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  if (!f_mu || !f_var || !mean || !status || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K_WIDE) return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
+  if (K > 16) return glm_sample_wide(lik, f_mu, f_var, eps, seed, S, N, K, mean, status, 1, 0, st);
 #define BNNP_CASE(KK) case KK: return launch_sample<KK>(lik, f_mu, f_var, eps, seed, S, N, mean, status, true, st);
   switch (K) {
     BNNP_CASE(1) BNNP_CASE(2) BNNP_CASE(3) BNNP_CASE(4) BNNP_CASE(5) BNNP_CASE(6) BNNP_CASE(7) BNNP_CASE(8)
@@ -998,7 +1000,8 @@ extern "C" int bnnp_glm_sample_mean(int lik, const float* f_mu, const float* f_v
 extern "C" int bnnp_glm_sample_diag_fallback(int lik, const float* f_mu, const float* f_var, const float* eps,
                                              uint64_t seed, int64_t S, int64_t N, int K, float* out,
                                              void* stream) {
-  if (!f_mu || !f_var || !out || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  if (!f_mu || !f_var || !out || S <= 0 || N <= 0 || K <= 0 || K > BNNP_MAX_K_WIDE) return BNNP_ERR_INVALID;
+  if (K > BNNP_MAX_K) return glm_sample_wide(lik, f_mu, f_var, eps, seed, S, N, K, out, nullptr, 0, 1, as_stream(stream));
   glm_sample_diag_kernel<<<(unsigned)ceil_div64(S * N, 128), 128, 0, as_stream(stream)>>>(lik, f_mu, f_var, eps, seed,
                                                                                        S, N, K, out);
   BNNP_LAUNCH_CHECK();

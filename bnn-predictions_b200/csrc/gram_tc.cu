@@ -1195,15 +1195,24 @@ int gram_tc_full_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
   return BNNP_OK;
 }
 
-// Row boundaries b[0] = 0 < b[1] < ... < b[n] = P that split the lower triangle of H into n_chunks chunks of roughly equal
-// area, each boundary legal for gram_tc_full_accum (a multiple of 256 rows inside its layer block, or a block edge).
-// Returns the number of chunks actually produced (<= n_chunks; boundaries that collapse are dropped).
+// Row boundaries b[0] = 0 < b[1] < ... < b[n] = P that split the lower triangle of H into n_chunks chunks whose AREAS
+// decrease geometrically (ratio 0.6): the exchange of a chunk overlaps the accumulation of the next ones, only the
+// last chunk's exchange is exposed, so the last chunk is made small (3 % of the triangle for 6 chunks) while the first
+// ones stay large enough to keep the per-launch tail negligible.  Each boundary is legal for gram_tc_full_accum (a
+// multiple of 256 rows inside its layer block, or a block edge).  Returns the number of chunks actually produced
+// (<= n_chunks; boundaries that collapse are dropped).
 int gram_row_chunks(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int n_chunks, int64_t* bounds) {
   const long long P = plan->P;
   int n = 0;
   bounds[n++] = 0;
+  double total = 0, w = 1;
+  for (int c = 0; c < n_chunks; ++c) { total += w; w *= 0.6; }
+  double cum = 0;
+  w = 1;
   for (int c = 1; c < n_chunks; ++c) {
-    long long want = (long long)((double)P * sqrt((double)c / n_chunks));
+    cum += w / total;
+    w *= 0.6;
+    long long want = (long long)((double)P * sqrt(cum));
     long long snapped = want;
     for (int i = 0; i < n_ops; ++i) {
       if (ops[i].kind != BNNP_OP_LINEAR) continue;

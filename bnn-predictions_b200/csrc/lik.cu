@@ -1,4 +1,5 @@
-// Likelihood terms of preds/likelihoods.py as device kernels (one thread per example; K <= 32).
+// Likelihood terms of preds/likelihoods.py as device kernels (one thread per example for K <= 32; wider outputs go
+// to the warp-per-example kernels of wide_k.cu).
 #include "common.cuh"
 
 namespace bnnp {
@@ -140,7 +141,8 @@ __global__ void lik_link_moments_kernel(int lik, const float* __restrict__ f, co
 using namespace bnnp;
 
 static int check_lik(int lik, int K) {
-  if (lik < 0 || lik > 2 || K <= 0 || K > BNNP_MAX_K) return BNNP_ERR_INVALID;
+  if (lik < 0 || lik > 2 || K <= 0 || K > BNNP_MAX_K_WIDE) return BNNP_ERR_INVALID;
+  if (K > BNNP_MAX_K && lik != BNNP_LIK_CATEGORICAL) return BNNP_ERR_INVALID;      // wide outputs: classification only
   if (lik != BNNP_LIK_CATEGORICAL && K != 1 && lik == BNNP_LIK_BERNOULLI) return BNNP_ERR_INVALID;
   return BNNP_OK;
 }
@@ -149,6 +151,7 @@ extern "C" int bnnp_lik_hessian(int lik, const float* f, int64_t N, int K, float
                                 float* Lambda, void* stream) {
   if (check_lik(lik, K) || !f || !Lambda || N <= 0) return BNNP_ERR_INVALID;
   if (lik != BNNP_LIK_CATEGORICAL && K != 1) return BNNP_ERR_INVALID;   // preds/likelihoods.py:51
+  if (K > BNNP_MAX_K) return lik_wide(0, f, nullptr, N, K, Lambda, as_stream(stream));
   lik_hessian_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, as_stream(stream)>>>(lik, f, N, K, sigma2, Lambda);
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
@@ -157,6 +160,7 @@ extern "C" int bnnp_lik_hessian(int lik, const float* f, int64_t N, int K, float
 extern "C" int bnnp_lik_sqrt_seed(int lik, const float* f, int64_t N, int K, float* seed, void* stream) {
   if (check_lik(lik, K) || !f || !seed || N <= 0) return BNNP_ERR_INVALID;
   if (lik == BNNP_LIK_BERNOULLI) return BNNP_ERR_INVALID;               // no nn_loss, :74-75
+  if (K > BNNP_MAX_K) return lik_wide(1, f, nullptr, N, K, seed, as_stream(stream));
   lik_sqrt_seed_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, as_stream(stream)>>>(lik, f, N, K, seed);
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
@@ -172,6 +176,7 @@ extern "C" int bnnp_identity_seed(int64_t N, int K, float* seed, void* stream) {
 extern "C" int bnnp_lik_residual(int lik, const float* f, const void* y, int64_t N, int K,
                                  float sigma2, float* rs, void* stream) {
   if (check_lik(lik, K) || !f || !y || !rs || N <= 0) return BNNP_ERR_INVALID;
+  if (K > BNNP_MAX_K) return lik_wide(2, f, y, N, K, rs, as_stream(stream));
   lik_residual_kernel<<<(unsigned)ceil_div64(N, 128), 128, 0, as_stream(stream)>>>(lik, f, y, N, K, sigma2, rs);
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
@@ -179,6 +184,7 @@ extern "C" int bnnp_lik_residual(int lik, const float* f, const void* y, int64_t
 
 extern "C" int bnnp_lik_inv_link(int lik, const float* f, int64_t rows, int K, float* out, void* stream) {
   if (check_lik(lik, K) || !f || !out || rows <= 0) return BNNP_ERR_INVALID;
+  if (K > BNNP_MAX_K) return lik_wide(3, f, nullptr, rows, K, out, as_stream(stream));
   lik_inv_link_kernel<<<(unsigned)ceil_div64(rows, 128), 128, 0, as_stream(stream)>>>(lik, f, rows, K, out);
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
@@ -189,6 +195,7 @@ extern "C" int bnnp_lik_link_moments(int lik, const float* f, const float* f_mu,
                                      void* stream) {
   if (check_lik(lik, K) || !f || !f_mu || !f_var || !mu_star || !var_f || !var_noise || N <= 0) return BNNP_ERR_INVALID;
   if (lik != BNNP_LIK_CATEGORICAL && K != 1) return BNNP_ERR_INVALID;
+  if (K > BNNP_MAX_K) return link_moments_wide(f, f_mu, f_var, sigma2, N, K, mu_star, var_f, var_noise, as_stream(stream));
   lik_link_moments_kernel<<<(unsigned)ceil_div64(N, 64), 64, 0, as_stream(stream)>>>(lik, f, f_mu, f_var, sigma2, N, K,
                                                                                     mu_star, var_f, var_noise);
   BNNP_LAUNCH_CHECK();

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libbnnp_b200.so')
 
 MAX_OPS = 64
 MAX_K = 32            # BNNP_MAX_K of include/bnnp_b200.h (register-resident K x K code)
+MAX_K_WIDE = 128      # BNNP_MAX_K_WIDE: likelihood terms / GLM sampler beyond that on warp- / block-per-example kernels
 OP_LINEAR, OP_CONV2D, OP_RELU, OP_TANH, OP_MAXPOOL2D, OP_AVGPOOL2D, OP_FLATTEN, OP_SIGMOID = range(1, 9)
 LIK_CATEGORICAL, LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1, 2
 ERR_INVALID = -1
@@ -67,6 +68,7 @@ _SIGS = {
     'bnnp_ggn_full_row_chunks': (_I, [_OPS, _I, _PLAN, _L, _I, _I, C.POINTER(C.c_int64)]),
     'bnnp_ggn_full_accum_rows': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _I, _L, _L, _I, _V]),
     'bnnp_symmetrize_lower': (_I, [_P, _L, _V]),
+    'bnnp_symmetrize_lower_rows': (_I, [_P, _L, _L, _L, _V]),
     'bnnp_exchange_lower_allreduce': (_I, [C.POINTER(_P), _P, _I, _I, _L, _L, _L, _P, _F, _I, _V]),
     'bnnp_packed_lower_floats': (_L, [_L, _L]),
     'bnnp_pack_lower': (_I, [_P, _L, _L, _L, _P, _V]),

@@ -268,8 +268,9 @@ class Laplace:
             exchange.agree(False)            # a rank without examples still takes part in the exchange (H_r = 0)
             exchange.rows_done(0, self.P)
         if exchange is not None:
-            exchange.finish()
-        check(lib.bnnp_symmetrize_lower(ptr(H), self.P, stream()), 'bnnp_symmetrize_lower')
+            exchange.finish()            # joins the side stream; the exchange has mirrored H chunk by chunk
+        else:
+            check(lib.bnnp_symmetrize_lower(ptr(H), self.P, stream()), 'bnnp_symmetrize_lower')
 
     def _factorise_full(self, H):
         """chol(H) -> Sigma = H^-1 -> chol(Sigma) (preds/laplace.py:43-45), one-off, on device

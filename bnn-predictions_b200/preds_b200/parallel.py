@@ -103,7 +103,7 @@ def reduce_factors_(qhs, timing=None):
 # full covariance: exchange of the lower triangle of H over peer memory (csrc/exchange.cu)
 # ----------------------------------------------------------------------------------------------
 EXCHANGE_CHUNKS = 6          # row chunks of the last super-batch (equal triangle area); the last one is not overlapped
-EXCHANGE_CTAS = 32
+EXCHANGE_CTAS = 0            # 0: the kernel's default (NVLS 16, P2P 64): few SMs, the rest keep accumulating
 
 
 _SYMMETRIC_POOL = {}         # (P, device index) -> [(tensor, handle)] handed back by Laplace.release_posterior()
@@ -182,7 +182,8 @@ class LowerExchange:
             self.prior_scalar = float(prior)
         self.comm = torch.cuda.Stream(device=H.device)
         self.events = []
-        self._first = True
+        self._unmirrored = None      # rows exchanged but not mirrored yet (their broadcasts land by the next barrier)
+        self.mirrors = True          # the exchange also mirrors the lower triangle into the upper one, chunk by chunk
         if hdl is not None:
             off = H.data_ptr() - int(hdl.buffer_ptrs[self.rank])
             self.peers = (C.c_void_p * self.world)(*[int(b) + off for b in hdl.buffer_ptrs])
@@ -214,6 +215,8 @@ class LowerExchange:
                 e1.record()
                 check(lib.bnnp_unpack_lower(ptr(buf), self.P, r0, r1, ptr(self.H), ptr(self.prior_vec),
                                             self.prior_scalar, self.comm.cuda_stream), 'bnnp_unpack_lower')
+                check(lib.bnnp_symmetrize_lower_rows(ptr(self.H), self.P, r0, r1, self.comm.cuda_stream),
+                      'bnnp_symmetrize_lower_rows')
                 buf.record_stream(self.comm)
             else:
                 # every rank has finished accumulating these rows (and the previous chunk's broadcasts have landed)
@@ -224,12 +227,23 @@ class LowerExchange:
                                                         self.prior_scalar, EXCHANGE_CTAS, self.comm.cuda_stream),
                       'bnnp_exchange_lower_allreduce')
                 e1.record()
+                # the barrier above also means the PREVIOUS chunk's broadcasts have landed here: mirror it now, beside
+                # the accumulation of the next chunk (only the last chunk's mirror is left for finish())
+                if self._unmirrored is not None:
+                    check(lib.bnnp_symmetrize_lower_rows(ptr(self.H), self.P, self._unmirrored[0], self._unmirrored[1],
+                                                         self.comm.cuda_stream), 'bnnp_symmetrize_lower_rows')
+                self._unmirrored = (r0, r1)
             self.events.append((r0, r1, e0, e1))
 
     def finish(self):
+        from ._cabi import lib, check, ptr
         with torch.cuda.stream(self.comm):
             if self.mode != 'nccl':
                 self.hdl.barrier(channel=0)          # every owner's broadcasts have landed in this rank's H
+                if self._unmirrored is not None:
+                    check(lib.bnnp_symmetrize_lower_rows(ptr(self.H), self.P, self._unmirrored[0], self._unmirrored[1],
+                                                         self.comm.cuda_stream), 'bnnp_symmetrize_lower_rows')
+                    self._unmirrored = None
         torch.cuda.current_stream().wait_stream(self.comm)
 
     def stats(self):

@@ -36,6 +36,7 @@ extern "C" {
 
 #define BNNP_MAX_OPS  64
 #define BNNP_MAX_K    32           /* max #outputs handled by the register-resident K x K code */
+#define BNNP_MAX_K_WIDE 128        /* likelihood terms and the GLM sampler beyond that: warp / block per example (wide_k.cu) */
 
 const char* bnnp_strerror(int code);
 int bnnp_version(void);
@@ -147,8 +148,9 @@ int bnnp_ggn_full_row_chunks(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t*
 int bnnp_ggn_full_accum_rows(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                              const float* ws, const float* Lambda, float* H, float* scratch, int engine,
                              int64_t row_begin, int64_t row_end, int prepared, void* stream);
-/* H[p,q] = H[q,p] for p < q. */
+/* H[p,q] = H[q,p] for p < q; _rows: only the source rows q in [row0,row1) (their mirror images H[p,q], p < q). */
 int bnnp_symmetrize_lower(float* H, int64_t P, void* stream);
+int bnnp_symmetrize_lower_rows(float* H, int64_t P, int64_t row0, int64_t row1, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * The one exchange step of the data-parallel full-covariance path (the reference loop

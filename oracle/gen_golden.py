@@ -281,7 +281,52 @@ def probe_case(preds, name):
     print('%-12s P=%d  %.1f KB' % (name, P, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
 
 
+def probe100_case(preds, name):
+    """CIFAR100Net (preds/models.py:182-236: nine convs incl. stride-2 and 1x1 ones, AvgPool2d(6), K = 100) on two
+    3x32x32 examples: probes of the Jacobians, the diagonal GGN, the KFLR factors and the Kron GLM moments."""
+    from preds.models import CIFAR100Net
+    from preds.likelihoods import CategoricalLh, GaussianLh
+    from preds.laplace import Laplace
+    from preds.gradients import Jacobians
+    from preds.predictives import functional_sampling_predictive
+    torch.manual_seed(71)
+    model = CIFAR100Net(in_channels=3, n_out=100)
+    X = randn(15, 2, 3, 32, 32)
+    y = torch.tensor([17, 93])
+    theta = flat(model)
+    P = len(theta)
+    idx = torch.randperm(P, generator=torch.Generator().manual_seed(4242))[:512]
+    v = randn(4243, P)
+    out = {'theta_idx': np_(idx), 'theta_at_idx': np_(theta[idx]), 'theta_dot_v': np_(theta @ v), 'y': np_(y)}
+    Js, f = Jacobians(model, X)
+    out['f'] = np_(f)
+    out['Js_at_idx'] = np_(Js[:, idx, :])
+    out['Js_dot_v'] = np_(torch.einsum('npk,p->nk', Js, v))
+    del Js
+    lh = CategoricalLh()
+    lap = Laplace(model, 1.0, lh)
+    lap.infer([(X, y)], cov_type='diag')
+    prec = 1 / lap.Sigma_chol ** 2
+    out['diag_prec_at_idx'] = np_(prec[idx])
+    out['diag_prec_sum'] = np_(prec.double().sum())
+    lap = Laplace(model, 1.0, lh)
+    lap.infer([(X, y)], cov_type='kron')
+    for pi, qh in enumerate(lap.Sigma_chol.qhs):
+        for fi, m in enumerate(qh):
+            pv = randn(5000 + 10 * pi + fi, m.shape[0])
+            out['kron_q_%d_%d_mv' % (pi, fi)] = np_(m @ pv)
+            out['kron_q_%d_%d_tr' % (pi, fi)] = np_(m.diagonal().double().sum())
+    Xte = randn(16, 1, 3, 32, 32)
+    fmu, fvar = functional_sampling_predictive(Xte, model, GaussianLh(), lap.mu, lap.Sigma_chol, 2)
+    out['glm_fmu_kron'], out['glm_fvar_kron'] = np_(fmu), np_(fvar)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('%-12s P=%d  %.1f KB' % (name, P, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'cifar100net_probe':      # one case only (the others are unchanged)
+        probe100_case(refharness.load(), 'cifar100net_probe')
+        return
     preds = refharness.load()
     from preds.models import MLPS
     from preds.likelihoods import CategoricalLh, GaussianLh, BernoulliLh
@@ -368,6 +413,9 @@ def main():
 
     # (G) the reference tests' own CIFAR10Net fixture, probed
     probe_case(preds, 'cifar10net_probe')
+
+    # (K) CIFAR100Net, K = 100
+    probe100_case(preds, 'cifar100net_probe')
 
 
 if __name__ == '__main__':

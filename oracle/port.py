@@ -112,6 +112,29 @@ def make_cifar10net(in_channels=3, n_out=10, use_tanh=False):
     return net
 
 
+def make_cifar100net(in_channels=3, n_out=100):
+    """DeepOBS All-CNN-C; restates preds/models.py:182-236 (flat module list; TF-"same" padding as an explicit
+    SamePad2d in front of the padding-0 conv, conv7 unpadded, no ReLU after conv9)."""
+    spec = [(in_channels, 96, 3, 1, True), (96, 96, 3, 1, True), (96, 96, 3, 2, True),
+            (96, 192, 3, 1, True), (192, 192, 3, 1, True), (192, 192, 3, 2, True),
+            (192, 192, 3, 1, False), (192, 192, 1, 1, True), (192, n_out, 1, 1, True)]
+    mods = []
+    for i, (cin, cout, k, s, same) in enumerate(spec):
+        if same:
+            mods.append(SamePad2d(k, s))
+        mods.append(nn.Conv2d(cin, cout, k, stride=s))
+        if i + 1 < len(spec):
+            mods.append(nn.ReLU())
+    mods += [nn.AvgPool2d(6), nn.Flatten()]
+    net = nn.Sequential(*mods)
+    for m in net.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.constant_(m.bias, 0.1)
+            nn.init.xavier_normal_(m.weight)
+    net.output_size = n_out
+    return net
+
+
 def n_params(model):
     return sum(p.numel() for p in model.parameters())
 

@@ -132,19 +132,14 @@ def _check_kron_factors(kron, qref, names):
 
 
 def _check_eigen(kron):
-    """W diag(l) W^T reproduces the factor (1e-5 of its norm) and W is orthogonal: what an eigensolver guarantees."""
+    """W diag(l) W^T reproduces the factor and W is orthogonal, both to float32 accuracy (cuSOLVER's float32 syevd measured
+    3e-5..1e-4 / 3e-4 on these factors, which is why kron.symeig decomposes in float64)."""
     for qh, Ws, Ls in zip(kron.qhs, kron.Ws, kron.Lams):
         for Q, W, l in zip(qh, Ws, Ls):
             Qd, Wd, ld = Q.double(), W.double(), l.double()
             Qs = torch.triu(Qd) + torch.triu(Qd, 1).T                    # symeig reads the upper triangle
             assert float(((Wd * ld) @ Wd.T - Qs).norm() / Qs.norm().clamp_min(1e-30)) < 1e-5
-            assert float((Wd.T @ Wd - torch.eye(len(ld), dtype=torch.float64, device=W.device)).abs().max()) < 1e-4
-
-
-def _inject_eigen(kron, okron):
-    dev = kron.qhs[0][0].device
-    kron.Ws = [[w.to(dev).contiguous() for w in ws] for ws in okron.Ws]
-    kron.Lams = [[l.to(dev).contiguous() for l in ls] for ls in okron.Lams]
+            assert float((Wd.T @ Wd - torch.eye(len(ld), dtype=torch.float64, device=W.device)).abs().max()) < 1e-5
 
 
 def test_cfg4_cifar10net_batch256_against_oracle():
@@ -194,18 +189,28 @@ def test_cfg4_cifar10net_batch256_against_oracle():
     lap.infer([(X, y)], cov_type='kron')
     assert type(lap.Sigma_chol) is Kron
     _check_kron_factors(lap.Sigma_chol, post['kron'].qhs, names)
-    # --- the device eigendecomposition (one-off, cuSOLVER) is backward stable and orthogonal ...
+    # --- the device eigendecomposition (one-off; float64 cuSOLVER rounded to float32, see kron.symeig) is backward stable
+    #     and orthogonal to float32 accuracy ...
     _check_eigen(lap.Sigma_chol)
     # --- ... and the Kron GLM moments on 8 inputs agree with the as-written oracle (materialised Jacobians rotated per
-    #     parameter group) GIVEN THE SAME EIGENPAIRS, with the decisions the device takes on those inputs.  (The fp32
-    #     eigenvalues of the 1152 x 1152 factors differ between LAPACK and cuSOLVER by ~1e-7 of the largest one; where
-    #     l1*l2 is comparable to delta that moves 1/(l1*l2 + delta) by ~3e-4 -- a property of any fp32 eigensolver pair,
-    #     separated here from the GLM kernels under test.)
-    _inject_eigen(lap.Sigma_chol, post['kron'])
+    #     parameter group, LAPACK float32 eigenpairs), with the decisions the device takes on those inputs.
+    #     f_var = J (G (x) A + delta)^-1 J^T is ill-conditioned in the factors here: the conv A factors have eigenvalues
+    #     from 1e4 down to 0 and delta = 1, so a factor error of 7e-6 of its largest entry (what the split-bf16 Grams
+    #     deliver, asserted above at 1e-4) moves 1/(l1 l2 + delta) in the small-eigenvalue directions and the variance
+    #     by 1.7e-4 (measured; the oracle itself is 3e-5 from a float64 evaluation).  Stated bounds: 5e-4 with the
+    #     device's own factors, and the north-star 1e-4 for the GLM kernels themselves, i.e. with the oracle's factors
+    #     injected on the device (same posterior on both sides).
     dec_te, _ = routing.device_decisions(model, Xte)
     fmu_ref, fvar_ref = port.glm_moments(routing.routed_oracle(omodel, dec_te), Xte, post)
     fmu, fvar = glm_moments(Xte.cuda(), model, lap.mu, lap.Sigma_chol)
     assert cases.rel_err(fmu.cpu(), fmu_ref) < 5e-5
+    for n in range(8):
+        assert cases.rel_err(fvar[n].cpu(), fvar_ref[n]) < 5e-4, n
+    for qh, qr in zip(lap.Sigma_chol.qhs, post['kron'].qhs):
+        for m, r in zip(qh, qr):
+            m.copy_(r)
+    lap.Sigma_chol.decompose()
+    fmu, fvar = glm_moments(Xte.cuda(), model, lap.mu, lap.Sigma_chol)
     for n in range(8):
         assert cases.rel_err(fvar[n].cpu(), fvar_ref[n]) < TOL, n
 
@@ -246,7 +251,6 @@ def test_cfg3_mlp_512_against_oracle():
     assert type(lap.Sigma_chol) is Kron
     _check_kron_factors(lap.Sigma_chol, post_k['kron'].qhs, names)
     _check_eigen(lap.Sigma_chol)
-    _inject_eigen(lap.Sigma_chol, post_k['kron'])          # same eigenpairs on both sides (see the cfg4 test)
     fmu_ref, fvar_ref = port.glm_moments(omodel, Xte, post_k)
     fmu, fvar = glm_moments(Xte.cuda(), model, lap.mu, lap.Sigma_chol)
     assert cases.rel_err(fmu.cpu(), fmu_ref) < 1e-5

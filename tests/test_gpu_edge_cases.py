@@ -168,3 +168,71 @@ def test_full_covariance_too_large_fails_with_a_clear_message():
     X, y = torch.randn(4, 1, 28, 28).cuda(), torch.randint(10, (4,)).cuda()
     with pytest.raises(cabi.BnnpError, match="needs about"):
         lap.infer([(X, y)], cov_type='full')
+
+
+def test_back_to_back_posteriors_do_not_share_the_sigma_split():
+    """Two posteriors of equal P >= 1024 inferred one after the other (a prior-precision sweep, as the reference
+    experiments do): the bf16 hi/lo copies of Sigma that the TMA-fed GLM kernel keeps live ON the covariance tensor, so
+    a new Sigma that the caching allocator places at the freed one's address can never be served the old split."""
+    from preds_b200 import Laplace, CategoricalLh
+    from preds_b200.predictives import glm_moments, FULL_TMA_MIN_P
+    model, omodel = _pair(din=40, hid=(24,), K=3)                  # P = 40*24+24 + 24*3+3 = 1059
+    assert sum(p.numel() for p in model.parameters()) >= FULL_TMA_MIN_P
+    X, y = _data(300, 40, 3)
+    Xte, _ = _data(130, 40, 3, seed=16)
+    addrs, outs = [], []
+    for prior in (0.3, 30.0):
+        post = port.infer(omodel, prior, port.CategoricalLh(), [(X, y)], 'full')
+        _, fvar_ref = port.glm_moments(omodel, Xte, post)
+        lap = Laplace(model, prior, CategoricalLh())
+        lap.infer([(X, y)], cov_type='full')
+        addrs.append(lap.Sigma.data_ptr())
+        _, fvar = glm_moments(Xte, model, lap.mu, lap.Sigma)
+        assert cases.rel_err(fvar.cpu(), fvar_ref) < TOL, prior
+        outs.append(fvar.cpu())
+        del lap                                                     # frees Sigma: the next one may land on its address
+    assert cases.rel_err(outs[0], outs[1]) > 0.5                    # the two posteriors really differ
+    # an in-place update of Sigma invalidates the split as well
+    lap = Laplace(model, 0.3, CategoricalLh())
+    lap.infer([(X, y)], cov_type='full')
+    _, a = glm_moments(Xte, model, lap.mu, lap.Sigma)
+    lap.Sigma.mul_(4.0)
+    _, b = glm_moments(Xte, model, lap.mu, lap.Sigma)
+    assert cases.rel_err(b.cpu(), 4.0 * a.cpu()) < 1e-5
+
+
+def test_scalar_likelihoods_are_elementwise_on_any_shape():
+    """BernoulliLh / GaussianLh act on one output: inv_link / Hessian / residual are elementwise on [S, N] samples of a
+    model that flattens its output (preds/likelihoods.py:61-75 are plain sigmoid / p(1-p))."""
+    from preds_b200 import BernoulliLh, GaussianLh
+    g = torch.Generator().manual_seed(2)
+    fs = torch.randn(7, 33, generator=g).cuda()                     # [S, N]
+    ys = (torch.rand(7, 33, generator=g) > 0.5).float().cuda()
+    lh = BernoulliLh()
+    p = torch.sigmoid(fs)
+    assert torch.allclose(lh.inv_link(fs), p, atol=1e-6) and lh.inv_link(fs).shape == fs.shape
+    assert torch.allclose(lh.Hessian(fs), (p * (1 - p)).clamp(1e-7, 1 - 1e-7), atol=1e-6)
+    assert torch.allclose(lh.residual(ys, fs), ys - p, atol=1e-6)
+    gl = GaussianLh(0.5)
+    assert torch.equal(gl.inv_link(fs), fs)
+    assert torch.allclose(gl.residual(ys, fs), (ys - fs) / 0.25, atol=1e-5)
+
+
+def test_descriptor_verification_catches_small_functional_changes():
+    """A model that rescales between its leaf modules by 0.1 % computes something the layer trace cannot represent; the
+    build-time probe (now at fp32-forward accuracy, 2e-4 of the output scale, eight probe inputs) must refuse it."""
+    from preds_b200 import Jacobians
+    from preds_b200._cabi import BnnpError
+
+    class Scaled(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.act, self.b = nn.Linear(6, 9), nn.Tanh(), nn.Linear(9, 3)
+            self.output_size = 3
+
+        def forward(self, x):
+            return self.b(self.act(self.a(x)) * 1.001)
+
+    torch.manual_seed(0)
+    with pytest.raises(BnnpError):
+        Jacobians(Scaled().cuda(), torch.randn(4, 6).cuda())

@@ -170,6 +170,64 @@ def test_cifar10net_probe():
     assert cases.rel_err(out.cpu(), g['glm_kron']) < TOL
 
 
+def test_cifar100net_probe():
+    """CIFAR100Net (preds/models.py:182-236: nine convs with stride-2 and 1x1 ones, AvgPool2d(6), K = 100) on two
+    3x32x32 examples against the reference golden: Jacobians, diagonal GGN, KFLR factors, Kron GLM moments -- and the
+    wide-output likelihood / sampler kernels (csrc/wide_k.cu) against the oracle on the same injected draws."""
+    from preds_b200 import CIFAR100Net, CategoricalLh, Jacobians, Laplace, GGN
+    from preds_b200.predictives import glm_moments
+    from tests import routing
+    g = cases.load_golden('cifar100net_probe')
+    torch.manual_seed(71)
+    model = CIFAR100Net(3, 100)
+    omodel = port.make_cifar100net(3, 100)
+    port.set_theta(omodel, port.get_theta(model))
+    model = model.cuda()
+    X = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(15))
+    y = torch.from_numpy(g['y'])
+    idx = torch.from_numpy(g['theta_idx'])
+    P = sum(p.numel() for p in model.parameters())
+    assert P == 1387108
+    v = torch.randn(P, generator=torch.Generator().manual_seed(4243))
+    Js, f = Jacobians(model, X)
+    assert tuple(Js.shape) == (2, P, 100)
+    assert cases.rel_err(f.cpu(), g['f']) < 2e-5
+    assert cases.rel_err(Js[:, idx.cuda(), :].cpu(), g['Js_at_idx']) < 5e-5
+    assert cases.rel_err(torch.einsum('npk,p->nk', Js, v.cuda()).cpu(), g['Js_dot_v']) < 1e-4
+    del Js
+    # likelihood terms at K = 100 (warp-per-example kernels) against the oracle
+    lh, olh = CategoricalLh(), port.CategoricalLh()
+    fo = f.cpu()
+    assert cases.rel_err(lh.Hessian(f).cpu(), olh.hessian(fo)) < 1e-5
+    assert cases.rel_err(lh.residual(y.cuda(), f).cpu(), olh.residual(y, fo)) < 1e-5
+    assert cases.rel_err(lh.inv_link(f).cpu(), olh.inv_link(fo)) < 1e-5
+    lap = Laplace(model, 1.0, lh)
+    lap.infer([(X, y)], cov_type='diag')
+    assert cases.rel_err(lap.precision[idx.cuda()].cpu(), g['diag_prec_at_idx']) < TOL
+    assert abs(float(lap.precision.double().sum()) - float(g['diag_prec_sum'])) < 1e-4 * float(g['diag_prec_sum'])
+    lap = Laplace(model, 1.0, lh)
+    lap.infer([(X, y)], cov_type='kron')
+    for pi, qh in enumerate(lap.Sigma_chol.qhs):
+        for fi, m in enumerate(qh):
+            pv = torch.randn(m.shape[0], generator=torch.Generator().manual_seed(5000 + 10 * pi + fi))
+            assert cases.rel_err((m @ pv.cuda()).cpu(), g['kron_q_%d_%d_mv' % (pi, fi)]) < TOL, (pi, fi)
+    Xte = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(16))
+    fmu, fvar = glm_moments(Xte, model, lap.mu, lap.Sigma_chol)
+    assert cases.rel_err(fmu.cpu(), g['glm_fmu_kron']) < 2e-5
+    assert cases.rel_err(fvar.cpu(), g['glm_fvar_kron']) < TOL
+    # the wide sampler (block per input, 100 x 100 Cholesky in shared memory) on injected draws, with and without the
+    # fused mean, against torch on the SAME moments
+    S = 6
+    eps = torch.randn(S, 1, 100, generator=torch.Generator().manual_seed(711))
+    out = lap.predictive_samples_glm(Xte, n_samples=S, eps=eps)
+    Lc = torch.linalg.cholesky(fvar.double().cpu())
+    ref = torch.softmax(fmu.double().cpu().unsqueeze(0) + torch.einsum('nkl,snl->snk', Lc, eps.double()), dim=-1)
+    assert tuple(out.shape) == (S, 1, 100)
+    assert cases.rel_err(out.cpu(), ref) < TOL
+    mean = lap.predictive_mean_glm(Xte, n_samples=S, eps=eps)
+    assert cases.rel_err(mean.cpu(), ref.mean(0)) < TOL
+
+
 def test_oracle_same_inputs_midsize():
     """CUDA path vs the CPU oracle on a banana-shaped (config 1) problem at a size the oracle
     finishes in seconds: MLPS(2,[50,50],2), N=600, two loader batches, all three structures."""

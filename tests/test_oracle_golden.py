@@ -123,3 +123,34 @@ def test_cifar10net_probe():
     fmu, fvar = port.glm_moments(model, Xte, post)
     assert cases.rel_err(fmu, g['glm_fmu_kron']) < 1e-5
     assert cases.rel_err(fvar, g['glm_fvar_kron']) < TOL
+
+
+def test_cifar100net_probe():
+    """CIFAR100Net (preds/models.py:182-236, K = 100: stride-2 and 1x1 convs, AvgPool2d(6)) on two 32x32 examples,
+    probed: the oracle's restatement of the model and of the BackPACK quantities at K = 100."""
+    g = cases.load_golden('cifar100net_probe')
+    torch.manual_seed(71)
+    model = port.make_cifar100net(3, 100)
+    theta = port.get_theta(model)
+    idx = torch.from_numpy(g['theta_idx'])
+    assert np.array_equal(theta[idx].numpy(), g['theta_at_idx'])   # same init stream
+    X = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(15))
+    y = torch.from_numpy(g['y'])
+    v = torch.randn(len(theta), generator=torch.Generator().manual_seed(4243))
+    Js, f = port.jacobians(model, X)
+    assert cases.rel_err(f, g['f']) < 1e-5
+    assert cases.rel_err(Js[:, idx, :], g['Js_at_idx']) < 1e-5
+    assert cases.rel_err(torch.einsum('npk,p->nk', Js, v), g['Js_dot_v']) < 1e-4
+    del Js
+    lh = port.CategoricalLh()
+    post = port.infer(model, 1.0, lh, [(X, y)], 'diag')
+    assert cases.rel_err(post['precision'][idx], g['diag_prec_at_idx']) < 1e-5
+    post = port.infer(model, 1.0, lh, [(X, y)], 'kron')
+    for pi, qh in enumerate(post['kron'].qhs):
+        for fi, m in enumerate(qh):
+            pv = torch.randn(m.shape[0], generator=torch.Generator().manual_seed(5000 + 10 * pi + fi))
+            assert cases.rel_err(m @ pv, g['kron_q_%d_%d_mv' % (pi, fi)]) < 1e-4
+    Xte = torch.randn(1, 3, 32, 32, generator=torch.Generator().manual_seed(16))
+    fmu, fvar = port.glm_moments(model, Xte, post)
+    assert cases.rel_err(fmu, g['glm_fmu_kron']) < 1e-5
+    assert cases.rel_err(fvar, g['glm_fvar_kron']) < TOL
