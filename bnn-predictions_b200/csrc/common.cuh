@@ -31,6 +31,7 @@ struct BnnpOptions {
   int glm_simt;        // kron / diag GLM contractions on the fp32 SIMT kernels with the unfused reductions
   int debug_sync;      // synchronise and report after every GLM TMA launch
   int net_simt;        // forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size (parity bisection)
+  int gemm_generated;  // 1: Linear-layer products / KFAC Grams on the generated-operand tensor-core GEMM instead of the TMA-fed one (A/B timing)
 };
 extern BnnpOptions g_bnnp_opt;
 

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 #include "gram_tc.cuh"
 
 namespace bnnp {
@@ -654,6 +655,10 @@ extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, con
       int64_t a = (int64_t)tcg::pick_ksplit(m, m, N * V, 1) * m * m, b = (int64_t)tcg::pick_ksplit(n, n, N, 1) * n * n;
       part = part > a ? part : a;
       part = part > b ? part : b;
+      a = gram_tma_scratch_floats(N * V, m);
+      b = gram_tma_scratch_floats(N, n);
+      part = part > a ? part : a;
+      part = part > b ? part : b;
     }
     if (ops[i].kind == BNNP_OP_CONV2D) {
       int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
@@ -686,7 +691,11 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
       float* wsk = scratch + kfac_conv_floats(ops, n_ops, N, V);
       // (a narrow Gram over many rows -- the 10 x 10 factor of the output layer over N*K rows -- is ONE SIMT block
       // walking all rows: 3.5 ms of a 6.2 ms pass; split-K on the tensor cores spreads it over the machine)
-      if (!g_bnnp_opt.net_simt && ((long long)o.out_c * o.out_c * R >= kTcMinMacsG || R >= 2048))
+      const bool tma = g_bnnp_opt.gemm_generated == 0;
+      if (!g_bnnp_opt.net_simt && tma && ((long long)o.out_c * o.out_c * R >= kTcMinMacsG || R >= 2048))
+        // G += factor * g^T g: transposed bf16 hi/lo split of the gradients once, then a TMA-fed tensor-core Gram
+        rc = gram_tma(G, q.grad_ld, R, o.out_c, factor, 1.f, Gf, o.out_c, wsk, st);
+      else if (!g_bnnp_opt.net_simt && ((long long)o.out_c * o.out_c * R >= kTcMinMacsG || R >= 2048))
         rc = tcg::gemm_tc_splitk(o.out_c, o.out_c, R, 1, tcg::TcColMajor{G, q.grad_ld, 0}, tcg::TcColMajor{G, q.grad_ld, 0},
                                  factor, 1.f, Gf, o.out_c, 0, wsk, tcg::pick_ksplit(o.out_c, o.out_c, R, 1), st);
       else
@@ -694,7 +703,9 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
                        AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       const float* A = ws + plan->acat_off;
-      if (!g_bnnp_opt.net_simt && ((long long)o.in_c * o.in_c * N >= kTcMinMacsG || N >= 2048))
+      if (!g_bnnp_opt.net_simt && tma && ((long long)o.in_c * o.in_c * N >= kTcMinMacsG || N >= 2048))
+        rc = gram_tma(A + q.lin_col, plan->Dtot, N, o.in_c, batch_factor / (float)N, 1.f, Af, o.in_c, wsk, st);
+      else if (!g_bnnp_opt.net_simt && ((long long)o.in_c * o.in_c * N >= kTcMinMacsG || N >= 2048))
         rc = tcg::gemm_tc_splitk(o.in_c, o.in_c, N, 1, tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0},
                                  tcg::TcColMajor{A + q.lin_col, plan->Dtot, 0}, batch_factor / (float)N, 1.f, Af, o.in_c,
                                  0, wsk, tcg::pick_ksplit(o.in_c, o.in_c, N, 1), st);

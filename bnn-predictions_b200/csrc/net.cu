@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace bnnp {
 
@@ -510,6 +511,14 @@ extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, 
         if (i > first_param && N * V * E * L > v) v = N * V * E * L;  // backward-data: dU^T [N*V, E, L]
         need = need > v ? need : v;
       }
+    // bf16 hi/lo operand copies of the TMA-fed Linear-layer products (forward over N rows, backward over N*V rows)
+    for (int i = 0; i < n_ops; ++i)
+      if (ops[i].kind == BNNP_OP_LINEAR) {
+        int64_t f = linear_tma_scratch_floats(N, ops[i].in_c, ops[i].out_c);
+        int64_t b = linear_tma_scratch_floats(N * V, ops[i].out_c, ops[i].in_c);
+        need = need > f ? need : f;
+        if (i > first_param) need = need > b ? need : b;
+      }
     if (need > 0) P.conv_scratch_off = take(need);
   }
   P.total_floats = cur;
@@ -544,7 +553,12 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
         fill_col_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(slice + o.in_c, plan->Dtot, N, 1.f);
         BNNP_LAUNCH_CHECK();
         int rc;
-        if (!g_bnnp_opt.net_simt && (long long)N * o.out_c * o.in_c >= kTcMinMacs)
+        if (!g_bnnp_opt.net_simt && (long long)N * o.out_c * o.in_c >= kTcMinMacs && plan->conv_scratch_off >= 0 &&
+            o.in_c <= 4096 && g_bnnp_opt.gemm_generated == 0)
+          // TMA-fed tensor-core product on bf16 hi/lo copies of the activations and the weights (gemm_tma.cu)
+          rc = linear_tma(slice, plan->Dtot, N, o.in_c, o.weight, o.in_c, o.out_c, 0, o.has_bias ? o.bias : nullptr, out,
+                          q.act_ld, ws + plan->conv_scratch_off, st);
+        else if (!g_bnnp_opt.net_simt && (long long)N * o.out_c * o.in_c >= kTcMinMacs)
           rc = tcg::gemm_tc(N, o.out_c, o.in_c, 1, tcg::TcRowMajor{slice, plan->Dtot, 0},
                             tcg::TcRowMajor{o.weight, o.in_c, 0},
                             TcStoreBias(out, q.act_ld, o.has_bias ? o.bias : nullptr), 1, st);
@@ -637,7 +651,11 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
     switch (o.kind) {
       case BNNP_OP_LINEAR: {
         int rc;
-        if (!g_bnnp_opt.net_simt && (long long)R * o.in_c * o.out_c >= kTcMinMacs)
+        if (!g_bnnp_opt.net_simt && (long long)R * o.in_c * o.out_c >= kTcMinMacs && plan->conv_scratch_off >= 0 &&
+            o.out_c <= 4096 && g_bnnp_opt.gemm_generated == 0)
+          rc = linear_tma(gout, q.grad_ld, R, o.out_c, o.weight, o.in_c, o.in_c, 1, nullptr, gin, qp.grad_ld,
+                          ws + plan->conv_scratch_off, st);
+        else if (!g_bnnp_opt.net_simt && (long long)R * o.in_c * o.out_c >= kTcMinMacs)
           rc = tcg::gemm_tc(R, o.in_c, o.out_c, 1, tcg::TcRowMajor{gout, q.grad_ld, 0},
                             tcg::TcColMajor{o.weight, o.in_c, 0},
                             tcg::TcStoreAxpby(gin, qp.grad_ld, 0, 1.f, 0.f), 1, st);

@@ -324,6 +324,18 @@ int64_t bnnp_sgemm_tc_scratch_floats(int64_t M, int64_t N, int64_t K);
 int bnnp_sgemm_tc(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
                   int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
                   float* scratch, void* stream);
+/* TMA-fed tensor-core GEMM on operands that were split ONCE into bf16 hi / lo copies (fp32-grade: three MMAs per product):
+ * C[M,N] = alpha * sum_k A[m,k] B[n,k] + beta * C; A [M, lda], B [N, ldb] k-contiguous, lda / ldb multiples of 8 elements,
+ * 16-byte aligned.  bnnp_split_bf16 makes such copies of a row-major matrix, bnnp_split_bf16_t of its transpose
+ * (hi/lo[c, r] = src[r, c], row pitch `pitch` >= rows).  scratch: bnnp_gemm_nt_scratch_floats() floats (split-K
+ * partials, one TMEM accumulation never spans more than 4096 k); may be NULL for K <= 4096.  Used by the Linear-layer
+ * products and the KFAC Grams (preds/kron.py:58-69, preds/laplace.py:69-78). */
+int64_t bnnp_gemm_nt_scratch_floats(int64_t M, int64_t N, int64_t K);
+int bnnp_gemm_nt_split(int64_t M, int64_t N, int64_t K, float alpha, const void* Ah, const void* Al, int64_t lda,
+                       const void* Bh, const void* Bl, int64_t ldb, float beta, float* C, int64_t ldc,
+                       float* scratch, void* stream);
+int bnnp_split_bf16_t(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t pitch, void* hi, void* lo,
+                      void* stream);
 /* y += alpha * x  (Kron.update axpy, preds/kron.py:62-66). */
 int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream);
 
@@ -336,7 +348,8 @@ uint64_t bnnp_launch_count(void);
  * environment; none of them makes a kernel skip work):  "gram_kernel" 0 auto / 1 single-CTA kernel,
  * "glm_single" 1 = single-CTA full-covariance GLM kernel, "glm_simt" 1 = kron / diag GLM contractions on the fp32
  * SIMT kernels, "debug_sync" 1 = synchronise after every GLM TMA launch,
- * "net_simt" 1 = forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size.  Unknown name: BNNP_ERR_INVALID. */
+ * "net_simt" 1 = forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size,
+ * "gemm_generated" 1 = Linear-layer products / KFAC Grams on the generated-operand GEMM instead of the TMA-fed one.  Unknown name: BNNP_ERR_INVALID. */
 int bnnp_set_option(const char* name, int value);
 int bnnp_get_option(const char* name);
 int bnnp_prof_enable(int on);

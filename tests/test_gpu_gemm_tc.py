@@ -42,3 +42,24 @@ def test_sgemm_simt_matches_too():
     C = torch.zeros(200, 150, device='cuda')
     check(lib.bnnp_sgemm(0, 0, 200, 150, 300, 1.0, ptr(A), 300, ptr(B), 150, 0.0, ptr(C), 150, stream()))
     assert float((C - A @ B).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize('shape', [(300, 200, 1000), (129, 17, 9000), (10, 10, 40960), (1024, 1024, 5000), (77, 513, 33)])
+def test_gemm_nt_split_tma(shape):
+    """bnnp_gemm_nt_split (TMA-fed, operands pre-split into bf16 hi/lo by bnnp_split_bf16 / bnnp_split_bf16_t) against
+    fp64: ragged M / N / K tails, K > 4096 (split-K partials, one TMEM accumulation <= 4096 k), alpha / beta."""
+    from preds_b200._cabi import lib, check, ptr, stream
+    M, N, K = shape
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(M, K, generator=g).cuda()
+    Bt = torch.randn(K, N, generator=g).cuda()                # B given transposed: exercises bnnp_split_bf16_t
+    C = torch.randn(M, N, generator=g).cuda()
+    Kp = (K + 7) // 8 * 8
+    ah, al = (torch.empty(M, Kp, dtype=torch.bfloat16, device='cuda') for _ in range(2))
+    bh, bl = (torch.empty(N, Kp, dtype=torch.bfloat16, device='cuda') for _ in range(2))
+    check(lib.bnnp_split_bf16(ptr(A), K, M, K, ptr(ah), ptr(al), stream()))
+    check(lib.bnnp_split_bf16_t(ptr(Bt), N, K, N, Kp, ptr(bh), ptr(bl), stream()))
+    sc = torch.empty(int(lib.bnnp_gemm_nt_scratch_floats(M, N, K)), device='cuda')
+    want = 0.7 * (A.double() @ Bt.double()) - 0.3 * C.double()
+    check(lib.bnnp_gemm_nt_split(M, N, K, 0.7, ptr(ah), ptr(al), Kp, ptr(bh), ptr(bl), Kp, -0.3, ptr(C), N, ptr(sc), stream()))
+    assert float((C.double() - want).abs().max() / want.abs().max()) < 2e-5
