@@ -25,7 +25,8 @@ constexpr int BK = 32, TILE_M = 128, MAX_N = 256, STAGES = 4;
 constexpr int A_TERM = TILE_M * BK * 2, A_STAGE = 2 * A_TERM;      // hi + lo: 16 KB
 constexpr int B_TERM = MAX_N * BK * 2, B_STAGE = 2 * B_TERM;       // 32 KB
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;                     // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int EPI_TILE_BYTES = 32 * 33 * 4 + 32;                   // per epilogue warp: [32][33] fp32 transpose tile
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_TILE_BYTES;
 constexpr int NUM_THREADS = 256;      // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue (one per TMEM lane quarter)
 constexpr int EPI_WARP0 = 4;
 constexpr int kMaxChunksPerAccum = 128;
@@ -117,34 +118,41 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         }
       }
     } else if (warp >= EPI_WARP0) {
-      // epilogue: thread = accumulator row, 32 columns per tcgen05.ld; every thread writes 128 contiguous bytes
+      // epilogue: tcgen05.ld hands every thread one accumulator row (32 columns per load); a per-warp shared-memory
+      // transpose turns that into lane = column, so that every store instruction of the warp writes 128 contiguous
+      // bytes of one output row (thread-per-row stores touch 32 cache lines per instruction: measured 41 us per
+      // 128 x 256 tile against 6.6 us of MMA time on the K = 512 backward product)
       const int q = warp - EPI_WARP0;
+      float* sc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + q * EPI_TILE_BYTES);
       mbar_wait(&acc_full[buf], buf_phase);
       tc_fence_after();
-      const long long row = m0 + q * 32 + lane;
+      const long long rbase = m0 + q * 32;
+      int nrows = (int)(args.M - rbase < 32 ? (args.M - rbase < 0 ? 0 : args.M - rbase) : 32);
       const int ncols = (int)(args.N - n0 < args.wn ? args.N - n0 : args.wn);
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
-        if (row < args.M) {
-          const int nv = ncols - c0 < 32 ? ncols - c0 : 32;
-          if (args.ksplit > 1) {
-            float* p = args.part + ((long long)ks * args.M + row) * args.N + n0 + c0;
+        __syncwarp();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) if (e < nv) p[e] = __uint_as_float(v[e]);
+        for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(v[e]);
+        __syncwarp();
+        const bool colok = c0 + lane < ncols;
+        if (args.ksplit > 1) {
+          float* p = args.part + ((long long)ks * args.M + rbase) * args.N + n0 + c0 + lane;
+#pragma unroll 8
+          for (int u = 0; u < 32; ++u)
+            if (colok && u < nrows) p[(long long)u * args.N] = sc[u * 33 + lane];
+        } else {
+          float* p = args.C + rbase * args.ldc + n0 + c0 + lane;
+          const float b = (args.bias && colok) ? __ldg(args.bias + n0 + c0 + lane) : 0.f;
+          if (args.beta == 0.f) {
+#pragma unroll 8
+            for (int u = 0; u < 32; ++u)
+              if (colok && u < nrows) p[(long long)u * args.ldc] = fmaf(args.alpha, sc[u * 33 + lane], b);
           } else {
-            float* p = args.C + row * args.ldc + n0 + c0;
-            if (args.bias) {
-              const float* b = args.bias + n0 + c0;
-#pragma unroll
-              for (int e = 0; e < 32; ++e) if (e < nv) p[e] = fmaf(args.alpha, __uint_as_float(v[e]), __ldg(b + e));
-            } else if (args.beta == 0.f) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) if (e < nv) p[e] = args.alpha * __uint_as_float(v[e]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) if (e < nv) p[e] = fmaf(args.alpha, __uint_as_float(v[e]), args.beta * p[e]);
-            }
+#pragma unroll 8
+            for (int u = 0; u < 32; ++u)
+              if (colok && u < nrows) p[(long long)u * args.ldc] = fmaf(args.alpha, sc[u * 33 + lane], args.beta * p[(long long)u * args.ldc]);
           }
         }
       }
@@ -173,18 +181,33 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int kspli
 }
 
 // ---- operand preparation ------------------------------------------------------------------------------------------
-// hi/lo[r, c] = bf16 split of f(src[r*lds + c]) for c < cols, 0 for cols <= c < pitch   (k = c contiguous)
+// hi/lo[r, c] = bf16 split of f(src[r*lds + c]) for c < cols, 0 for cols <= c < pitch   (k = c contiguous).
+// One thread per 8 consecutive columns (pitch is a multiple of 8): two 16-byte stores; 16-byte loads when the source
+// row allows it.
 template <bool SQUARE>
 __global__ void split_rows_kernel(const float* __restrict__ src, long long lds, long long rows, long long cols,
                                   long long pitch, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * pitch) return;
-  const long long r = i / pitch, c = i % pitch;
-  float v = c < cols ? src[r * lds + c] : 0.f;
-  if (SQUARE) v *= v;
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  hi[i] = h;
-  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  const long long p8 = pitch >> 3;
+  if (i >= rows * p8) return;
+  const long long r = i / p8, c = (i % p8) << 3;
+  const float* q = src + r * lds + c;
+  float v[8];
+  if (c + 8 <= cols && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(q)), y = __ldg(reinterpret_cast<const float4*>(q) + 1);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = c + e < cols ? __ldg(q + e) : 0.f;
+  }
+  if (SQUARE) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= v[e];
+  }
+  uint4 h, l;
+  split8(v, h, l);
+  *reinterpret_cast<uint4*>(hi + r * pitch + c) = h;
+  *reinterpret_cast<uint4*>(lo + r * pitch + c) = l;
 }
 // hi/lo[c, r] = bf16 split of f(src[r*lds + c])  (k = r contiguous, pitch >= rows, zero padded); 32 x 32 smem transpose
 template <bool SQUARE>
@@ -321,7 +344,7 @@ int split_rows(const float* src, int64_t lds, int64_t rows, int64_t cols, int64_
                __nv_bfloat16* lo, bool square, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return BNNP_OK;
   if (pitch < cols || (pitch & 7)) return BNNP_ERR_INVALID;
-  const unsigned grid = (unsigned)ceil_div64(rows * pitch, 256);
+  const unsigned grid = (unsigned)ceil_div64(rows * (pitch >> 3), 256);
   if (square) tg::split_rows_kernel<true><<<grid, 256, 0, st>>>(src, lds, rows, cols, pitch, hi, lo);
   else tg::split_rows_kernel<false><<<grid, 256, 0, st>>>(src, lds, rows, cols, pitch, hi, lo);
   BNNP_LAUNCH_CHECK();
@@ -363,7 +386,8 @@ int64_t linear_tma_scratch_floats(int64_t R, int64_t k, int64_t n_out) {
   return up64(R * up8(k)) + up64(n_out * up8(k)) + 128;
 }
 int linear_tma(const float* X, int64_t ldx, int64_t R, int64_t k, const float* W, int64_t ldw, int64_t n_out,
-               int w_transposed, const float* bias, float* Y, int64_t ldy, float* scratch, cudaStream_t st) {
+               int w_transposed, const float* bias, float* Y, int64_t ldy, float* scratch, cudaStream_t st,
+               int square_x) {
   if (k > 4096) return BNNP_ERR_UNSUPPORTED;             // one TMEM accumulation per output (no partials here)
   const int64_t kp = up8(k);
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 15) & ~uintptr_t(15));
@@ -371,7 +395,7 @@ int linear_tma(const float* X, int64_t ldx, int64_t R, int64_t k, const float* W
   __nv_bfloat16* xl = xh + R * kp;
   __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(base + up64(R * kp));
   __nv_bfloat16* wl = wh + n_out * kp;
-  int rc = split_rows(X, ldx, R, k, kp, xh, xl, false, st);
+  int rc = split_rows(X, ldx, R, k, kp, xh, xl, square_x != 0, st);
   if (rc) return rc;
   rc = w_transposed ? split_transposed(W, ldw, k, n_out, kp, wh, wl, false, st)
                     : split_rows(W, ldw, n_out, k, kp, wh, wl, false, st);

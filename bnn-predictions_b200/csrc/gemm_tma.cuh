@@ -24,6 +24,8 @@ int gram_tma(const float* S, int64_t lds, int64_t R, int64_t m, float alpha, flo
 // Y[R, n_out] = X[R, k] * op(W) (+ bias):  w_transposed == 0: W is [n_out, k] (row pitch ldw), Y = X W^T  (forward);
 // w_transposed == 1: W is [k, n_out], Y = X W (backward-data).  scratch: linear_tma_scratch_floats().
 int64_t linear_tma_scratch_floats(int64_t R, int64_t k, int64_t n_out);
+// square_x != 0: X is squared element-wise before the split (the diagonal / Kronecker variance contractions).
 int linear_tma(const float* X, int64_t ldx, int64_t R, int64_t k, const float* W, int64_t ldw, int64_t n_out,
-               int w_transposed, const float* bias, float* Y, int64_t ldy, float* scratch, cudaStream_t st);
+               int w_transposed, const float* bias, float* Y, int64_t ldy, float* scratch, cudaStream_t st,
+               int square_x = 0);
 }  // namespace bnnp

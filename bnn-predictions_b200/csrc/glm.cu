@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace bnnp {
 
@@ -692,6 +693,13 @@ static int64_t conv_block_floats(const bnnp_op_t* ops, int n_ops, int64_t N, int
 extern "C" int64_t bnnp_glm_fvar_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                                      int64_t N) {
   int64_t lin = N * (int64_t)plan->Mtot;
+  int64_t tma = 0;                    // bf16 hi/lo operand copies of the TMA-fed contraction T = (a^2) sigma2^T
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == BNNP_OP_LINEAR) {
+      int64_t t = linear_tma_scratch_floats(N, ops[i].in_c, ops[i].out_c);
+      tma = tma > t ? tma : t;
+    }
+  lin += tma + 64;
   int64_t cv = conv_block_floats(ops, n_ops, N, plan->K);
   return (lin > cv ? lin : cv) + 64;
 }
@@ -714,7 +722,10 @@ extern "C" int bnnp_glm_fvar_diag(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       // (the bias variance is the constant term wb[u] of the fused reduction when the tensor-core path is taken)
       const bool simt = glm_force_simt();
       const bool tcpath = !simt && (long long)N * o.out_c * o.in_c >= kTcMinMacsK && K <= 16;
-      if (tcpath)
+      if (tcpath && g_bnnp_opt.gemm_generated == 0 && o.in_c <= 4096)
+        rc = linear_tma(ws + plan->acat_off + q.lin_col, plan->Dtot, N, o.in_c, sigma2 + o.theta_off_w, o.in_c, o.out_c, 0,
+                        nullptr, scratch, o.out_c, scratch + N * (int64_t)plan->Mtot + 32, st, 1);
+      else if (tcpath)
         rc = tcg::gemm_tc(N, o.out_c, o.in_c, 1, TcRowMajorSq{ws + plan->acat_off + q.lin_col, plan->Dtot},
                           tcg::TcRowMajor{sigma2 + o.theta_off_w, o.in_c, 0}, tcg::TcStoreAxpby(scratch, o.out_c, 0, 1.f, 0.f),
                           1, st);
@@ -855,7 +866,12 @@ extern "C" int64_t bnnp_glm_fvar_kron_scratch_floats(const bnnp_op_t* ops, int n
     const bnnp_op_t& o = ops[i];
     if (!is_param_op(o)) continue;
     int64_t m = o.out_c, n = (int64_t)o.in_c * o.kh * o.kw, v;
-    if (o.kind == BNNP_OP_LINEAR) v = N * n + N * K * m + N * m + m * n + m;
+    if (o.kind == BNNP_OP_LINEAR) {
+      v = N * n + N * K * m + N * m + m * n + m;
+      // bf16 hi/lo operand copies of the TMA-fed rotations
+      int64_t t = linear_tma_scratch_floats(N * K, m, m), t2 = linear_tma_scratch_floats(N, n, n > m ? n : m);
+      v += (t > t2 ? t : t2) + 64;
+    }
     else v = 3 * N * K * m * n + 2 * N * K * m + m * n + m + 128 +
              N * (int64_t)o.out_h * o.out_w * ((n + 3) / 4 * 4);      // + unfolded input of the tensor-core path
     mx = v > mx ? v : mx;
@@ -888,16 +904,23 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       float* T = Gh + R * m;               // [N, m]    Dinv (Ah^2)
       float* D = T + N * m;                // [m, n]
       float* db = D + (int64_t)m * n;      // [m]
-      // the three contractions go to the tensor cores (split-bf16, fp32-grade) once they are large enough
+      float* tsc = db + m + 32;            // operand copies of the TMA-fed products
+      // the three contractions go to the tensor cores (split-bf16, fp32-grade) once they are large enough: TMA-fed
+      // on bf16 hi/lo copies of the operands (gemm_tma.cu), or with generated operands (option gemm_generated)
       const float* Ain = ws + plan->acat_off + q.lin_col;
       const bool simt = glm_force_simt();
-      if (!simt && (long long)N * n * n >= kTcMinMacsK)
+      const bool tma = g_bnnp_opt.gemm_generated == 0 && n <= 4096 && m <= 4096;
+      if (!simt && tma && (long long)N * n * n >= kTcMinMacsK)
+        rc = linear_tma(Ain, plan->Dtot, N, n, W2, n, n, 1, nullptr, Ah, n, tsc, st);
+      else if (!simt && (long long)N * n * n >= kTcMinMacsK)
         rc = tcg::gemm_tc(N, n, n, 1, tcg::TcRowMajor{Ain, plan->Dtot, 0}, tcg::TcColMajor{W2, n, 0},
                           tcg::TcStoreAxpby(Ah, n, 0, 1.f, 0.f), 1, st);
       else
         rc = gemm_simt(N, n, n, 1, LoadRowMajorA{Ain, plan->Dtot, 0}, LoadRowMajorB{W2, n, 0}, StoreAxpby{Ah, n, 0, 1.f, 0.f}, st);
       if (rc) return rc;
-      if (!simt && (long long)R * m * m >= kTcMinMacsK)
+      if (!simt && tma && (long long)R * m * m >= kTcMinMacsK)
+        rc = linear_tma(G, q.grad_ld, R, m, W1, m, m, 1, nullptr, Gh, m, tsc, st);
+      else if (!simt && (long long)R * m * m >= kTcMinMacsK)
         rc = tcg::gemm_tc(R, m, m, 1, tcg::TcRowMajor{G, q.grad_ld, 0}, tcg::TcColMajor{W1, m, 0},
                           tcg::TcStoreAxpby(Gh, m, 0, 1.f, 0.f), 1, st);
       else
@@ -905,7 +928,9 @@ extern "C" int bnnp_glm_fvar_kron(const bnnp_op_t* ops, int n_ops, const bnnp_pl
       if (rc) return rc;
       kron_dinv_kernel<<<(unsigned)ceil_div64((int64_t)m * n, 256), 256, 0, st>>>(l1, l2, m, n, delta_w[i], dampen, 0, D);
       BNNP_LAUNCH_CHECK();
-      if (!simt && (long long)N * m * n >= kTcMinMacsK)
+      if (!simt && tma && (long long)N * m * n >= kTcMinMacsK)
+        rc = linear_tma(Ah, n, N, n, D, n, m, 0, nullptr, T, m, tsc, st, 1);           // T = (Ah^2) D^T
+      else if (!simt && (long long)N * m * n >= kTcMinMacsK)
         rc = tcg::gemm_tc(N, m, n, 1, TcRowMajorSq{Ah, n}, tcg::TcRowMajor{D, n, 0}, tcg::TcStoreAxpby(T, m, 0, 1.f, 0.f), 1, st);
       else
         rc = gemm_simt(N, m, n, 1, LoadSqRows{Ah, n}, LoadDinvT{D, n}, StoreAxpby{T, m, 0, 1.f, 0.f}, st);

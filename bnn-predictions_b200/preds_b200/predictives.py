@@ -70,23 +70,32 @@ def glm_moments(X, model, mu, Sigma, engine=0, return_f=False):
     N, K, P = X.shape[0], None, net.P
     net.prepare(X[:1])
     K = net.K
-    # chunk size from the scratch the chosen structure needs per input
+    # chunk size from the scratch the chosen structure needs: a constant part (weight-sized buffers) plus a part per input,
+    # separated by evaluating the library's own sizing function at two batch sizes
+    def per_input(fn):
+        lo, hi = int(fn(1)), int(fn(257))
+        per = max(1, (hi - lo) // 256)
+        return per, max(0, lo - per)
+
     if isinstance(Sigma, Kron):
-        per = max(1, int(lib.bnnp_glm_fvar_kron_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(1, K)), 1)))
+        per, const = per_input(lambda n: lib.bnnp_glm_fvar_kron_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(n, K)), n))
         cap = 65535 // K if not net.linear_only else 1 << 30      # the batched conv kernels index rows with 16 bits
     elif Sigma.dim() == 2:
         if engine == 0:
             engine = 3 if P >= FULL_TMA_MIN_P else 1
         if engine == 3:
-            per = max(1, int(lib.bnnp_glm_fvar_full_tma_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(64, K)), 64)) // 64)
+            per, const = per_input(lambda n: lib.bnnp_glm_fvar_full_tma_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(n, K)), n))
             split = sigma_split(Sigma)
         else:
-            per = max(1, int(lib.bnnp_glm_fvar_full_scratch_floats(C.byref(net.plan(64, K)), 64, engine)) // 64)
+            per, const = per_input(lambda n: lib.bnnp_glm_fvar_full_scratch_floats(C.byref(net.plan(n, K)), n, engine))
         cap = 1 << 30
     else:
-        per = max(1, int(lib.bnnp_glm_fvar_diag_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(1, K)), 1)))
+        per, const = per_input(lambda n: lib.bnnp_glm_fvar_diag_scratch_floats(net.ops, net.n_ops, C.byref(net.plan(n, K)), n))
         cap = 65535 // K if not net.linear_only else 1 << 30
-    chunk = max(1, min(N, cap, SCRATCH_BUDGET_FLOATS // per))
+    # the layer-factor workspace of the same chunk counts against the budget too
+    wper = max(1, (int(net.plan(257, K).total_floats) - int(net.plan(1, K).total_floats)) // 256)
+    per += wper
+    chunk = max(1, min(N, cap, max(1, SCRATCH_BUDGET_FLOATS - const) // per))
     f_mu = torch.empty(N, K, dtype=torch.float32, device=net.device)
     f_var = torch.empty(N, K, K, dtype=torch.float32, device=net.device)
     f_all = torch.empty(N, K, dtype=torch.float32, device=net.device) if return_f else None
