@@ -5,6 +5,7 @@
 //   kron : G_l += factor * sum s s^T, A_l += bf/N * sum a a^T   preds/laplace.py:73-78, kron.py:58-69
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "tc_common.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tma.cuh"
 #include "gram_tc.cuh"
@@ -231,6 +232,29 @@ __global__ void im2col_kernel(Im2col u, int64_t N, int L, int E, int Epad, float
   const int e = (int)(i % Epad);
   const int64_t rp = i / Epad;
   U[i] = e < E ? u.at(rp / L, (int)(rp % L), e) : 0.f;
+}
+
+// Ut_hi/lo[e, rp] = bf16 split of unfold(in[n])[e, pos], rp = n*L + pos (k = rp contiguous, row pitch NLp, zero padded):
+// the transposed, pre-split operand of the TMA-fed A-factor Gram  A = U^T U  (BackPACK KFLR, conv layers), written in one
+// pass over the layer input instead of an fp32 im2col buffer that a generated-operand GEMM then re-reads.
+// One thread per 8 consecutive rp (16-byte stores).
+__global__ void im2col_t_split_kernel(Im2col u, int64_t N, int L, int E, int64_t NLp, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p8 = NLp >> 3;
+  if (i >= (int64_t)E * p8) return;
+  const int e = (int)(i / p8);
+  const int64_t rp0 = (i % p8) << 3;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int64_t rp = rp0 + k;
+    v[k] = rp < N * L ? u.at(rp / L, (int)(rp % L), e) : 0.f;
+  }
+  uint4 h, l;
+  tcp::split8(v, h, l);
+  *reinterpret_cast<uint4*>(hi + (int64_t)e * NLp + rp0) = h;
+  *reinterpret_cast<uint4*>(lo + (int64_t)e * NLp + rp0) = l;
 }
 
 // ---- conv weight diag on the tensor cores: one [Cout x L]·[L x E] product per row r = (n,v) as a batched gemm_tc whose
@@ -545,6 +569,10 @@ extern "C" int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops,
       int64_t mm = ops[i].out_c, nn = ops[i].in_c + 1;
       int64_t v = (1 + tcg::pick_ksplit(mm, nn, N, 1)) * mm * nn + 128;
       lin = lin > v ? lin : v;
+      // TMA-fed variant: transposed bf16 hi/lo copies of Q and a^2 + the split-K partials
+      const int64_t Np = (N + 7) / 8 * 8;
+      v = mm * nn + 64 + (mm * Np + 63) / 64 * 64 + (nn * Np + 63) / 64 * 64 + gemm_tma_scratch_floats(mm, nn, N) + 128;
+      lin = lin > v ? lin : v;
     }
   }
   return need + lin + 64;
@@ -571,6 +599,23 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
         const long long mm = o.out_c, nn = o.in_c + 1;
         float* T = scratch + N * (int64_t)M + 64;
         float* wsk = T + mm * nn + 64;
+        if (g_bnnp_opt.gemm_generated == 0) {
+          // transposed bf16 hi/lo copies of Q [N, m] and of the squared inputs [N, n + 1] (the constant-1 column carries
+          // the bias row), then one TMA-fed product over the examples
+          const int64_t Np = (N + 7) / 8 * 8;
+          float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wsk) + 15) & ~uintptr_t(15));
+          __nv_bfloat16* qh = reinterpret_cast<__nv_bfloat16*>(base);
+          __nv_bfloat16* ql = qh + mm * Np;
+          float* base2 = base + (mm * Np + 63) / 64 * 64;
+          __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base2);
+          __nv_bfloat16* al = ah + nn * Np;
+          float* part = base2 + (nn * Np + 63) / 64 * 64;
+          rc = split_transposed(scratch + q.lin_unit, M, N, mm, Np, qh, ql, false, st);
+          if (rc) return rc;
+          rc = split_transposed(ws + plan->acat_off + q.lin_col, plan->Dtot, N, nn, Np, ah, al, true, st);
+          if (rc) return rc;
+          rc = gemm_tma_nt(mm, nn, N, 1.f, qh, ql, Np, ah, al, Np, 0.f, T, nn, part, st);
+        } else
         rc = tcg::gemm_tc_splitk(mm, nn, N, 1, tcg::TcColMajor{scratch + q.lin_unit, M, 0},
                                  TcColMajorSq{ws + plan->acat_off + q.lin_col, plan->Dtot}, 1.f, 0.f, T, nn, 0, wsk,
                                  tcg::pick_ksplit(mm, nn, N, 1), st);
@@ -664,7 +709,11 @@ extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, con
       int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
       int64_t v = N * L * ((E + 3) / 4 * 4) + 64 + (int64_t)tcg::pick_ksplit(E, E, N * L, 1) * E * E;
       part = part > v ? part : v;
+      v = (E * ((N * L + 7) / 8 * 8) + 63) / 64 * 64 + gemm_tma_scratch_floats(E, E, N * L) + 128;     // TMA-fed A-factor Gram
+      part = part > v ? part : v;
       int64_t m = ops[i].out_c;
+      v = gram_tma_scratch_floats(N * V, m) + 64;
+      part = part > v ? part : v;
       int64_t gsplit = (int64_t)(tcg::pick_ksplit(m, m, N * V, 1) + (N * V + 4095) / 4096 + 1) * m * m;
       part = part > gsplit ? part : gsplit;
     }
@@ -675,7 +724,17 @@ extern "C" int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, con
 extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
                                const float* X, const float* ws, float factor, float batch_factor,
                                float* const* factors, float* scratch, void* stream) {
+  return bnnp_kfac_accum_ex(ops, n_ops, plan, N, V, X, ws, factor, batch_factor, factors, scratch, 0, stream);
+}
+
+// flags & BNNP_BWD_FIRST_CONV_POSSUM: the backward ran with the same flag, i.e. the gradient buffer of the first
+// parameterised (conv) layer holds its position sums [N*V, Cout] instead of the full [N*V, Cout, L] gradient
+extern "C" int bnnp_kfac_accum_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
+                                  const float* X, const float* ws, float factor, float batch_factor,
+                                  float* const* factors, float* scratch, int flags, void* stream) {
   if (!ops || !plan || !ws || !factors || !scratch || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
+  int first_param = -1;
+  for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { first_param = i; break; }
   cudaStream_t st = as_stream(stream);
   const int64_t R = N * V;
   for (int i = 0; i < n_ops; ++i) {
@@ -717,13 +776,20 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
       int64_t ild; const float* in = op_input(ops, plan, i, X, ws, &ild);
       if (!in) return BNNP_ERR_INVALID;
       int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
-      conv_possum_kernel<<<(unsigned)ceil_div64(R * o.out_c * 32, 256), 256, 0, st>>>(G, q.grad_ld, R, o.out_c, L,
-                                                                                       scratch, o.out_c);
-      BNNP_LAUNCH_CHECK();
+      if ((flags & BNNP_BWD_FIRST_CONV_POSSUM) && i == first_param) {
+        BNNP_CUDA_CHECK(cudaMemcpyAsync(scratch, G, sizeof(float) * R * o.out_c, cudaMemcpyDeviceToDevice, st));
+      } else {
+        conv_possum_kernel<<<(unsigned)ceil_div64(R * o.out_c * 32, 256), 256, 0, st>>>(G, q.grad_ld, R, o.out_c, L,
+                                                                                         scratch, o.out_c);
+        BNNP_LAUNCH_CHECK();
+      }
       int rc;
       // G += factor * S^T S over the R position-summed rows: a 64..128-wide Gram is one to four SIMT blocks walking
       // all R rows -- the split-K tensor-core Gram spreads it over the machine
-      if (!g_bnnp_opt.net_simt && (long long)o.out_c * o.out_c * R >= (1LL << 22))
+      const bool tma = g_bnnp_opt.gemm_generated == 0;
+      if (!g_bnnp_opt.net_simt && tma && (long long)o.out_c * o.out_c * R >= (1LL << 22))
+        rc = gram_tma(scratch, o.out_c, R, o.out_c, factor, 1.f, Gf, o.out_c, scratch + kfac_conv_floats(ops, n_ops, N, V), st);
+      else if (!g_bnnp_opt.net_simt && (long long)o.out_c * o.out_c * R >= (1LL << 22))
         rc = tcg::gemm_tc_splitk(o.out_c, o.out_c, R, 1, tcg::TcColMajor{scratch, o.out_c, 0}, tcg::TcColMajor{scratch, o.out_c, 0},
                                  factor, 1.f, Gf, o.out_c, 0, scratch + kfac_conv_floats(ops, n_ops, N, V),
                                  tcg::pick_ksplit(o.out_c, o.out_c, R, 1), st);
@@ -732,7 +798,17 @@ extern "C" int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_
                        AccumScaled{Gf, o.out_c, factor}, st);
       if (rc) return rc;
       Im2col u = make_im2col(o, in, ild, 1);
-      if (!g_bnnp_opt.net_simt && (long long)E * E * N * L >= kTcMinMacsG) {
+      if (!g_bnnp_opt.net_simt && tma && (long long)E * E * N * L >= kTcMinMacsG) {
+        // the unfolded input written once, transposed and pre-split (bf16 hi/lo), then A += (bf/N) U^T U as a TMA-fed Gram
+        const int64_t NL = N * L, NLp = (NL + 7) / 8 * 8;
+        float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch + kfac_conv_floats(ops, n_ops, N, V)) + 15) & ~uintptr_t(15));
+        __nv_bfloat16* uh = reinterpret_cast<__nv_bfloat16*>(base);
+        __nv_bfloat16* ul = uh + (int64_t)E * NLp;
+        float* part = base + ((int64_t)E * NLp + 63) / 64 * 64;
+        im2col_t_split_kernel<<<(unsigned)ceil_div64((int64_t)E * (NLp >> 3), 256), 256, 0, st>>>(u, N, L, E, NLp, uh, ul);
+        BNNP_LAUNCH_CHECK();
+        rc = gemm_tma_nt(E, E, NL, batch_factor / (float)N, uh, ul, NLp, uh, ul, NLp, 1.f, Af, E, part, st);
+      } else if (!g_bnnp_opt.net_simt && (long long)E * E * N * L >= kTcMinMacsG) {
         // materialise the unfolded input once, then A += (bf/N) U^T U as a tensor-core Gram (split-K)
         const int Epad = (E + 3) / 4 * 4;
         float* U = scratch + kfac_conv_floats(ops, n_ops, N, V);

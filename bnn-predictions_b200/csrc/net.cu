@@ -274,6 +274,41 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
   }
 }
 
+// KFAC needs only the POSITION SUMS of the gradient at a conv layer's output (BackPACK KFLR: G = sum (sum_pos g)(sum_pos
+// g)^T, preds/laplace.py:73-78).  For the first parameterised layer nothing upstream needs the full gradient either, so
+// when it is followed by (activation,) max-pool the [R, C, H, W] gradient (2 MB per example at CIFAR10Net's conv1 and
+// the single most expensive pass of the K-column backward) is never materialised: a max-pool routes each pooled
+// gradient to exactly one input position (or to a padding zero), hence
+//   S[r, c] = sum_pos g_conv[r, c, pos] = sum_windows [winner inside] * act'(act[n, c, winner]) * g_pool[r, c, window].
+// One warp per (r, c).
+__global__ void maxpool_bwd_possum_kernel(const float* __restrict__ gout, int64_t gold, float* __restrict__ S,
+                                          const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g,
+                                          const float* __restrict__ act, int64_t actld, int act_kind) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int C = g.Cout, OL = g.OH * g.OW, HW = g.H * g.W;
+  if (w >= N * V * C) return;
+  const int c = (int)(w % C);
+  const int64_t r = w / C, n = r / V;
+  const float* go = gout + r * gold + (int64_t)c * OL;
+  const int32_t* id = idx + (n * C + c) * (int64_t)OL;
+  const float* a = act ? act + n * actld + (int64_t)c * HW : nullptr;
+  float acc = 0.f;
+  for (int i = lane; i < OL; i += 32) {
+    const int win = id[i];
+    if (win >= 0) {
+      float d = 1.f;
+      if (a) {
+        const float o = a[win];
+        d = act_kind == BNNP_OP_RELU ? (o > 0.f ? 1.f : 0.f) : (act_kind == BNNP_OP_TANH ? 1.f - o * o : o * (1.f - o));
+      }
+      acc = fmaf(go[i], d, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) S[r * C + c] = acc;
+}
+
 __global__ void avgpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
                                    float* __restrict__ out, int64_t old, int64_t N, ConvGeom g) {
   int64_t per = (int64_t)g.Cout * g.OH * g.OW;
@@ -624,7 +659,24 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
 // ------------------------------------------------------------------------------------------
 extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                  const float* seed, int64_t N, int V, float* ws, void* stream) {
+  return bnnp_net_backward_ex(ops, n_ops, plan, seed, N, V, ws, 0, stream);
+}
+
+// 1 when BNNP_BWD_FIRST_CONV_POSSUM applies to this network: first parameterised op is a conv followed by
+// (an optional elementwise activation and) a max-pool
+extern "C" int bnnp_net_first_conv_possum_ok(const bnnp_op_t* ops, int n_ops) {
+  if (!ops) return 0;
+  int fp = -1;
+  for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { fp = i; break; }
+  if (fp < 0 || ops[fp].kind != BNNP_OP_CONV2D) return 0;
+  int j = fp + 1;
+  if (j < n_ops && is_elementwise_op(ops[j])) ++j;
+  return j < n_ops && ops[j].kind == BNNP_OP_MAXPOOL2D && ops[j].kh <= 3 && ops[j].kw <= 3 ? 1 : 0;
+}
+extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                                    const float* seed, int64_t N, int V, float* ws, int flags, void* stream) {
   if (!ops || !plan || !seed || !ws || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
+  if ((flags & BNNP_BWD_FIRST_CONV_POSSUM) && !bnnp_net_first_conv_possum_ok(ops, n_ops)) return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
   const int K = plan->K;
   const int64_t R = N * V;
@@ -702,6 +754,16 @@ extern "C" int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_pla
           gz = gz < 1 ? 1 : (gz > N ? N : gz);
           const dim3 grid((unsigned)ceil_div64((int64_t)o.in_h * o.in_w, 256), (unsigned)o.in_c, (unsigned)gz);
           const int32_t* idxp = reinterpret_cast<const int32_t*>(ws) + q.idx_off;
+          // position sums only for the first conv (KFAC): see maxpool_bwd_possum_kernel
+          const bool act_before = i - 1 > first_param && is_elementwise_op(ops[i - 1]);
+          if ((flags & BNNP_BWD_FIRST_CONV_POSSUM) && (act_before ? i - 2 : i - 1) == first_param) {
+            const bnnp_op_plan_t& qc = plan->op[first_param];
+            maxpool_bwd_possum_kernel<<<(unsigned)ceil_div64(R * o.in_c * 32, 256), 256, 0, st>>>(
+                gout, q.grad_ld, ws + qc.grad_off, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr,
+                qp.act_ld, act_before ? ops[i - 1].kind : 0);
+            BNNP_LAUNCH_CHECK();
+            return BNNP_OK;                  // nothing upstream of the first parameterised layer
+          }
           // an elementwise activation right in front of the pool (conv -> relu -> pool): its backward is folded into
           // this kernel's store and the op is skipped below
           if (i - 1 > first_param && is_elementwise_op(ops[i - 1])) {

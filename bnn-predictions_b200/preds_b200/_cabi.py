@@ -17,6 +17,7 @@ MAX_K = 32            # BNNP_MAX_K of include/bnnp_b200.h (register-resident K x
 MAX_K_WIDE = 128      # BNNP_MAX_K_WIDE: likelihood terms / GLM sampler beyond that on warp- / block-per-example kernels
 OP_LINEAR, OP_CONV2D, OP_RELU, OP_TANH, OP_MAXPOOL2D, OP_AVGPOOL2D, OP_FLATTEN, OP_SIGMOID = range(1, 9)
 LIK_CATEGORICAL, LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1, 2
+BWD_FIRST_CONV_POSSUM = 1
 ERR_INVALID = -1
 
 
@@ -57,6 +58,8 @@ _SIGS = {
     'bnnp_net_plan': (_I, [_OPS, _I, _L, _I, _PLAN]),
     'bnnp_net_forward': (_I, [_OPS, _I, _PLAN, _P, _L, _P, _P, _V]),
     'bnnp_net_backward': (_I, [_OPS, _I, _PLAN, _P, _L, _I, _P, _V]),
+    'bnnp_net_backward_ex': (_I, [_OPS, _I, _PLAN, _P, _L, _I, _P, _I, _V]),
+    'bnnp_net_first_conv_possum_ok': (_I, [_OPS, _I]),
     'bnnp_lik_hessian': (_I, [_I, _P, _L, _I, _F, _P, _V]),
     'bnnp_lik_sqrt_seed': (_I, [_I, _P, _L, _I, _P, _V]),
     'bnnp_identity_seed': (_I, [_L, _I, _P, _V]),
@@ -76,6 +79,7 @@ _SIGS = {
     'bnnp_ggn_diag_accum': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _P, _P, _V]),
     'bnnp_ggn_diag_scratch_floats': (_L, [_OPS, _I, _PLAN, _L, _I]),
     'bnnp_kfac_accum': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _F, C.POINTER(_P), _P, _V]),
+    'bnnp_kfac_accum_ex': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _F, C.POINTER(_P), _P, _I, _V]),
     'bnnp_kfac_scratch_floats': (_L, [_OPS, _I, _PLAN, _L, _I]),
     'bnnp_glm_fmu': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _P, _V]),
     'bnnp_glm_fvar_full_scratch_floats': (_L, [_PLAN, _L, _I]),

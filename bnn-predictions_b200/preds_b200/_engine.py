@@ -298,9 +298,9 @@ class Net:
                                    stream()), 'bnnp_net_forward')
         return pl, ws, f
 
-    def backward(self, pl, ws, seed, N, V):
-        check(lib.bnnp_net_backward(self.ops, self.n_ops, C.byref(pl), ptr(seed), N, V, ptr(ws),
-                                    stream()), 'bnnp_net_backward')
+    def backward(self, pl, ws, seed, N, V, flags=0):
+        check(lib.bnnp_net_backward_ex(self.ops, self.n_ops, C.byref(pl), ptr(seed), N, V, ptr(ws), flags,
+                                       stream()), 'bnnp_net_backward_ex')
 
     def identity_seed(self, N):
         seed = torch.empty(N, self.K, self.K, dtype=torch.float32, device=self.device)
@@ -315,14 +315,19 @@ class Net:
         self.backward(pl, ws, self.identity_seed(N), N, self.K)
         return X2d, pl, ws, f
 
-    def sqrt_factors(self, X, lik_code):
-        """forward + backward seeded with the loss-Hessian square root (BackPACK convention)."""
+    def sqrt_factors(self, X, lik_code, kfac_only=False):
+        """forward + backward seeded with the loss-Hessian square root (BackPACK convention).  ``kfac_only``: the
+        consumer is the KFAC accumulation, which needs only position sums at a first conv layer; returns the flags to
+        hand to ``bnnp_kfac_accum_ex`` as a fifth element."""
         X2d = self.prepare(X)
+        flags = cabi.BWD_FIRST_CONV_POSSUM if kfac_only and lib.bnnp_net_first_conv_possum_ok(self.ops, self.n_ops) else 0
         N = X2d.shape[0]
         pl, ws, f = self.forward(X2d, self.K)
         seed = torch.empty(N, self.K, self.K, dtype=torch.float32, device=self.device)
         check(lib.bnnp_lik_sqrt_seed(lik_code, ptr(f), N, self.K, ptr(seed), stream()), 'bnnp_lik_sqrt_seed')
-        self.backward(pl, ws, seed, N, self.K)
+        self.backward(pl, ws, seed, N, self.K, flags)
+        if kfac_only:
+            return X2d, pl, ws, f, flags
         return X2d, pl, ws, f
 
     def materialise_jacobians(self, X):

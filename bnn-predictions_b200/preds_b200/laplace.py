@@ -319,7 +319,7 @@ class Laplace:
         index = {id(p): i for i, p in enumerate(net.params)}
         table = None
         for X, M in self._superbatches(batches):
-            X2d, pl, ws, f = net.sqrt_factors(X, self.likelihood.code)
+            X2d, pl, ws, f, flags = net.sqrt_factors(X, self.likelihood.code, kfac_only=True)
             if table is None:
                 ptrs = []
                 for op, mod in zip(net.ops, net.mods):
@@ -330,8 +330,8 @@ class Laplace:
                         ptrs += [None, None]
                 table = ptr_array(ptrs)
             sc = net.scratch(lib.bnnp_kfac_scratch_floats(net.ops, net.n_ops, C.byref(pl), M, net.K))
-            check(lib.bnnp_kfac_accum(net.ops, net.n_ops, C.byref(pl), M, net.K, ptr(X2d), ptr(ws), hess_factor,
-                                      M / N_total, table, ptr(sc), stream()), 'bnnp_kfac_accum')
+            check(lib.bnnp_kfac_accum_ex(net.ops, net.n_ops, C.byref(pl), M, net.K, ptr(X2d), ptr(ws), hess_factor,
+                                         M / N_total, table, ptr(sc), flags, stream()), 'bnnp_kfac_accum_ex')
         # a bias shares its layer's output-side factor (BackPACK KFLR: p.kflr = [G] for biases)
         for mod in net.mods:
             if getattr(mod, 'bias', None) is not None and id(mod.bias) in index:

@@ -101,6 +101,14 @@ int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
  * preds/gradients.py:24-36); seed = S_n^T gives BackPACK's sqrt-GGN backprop (Appendix A). */
 int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                       const float* seed, int64_t N, int V, float* ws, void* stream);
+/* The same with flags.  BNNP_BWD_FIRST_CONV_POSSUM (KFAC only): when the first parameterised layer is a conv followed
+ * by (activation,) max-pool, its [N*V, Cout, L] output gradient is never materialised; the head of its gradient
+ * buffer receives the position sums [N*V, Cout] that KFLR needs (preds/laplace.py:73-78), to be consumed by
+ * bnnp_kfac_accum_ex with the same flag.  bnnp_net_first_conv_possum_ok() says whether the network qualifies. */
+#define BNNP_BWD_FIRST_CONV_POSSUM 1
+int bnnp_net_first_conv_possum_ok(const bnnp_op_t* ops, int n_ops);
+int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
+                         const float* seed, int64_t N, int V, float* ws, int flags, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Likelihood terms (preds/likelihoods.py).  lik: 0 categorical, 1 gaussian, 2 bernoulli.
@@ -186,6 +194,9 @@ int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp
 int bnnp_kfac_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
                     const float* X, const float* ws, float factor, float batch_factor,
                     float* const* factors, float* scratch, void* stream);
+int bnnp_kfac_accum_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
+                       const float* X, const float* ws, float factor, float batch_factor,
+                       float* const* factors, float* scratch, int flags, void* stream);
 int64_t bnnp_kfac_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                  int64_t N, int V);
 
