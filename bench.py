@@ -438,10 +438,10 @@ def run_ours(args):
     if Sigma_for_cpu is not None:
         try:
             torch.set_num_threads(os.cpu_count())
-            rate, sec = cpu_glm_rate(Sigma_for_cpu, 20, 100)
+            rate, sec = cpu_glm_rate(Sigma_for_cpu, 160, 100)
             secondary['glm_predictive']['cpu_baseline'] = {
                 'value': rate, 'unit': '(inputs x samples)/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                'sample': '20 inputs x 100 samples (experiments/imginference.py:45,391), Jacobians + einsum with the full '
+                'sample': '160 inputs x 100 samples (8 batches of 20 as experiments/imginference.py:45,391), Jacobians + einsum with the full '
                           '[P,P] covariance + sampling, oracle/port.py, %.1f s; the reference\'s per-call Sigma = L L^T '
                           '(2 P^3 flops) excluded' % sec}
         except Exception as exc:
@@ -489,9 +489,9 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:        # reported at N=1 only (rank 0)
         torch.set_num_threads(os.cpu_count())
-        rate, sec = cpu_full_ggn_rate(args.cpu_sample, 1, 1)
+        rate, sec = cpu_full_ggn_rate(4 * args.cpu_sample, 1, 0)
         cpu = {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': '%d examples, Jacobians + einsum into the 14.2 GB H (oracle/port.py), %.1f s' % (args.cpu_sample, sec)}
+               'sample': '%d examples, Jacobians + einsum into the 14.2 GB H (oracle/port.py), %.1f s' % (4 * args.cpu_sample, sec)}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,

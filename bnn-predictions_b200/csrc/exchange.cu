@@ -186,6 +186,23 @@ __global__ void unpack_lower_kernel(const float* __restrict__ packed, long long 
   }
 }
 
+// H[p, 0..p] = 0: the accumulation only ever adds into the lower triangle (plus the above-diagonal part of tiles that
+// cross the diagonal, which the mirror overwrites), so a fresh accumulator needs half the bytes of a full memset.
+__global__ void zero_lower_kernel(float* __restrict__ H, long long P) {
+  for (long long p = blockIdx.x; p < P; p += gridDim.x) {
+    float* row = H + p * P;
+    const long long n = p + 1;
+    const long long head = ((4 - ((reinterpret_cast<uintptr_t>(row) >> 2) & 3)) & 3);      // floats up to a 16-byte boundary
+    const long long h = head < n ? head : n;
+    if ((long long)threadIdx.x < h) row[threadIdx.x] = 0.f;
+    const long long nv = (n - h) >> 2;
+    float4* v = reinterpret_cast<float4*>(row + h);
+    for (long long i = threadIdx.x; i < nv; i += blockDim.x) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long t0 = h + (nv << 2);
+    if (t0 + (long long)threadIdx.x < n) row[t0 + threadIdx.x] = 0.f;
+  }
+}
+
 }  // namespace xch
 }  // namespace bnnp
 
@@ -237,6 +254,13 @@ extern "C" int bnnp_unpack_lower(const float* packed, int64_t P, int64_t row0, i
   const int64_t rows = row1 - row0;
   xch::unpack_lower_kernel<<<(unsigned)(rows < 148 * 8 ? rows : 148 * 8), 512, 0, as_stream(stream)>>>(
       packed, P, row0, row1, H, prior_vec, prior_scalar);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+
+extern "C" int bnnp_zero_lower(float* H, int64_t P, void* stream) {
+  if (!H || P <= 0) return BNNP_ERR_INVALID;
+  xch::zero_lower_kernel<<<(unsigned)(P < 148 * 16 ? P : 148 * 16), 256, 0, as_stream(stream)>>>(H, P);
   BNNP_LAUNCH_CHECK();
   return BNNP_OK;
 }

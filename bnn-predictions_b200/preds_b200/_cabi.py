@@ -70,6 +70,7 @@ _SIGS = {
     'bnnp_ggn_full_accum': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _I, _V]),
     'bnnp_ggn_full_row_chunks': (_I, [_OPS, _I, _PLAN, _L, _I, _I, C.POINTER(C.c_int64)]),
     'bnnp_ggn_full_accum_rows': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _I, _L, _L, _I, _V]),
+    'bnnp_zero_lower': (_I, [_P, _L, _V]),
     'bnnp_symmetrize_lower': (_I, [_P, _L, _V]),
     'bnnp_symmetrize_lower_rows': (_I, [_P, _L, _L, _L, _V]),
     'bnnp_exchange_lower_allreduce': (_I, [C.POINTER(_P), _P, _I, _I, _L, _L, _L, _P, _F, _I, _V]),

@@ -120,12 +120,15 @@ class Laplace:
                 acc, hdl = (None, None) if exchange == 'nccl' else parallel.symmetric_zeros(self.P, self.device)
                 self._symmetric = (acc, hdl) if acc is not None else None
                 if acc is None:
-                    acc = torch.zeros(self.P, self.P, device=self.device)
+                    acc = torch.empty(self.P, self.P, device=self.device)
+                    check(lib.bnnp_zero_lower(ptr(acc), self.P, stream()), 'bnnp_zero_lower')
                 ex = parallel.LowerExchange(acc, hdl, diag_prior, mode=exchange)
             elif dense_prior:           # accumulate on top of the prior; never mutate a caller-owned prior matrix
                 acc = prior.to(device=self.device, dtype=torch.float32).clone().contiguous()
             else:
-                acc = torch.zeros(self.P, self.P, device=self.device)
+                # only the lower triangle is accumulated into (and zeroed); the mirror rewrites the upper one
+                acc = torch.empty(self.P, self.P, device=self.device)
+                check(lib.bnnp_zero_lower(ptr(acc), self.P, stream()), 'bnnp_zero_lower')
             self._accumulate_full(my_batches(), acc, exchange=ex)
             if ex is not None:
                 self.exchange_stats = ex

@@ -121,10 +121,11 @@ def symmetric_zeros(P, device):
     torch / system cannot provide peer mappings (then the packed NCCL exchange is used).  Collective: every rank must
     call it (and ``symmetric_release``) in the same order."""
     import torch.distributed as dist
+    from ._cabi import lib, check, ptr, stream
     pool = _SYMMETRIC_POOL.get((P, torch.device(device).index))
     if pool:
         t, hdl = pool.pop()
-        t.zero_()
+        check(lib.bnnp_zero_lower(ptr(t), P, stream()), 'bnnp_zero_lower')     # the upper triangle is rewritten by the mirror
         return t, hdl
     try:
         import warnings

@@ -156,6 +156,9 @@ int bnnp_ggn_full_row_chunks(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t*
 int bnnp_ggn_full_accum_rows(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                              const float* ws, const float* Lambda, float* H, float* scratch, int engine,
                              int64_t row_begin, int64_t row_end, int prepared, void* stream);
+/* H[p, 0..p] = 0 for all rows: a fresh accumulator for bnnp_ggn_full_accum (which adds into the lower triangle only;
+ * whatever the upper triangle holds is overwritten by bnnp_symmetrize_lower) at half the bytes of a full memset. */
+int bnnp_zero_lower(float* H, int64_t P, void* stream);
 /* H[p,q] = H[q,p] for p < q; _rows: only the source rows q in [row0,row1) (their mirror images H[p,q], p < q). */
 int bnnp_symmetrize_lower(float* H, int64_t P, void* stream);
 int bnnp_symmetrize_lower_rows(float* H, int64_t P, int64_t row0, int64_t row1, void* stream);
