@@ -363,7 +363,7 @@ def run_ours(args):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         barrier()
         ev[0].record()
-        Sigma_chol, Sigma = lap._factorise_full(H)
+        Sigma_chol, Sigma = lap._factorise_full(H, sharded=world > 1)
         ev[1].record()
         del H
         lap.mu = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
@@ -413,7 +413,7 @@ def run_ours(args):
                                       'as written the reference einsum costs 2 K P^2 + 2 K^2 P per input'}
         secondary = {
             'factorise_full_ms': ev[0].elapsed_time(ev[1]),
-            'factorise_note': 'one-off chol(H), inverse, chol(Sigma), P=59635 (timed separately, north star (3))',
+            'factorise_note': 'one-off chol(H), inverse, chol(Sigma), P=59635 (timed separately, north star (3)); N > 1: the inverse is split between the ranks',
             'glm_predictive': {
                 'metric': 'glm_predictive_input_samples_per_s', 'value': nte * S * world / (glm_ms * 1e-3),
                 'unit': '(inputs x samples)/s', 'inputs_per_gpu': nte, 'samples': S, 'ms': glm_ms,
@@ -489,7 +489,7 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:        # reported at N=1 only (rank 0)
         torch.set_num_threads(os.cpu_count())
-        rate, sec = cpu_full_ggn_rate(4 * args.cpu_sample, 1, 0)
+        rate, sec = cpu_full_ggn_rate(4 * args.cpu_sample, 1, 1)
         cpu = {'value': rate, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': '%d examples, Jacobians + einsum into the 14.2 GB H (oracle/port.py), %.1f s' % (4 * args.cpu_sample, sec)}
 

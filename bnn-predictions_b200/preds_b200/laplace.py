@@ -140,7 +140,7 @@ class Laplace:
             self.precision = acc
             t1.record()
             if factorise:
-                self.Sigma_chol, self._Sigma = self._factorise_full(acc)
+                self.Sigma_chol, self._Sigma = self._factorise_full(acc, sharded=bool(dist))
         elif cov_type == 'diag':
             _, hess_factor = self.likelihood.nn_loss()
             prior = self.expand_prior_precision(cov_type)
@@ -275,14 +275,15 @@ class Laplace:
         else:
             check(lib.bnnp_symmetrize_lower(ptr(H), self.P, stream()), 'bnnp_symmetrize_lower')
 
-    def _factorise_full(self, H):
+    def _factorise_full(self, H, sharded=False):
         """chol(H) -> Sigma = H^-1 -> chol(Sigma) (preds/laplace.py:43-45), one-off, on device
         through cuSOLVER (torch.linalg).  Sigma itself is kept: the reference recomputes
-        L L^T on every predictive call (preds/laplace.py:111)."""
+        L L^T on every predictive call (preds/laplace.py:111).  ``sharded`` (data-parallel mode, every rank holds the
+        same H): the inverse -- half of the one-off time -- is split between the ranks (dense.spd_inverse_sharded)."""
         chol = torch.linalg.cholesky(H)
         # potri is the slow third of the three factorisations (7.1 of 10.2 s at P = 59 635): above dense.MIN_P the
         # inverse comes from a blocked triangular inverse + blocked Gram (same fp32 arithmetic class, 2.9 s)
-        Sigma = dense.spd_inverse_from_chol(chol)
+        Sigma = dense.spd_inverse_from_chol(chol, sharded=sharded)
         del chol
         return torch.linalg.cholesky(Sigma), Sigma
 

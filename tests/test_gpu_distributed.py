@@ -19,6 +19,18 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _spawn(fn, out_dir, nprocs=2):
+    """mp.spawn with a fresh rendezvous port; a port that another process grabbed between the probe and the bind
+    ("address already in use") is retried, anything else propagates."""
+    for attempt in range(3):
+        try:
+            mp.spawn(fn, args=(nprocs, _free_port(), out_dir), nprocs=nprocs, join=True)
+            return
+        except Exception as exc:
+            if attempt == 2 or 'address already in use' not in str(exc).lower():
+                raise
+
+
 def _problem():
     from preds_b200 import MLPS
     torch.manual_seed(71)
@@ -63,7 +75,7 @@ def test_two_gpu_sharded_infer_and_predictive(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     from preds_b200 import Laplace, CategoricalLh
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    _spawn(_worker, str(tmp_path))
     res = [torch.load(os.path.join(str(tmp_path), 'r%d.pt' % r), weights_only=False) for r in range(2)]
     model, batches, Xte, eps = _problem()
     model = model.cuda()
@@ -109,6 +121,12 @@ def _exchange_worker(rank, world, port_no, out_dir):
             res[mode + '_' + pname] = lap.precision.cpu()
             res[mode + '_chunks'] = len(lap.exchange_stats.events)
             lap.precision = None
+    # the one-off factorisation with the inverse split between the ranks (dense.spd_inverse_sharded, P >= dense.MIN_P)
+    lap = Laplace(model, 0.6, CategoricalLh())
+    lap.infer(batches, cov_type='full', shard='batches')
+    res['Sigma_rows'] = lap.Sigma[::97].cpu()
+    res['Sigma_chol_rows'] = lap.Sigma_chol[::97].cpu()
+    lap.release_posterior()
     # a rank without examples still takes part (rank 1 owns nothing when there is one batch)
     lap = Laplace(model, 0.6, CategoricalLh())
     lap.infer(batches[:1], cov_type='full', shard='batches', factorise=False)
@@ -127,7 +145,7 @@ def test_two_gpu_lower_triangle_exchange(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     from preds_b200 import Laplace, CategoricalLh, MLPS
-    mp.spawn(_exchange_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    _spawn(_exchange_worker, str(tmp_path))
     res = [torch.load(os.path.join(str(tmp_path), 'x%d.pt' % r), weights_only=False) for r in range(2)]
     torch.manual_seed(11)
     model = MLPS(300, [40, 24], 7, 'tanh').cuda()
@@ -148,6 +166,12 @@ def test_two_gpu_lower_triangle_exchange(tmp_path):
             # the prior entered exactly once: compare the diagonal on its own scale
             assert float((a.diagonal() - ref.diagonal()).abs().max() / ref.diagonal().abs().max()) < 1e-4, (mode, pname)
             assert res[0][mode + '_chunks'] > 1
+    lap = Laplace(model, 0.6, CategoricalLh())
+    lap.infer(batches, cov_type='full')
+    Sref, Lref = lap.Sigma[::97].cpu(), lap.Sigma_chol[::97].cpu()
+    assert torch.equal(res[0]['Sigma_rows'], res[1]['Sigma_rows'])            # identical bits on every rank
+    assert float((res[0]['Sigma_rows'] - Sref).abs().max() / Sref.abs().max()) < 1e-4
+    assert float((res[0]['Sigma_chol_rows'] - Lref).abs().max() / Lref.abs().max()) < 1e-4
     lap = Laplace(model, 0.6, CategoricalLh())
     lap.infer(batches[:1], cov_type='full', factorise=False)
     ref = lap.precision.cpu()
