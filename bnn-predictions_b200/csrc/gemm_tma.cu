@@ -38,6 +38,8 @@ struct Args {
   float* C; long long ldc;
   float* part;                 // [ksplit, M, N] partial sums when ksplit > 1
   const float* bias;           // [N] added to every row (ksplit == 1 only) or nullptr
+  int ct_L;                    // > 0: rows are (batch b, position p) = (m / ct_L, m % ct_L) and C is stored transposed per batch:
+                               //      C[(b * N + n) * ct_L + p]  (the [R, E, L] buffer of the conv backward-data product)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -126,6 +128,29 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       float* sc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + q * EPI_TILE_BYTES);
       mbar_wait(&acc_full[buf], buf_phase);
       tc_fence_after();
+      if (args.ct_L > 0) {
+        // transposed-per-batch store: the thread's row m = (b, p) is the contiguous index of the output, so the
+        // tcgen05.ld layout (thread = row) is already the coalesced one -- no transpose
+        const long long m = m0 + q * 32 + lane;
+        const int ncols_t = (int)(args.N - n0 < args.wn ? args.N - n0 : args.wn);
+        float* pt = args.C + ((m / args.ct_L) * args.N + n0) * args.ct_L + (m % args.ct_L);
+        for (int c0 = 0; c0 < ncols_t; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
+          if (m < args.M) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e < ncols_t) pt[(long long)(c0 + e) * args.ct_L] = args.alpha * __uint_as_float(v[e]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        const uint32_t tot_t = stage + (uint32_t)n_chunks;
+        phase ^= (tot_t / STAGES) & 1;
+        stage = tot_t % STAGES;
+        continue;
+      }
       const long long rbase = m0 + q * 32;
       int nrows = (int)(args.M - rbase < 32 ? (args.M - rbase < 0 ? 0 : args.M - rbase) : 32);
       const int ncols = (int)(args.N - n0 < args.wn ? args.N - n0 : args.wn);
@@ -233,6 +258,30 @@ __global__ void split_transposed_kernel(const float* __restrict__ src, long long
   }
 }
 
+// Conv gradients gout[r, co, pos] (row pitch gld) -> hi/lo[(r * L + pos), co] (row pitch Cp >= Cout, zero padded): the
+// K-major A operand of the backward-data product dU[(r,pos), e] = sum_co gout[r, co, pos] W[co, e].  32 x 32 smem transposes.
+__global__ void split_conv_grad_kernel(const float* __restrict__ g, long long gld, int Cout, int L, int Cp,
+                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const long long r = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < Cout && p < L) ? g[r * gld + (long long)c * L + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < L && c < Cp) {
+      const float v = tile[threadIdx.x][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const long long o = (r * L + p) * Cp + c;
+      hi[o] = h;
+      lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -293,7 +342,7 @@ int64_t gemm_tma_scratch_floats(int64_t M, int64_t N, int64_t K) {
 
 int gemm_tma_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int64_t lda,
                 const __nv_bfloat16* Bh, const __nv_bfloat16* Bl, int64_t ldb, float beta, float* C, int64_t ldc,
-                float* scratch, cudaStream_t st, const float* bias) {
+                float* scratch, cudaStream_t st, const float* bias, int ct_L) {
   using namespace tg;
   if (M <= 0 || N <= 0 || K <= 0) return BNNP_OK;
   if (!Ah || !Al || !Bh || !Bl || !C || (lda & 7) || (ldb & 7)) return BNNP_ERR_INVALID;
@@ -311,7 +360,9 @@ int gemm_tma_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat1
   if (!scratch && a.chunks_total > kMaxChunksPerAccum) return BNNP_ERR_INVALID;      // a long K needs the partials
   a.alpha = alpha; a.beta = beta; a.C = C; a.ldc = ldc; a.part = scratch;
   a.bias = bias;
+  a.ct_L = ct_L;
   if (bias && (a.ksplit > 1 || beta != 0.f)) return BNNP_ERR_INVALID;
+  if (ct_L > 0 && (a.ksplit > 1 || beta != 0.f || bias)) return BNNP_ERR_INVALID;
   CUtensorMap mah, mal, mbh, mbl;
   int rc;
   if ((rc = make_map(&mah, Ah, M, K, lda, TILE_M))) return rc;
@@ -382,6 +433,28 @@ int gram_tma(const float* S, int64_t lds, int64_t R, int64_t m, float alpha, flo
   return gemm_tma_nt(m, m, R, alpha, hi, lo, Rp, hi, lo, Rp, beta, C, ldc, part, st);
 }
 
+// conv backward-data product on TMA-fed tensor cores: dUt[r, e, pos] = sum_co gout[r, co, pos] W[co, e]
+// (W [Cout, E] row-major; the col2im gather that follows reads dUt).  scratch: conv_bwd_tma_scratch_floats().
+int64_t conv_bwd_tma_scratch_floats(int64_t R, int64_t Cout, int64_t L, int64_t E) {
+  return up64(R * L * up8(Cout)) + up64(E * up8(Cout)) + 128;
+}
+int conv_bwd_tma(const float* gout, int64_t gld, int64_t R, int Cout, int L, const float* W, int E, float* dUt,
+                 float* scratch, cudaStream_t st) {
+  if (Cout > 4096 || R > 65535) return BNNP_ERR_UNSUPPORTED;
+  const int Cp = (int)up8(Cout);
+  float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 15) & ~uintptr_t(15));
+  __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* al = ah + R * L * Cp;
+  __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(base + up64(R * L * Cp));
+  __nv_bfloat16* wl = wh + (int64_t)E * Cp;
+  tg::split_conv_grad_kernel<<<dim3((unsigned)ceil_div64(L, 32), (unsigned)ceil_div64(Cp, 32), (unsigned)R), dim3(32, 8), 0, st>>>(
+      gout, gld, Cout, L, Cp, ah, al);
+  BNNP_LAUNCH_CHECK();
+  int rc = split_transposed(W, E, Cout, E, Cp, wh, wl, false, st);          // [E, Cp]: k = co contiguous
+  if (rc) return rc;
+  return gemm_tma_nt(R * L, E, Cout, 1.f, ah, al, Cp, wh, wl, Cp, 0.f, dUt, 0, nullptr, st, nullptr, L);
+}
+
 int64_t linear_tma_scratch_floats(int64_t R, int64_t k, int64_t n_out) {
   return up64(R * up8(k)) + up64(n_out * up8(k)) + 128;
 }
@@ -415,7 +488,7 @@ extern "C" int bnnp_gemm_nt_split(int64_t M, int64_t N, int64_t K, float alpha, 
   if (M <= 0 || N <= 0 || K <= 0) return BNNP_ERR_INVALID;
   return gemm_tma_nt(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(Ah), reinterpret_cast<const __nv_bfloat16*>(Al),
                      lda, reinterpret_cast<const __nv_bfloat16*>(Bh), reinterpret_cast<const __nv_bfloat16*>(Bl), ldb, beta, C,
-                     ldc, scratch, as_stream(stream), nullptr);
+                     ldc, scratch, as_stream(stream), nullptr, 0);
 }
 
 extern "C" int bnnp_split_bf16_t(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t pitch, void* hi,

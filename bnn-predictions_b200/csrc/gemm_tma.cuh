@@ -10,7 +10,12 @@ namespace bnnp {
 int64_t gemm_tma_scratch_floats(int64_t M, int64_t N, int64_t K);
 int gemm_tma_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int64_t lda,
                 const __nv_bfloat16* Bh, const __nv_bfloat16* Bl, int64_t ldb, float beta, float* C, int64_t ldc,
-                float* scratch, cudaStream_t st, const float* bias = nullptr);
+                float* scratch, cudaStream_t st, const float* bias = nullptr, int ct_L = 0);
+// conv backward-data product dUt[r, e, pos] = sum_co gout[r, co, pos] W[co, e] (gout row pitch gld, W [Cout, E]) with the
+// gradients transposed + split once ([(r,pos), co] bf16 hi/lo) and the result stored transposed per row for the col2im gather
+int64_t conv_bwd_tma_scratch_floats(int64_t R, int64_t Cout, int64_t L, int64_t E);
+int conv_bwd_tma(const float* gout, int64_t gld, int64_t R, int Cout, int L, const float* W, int E, float* dUt,
+                 float* scratch, cudaStream_t st);
 // hi/lo[r, c] = split(src[r*lds + c]) (optionally squared first), row pitch `pitch` >= cols (multiple of 8), zero padded
 int split_rows(const float* src, int64_t lds, int64_t rows, int64_t cols, int64_t pitch, __nv_bfloat16* hi,
                __nv_bfloat16* lo, bool square, cudaStream_t st);

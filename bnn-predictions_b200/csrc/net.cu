@@ -543,7 +543,9 @@ extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, 
       if (ops[i].kind == BNNP_OP_CONV2D) {
         const int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
         int64_t v = N * L * ((E + 3) / 4 * 4);                    // forward: unfolded input [N*L, Epad]
-        if (i > first_param && N * V * E * L > v) v = N * V * E * L;  // backward-data: dU^T [N*V, E, L]
+        // backward-data: dU^T [N*V, E, L] + the transposed bf16 hi/lo gradients and weights of the TMA-fed product
+        const int64_t bwd = (N * V * E * L + 63) / 64 * 64 + conv_bwd_tma_scratch_floats(N * V, ops[i].out_c, L, E);
+        if (i > first_param && bwd > v) v = bwd;
         need = need > v ? need : v;
       }
     // bf16 hi/lo operand copies of the TMA-fed Linear-layer products (forward over N rows, backward over N*V rows)
@@ -722,8 +724,12 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
         if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)R * o.out_c * o.out_h * o.out_w * o.in_c * o.kh * o.kw >= kTcMinMacs) {
           const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
           float* dUt = ws + plan->conv_scratch_off;
-          int rc = tcg::gemm_tc(R * L, E, o.out_c, 1, ConvGoutRowsA{gout, q.grad_ld, L}, tcg::TcColMajor{o.weight, E, 0},
-                                ConvStoreDUt(dUt, E, L), 1, st);
+          int rc;
+          if (g_bnnp_opt.gemm_generated == 0 && R <= 65535)
+            rc = conv_bwd_tma(gout, q.grad_ld, R, o.out_c, L, o.weight, E, dUt, dUt + ((int64_t)R * E * L + 63) / 64 * 64, st);
+          else
+            rc = tcg::gemm_tc(R * L, E, o.out_c, 1, ConvGoutRowsA{gout, q.grad_ld, L}, tcg::TcColMajor{o.weight, E, 0},
+                              ConvStoreDUt(dUt, E, L), 1, st);
           if (rc) return rc;
           if (o.kh * o.kw > 25) return BNNP_ERR_UNSUPPORTED;
           {
