@@ -1,0 +1,134 @@
+"""The one-off factorisation chain of the full-covariance posterior on the library's own tensor-core GEMM
+(preds/laplace.py:43-45: ``Chol = cholesky(H)``, ``Sigma = cholesky_inverse(Chol)``, ``Sigma_chol = cholesky(Sigma)``).
+
+Every O(P^3) product runs on ``bnnp_gemm3_nt`` (csrc/gemm3.cu): three-term bf16 split, six MMAs per product, chunked main
+accumulation -- the error class of an fp32 library GEMM at ~5x its rate.  Only the NB x NB diagonal blocks (a Cholesky and
+a triangular inverse of a 1024 x 1024 matrix per panel, O(P NB^2) in total) go through the library (cuSOLVER / cuBLAS
+through torch), as the north star allows for the factorisation.
+
+  cholesky_lower(A)       right-looking blocked Cholesky, in place: panel L21 = A21 L11^-T as a GEMM with the inverted
+                          diagonal block, trailing update A22 -= L21 L21^T on the lower tiles only.
+  inverse_from_chol(L)    Y = L^-T is built block column by block column *as bf16 planes* (it only ever enters products):
+                          Y[:i0, I] = -(Y[:i0, :i0] L[I, :i0]^T) L_II^-T, skipping the zero part of the triangular operand
+                          per tile; then Sigma = Y Y^T on the lower tiles, K walked in 4096-wide segments.
+"""
+import torch
+
+from ._cabi import lib, check, ptr, stream
+
+NB = 1024            # panel width = K of every trailing update (one correction accumulation)
+KSEG = 4096          # longest K of one bnnp_gemm3_nt call
+MIN_P = 4096         # below this the library calls are used as they are
+
+
+def _up8(v):
+    return (v + 7) // 8 * 8
+
+
+class _Planes:
+    """Three bf16 planes (hi, mid, lo) of a [rows, cols] matrix, rows k-contiguous with pitch up8(cols)."""
+
+    def __init__(self, rows, cols, device, zero=False):
+        self.rows, self.cols, self.pitch = rows, cols, _up8(cols)
+        self.pstride = rows * self.pitch
+        alloc = torch.zeros if zero else torch.empty
+        self.buf = alloc(3 * self.pstride, dtype=torch.bfloat16, device=device)
+
+    def addr(self, r=0, c=0):
+        return self.buf.data_ptr() + 2 * (r * self.pitch + c)
+
+    def fill(self, src_addr, ld, rows, cols, r=0, c=0, transposed=False, scale=1.0):
+        """planes[r:r+rows, c:c+cols] <- scale * src (transposed: planes[r:r+cols, c:c+rows] <- scale * src^T)."""
+        check(lib.bnnp_split3_bf16(src_addr, ld, rows, cols, self.addr(r, c), self.pitch, self.pstride, int(transposed),
+                                   scale, stream()), 'bnnp_split3_bf16')
+
+
+def _gemm3(M, N, K, alpha, A, a_addr, B, b_addr, beta, c_addr, ldc, lower=0, ktri=0, koff=0):
+    check(lib.bnnp_gemm3_nt(M, N, K, alpha, a_addr, A.pitch, A.pstride, b_addr, B.pitch, B.pstride, beta, c_addr, ldc,
+                            lower, ktri, koff, stream()), 'bnnp_gemm3_nt')
+
+
+def _addr(t, r, c):
+    return t.data_ptr() + 4 * (r * t.stride(0) + c)
+
+
+def _tri_inv(Lii):
+    eye = torch.eye(Lii.shape[0], dtype=torch.float32, device=Lii.device)
+    return torch.linalg.solve_triangular(Lii, eye, upper=False).contiguous()      # (the library hands back column-major)
+
+
+def cholesky_lower(A):
+    """In-place lower Cholesky factor of the symmetric positive definite A [P,P] (fp32, contiguous; only the lower triangle
+    is read); the strict upper triangle of the result is zero.  Raises like torch.linalg.cholesky when A is not SPD."""
+    P = A.shape[0]
+    assert A.is_contiguous() and A.dtype == torch.float32
+    dev = A.device
+    panel = _Planes(max(P - NB, 1), NB, dev)
+    wpl = _Planes(NB, NB, dev)
+    infos = []
+    for j0 in range(0, P, NB):
+        nb = min(NB, P - j0)
+        D = A[j0:j0 + nb, j0:j0 + nb]
+        L11, info = torch.linalg.cholesky_ex(D)
+        infos.append(info)
+        D.copy_(L11)
+        if j0 + nb >= P:
+            break
+        m = P - j0 - nb
+        W = _tri_inv(L11)
+        # panel: L21[r, n] = sum_k A21[r, k] W[n, k]
+        panel.fill(_addr(A, j0 + nb, j0), P, m, nb)
+        wpl.fill(W.data_ptr(), nb, nb, nb)
+        _gemm3(m, nb, nb, 1.0, panel, panel.addr(), wpl, wpl.addr(), 0.0, _addr(A, j0 + nb, j0), P)
+        # trailing update, lower tiles: A22 -= L21 L21^T
+        panel.fill(_addr(A, j0 + nb, j0), P, m, nb)
+        _gemm3(m, m, nb, -1.0, panel, panel.addr(), panel, panel.addr(), 1.0, _addr(A, j0 + nb, j0 + nb), P, lower=1)
+    if bool(torch.stack(infos).ne(0).any()) or not bool(torch.isfinite(A.diagonal()).all()):      # the only sync
+        raise torch.linalg.LinAlgError('cholesky_lower: the matrix is not positive definite')
+    A.tril_()
+    return A
+
+
+def inverse_from_chol(L):
+    """Sigma = (L L^T)^-1 [P,P] (symmetric, both triangles filled) from the lower Cholesky factor L."""
+    P = L.shape[0]
+    assert L.is_contiguous() and L.dtype == torch.float32
+    dev = L.device
+    Y = _Planes(P, P, dev, zero=True)                      # Y = L^-T (upper triangular), only ever an operand
+    lrow = _Planes(NB, max(P - 1, 1), dev)
+    tpl = _Planes(max(P - 1, 1), NB, dev)
+    xpl = _Planes(NB, NB, dev)
+    T = torch.empty(max(P - 1, 1) * NB, dtype=torch.float32, device=dev)
+    for i0 in range(0, P, NB):
+        nb = min(NB, P - i0)
+        Xii = _tri_inv(L[i0:i0 + nb, i0:i0 + nb])
+        Y.fill(Xii.data_ptr(), nb, nb, nb, r=i0, c=i0, transposed=True)
+        if i0 == 0:
+            continue
+        # Tt[n, m] = sum_{n <= k < i0} Y[n, k] L[i0 + m, k]
+        lrow.fill(_addr(L, i0, 0), P, nb, i0)
+        Tt = T[:i0 * nb].view(i0, nb)
+        Tt.zero_()
+        for k0 in range(0, i0, KSEG):
+            kk = min(KSEG, i0 - k0)
+            rows = min(i0, k0 + kk)                        # rows n >= k0 + kk have no entry in this segment
+            _gemm3(rows, nb, kk, 1.0, Y, Y.addr(0, k0), lrow, lrow.addr(0, k0), 1.0, Tt.data_ptr(), nb, ktri=2, koff=-k0)
+        # Y[:i0, I] = -Tt Xii^T :  out[n, m'] = -sum_m Tt[n, m] Xii[m', m]
+        tpl.fill(Tt.data_ptr(), nb, i0, nb)
+        xpl.fill(Xii.data_ptr(), nb, nb, nb)
+        _gemm3(i0, nb, nb, -1.0, tpl, tpl.addr(), xpl, xpl.addr(), 0.0, Tt.data_ptr(), nb)
+        Y.fill(Tt.data_ptr(), nb, i0, nb, r=0, c=i0)
+    del lrow, tpl, xpl, T
+    S = torch.zeros(P, P, dtype=torch.float32, device=dev)
+    for k0 in range(0, P, KSEG):
+        kk = min(KSEG, P - k0)
+        rows = min(P, k0 + kk)
+        _gemm3(rows, rows, kk, 1.0, Y, Y.addr(0, k0), Y, Y.addr(0, k0), 1.0, S.data_ptr(), P, lower=1, ktri=2, koff=-k0)
+    del Y
+    check(lib.bnnp_symmetrize_lower(ptr(S), P, stream()), 'bnnp_symmetrize_lower')
+    return S
+
+
+def planes_bytes(P):
+    """Peak extra device memory of ``inverse_from_chol`` beside L and Sigma (the planes of Y and the block temporaries)."""
+    return 6 * P * _up8(P) + 6 * NB * _up8(P) + 6 * P * NB + 6 * NB * NB + 4 * P * NB

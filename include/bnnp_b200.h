@@ -350,6 +350,19 @@ int bnnp_gemm_nt_split(int64_t M, int64_t N, int64_t K, float alpha, const void*
                        float* scratch, void* stream);
 int bnnp_split_bf16_t(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t pitch, void* hi, void* lo,
                       void* stream);
+/* Tensor-core GEMM of the one-off factorisation (preds/laplace.py:43-45: torch.cholesky, torch.cholesky_inverse,
+ * torch.cholesky on [P,P]) with the accuracy of an fp32 library GEMM: operands split into THREE bf16 planes (hi, mid, lo;
+ * `plane_stride` elements apart, rows k-contiguous with pitch lda / ldb, multiples of 8 elements, 16-byte aligned), six MMAs
+ * per K-step, hi*hi accumulated in 128-k chunks that are summed in registers (round to nearest), the five correction terms in
+ * their own accumulator.  C[M,N] = alpha * sum_k A[m,k] B[n,k] + beta * C, K <= 4096 per call (longer K: segments with
+ * beta = 1).  lower != 0: only the tiles on / below the diagonal (M == N).  ktri = 1 / 2: the K loop of a 128 x 128 tile
+ * starts at its column / row origin + koff (triangular operands); a tile without work leaves C untouched when beta == 1.
+ * bnnp_split3_bf16 writes the planes of scale * src (transposed != 0: of its transpose, planes[c, r] = src[r, c]). */
+int bnnp_split3_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, void* planes, int64_t pitch,
+                     int64_t plane_stride, int transposed, float scale, void* stream);
+int bnnp_gemm3_nt(int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda, int64_t a_plane_stride,
+                  const void* B, int64_t ldb, int64_t b_plane_stride, float beta, float* C, int64_t ldc, int lower,
+                  int ktri, int64_t koff, void* stream);
 /* y += alpha * x  (Kron.update axpy, preds/kron.py:62-66). */
 int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream);
 
