@@ -19,6 +19,7 @@ from ._cabi import lib, check, ptr, stream
 NB = 1024            # panel width = K of every trailing update (one correction accumulation)
 KSEG = 4096          # longest K of one bnnp_gemm3_nt call
 MIN_P = 4096         # below this the library calls are used as they are
+ENGINE = 'tc'        # 'library': cuSOLVER / cuBLAS through torch whatever the size (A/B timing, scripts/factor_check.py)
 
 
 def _up8(v):
@@ -26,10 +27,12 @@ def _up8(v):
 
 
 class _Planes:
-    """Three bf16 planes (hi, mid, lo) of a [rows, cols] matrix, rows k-contiguous with pitch up8(cols)."""
+    """Three bf16 planes (hi, mid, lo) of a [rows, cols] matrix, rows k-contiguous; the pitch is a multiple of 64 elements so
+    that every row starts on a 128-byte line (with 8-element granularity the 64-byte rows of a TMA box straddle sectors and
+    the L2 -> SM traffic, already at 72 % of its peak in this kernel, grows by a third: measured 850 vs 1270 TFLOP/s)."""
 
     def __init__(self, rows, cols, device, zero=False):
-        self.rows, self.cols, self.pitch = rows, cols, _up8(cols)
+        self.rows, self.cols, self.pitch = rows, cols, (cols + 63) // 64 * 64
         self.pstride = rows * self.pitch
         alloc = torch.zeros if zero else torch.empty
         self.buf = alloc(3 * self.pstride, dtype=torch.bfloat16, device=device)
@@ -131,4 +134,29 @@ def inverse_from_chol(L):
 
 def planes_bytes(P):
     """Peak extra device memory of ``inverse_from_chol`` beside L and Sigma (the planes of Y and the block temporaries)."""
-    return 6 * P * _up8(P) + 6 * NB * _up8(P) + 6 * P * NB + 6 * NB * NB + 4 * P * NB
+    return 6 * P * (_up8(P) + 56) + 6 * NB * (_up8(P) + 56) + 6 * P * NB + 6 * NB * NB + 4 * P * NB
+
+
+def use_tc(P):
+    return ENGINE == 'tc' and P >= MIN_P
+
+
+def cholesky(A):
+    """Lower Cholesky factor of A as a new tensor (torch.linalg.cholesky semantics; A is left untouched)."""
+    if use_tc(A.shape[0]):
+        return cholesky_lower(A.clone(memory_format=torch.contiguous_format))
+    return torch.linalg.cholesky(A)
+
+
+def posterior_from_precision(H):
+    """(Sigma_chol, Sigma) of preds/laplace.py:43-45 from the precision H: chol(H) -> Sigma = H^-1 -> chol(Sigma)."""
+    if not use_tc(H.shape[0]):
+        from . import dense
+        chol = torch.linalg.cholesky(H)
+        Sigma = dense.spd_inverse_from_chol(chol)
+        del chol
+        return torch.linalg.cholesky(Sigma), Sigma
+    chol = cholesky(H)
+    Sigma = inverse_from_chol(chol)
+    del chol
+    return cholesky(Sigma), Sigma

@@ -23,6 +23,7 @@ from .kron import Kron
 from .predictives import functional_sampling_predictive, nn_sampling_predictive, functional_mean_predictive
 from . import parallel
 from . import dense
+from . import factor
 
 # Full GGN: loader batches are concatenated into super-batches of up to this many examples per
 # accumulation call (bounded by FULL_SCRATCH_FLOATS of kernel scratch).  Inside the library one
@@ -276,13 +277,17 @@ class Laplace:
             check(lib.bnnp_symmetrize_lower(ptr(H), self.P, stream()), 'bnnp_symmetrize_lower')
 
     def _factorise_full(self, H, sharded=False):
-        """chol(H) -> Sigma = H^-1 -> chol(Sigma) (preds/laplace.py:43-45), one-off, on device
-        through cuSOLVER (torch.linalg).  Sigma itself is kept: the reference recomputes
-        L L^T on every predictive call (preds/laplace.py:111).  ``sharded`` (data-parallel mode, every rank holds the
-        same H): the inverse -- half of the one-off time -- is split between the ranks (dense.spd_inverse_sharded)."""
+        """chol(H) -> Sigma = H^-1 -> chol(Sigma) (preds/laplace.py:43-45), one-off, on device.  Sigma itself is kept: the
+        reference recomputes L L^T on every predictive call (preds/laplace.py:111).
+
+        From factor.MIN_P parameters on, every O(P^3) product of the chain runs on the library's own tensor-core GEMM
+        (factor.py / csrc/gemm3.cu: 1.75 s at P = 59 635 against 10.0 s for the three cuSOLVER calls, residual
+        |H Sigma - I| 7e-5 against potri's 2.7e-4); in the data-parallel mode every rank holds the same H and runs the same
+        deterministic chain, so all ranks end with identical bits.  factor.ENGINE = 'library' restores the cuSOLVER path,
+        whose inverse is split between the ranks when ``sharded`` (dense.spd_inverse_sharded)."""
+        if factor.use_tc(H.shape[0]):
+            return factor.posterior_from_precision(H)
         chol = torch.linalg.cholesky(H)
-        # potri is the slow third of the three factorisations (7.1 of 10.2 s at P = 59 635): above dense.MIN_P the
-        # inverse comes from a blocked triangular inverse + blocked Gram (same fp32 arithmetic class, 2.9 s)
         Sigma = dense.spd_inverse_from_chol(chol, sharded=sharded)
         del chol
         return torch.linalg.cholesky(Sigma), Sigma

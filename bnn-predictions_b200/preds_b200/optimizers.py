@@ -10,6 +10,7 @@ from torch.nn.utils import parameters_to_vector
 from torch.optim import Adam
 
 from . import dense
+from . import factor
 from .gradients import Jacobians
 
 
@@ -98,13 +99,13 @@ class LaplaceGGN(Adam):
         model.train(was_training)
         rhs = grad_term + curvature @ theta_star + P0 @ mu0
         precision = curvature.add_(P0)
-        factor = torch.linalg.cholesky(precision)
+        pchol = factor.cholesky(precision)              # library below factor.MIN_P, own tensor-core chain above
         self.state['precision'] = precision
-        self.state['mu'] = torch.cholesky_solve(rhs.unsqueeze(1), factor, upper=False).squeeze(1)
-        Sigma = dense.spd_inverse_from_chol(factor)     # potri below dense.MIN_P, blocked inverse above
-        del factor
+        self.state['mu'] = torch.cholesky_solve(rhs.unsqueeze(1), pchol, upper=False).squeeze(1)
+        Sigma = factor.inverse_from_chol(pchol) if factor.use_tc(pchol.shape[0]) else dense.spd_inverse_from_chol(pchol)
+        del pchol
         self.state['Sigma'] = Sigma
-        self.state['Sigma_chol'] = torch.linalg.cholesky(Sigma)
+        self.state['Sigma_chol'] = factor.cholesky(Sigma)
         return self
 
 

@@ -19,6 +19,7 @@ from torch.optim import Adam
 
 from . import _cabi as cabi
 from . import dense
+from . import factor
 from ._cabi import lib, check, ptr, stream
 from ._engine import net_for
 
@@ -76,8 +77,9 @@ class _Linearised:
 
 def _chol_inverse_chol(prec):
     """(chol(prec), chol(prec^-1)) -- preds/refine.py:36-38,72,75."""
-    pchol = torch.linalg.cholesky(prec)
-    return pchol, torch.linalg.cholesky(dense.spd_inverse_from_chol(pchol))
+    pchol = factor.cholesky(prec)
+    Sigma = factor.inverse_from_chol(pchol) if factor.use_tc(pchol.shape[0]) else dense.spd_inverse_from_chol(pchol)
+    return pchol, factor.cholesky(Sigma)
 
 
 def laplace_refine(model, X, y, likelihood, prior_prec, n_epochs=1000, lr=1e-3):

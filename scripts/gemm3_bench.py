@@ -41,3 +41,13 @@ if which in ('all', 'diag'):
     L = torch.linalg.cholesky(D)
     ms2 = timeit(lambda: _tri_inv(L), 10)
     print('diag block %d: cholesky_ex %.3f ms, triangular inverse %.3f ms' % (K, ms, ms2))
+if which in ('sigma',):
+    # one K segment of Sigma = Y Y^T: operands are 4096-wide column slices of [m, m] planes (row pitch 2 m bytes)
+    py = _Planes(m, m, 'cuda', zero=True)
+    py.buf.copy_(torch.randn(py.buf.numel(), device='cuda').to(torch.bfloat16))
+    k0, kk = m - 8192, 4096
+    rows = k0 + kk
+    ms = timeit(lambda: _gemm3(rows, rows, kk, 1.0, py, py.addr(0, k0), py, py.addr(0, k0), 1.0, C.data_ptr(), m, lower=1, ktri=2, koff=-k0))
+    nt = (rows + 127) // 128
+    macs = sum((mt + 1) * 128 * 128 * (kk - max(0, mt * 128 - k0) // 32 * 32) for mt in range(nt))
+    print('sigma segment rows %d K %d: %.3f ms  %.0f TFLOP/s bf16' % (rows, kk, ms, macs * 12 / ms / 1e9))
