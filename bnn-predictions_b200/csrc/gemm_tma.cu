@@ -497,3 +497,10 @@ extern "C" int bnnp_split_bf16_t(const float* src, int64_t ld_src, int64_t rows,
   return split_transposed(src, ld_src, rows, cols, pitch, reinterpret_cast<__nv_bfloat16*>(hi),
                           reinterpret_cast<__nv_bfloat16*>(lo), false, as_stream(stream));
 }
+
+extern "C" int bnnp_split_bf16_rows(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t pitch, void* hi,
+                                    void* lo, void* stream) {
+  if (!src || !hi || !lo || rows <= 0 || cols <= 0) return BNNP_ERR_INVALID;
+  return split_rows(src, ld_src, rows, cols, pitch, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo),
+                    false, as_stream(stream));
+}

@@ -443,9 +443,14 @@ static int build_param_maps(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* 
 
 extern "C" int bnnp_jacobians(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                               const float* X, const float* ws, float* Js, void* stream) {
-  if (!ops || !plan || !ws || !Js || N <= 0) return BNNP_ERR_INVALID;
+  if (!plan) return BNNP_ERR_INVALID;
+  return bnnp_jacobians_cols(ops, n_ops, plan, N, plan->K, X, ws, Js, stream);
+}
+
+extern "C" int bnnp_jacobians_cols(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
+                                   const float* X, const float* ws, float* Js, void* stream) {
+  if (!ops || !plan || !ws || !Js || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
-  const int V = plan->K;
   for (int i = 0; i < n_ops; ++i) {
     const bnnp_op_t& o = ops[i];
     if (!is_param_op(o)) continue;

@@ -66,6 +66,7 @@ _SIGS = {
     'bnnp_lik_residual': (_I, [_I, _P, _P, _L, _I, _F, _P, _V]),
     'bnnp_lik_inv_link': (_I, [_I, _P, _L, _I, _P, _V]),
     'bnnp_jacobians': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _V]),
+    'bnnp_jacobians_cols': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _P, _V]),
     'bnnp_ggn_full_scratch_floats': (_L, [_PLAN, _L, _I]),
     'bnnp_ggn_full_accum': (_I, [_OPS, _I, _PLAN, _L, _P, _P, _P, _P, _I, _V]),
     'bnnp_ggn_full_row_chunks': (_I, [_OPS, _I, _PLAN, _L, _I, _I, C.POINTER(C.c_int64)]),
@@ -114,6 +115,7 @@ _SIGS = {
     'bnnp_gemm_nt_scratch_floats': (_L, [_L, _L, _L]),
     'bnnp_gemm_nt_split': (_I, [_L, _L, _L, _F, _P, _P, _L, _P, _P, _L, _F, _P, _L, _P, _V]),
     'bnnp_split_bf16_t': (_I, [_P, _L, _L, _L, _L, _P, _P, _V]),
+    'bnnp_split_bf16_rows': (_I, [_P, _L, _L, _L, _L, _P, _P, _V]),
     'bnnp_split3_bf16': (_I, [_P, _L, _L, _L, _P, _L, _L, _I, _F, _V]),
     'bnnp_gemm3_nt': (_I, [_L, _L, _L, _F, _P, _L, _L, _P, _L, _L, _F, _P, _L, _I, _I, _L, _V]),
     'bnnp_sgemm_tc_scratch_floats': (_L, [_L, _L, _L]),

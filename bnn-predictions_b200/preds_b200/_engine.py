@@ -339,6 +339,21 @@ class Net:
         return Js, f
 
 
+    def output_jacobian(self, X, output):
+        """(J [N,P], f [N,K]) for ONE network output: forward + a one-column backward seeded with e_output
+        (preds/gradients.py:49-77 ``Jacobians_gp`` with a single output)."""
+        X2d = self.prepare(X)
+        N = X2d.shape[0]
+        pl, ws, f = self.forward(X2d, 1)
+        seed = torch.zeros(N, 1, self.K, dtype=torch.float32, device=self.device)
+        seed[:, 0, int(output)] = 1.0
+        self.backward(pl, ws, seed, N, 1)
+        J = torch.empty(N, self.P, dtype=torch.float32, device=self.device)
+        check(lib.bnnp_jacobians_cols(self.ops, self.n_ops, C.byref(pl), N, 1, ptr(X2d), ptr(ws), ptr(J), stream()),
+              'bnnp_jacobians_cols')
+        return J, f
+
+
 _NETS = weakref.WeakKeyDictionary()        # model -> Net; entries die with the model
 
 

@@ -24,6 +24,8 @@ from .predictives import functional_sampling_predictive, nn_sampling_predictive,
 from . import parallel
 from . import dense
 from . import factor
+from . import gps
+from .likelihoods import CategoricalLh
 
 # Full GGN: loader batches are concatenated into super-batches of up to this many examples per
 # accumulation call (bounded by FULL_SCRATCH_FLOATS of kernel scratch).  Inside the library one
@@ -397,3 +399,56 @@ class Laplace:
             return self.prior_prec.to(self.device)
         else:
             raise ValueError('Invalid shape for prior precision')
+
+
+class FunctionaLaplace:
+    """Function-space Laplace of ``preds/laplace.py:138-207``: the GP whose kernel is the NTK ``J J^T / delta`` of the
+    trained network on a subset of the training inputs, evaluated at the test inputs.  Same constructor, ``infer`` and
+    ``predictive_samples`` signatures; ``gp_quantities`` holds the reference's dictionary with the tensors left on the
+    model's device (the reference keeps them on the host and moves them back for every predictive call).  Categorical
+    likelihoods only (the reference's Bernoulli branch hands a [m, 1] mean to a [m]-variate normal).  Additive:
+    ``eps`` / ``seed`` on ``predictive_samples`` to inject or fix the standard-normal draws."""
+
+    def __init__(self, model, prior_prec, likelihood, cache_Js=True):
+        assert np.isscalar(prior_prec)
+        self.model = model
+        self.prior_prec = prior_prec
+        self.likelihood = likelihood
+        self.device = next(model.parameters()).device
+        self.Kwinvs = None
+        self.cache_Js = cache_Js
+        self.Js = None
+        self.train_loader = None
+        self.log_likelihood = None
+        self.inferred = False
+        self.gp_quantities = None
+        self.P = len(parameters_to_vector(model.parameters()))
+        # gp_quantities reads these (preds/laplace.py:155-160)
+        model.likelihood = likelihood
+        log_var = -torch.log(torch.tensor(prior_prec))
+        for p in model.parameters():
+            setattr(p, 'log_prior_var', log_var)
+
+    def infer(self, train_loadera, train_loaderb, max_ram_gb=10, batch_size_per_gpu=512, print_progress=False):
+        cabi.require_device(next(self.model.parameters()))
+        self.train_loader = train_loadera
+        X1 = torch.cat([batch[0] for batch in train_loadera], dim=0)
+        X2 = torch.cat([batch[0] for batch in train_loaderb], dim=0)
+        self.gp_quantities = gps.gp_quantities_device(self.model, X1, X2, collapse_groups=True, with_prior_prec=False,
+                                                      max_ram_gb=max_ram_gb)
+        self.inferred = True
+
+    def predictive_moments(self, indep=False):
+        """(f_mu [m, C], f_var [m, C, C]) of the predictive at the inputs of ``train_loaderb`` (additive API)."""
+        if not self.inferred or 'f_star_test' not in self.gp_quantities:
+            raise ValueError('Need to infer first.')
+        if not isinstance(self.likelihood, CategoricalLh):
+            raise NotImplementedError('FunctionaLaplace: categorical likelihoods only')
+        return gps.gp_predictive_moments(self.gp_quantities, self.prior_prec, indep=indep)
+
+    def predictive_samples(self, n_samples=1000, batch_size=1024, indep=False, eps=None, seed=None):
+        """Monte-Carlo mean of the class probabilities at the test inputs, [m, C] (preds/laplace.py:175-207 returns the
+        first value of ``mc_preds``)."""
+        self.model.eval()
+        f_mu, f_var = self.predictive_moments(indep=indep)
+        return gps.mc_mean(self.likelihood, f_mu, f_var, n_samples=n_samples, batch_size=batch_size, eps=eps, seed=seed)

@@ -137,6 +137,11 @@ int bnnp_lik_inv_link(int lik, const float* f, int64_t rows, int K, float* out, 
  * preds/gradients.py:20-46; small shapes only.  Requires backward with V = K, seed = I. */
 int bnnp_jacobians(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                    const float* X, const float* ws, float* Js, void* stream);
+/* The same after a backward pass with V columns and an arbitrary seed [N,V,K]: Js [N,P,V] = seed-weighted output
+ * Jacobians.  V = 1 with a one-hot seed gives the [N,P] Jacobian of one output, the operand of the function-space kernels
+ * J_c J_c^T (preds/gradients.py:49-77 Jacobians_gp, preds/gps.py:30-53). */
+int bnnp_jacobians_cols(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V,
+                        const float* X, const float* ws, float* Js, void* stream);
 
 /* H[P,P] += sum_n J_n^T Lambda_n J_n  (preds/laplace.py:42, preds/optimizers.py:94), Linear-only
  * networks.  Only tiles on/below the diagonal are touched; call bnnp_symmetrize_lower() once
@@ -350,6 +355,11 @@ int bnnp_gemm_nt_split(int64_t M, int64_t N, int64_t K, float alpha, const void*
                        float* scratch, void* stream);
 int bnnp_split_bf16_t(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t pitch, void* hi, void* lo,
                       void* stream);
+/* bnnp_split_bf16 with an explicit destination pitch (>= cols, multiple of 8; columns cols..pitch-1 are zeroed): rows that
+ * start on 128-byte lines keep the 64-byte rows of the TMA boxes inside one sector pair (function-space kernels,
+ * preds/gps.py:56-88). */
+int bnnp_split_bf16_rows(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t pitch, void* hi, void* lo,
+                         void* stream);
 /* Tensor-core GEMM of the one-off factorisation (preds/laplace.py:43-45: torch.cholesky, torch.cholesky_inverse,
  * torch.cholesky on [P,P]) with the accuracy of an fp32 library GEMM: operands split into THREE bf16 planes (hi, mid, lo;
  * `plane_stride` elements apart, rows k-contiguous with pitch lda / ldb, multiples of 8 elements, 16-byte aligned), six MMAs

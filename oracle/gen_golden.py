@@ -323,7 +323,69 @@ def probe100_case(preds, name):
     print('%-12s P=%d  %.1f KB' % (name, P, os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
 
 
+def gp_case(preds, name, model, Xa, Xb, Xte, prior, S):
+    """Function-space inference (preds/laplace.py:138-207, preds/gps.py:664-927) of the UNMODIFIED reference, run on the
+    CPU through ``refharness.cuda_standins`` (the reference hard-codes CUDA devices; the stand-ins carry no arithmetic)."""
+    from preds.laplace import FunctionaLaplace
+    from preds.likelihoods import CategoricalLh
+    from preds.gps import gp_quantities, GP_predictive
+    from oracle.refharness.cuda_standins import cpu_as_cuda
+    out = {'theta': np_(flat(model)), 'Xa': np_(Xa), 'Xb': np_(Xb), 'Xte': np_(Xte), 'prior': np.array(prior)}
+    lh = CategoricalLh()
+    lap = FunctionaLaplace(model, prior, lh)
+    C = model.output_size
+    with cpu_as_cuda():
+        lap.infer([(Xa, None), (Xb, None)], [(Xte, None)], batch_size_per_gpu=5)
+        q = lap.gp_quantities
+        for k, v in q.items():
+            if torch.is_tensor(v):
+                out['q_' + k] = np_(v)
+        out['q_prior_var'] = np.array(q['prior_var'])
+        for indep in (0, 1):
+            eps = randn(900 + indep, S, len(Xte), C)
+            out['eps_%d' % indep] = np_(eps)
+            with refharness.inject_normals([eps]):
+                out['pred_%d' % indep] = np_(lap.predictive_samples(n_samples=S, batch_size=S, indep=bool(indep)))
+        # the distribution behind indep=False before its mean is replaced (preds/laplace.py:200-205)
+        fd = GP_predictive(lh, q['f_star_train'] - q['f_gp_train'], q['f_star_test'] - q['f_gp_test'],
+                           q['K_train'] / prior, q['K_train_test'] / prior, q['K_test'] / prior, q['f_gp_train'],
+                           out_device_id=-1, diag_only=True, batch_size_C=1, batch_size_M=len(Xte))
+        out['gp_mu'], out['gp_Sigma'] = np_(fd.mean), np_(fd.covariance_matrix)
+        # the other option paths: prior variance inside the kernel, groups not collapsed, full test block, two outputs
+        Xtr = torch.cat([Xa, Xb])
+        q2 = gp_quantities(model, Xtr, Xte, outputs=[0, C - 1], only_pred_var=False, collapse_groups=False,
+                           with_prior_prec=True, batch_size_per_gpu=4)
+        for k in ('K_train', 'K_train_test', 'K_test', 'f_gp_train', 'f_star_train', 'f_gp_test', 'f_star_test'):
+            out['q2_' + k] = np_(q2[k])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print('%-12s P=%d  %.1f KB' % (name, len(out['theta']), os.path.getsize(os.path.join(OUT, name + '.npz')) / 1e3))
+
+
+def gp_cases(preds):
+    from preds.models import MLPS
+    from deepobs.pytorch.testproblems.testproblems_utils import tfconv2d, tfmaxpool2d
+    torch.manual_seed(81)
+    model = MLPS(5, [8, 6], 3, 'tanh')
+    X = randn(40, 20, 5)
+    gp_case(preds, 'gp_mlp', model, X[:12], X[12:], randn(41, 7, 5), 0.7, 64)
+    torch.manual_seed(82)
+    model = torch.nn.Sequential()
+    model.add_module('conv1', tfconv2d(2, 4, 3, tf_padding_type='same'))
+    model.add_module('relu1', torch.nn.ReLU())
+    model.add_module('pool1', tfmaxpool2d(3, stride=2, tf_padding_type='same'))
+    model.add_module('conv2', tfconv2d(4, 5, 3))
+    model.add_module('tanh2', torch.nn.Tanh())
+    model.add_module('flatten', torch.nn.Flatten())
+    model.add_module('dense', torch.nn.Linear(45, 4))
+    model.output_size = 4
+    X = randn(42, 14, 2, 9, 9)
+    gp_case(preds, 'gp_cnn', model, X[:8], X[8:], randn(43, 6, 2, 9, 9), 1.5, 48)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'gp':                     # the function-space cases only
+        gp_cases(refharness.load())
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'cifar100net_probe':      # one case only (the others are unchanged)
         probe100_case(refharness.load(), 'cifar100net_probe')
         return
@@ -416,6 +478,9 @@ def main():
 
     # (K) CIFAR100Net, K = 100
     probe100_case(preds, 'cifar100net_probe')
+
+    # (L) function-space inference
+    gp_cases(preds)
 
 
 if __name__ == '__main__':

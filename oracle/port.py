@@ -749,3 +749,75 @@ def vi_diag_refine(model, post, prior_prec_matrix, X, y, lh, eps, lr=1e-3):
         sigma_chol = torch.sqrt(1 / prec)
         losses.append((-_log_lik(lh, y, f_t) + kl_divergence(Normal(loc=mu, scale=sigma_chol), m_prior).sum()).item())
     return mu, torch.diag(sigma_chol), losses
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Function-space inference: preds/gps.py:664-927 gp_quantities, preds/laplace.py:138-207
+# FunctionaLaplace, preds/gps.py:384-447 GP_predictive, preds/gps.py:930-952 mc_preds.  Pinned against the unmodified
+# reference by tests/golden/gp_*.npz (oracle/gen_golden.py, run through refharness.cuda_standins).
+# ---------------------------------------------------------------------------------------------------------------------
+def gp_quantities(model, X_train, X_test, prior_var=None, outputs=None, only_pred_var=True):
+    """The dictionary of preds/gps.py:910-925 for one prior-variance group (kernel slot axis dropped, as
+    ``collapse_groups=True`` does): per output c K_train[c] = J_c J_c^T (preds/gps.py:64-88 ``Parallel_calc_kernel`` summed
+    over the parameter slices), K_train_test, K_test = its diagonal (``only_pred_var``) or the full block,
+    f_gp = J_c theta (``Parallel_calc_gp_function``, :91-97), f_star = f^T[outputs].  ``prior_var`` scales the kernels
+    (``with_prior_prec=True``); FunctionaLaplace passes ``with_prior_prec=False``."""
+    theta = get_theta(model)
+    Jtr, ftr = jacobians(model, X_train)              # [n, P, C]
+    Jte, fte = jacobians(model, X_test)
+    if Jtr.dim() == 2:
+        Jtr, Jte = Jtr.unsqueeze(2), Jte.unsqueeze(2)
+    ftr, fte = ftr.reshape(len(X_train), -1), fte.reshape(len(X_test), -1)
+    if outputs is not None:
+        Jtr, Jte, ftr, fte = Jtr[:, :, outputs], Jte[:, :, outputs], ftr[:, outputs], fte[:, outputs]
+    s = 1.0 if prior_var is None else float(prior_var)
+    return {
+        'K_train': s * torch.einsum('npc,mpc->cnm', Jtr, Jtr),
+        'K_train_test': s * torch.einsum('npc,mpc->cnm', Jtr, Jte),
+        'K_test': s * (torch.einsum('mpc,mpc->cm', Jte, Jte) if only_pred_var else torch.einsum('npc,mpc->cnm', Jte, Jte)),
+        'f_gp_train': torch.einsum('npc,p->cn', Jtr, theta),
+        'f_gp_test': torch.einsum('mpc,p->cm', Jte, theta),
+        'f_star_train': ftr.t().contiguous(),
+        'f_star_test': fte.t().contiguous(),
+    }
+
+
+def gp_predictive_moments(q, prior_prec, indep=False):
+    """(mean [m, C], covariance [m, C, C]) of the distribution FunctionaLaplace.predictive_samples draws from
+    (preds/laplace.py:180-205): the kernels divided by the prior precision; ``indep`` -> per-class binary GPs with
+    W = p (1 - p) (:186-199); otherwise GP_predictive's categorical branch (preds/gps.py:411-426, E / M / b / c of
+    ``Parallel_calc_E_z`` :99-110 and ``Parallel_calc_b_c_pred`` :113-122); the mean is replaced by f_star_test (:205)."""
+    K_nn, K_nm, K_m = q['K_train'] / prior_prec, q['K_train_test'] / prior_prec, q['K_test'] / prior_prec
+    C, n, m = K_nm.shape
+    mean = q['f_star_test'].t()
+    cov = torch.zeros(m, C, C)
+    if indep:
+        p = torch.softmax(q['f_star_train'], dim=0)
+        w = torch.sqrt(p * (1 - p))
+        B = w.unsqueeze(2) * K_nn * w.unsqueeze(1)
+        B.diagonal(dim1=1, dim2=2).add_(1.0)
+        Kinv = w.unsqueeze(2) * torch.inverse(B) * w.unsqueeze(1)
+        gain = torch.einsum('cnm,cnp,cpm->cm', K_nm, Kinv, K_nm)
+        cov.diagonal(dim1=1, dim2=2).copy_((K_m - gain).t())
+        return mean, cov
+    pi = torch.softmax(q['f_star_train'], dim=0)
+    d = pi.sqrt()
+    A = K_nn * d.unsqueeze(1) * d.unsqueeze(2)
+    A.diagonal(dim1=1, dim2=2).add_(1.0)
+    L = torch.linalg.cholesky(A)
+    E = torch.cholesky_solve(torch.diag_embed(d), L) * d.unsqueeze(2)
+    M = torch.linalg.cholesky(E.sum(0))
+    b = torch.einsum('cnm,cni->cmi', E, K_nm)
+    c_ = torch.cholesky_solve(b, M)
+    cov = torch.einsum('mcn,mnd->mcd', b.permute(2, 0, 1), c_.permute(2, 1, 0)).contiguous()
+    diag_term = torch.einsum('mcn,mnc->mc', K_nm.permute(2, 0, 1), b.permute(2, 1, 0))
+    cov.diagonal(dim1=1, dim2=2).add_(K_m.t() - diag_term)
+    return mean, cov
+
+
+def gp_mc_mean(mean, cov, eps):
+    """mc_preds' Monte-Carlo mean of softmax(f) (preds/gps.py:930-952) for injected eps [S, m, C]:
+    f = mean + chol(cov) eps (MultivariateNormal) -- for a diagonal cov that is Normal(mean, sqrt(var)) (:199)."""
+    L = torch.linalg.cholesky(cov)
+    fs = mean.unsqueeze(0) + torch.einsum('mcd,smd->smc', L, eps)
+    return torch.softmax(fs, dim=-1).mean(0)

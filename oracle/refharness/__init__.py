@@ -74,7 +74,13 @@ class inject_normals:
         def std(shape, dtype, device):
             return take(tuple(shape))
 
+        def normal(mean, std_, *a, **k):
+            # Normal.sample draws through torch.normal(loc.expand(shape), scale.expand(shape)) (preds/laplace.py:199)
+            return mean + std_ * take(tuple(mean.shape))
+
+        self._normal = torch.normal
         torch.randn = randn
+        torch.normal = normal
         mvn._standard_normal = std
         nrm._standard_normal = std
         return self
@@ -84,6 +90,7 @@ class inject_normals:
         import torch.distributions.multivariate_normal as mvn
         import torch.distributions.normal as nrm
         torch.randn = self._randn
+        torch.normal = self._normal
         mvn._standard_normal = self._std
         nrm._standard_normal = self._nstd
         return False

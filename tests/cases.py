@@ -100,3 +100,31 @@ def ggn_prior(g, P):
     pp = torch.from_numpy(g['prior_prec'])
     pm = torch.from_numpy(g['prior_mu'])
     return (float(pp) if pp.dim() == 0 else pp), (float(pm) if pm.dim() == 0 else pm)
+
+
+# ---- function-space inference (preds/gps.py:664-927, preds/laplace.py:138-207) --------
+GP_CASES = ['gp_mlp', 'gp_cnn']
+
+
+def make_gp_port_model(name):
+    if name == 'gp_mlp':
+        return port.make_mlps(5, [8, 6], 3, 'tanh')
+    net = nn.Sequential(port.SamePad2d(3, 1), nn.Conv2d(2, 4, 3), nn.ReLU(), port.SamePad2d(3, 2), nn.MaxPool2d(3, 2),
+                        nn.Conv2d(4, 5, 3), nn.Tanh(), nn.Flatten(), nn.Linear(45, 4))
+    net.output_size = 4
+    return net
+
+
+def make_gp_product_model(name, models):
+    if name == 'gp_mlp':
+        return models.MLPS(5, [8, 6], 3, 'tanh')
+    net = nn.Sequential()
+    net.add_module('conv1', models.tfconv2d(2, 4, 3, tf_padding_type='same'))
+    net.add_module('relu1', nn.ReLU())
+    net.add_module('pool1', models.tfmaxpool2d(3, stride=2, tf_padding_type='same'))
+    net.add_module('conv2', models.tfconv2d(4, 5, 3))
+    net.add_module('tanh2', nn.Tanh())
+    net.add_module('flatten', nn.Flatten())
+    net.add_module('dense', nn.Linear(45, 4))
+    net.output_size = 4
+    return net
