@@ -43,6 +43,8 @@ struct Args {
   long long n_tiles;
   float alpha, beta;
   float* C; long long ldc;
+  int own_mod, own_rank, own_dim;   // own_mod > 1: this process computes only the tiles whose global column (own_dim 0) /
+  long long own_off;                //   row (own_dim 1) tile index (local index + own_off) is congruent to own_rank
 };
 
 struct Maps { CUtensorMap a[3], b[3]; };
@@ -84,6 +86,13 @@ __device__ __forceinline__ void tile_of(const Args& g, long long t, int& mt, int
     mt = (int)(r0 + v % h);
     nt = (int)(J * SUPER + v / h);
   }
+}
+// tiles of other ranks (the factorisation shared between the GPUs of a data-parallel job: every tile has one owner, fixed in
+// global tile coordinates, so a rank's copy of the matrix is always complete on the tiles it owns)
+__device__ __forceinline__ bool tile_is_mine(const Args& g, int mt, int nt) {
+  if (g.own_mod <= 1) return true;
+  const long long i = (g.own_dim ? (long long)mt : (long long)nt) + g.own_off;
+  return (int)(i % g.own_mod) == g.own_rank;
 }
 // first K-stage of a tile (operands that are triangular: everything before the tile's origin is zero)
 __device__ __forceinline__ int first_stage(const Args& g, int mt, int nt) {
@@ -131,6 +140,7 @@ gemm3_kernel(const __grid_constant__ Maps maps, Args args) {
       for (long long tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
         int mt, nt;
         tile_of(args, tile, mt, nt);
+        if (!tile_is_mine(args, mt, nt)) continue;
         const int s_beg = first_stage(args, mt, nt);
         for (int c = s_beg; c < tot_stages; ++c) {
           mbar_wait(&empty[s], ph ^ 1);
@@ -153,6 +163,7 @@ gemm3_kernel(const __grid_constant__ Maps maps, Args args) {
       for (long long tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
         int mt, nt;
         tile_of(args, tile, mt, nt);
+        if (!tile_is_mine(args, mt, nt)) continue;
         const int n_st = tot_stages - first_stage(args, mt, nt);
         if (n_st <= 0) continue;
         const uint32_t cb = cc & 1;
@@ -200,6 +211,7 @@ gemm3_kernel(const __grid_constant__ Maps maps, Args args) {
     for (long long tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
       int mt, nt;
       tile_of(args, tile, mt, nt);
+      if (!tile_is_mine(args, mt, nt)) continue;
       const int n_st = tot_stages - first_stage(args, mt, nt);
       float acc[TILE];
 #pragma unroll
@@ -369,7 +381,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 
 int gemm3_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* A, int64_t lda, int64_t a_pstride,
              const __nv_bfloat16* B, int64_t ldb, int64_t b_pstride, float beta, float* C, int64_t ldc, int lower, int ktri,
-             int64_t koff, cudaStream_t st) {
+             int64_t koff, cudaStream_t st, int own_mod, int own_rank, int own_dim, int64_t own_off) {
   using namespace t3;
   if (M <= 0 || N <= 0 || K <= 0) return BNNP_OK;
   if (!A || !B || !C || (lda & 7) || (ldb & 7) || (a_pstride & 7) || (b_pstride & 7)) return BNNP_ERR_INVALID;
@@ -384,6 +396,8 @@ int gemm3_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* 
   a.lower = lower; a.ktri = ktri; a.koff = koff;
   a.n_tiles = lower ? (long long)a.n_mt * (a.n_mt + 1) / 2 : (long long)a.n_mt * a.n_nt;
   a.alpha = alpha; a.beta = beta; a.C = C; a.ldc = ldc;
+  if (own_mod > 1 && (own_rank < 0 || own_rank >= own_mod || own_off < 0)) return BNNP_ERR_INVALID;
+  a.own_mod = own_mod; a.own_rank = own_rank; a.own_dim = own_dim; a.own_off = own_off;
   Maps maps;
   int rc;
   for (int p = 0; p < 3; ++p) {
@@ -442,5 +456,15 @@ extern "C" int bnnp_gemm3_nt(int64_t M, int64_t N, int64_t K, float alpha, const
   if (M <= 0 || N <= 0 || K <= 0) return BNNP_ERR_INVALID;
   return gemm3_nt(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(A), lda, a_plane_stride,
                   reinterpret_cast<const __nv_bfloat16*>(B), ldb, b_plane_stride, beta, C, ldc, lower, ktri, koff,
-                  as_stream(stream));
+                  as_stream(stream), 1, 0, 0, 0);
+}
+
+extern "C" int bnnp_gemm3_nt_owned(int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda,
+                                   int64_t a_plane_stride, const void* B, int64_t ldb, int64_t b_plane_stride, float beta,
+                                   float* C, int64_t ldc, int lower, int ktri, int64_t koff, int own_mod, int own_rank,
+                                   int own_dim, int64_t own_off, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return BNNP_ERR_INVALID;
+  return gemm3_nt(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(A), lda, a_plane_stride,
+                  reinterpret_cast<const __nv_bfloat16*>(B), ldb, b_plane_stride, beta, C, ldc, lower, ktri, koff,
+                  as_stream(stream), own_mod, own_rank, own_dim, own_off);
 }

@@ -118,6 +118,7 @@ _SIGS = {
     'bnnp_split_bf16_rows': (_I, [_P, _L, _L, _L, _L, _P, _P, _V]),
     'bnnp_split3_bf16': (_I, [_P, _L, _L, _L, _P, _L, _L, _I, _F, _V]),
     'bnnp_gemm3_nt': (_I, [_L, _L, _L, _F, _P, _L, _L, _P, _L, _L, _F, _P, _L, _I, _I, _L, _V]),
+    'bnnp_gemm3_nt_owned': (_I, [_L, _L, _L, _F, _P, _L, _L, _P, _L, _L, _F, _P, _L, _I, _I, _L, _I, _I, _I, _L, _V]),
     'bnnp_sgemm_tc_scratch_floats': (_L, [_L, _L, _L]),
     'bnnp_sgemm_tc': (_I, [_I, _I, _L, _L, _L, _F, _P, _L, _P, _L, _F, _P, _L, _P, _V]),
     'bnnp_launch_count': (C.c_uint64, []),

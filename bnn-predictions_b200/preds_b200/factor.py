@@ -46,9 +46,34 @@ class _Planes:
                                    scale, stream()), 'bnnp_split3_bf16')
 
 
-def _gemm3(M, N, K, alpha, A, a_addr, B, b_addr, beta, c_addr, ldc, lower=0, ktri=0, koff=0):
-    check(lib.bnnp_gemm3_nt(M, N, K, alpha, a_addr, A.pitch, A.pstride, b_addr, B.pitch, B.pstride, beta, c_addr, ldc,
-                            lower, ktri, koff, stream()), 'bnnp_gemm3_nt')
+def _gemm3(M, N, K, alpha, A, a_addr, B, b_addr, beta, c_addr, ldc, lower=0, ktri=0, koff=0, own=None):
+    """own = (world, rank, dim, offset): only the tiles of C whose global column (dim 0) / row (dim 1) tile index is
+    congruent to rank modulo world are computed (the chain shared between the ranks of a data-parallel job)."""
+    if own is None or own[0] <= 1:
+        check(lib.bnnp_gemm3_nt(M, N, K, alpha, a_addr, A.pitch, A.pstride, b_addr, B.pitch, B.pstride, beta, c_addr, ldc,
+                                lower, ktri, koff, stream()), 'bnnp_gemm3_nt')
+    else:
+        check(lib.bnnp_gemm3_nt_owned(M, N, K, alpha, a_addr, A.pitch, A.pstride, b_addr, B.pitch, B.pstride, beta, c_addr,
+                                      ldc, lower, ktri, koff, own[0], own[1], own[2], own[3], stream()),
+              'bnnp_gemm3_nt_owned')
+
+
+TILE = 128           # tile edge of bnnp_gemm3_nt: the unit of ownership when the chain is shared between ranks
+
+
+def _group(shared):
+    """(dist, rank, world) of the default process group when the chain is to be shared between its ranks."""
+    if shared:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def _own_cols_mask(c0, ncols, rank, world, device):
+    """1.0 for the columns c0 .. c0+ncols-1 (global indices) whose 128-wide tile column belongs to ``rank``."""
+    t = (torch.arange(c0, c0 + ncols, device=device) // TILE) % world
+    return (t == rank).to(torch.float32)
 
 
 def _addr(t, r, c):
@@ -60,12 +85,19 @@ def _tri_inv(Lii):
     return torch.linalg.solve_triangular(Lii, eye, upper=False).contiguous()      # (the library hands back column-major)
 
 
-def cholesky_lower(A):
+def cholesky_lower(A, shared=False):
     """In-place lower Cholesky factor of the symmetric positive definite A [P,P] (fp32, contiguous; only the lower triangle
-    is read); the strict upper triangle of the result is zero.  Raises like torch.linalg.cholesky when A is not SPD."""
+    is read); the strict upper triangle of the result is zero.  Raises like torch.linalg.cholesky when A is not SPD.
+
+    ``shared``: every rank of the default process group calls this with the same A.  The tiles of the trailing update are
+    dealt out by global tile column (rank = column tile mod world), so a rank's copy is always complete on its own tiles;
+    after each update the NEXT panel column -- the only part anyone else needs -- is gathered (an all-reduce of a buffer
+    holding each rank's own 128-column strips and zeros elsewhere: 240 MB at P = 59 635).  Every tile is computed by the
+    same kernel on the same inputs as in the single-process chain, so every rank ends with exactly its bits."""
     P = A.shape[0]
     assert A.is_contiguous() and A.dtype == torch.float32
     dev = A.device
+    dist, rank, world = _group(shared)
     panel = _Planes(max(P - NB, 1), NB, dev)
     wpl = _Planes(NB, NB, dev)
     infos = []
@@ -85,18 +117,36 @@ def cholesky_lower(A):
         _gemm3(m, nb, nb, 1.0, panel, panel.addr(), wpl, wpl.addr(), 0.0, _addr(A, j0 + nb, j0), P)
         # trailing update, lower tiles: A22 -= L21 L21^T
         panel.fill(_addr(A, j0 + nb, j0), P, m, nb)
-        _gemm3(m, m, nb, -1.0, panel, panel.addr(), panel, panel.addr(), 1.0, _addr(A, j0 + nb, j0 + nb), P, lower=1)
+        j1 = j0 + nb
+        _gemm3(m, m, nb, -1.0, panel, panel.addr(), panel, panel.addr(), 1.0, _addr(A, j1, j1), P, lower=1,
+               own=(world, rank, 0, j1 // TILE))
+        if dist is not None:
+            nb1 = min(NB, P - j1)
+            col = A[j1:, j1:j1 + nb1]
+            stage = col * _own_cols_mask(j1, nb1, rank, world, dev)
+            dist.all_reduce(stage)
+            col.copy_(stage)
+            del stage
     if bool(torch.stack(infos).ne(0).any()) or not bool(torch.isfinite(A.diagonal()).all()):      # the only sync
         raise torch.linalg.LinAlgError('cholesky_lower: the matrix is not positive definite')
     A.tril_()
     return A
 
 
-def inverse_from_chol(L):
-    """Sigma = (L L^T)^-1 [P,P] (symmetric, both triangles filled) from the lower Cholesky factor L."""
+def inverse_from_chol(L, shared=False):
+    """Sigma = (L L^T)^-1 [P,P] (symmetric, both triangles filled) from the lower Cholesky factor L.
+
+    ``shared`` (every rank holds the same L): the rows of Y = L^-T are independent of each other -- row n of a new block
+    column needs row n of the earlier ones only -- so they are dealt out by 128-row tile and built without any
+    communication; one all-reduce of the planes (disjoint supports: a gather) completes Y everywhere, then the tiles of
+    Sigma = Y Y^T are dealt out by tile column and gathered the same way.  Same kernels on the same inputs per tile as the
+    single-process chain: identical bits."""
     P = L.shape[0]
     assert L.is_contiguous() and L.dtype == torch.float32
     dev = L.device
+    dist, rank, world = _group(shared)
+    by_row, by_col = (world, rank, 1, 0), (world, rank, 0, 0)
+    diag_blocks = []
     Y = _Planes(P, P, dev, zero=True)                      # Y = L^-T (upper triangular), only ever an operand
     lrow = _Planes(NB, max(P - 1, 1), dev)
     tpl = _Planes(max(P - 1, 1), NB, dev)
@@ -106,6 +156,8 @@ def inverse_from_chol(L):
         nb = min(NB, P - i0)
         Xii = _tri_inv(L[i0:i0 + nb, i0:i0 + nb])
         Y.fill(Xii.data_ptr(), nb, nb, nb, r=i0, c=i0, transposed=True)
+        if dist is not None:
+            diag_blocks.append((i0, nb, Xii))
         if i0 == 0:
             continue
         # Tt[n, m] = sum_{n <= k < i0} Y[n, k] L[i0 + m, k]
@@ -115,19 +167,29 @@ def inverse_from_chol(L):
         for k0 in range(0, i0, KSEG):
             kk = min(KSEG, i0 - k0)
             rows = min(i0, k0 + kk)                        # rows n >= k0 + kk have no entry in this segment
-            _gemm3(rows, nb, kk, 1.0, Y, Y.addr(0, k0), lrow, lrow.addr(0, k0), 1.0, Tt.data_ptr(), nb, ktri=2, koff=-k0)
+            _gemm3(rows, nb, kk, 1.0, Y, Y.addr(0, k0), lrow, lrow.addr(0, k0), 1.0, Tt.data_ptr(), nb, ktri=2, koff=-k0,
+                   own=by_row)
         # Y[:i0, I] = -Tt Xii^T :  out[n, m'] = -sum_m Tt[n, m] Xii[m', m]
         tpl.fill(Tt.data_ptr(), nb, i0, nb)
         xpl.fill(Xii.data_ptr(), nb, nb, nb)
-        _gemm3(i0, nb, nb, -1.0, tpl, tpl.addr(), xpl, xpl.addr(), 0.0, Tt.data_ptr(), nb)
+        # (rows of other ranks: Tt stays zero there, and so do their planes)
+        _gemm3(i0, nb, nb, -1.0, tpl, tpl.addr(), xpl, xpl.addr(), 0.0, Tt.data_ptr(), nb, own=by_row)
         Y.fill(Tt.data_ptr(), nb, i0, nb, r=0, c=i0)
     del lrow, tpl, xpl, T
+    if dist is not None:
+        dist.all_reduce(Y.buf)                             # disjoint row supports: exact in bf16
+        for i0, nb, Xii in diag_blocks:                    # (every rank had written every diagonal block)
+            Y.fill(Xii.data_ptr(), nb, nb, nb, r=i0, c=i0, transposed=True)
+        del diag_blocks
     S = torch.zeros(P, P, dtype=torch.float32, device=dev)
     for k0 in range(0, P, KSEG):
         kk = min(KSEG, P - k0)
         rows = min(P, k0 + kk)
-        _gemm3(rows, rows, kk, 1.0, Y, Y.addr(0, k0), Y, Y.addr(0, k0), 1.0, S.data_ptr(), P, lower=1, ktri=2, koff=-k0)
+        _gemm3(rows, rows, kk, 1.0, Y, Y.addr(0, k0), Y, Y.addr(0, k0), 1.0, S.data_ptr(), P, lower=1, ktri=2, koff=-k0,
+               own=by_col)
     del Y
+    if dist is not None:
+        dist.all_reduce(S)                                 # disjoint tile supports: a gather
     check(lib.bnnp_symmetrize_lower(ptr(S), P, stream()), 'bnnp_symmetrize_lower')
     return S
 
@@ -141,22 +203,23 @@ def use_tc(P):
     return ENGINE == 'tc' and P >= MIN_P
 
 
-def cholesky(A):
+def cholesky(A, shared=False):
     """Lower Cholesky factor of A as a new tensor (torch.linalg.cholesky semantics; A is left untouched)."""
     if use_tc(A.shape[0]):
-        return cholesky_lower(A.clone(memory_format=torch.contiguous_format))
+        return cholesky_lower(A.clone(memory_format=torch.contiguous_format), shared=shared)
     return torch.linalg.cholesky(A)
 
 
-def posterior_from_precision(H):
-    """(Sigma_chol, Sigma) of preds/laplace.py:43-45 from the precision H: chol(H) -> Sigma = H^-1 -> chol(Sigma)."""
+def posterior_from_precision(H, shared=False):
+    """(Sigma_chol, Sigma) of preds/laplace.py:43-45 from the precision H: chol(H) -> Sigma = H^-1 -> chol(Sigma).
+    ``shared``: all ranks of the default process group hold the same H and split the work (identical bits everywhere)."""
     if not use_tc(H.shape[0]):
         from . import dense
         chol = torch.linalg.cholesky(H)
-        Sigma = dense.spd_inverse_from_chol(chol)
+        Sigma = dense.spd_inverse_from_chol(chol, sharded=shared)
         del chol
         return torch.linalg.cholesky(Sigma), Sigma
-    chol = cholesky(H)
-    Sigma = inverse_from_chol(chol)
+    chol = cholesky(H, shared=shared)
+    Sigma = inverse_from_chol(chol, shared=shared)
     del chol
-    return cholesky(Sigma), Sigma
+    return cholesky(Sigma, shared=shared), Sigma

@@ -284,11 +284,12 @@ class Laplace:
 
         From factor.MIN_P parameters on, every O(P^3) product of the chain runs on the library's own tensor-core GEMM
         (factor.py / csrc/gemm3.cu: 1.75 s at P = 59 635 against 10.0 s for the three cuSOLVER calls, residual
-        |H Sigma - I| 7e-5 against potri's 2.7e-4); in the data-parallel mode every rank holds the same H and runs the same
-        deterministic chain, so all ranks end with identical bits.  factor.ENGINE = 'library' restores the cuSOLVER path,
-        whose inverse is split between the ranks when ``sharded`` (dense.spd_inverse_sharded)."""
+        |H Sigma - I| 7e-5 against potri's 2.7e-4).  ``sharded`` (data-parallel mode, every rank holds the same H): the tiles
+        of every product are dealt out between the ranks and gathered (factor.py), every rank ends with the bits of the
+        single-process chain.  factor.ENGINE = 'library' restores the cuSOLVER path, whose inverse is split between the
+        ranks when ``sharded`` (dense.spd_inverse_sharded)."""
         if factor.use_tc(H.shape[0]):
-            return factor.posterior_from_precision(H)
+            return factor.posterior_from_precision(H, shared=sharded)
         chol = torch.linalg.cholesky(H)
         Sigma = dense.spd_inverse_from_chol(chol, sharded=sharded)
         del chol

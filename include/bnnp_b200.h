@@ -373,6 +373,15 @@ int bnnp_split3_bf16(const float* src, int64_t ld_src, int64_t rows, int64_t col
 int bnnp_gemm3_nt(int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda, int64_t a_plane_stride,
                   const void* B, int64_t ldb, int64_t b_plane_stride, float beta, float* C, int64_t ldc, int lower,
                   int ktri, int64_t koff, void* stream);
+/* The same with the 128 x 128 tiles of C dealt out between the `own_mod` processes of a data-parallel job: only the tiles
+ * whose global column (own_dim = 0) or row (own_dim = 1) tile index -- local index + own_off -- is congruent to own_rank
+ * modulo own_mod are computed, every other tile of C is left untouched.  Ownership is fixed in global coordinates, so across
+ * the panels of a blocked factorisation a rank's copy stays complete on its own tiles; the caller gathers what the next
+ * step needs (preds_b200/factor.py: the one-off factorisation shared between the ranks, every rank ends with the bits of
+ * the single-GPU chain). */
+int bnnp_gemm3_nt_owned(int64_t M, int64_t N, int64_t K, float alpha, const void* A, int64_t lda, int64_t a_plane_stride,
+                        const void* B, int64_t ldb, int64_t b_plane_stride, float beta, float* C, int64_t ldc, int lower,
+                        int ktri, int64_t koff, int own_mod, int own_rank, int own_dim, int64_t own_off, void* stream);
 /* y += alpha * x  (Kron.update axpy, preds/kron.py:62-66). */
 int bnnp_axpy(int64_t n, float alpha, const float* x, float* y, void* stream);
 

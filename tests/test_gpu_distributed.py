@@ -183,3 +183,42 @@ def test_two_gpu_lower_triangle_exchange(tmp_path):
         for qa, qb in zip(r['one_batch_kron'], lap.Sigma_chol.qhs):
             for a, b in zip(qa, qb):
                 assert torch.allclose(a, b.cpu(), rtol=1e-4, atol=1e-6)
+
+
+def _factor_worker(rank, world, port_no, out_dir):
+    for p in (ROOT, os.path.join(ROOT, 'bnn-predictions_b200')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from preds_b200 import factor
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port_no))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    g = torch.Generator(device='cuda').manual_seed(3)
+    P = 5003
+    A = torch.randn(P, 700, device='cuda', generator=g)
+    H = A @ A.T
+    H.diagonal().add_(float(H.diagonal().mean()) * 0.02)
+    dist.broadcast(H, 0)                                   # (two GPUs may round the product differently)
+    chol1, Sigma1 = factor.posterior_from_precision(H)
+    chol2, Sigma2 = factor.posterior_from_precision(H, shared=True)
+    L1 = factor.cholesky(H)
+    L2 = factor.cholesky(H, shared=True)
+    torch.save({'same_L': bool(torch.equal(L1, L2)), 'same_Sigma': bool(torch.equal(Sigma1, Sigma2)),
+                'same_chol': bool(torch.equal(chol1, chol2)), 'Sigma_rows': Sigma2[::53].cpu(),
+                'chol_rows': chol2[::53].cpu()}, os.path.join(out_dir, 'f%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_shared_factorisation(tmp_path):
+    """The one-off factorisation shared between two ranks (tiles of every product dealt out, panels / planes / Sigma
+    gathered): bit-identical to the single-process chain on both ranks."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    _spawn(_factor_worker, str(tmp_path))
+    res = [torch.load(os.path.join(str(tmp_path), 'f%d.pt' % r), weights_only=False) for r in range(2)]
+    for r in res:
+        assert r['same_L'] and r['same_Sigma'] and r['same_chol'], {k: v for k, v in r.items() if k.startswith('same')}
+    assert torch.equal(res[0]['Sigma_rows'], res[1]['Sigma_rows'])
+    assert torch.equal(res[0]['chol_rows'], res[1]['chol_rows'])
