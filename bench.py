@@ -361,6 +361,12 @@ def run_ours(args):
     if not args.no_glm:
         H.diagonal().add_(1.0 if world == 1 else 0.0)   # prior precision (N > 1: the exchange kernel already added it)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        if world > 1:
+            # the shared chain gathers panels (fp32) and planes (bf16) through NCCL: warm both paths of the communicator
+            for dt in (torch.float32, torch.bfloat16):
+                wbuf = torch.zeros(1 << 27, dtype=dt, device=dev)
+                dist.all_reduce(wbuf)
+                del wbuf
         barrier()
         ev[0].record()
         Sigma_chol, Sigma = lap._factorise_full(H, sharded=world > 1)
@@ -400,6 +406,12 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             glm_ms, e2e_glm_s, e2e_fused_s = float(t[0]), float(t[1]), float(t[2])
         pk, _ = peaks()
+        fact_ms = ev[0].elapsed_time(ev[1])
+        if world > 1:
+            t = torch.tensor([fact_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fact_ms = float(t[0])
+        fact_tf = 4.0 * lap.P ** 3 / 6.0 * 12.0 / (fact_ms * 1e-3) / 1e12
         glm_roof = None
         if gn > 0:
             kms = sum(gms[i] for i in range(gn))
@@ -412,8 +424,18 @@ def run_ours(args):
                                       '(f_var = J Sigma J^T evaluated as T[n,u,u\'] = a^T Sigma_uu\' a\' for u\' <= u); '
                                       'as written the reference einsum costs 2 K P^2 + 2 K^2 P per input'}
         secondary = {
-            'factorise_full_ms': ev[0].elapsed_time(ev[1]),
-            'factorise_note': 'one-off chol(H), inverse, chol(Sigma), P=59635 (timed separately, north star (3)); N > 1: the inverse is split between the ranks',
+            'factorise_full_ms': fact_ms,
+            'factorise_note': 'one-off chol(H), Sigma = H^-1, chol(Sigma) at P=59635 on the library\'s own three-term split-bf16 '
+                              'tensor-core GEMM (csrc/gemm3.cu, preds_b200/factor.py; timed separately, north star (3)); '
+                              'N > 1: the tiles of every product are dealt out between the ranks and gathered, every rank ends '
+                              'with the bits of the single-GPU chain',
+            'factorise_roofline': {'bound': 'tensor', 'kernel': 'gemm3_kernel (6 bf16 MMAs per product, fp32-grade)',
+                                   'achieved': fact_tf, 'peak': pk.get('bf16_tflops_sustained', pk['bf16_tflops']), 'unit': 'TFLOP/s',
+                                   'frac': fact_tf / pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
+                                   'fp32_equivalent_tflops': fact_tf / 6.0,
+                                   'flops_note': 'whole chain incl. the library calls on the 1024 x 1024 diagonal blocks, gathers '
+                                                 'and splits: 4 x P^3/6 MACs (two Cholesky, triangular inverse, Gram) x 12 bf16 '
+                                                 'flop per MAC / wall time of the chain, whole job (all ranks)'},
             'glm_predictive': {
                 'metric': 'glm_predictive_input_samples_per_s', 'value': nte * S * world / (glm_ms * 1e-3),
                 'unit': '(inputs x samples)/s', 'inputs_per_gpu': nte, 'samples': S, 'ms': glm_ms,
@@ -563,6 +585,30 @@ def other_configs(dev):
         acc_ms = timed(lambda: lap.infer(batches, cov_type='kron', factorise=False))
         out.append({'config': 'cfg4 CIFAR10Net(3,10) (P=895210), loader batch 256', 'cov_type': 'kron',
                     'accum_examples_per_s': N / acc_ms * 1e3})
+        del model, lap, batches
+        torch.cuda.empty_cache()
+        # function-space inference (experiments/imginference.py:343-372: subset of M training inputs against
+        # the validation / test inputs) on the cfg5 network: NTK Grams per output + the GP predictive
+        from preds_b200 import FunctionaLaplace
+        torch.manual_seed(71)
+        model = MLPS(784, [75], 10, 'tanh', flatten=True).to(dev)
+        M, nte = 1600, 10000
+        Xtr = torch.randn(M, 1, 28, 28, generator=g)
+        Xte = torch.randn(nte, 1, 28, 28, generator=g)
+        lap = FunctionaLaplace(model, 1.0 * 60000 / M, CategoricalLh())
+        lap.infer([(Xtr[:64], None)], [(Xte[:64], None)])
+        inf_ms = timed(lambda: lap.infer([(Xtr, None)], [(Xte, None)]), reps=2)
+        lap.predictive_samples(n_samples=8, batch_size=8, seed=1)
+        pred_ms = timed(lambda: lap.predictive_samples(n_samples=1000, batch_size=1000, seed=2), reps=2)
+        P = lap.P
+        macs = 10.0 * (M * M + M * nte) * P
+        out.append({'config': 'function-space Laplace, MLPS(784,[75],10) P=59635, M=1600 training x 10000 test inputs, 10 outputs',
+                    'infer_ms': inf_ms, 'kernel_entries_per_s': 10.0 * (M * M + M * nte + nte) / inf_ms * 1e3,
+                    'ntk_bf16_tflops': macs * 6.0 / (inf_ms * 1e-3) / 1e12,
+                    'predictive_ms': pred_ms, 'predictive_input_samples_per_s': nte * 1000 / pred_ms * 1e3,
+                    'note': 'infer = one-column Jacobians of every input and output + J J^T on the TMA-fed tensor-core GEMM '
+                            '(3 bf16 MMAs per product, flops counted for the Grams only); predictive = GP moments '
+                            '(preds/gps.py:411-426) + 1000-sample Monte-Carlo mean'})
     except Exception as exc:       # secondary numbers must not cost the headline
         out.append({'error': repr(exc)[:200]})
     return out
