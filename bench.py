@@ -430,8 +430,8 @@ def run_ours(args):
                               'N > 1: the tiles of every product are dealt out between the ranks and gathered, every rank ends '
                               'with the bits of the single-GPU chain',
             'factorise_roofline': {'bound': 'tensor', 'kernel': 'gemm3_kernel (6 bf16 MMAs per product, fp32-grade)',
-                                   'achieved': fact_tf, 'peak': pk.get('bf16_tflops_sustained', pk['bf16_tflops']), 'unit': 'TFLOP/s',
-                                   'frac': fact_tf / pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
+                                   'achieved': fact_tf, 'peak': world * pk.get('bf16_tflops_sustained', pk['bf16_tflops']),
+                                   'unit': 'TFLOP/s', 'frac': fact_tf / (world * pk.get('bf16_tflops_sustained', pk['bf16_tflops'])),
                                    'fp32_equivalent_tflops': fact_tf / 6.0,
                                    'flops_note': 'whole chain incl. the library calls on the 1024 x 1024 diagonal blocks, gathers '
                                                  'and splits: 4 x P^3/6 MACs (two Cholesky, triangular inverse, Gram) x 12 bf16 '
