@@ -601,13 +601,24 @@ def other_configs(dev):
         lap.predictive_samples(n_samples=8, batch_size=8, seed=1)
         pred_ms = timed(lambda: lap.predictive_samples(n_samples=1000, batch_size=1000, seed=2), reps=2)
         P = lap.P
-        macs = 10.0 * (M * M + M * nte) * P
+        from preds_b200 import gps as _gps
+        _gps.STRUCTURED = False
+        lap.infer([(Xtr[:64], None)], [(Xte[:64], None)])
+        mat_ms = timed(lambda: lap.infer([(Xtr, None)], [(Xte, None)]), reps=2)
+        _gps.STRUCTURED = True
+        pairs = float(M * M + M * nte)
         out.append({'config': 'function-space Laplace, MLPS(784,[75],10) P=59635, M=1600 training x 10000 test inputs, 10 outputs',
-                    'infer_ms': inf_ms, 'kernel_entries_per_s': 10.0 * (M * M + M * nte + nte) / inf_ms * 1e3,
-                    'ntk_bf16_tflops': macs * 6.0 / (inf_ms * 1e-3) / 1e12,
+                    'infer_ms': inf_ms, 'kernel_entries_per_s': 10.0 * (pairs + nte) / inf_ms * 1e3,
+                    'as_written_tflops_equivalent': 10.0 * pairs * P * 2.0 / (inf_ms * 1e-3) / 1e12,
+                    'structured_macs_per_entry': (785 + 76) / 10.0 + 75 + 10,
+                    'infer_ms_materialised_jacobians': mat_ms,
+                    'materialised_bf16_tflops': 10.0 * pairs * P * 6.0 / (mat_ms * 1e-3) / 1e12,
                     'predictive_ms': pred_ms, 'predictive_input_samples_per_s': nte * 1000 / pred_ms * 1e3,
-                    'note': 'infer = one-column Jacobians of every input and output + J J^T on the TMA-fed tensor-core GEMM '
-                            '(3 bf16 MMAs per product, flops counted for the Grams only); predictive = GP moments '
+                    'note': 'infer = kernels K_train / K_train_test / K_test + f_gp for all outputs.  Linear-only networks: one '
+                            'forward + one K-column backward per chunk, per layer A~ A~^T once and (G_c G_c^T) o (A~ A~^T) per '
+                            'output on the TMA-fed tensor-core GEMM (Hadamard in the epilogue), J never formed; '
+                            'infer_ms_materialised_jacobians = the general route (conv nets): one-column Jacobians + J J^T, '
+                            'P walked in 4096-wide segments, 3 bf16 MMAs per product.  predictive = GP moments '
                             '(preds/gps.py:411-426) + 1000-sample Monte-Carlo mean'})
     except Exception as exc:       # secondary numbers must not cost the headline
         out.append({'error': repr(exc)[:200]})

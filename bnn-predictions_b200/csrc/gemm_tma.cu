@@ -40,6 +40,8 @@ struct Args {
   const float* bias;           // [N] added to every row (ksplit == 1 only) or nullptr
   int ct_L;                    // > 0: rows are (batch b, position p) = (m / ct_L, m % ct_L) and C is stored transposed per batch:
                                //      C[(b * N + n) * ct_L + p]  (the [R, E, L] buffer of the conv backward-data product)
+  const float* had;            // != nullptr: the product is multiplied elementwise by had[m, n] (row pitch ldh) before it enters C
+  long long ldh;               //   (function-space kernels: K_c += (G G^T) o (A A^T), preds/gps.py:56-88 per layer)
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -170,7 +172,21 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         } else {
           float* p = args.C + rbase * args.ldc + n0 + c0 + lane;
           const float b = (args.bias && colok) ? __ldg(args.bias + n0 + c0 + lane) : 0.f;
-          if (args.beta == 0.f) {
+          if (args.had) {
+            const float* h = args.had + rbase * args.ldh + n0 + c0 + lane;
+            if (args.beta == 1.f) {          // fire-and-forget adds in L2: one add per element per launch (deterministic)
+#pragma unroll 8
+              for (int u = 0; u < 32; ++u)
+                if (colok && u < nrows) atomicAdd(&p[(long long)u * args.ldc], args.alpha * sc[u * 33 + lane] * __ldg(h + (long long)u * args.ldh));
+            } else {
+#pragma unroll 8
+              for (int u = 0; u < 32; ++u)
+                if (colok && u < nrows) {
+                  const float v = args.alpha * sc[u * 33 + lane] * __ldg(h + (long long)u * args.ldh);
+                  p[(long long)u * args.ldc] = args.beta == 0.f ? v : fmaf(args.beta, p[(long long)u * args.ldc], v);
+                }
+            }
+          } else if (args.beta == 0.f) {
 #pragma unroll 8
             for (int u = 0; u < 32; ++u)
               if (colok && u < nrows) p[(long long)u * args.ldc] = fmaf(args.alpha, sc[u * 33 + lane], b);
@@ -342,7 +358,7 @@ int64_t gemm_tma_scratch_floats(int64_t M, int64_t N, int64_t K) {
 
 int gemm_tma_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int64_t lda,
                 const __nv_bfloat16* Bh, const __nv_bfloat16* Bl, int64_t ldb, float beta, float* C, int64_t ldc,
-                float* scratch, cudaStream_t st, const float* bias, int ct_L) {
+                float* scratch, cudaStream_t st, const float* bias, int ct_L, const float* had, int64_t ldh) {
   using namespace tg;
   if (M <= 0 || N <= 0 || K <= 0) return BNNP_OK;
   if (!Ah || !Al || !Bh || !Bl || !C || (lda & 7) || (ldb & 7)) return BNNP_ERR_INVALID;
@@ -361,6 +377,8 @@ int gemm_tma_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat1
   a.alpha = alpha; a.beta = beta; a.C = C; a.ldc = ldc; a.part = scratch;
   a.bias = bias;
   a.ct_L = ct_L;
+  a.had = had; a.ldh = ldh;
+  if (had && (a.ksplit > 1 || bias || ct_L > 0)) return BNNP_ERR_INVALID;
   if (bias && (a.ksplit > 1 || beta != 0.f)) return BNNP_ERR_INVALID;
   if (ct_L > 0 && (a.ksplit > 1 || beta != 0.f || bias)) return BNNP_ERR_INVALID;
   CUtensorMap mah, mal, mbh, mbl;
@@ -503,4 +521,13 @@ extern "C" int bnnp_split_bf16_rows(const float* src, int64_t ld_src, int64_t ro
   if (!src || !hi || !lo || rows <= 0 || cols <= 0) return BNNP_ERR_INVALID;
   return split_rows(src, ld_src, rows, cols, pitch, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo),
                     false, as_stream(stream));
+}
+
+extern "C" int bnnp_gemm_nt_split_had(int64_t M, int64_t N, int64_t K, float alpha, const void* Ah, const void* Al, int64_t lda,
+                                      const void* Bh, const void* Bl, int64_t ldb, float beta, float* C, int64_t ldc,
+                                      const float* had, int64_t ldh, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || !had) return BNNP_ERR_INVALID;
+  return gemm_tma_nt(M, N, K, alpha, reinterpret_cast<const __nv_bfloat16*>(Ah), reinterpret_cast<const __nv_bfloat16*>(Al),
+                     lda, reinterpret_cast<const __nv_bfloat16*>(Bh), reinterpret_cast<const __nv_bfloat16*>(Bl), ldb, beta, C,
+                     ldc, nullptr, as_stream(stream), nullptr, 0, had, ldh);
 }

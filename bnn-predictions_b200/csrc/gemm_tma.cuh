@@ -10,7 +10,8 @@ namespace bnnp {
 int64_t gemm_tma_scratch_floats(int64_t M, int64_t N, int64_t K);
 int gemm_tma_nt(int64_t M, int64_t N, int64_t K, float alpha, const __nv_bfloat16* Ah, const __nv_bfloat16* Al, int64_t lda,
                 const __nv_bfloat16* Bh, const __nv_bfloat16* Bl, int64_t ldb, float beta, float* C, int64_t ldc,
-                float* scratch, cudaStream_t st, const float* bias = nullptr, int ct_L = 0);
+                float* scratch, cudaStream_t st, const float* bias = nullptr, int ct_L = 0, const float* had = nullptr,
+                int64_t ldh = 0);
 // conv backward-data product dUt[r, e, pos] = sum_co gout[r, co, pos] W[co, e] (gout row pitch gld, W [Cout, E]) with the
 // gradients transposed + split once ([(r,pos), co] bf16 hi/lo) and the result stored transposed per row for the col2im gather
 int64_t conv_bwd_tma_scratch_floats(int64_t R, int64_t Cout, int64_t L, int64_t E);

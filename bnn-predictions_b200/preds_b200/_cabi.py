@@ -116,6 +116,7 @@ _SIGS = {
     'bnnp_gemm_nt_split': (_I, [_L, _L, _L, _F, _P, _P, _L, _P, _P, _L, _F, _P, _L, _P, _V]),
     'bnnp_split_bf16_t': (_I, [_P, _L, _L, _L, _L, _P, _P, _V]),
     'bnnp_split_bf16_rows': (_I, [_P, _L, _L, _L, _L, _P, _P, _V]),
+    'bnnp_gemm_nt_split_had': (_I, [_L, _L, _L, _F, _P, _P, _L, _P, _P, _L, _F, _P, _L, _P, _L, _V]),
     'bnnp_split3_bf16': (_I, [_P, _L, _L, _L, _P, _L, _L, _I, _F, _V]),
     'bnnp_gemm3_nt': (_I, [_L, _L, _L, _F, _P, _L, _L, _P, _L, _L, _F, _P, _L, _I, _I, _L, _V]),
     'bnnp_gemm3_nt_owned': (_I, [_L, _L, _L, _F, _P, _L, _L, _P, _L, _L, _F, _P, _L, _I, _I, _L, _I, _I, _I, _L, _V]),

@@ -15,6 +15,13 @@ scatters Jacobian batches over ``nn.parallel`` replicas and contracts with ``opt
 add through C.  The Jacobian of the training inputs of one output stays resident as bf16 planes (4 bytes per entry: 11 GB
 for CIFAR10Net and 3200 inputs), the test inputs stream through in chunks, so nothing of size [n, P, K] ever exists.
 
+**Linear-only networks take a structured route** (``_structured``): the Jacobian of a Linear layer is rank one per output,
+``J_c[n, (i, j)] = g_c[n, i] a~[n, j]`` (a~ = layer input with a constant 1 for the bias), so the layer's term of the kernel is
+a Hadamard product of two SHORT Grams, ``K_c += (G_c G_c^T) o (A~ A~^T)`` -- reductions over the layer's fan-out and fan-in
+instead of over its m x n parameters (63x fewer flops on MLPS(784,[75],10)) -- evaluated as ``A~ A~^T`` once per layer and
+one product per output whose epilogue multiplies by it and adds into K_c (``bnnp_gemm_nt_split_had``).  The factors of
+ALL outputs come from one forward + one K-column backward per chunk; ``f_gp = J theta`` from ``bnnp_glm_fmu``; J never exists.
+
 Prior-variance groups (``p.log_prior_var``; ``optimize_params`` puts a group's kernel into its own slot, the rest is
 summed into the last slot and scaled by its prior variance when ``with_prior_prec``) follow the reference; every group is
 a set of contiguous parameter ranges, i.e. of K ranges of the same product.
@@ -23,6 +30,8 @@ Not carried over: ``train_jacobians`` / ``save_jacobians`` (host-pinned Jacobian
 ``device_ids`` (one process per GPU here; the argument is accepted and ignored).  ``jacobian_method`` selects nothing: both
 of the reference's methods give the same Jacobian.
 """
+import ctypes as ct
+
 import numpy as np
 import torch
 
@@ -31,6 +40,7 @@ from ._cabi import lib, check, ptr, stream
 from ._engine import net_for
 
 KSEG = 4096                    # one tensor-core accumulation never spans more (gemm_tma.cu)
+STRUCTURED = True              # Linear-only networks: Hadamard-of-Grams kernels (False: materialised one-column Jacobians)
 JAC_CHUNK_FLOATS = 1 << 29     # fp32 Jacobian of one chunk of inputs (2 GB)
 
 
@@ -100,6 +110,109 @@ def _groups(model, optimize_params):
     return all_vars, opt_vars, n_slots, slots, off
 
 
+class _Factors:
+    """bf16 hi / lo copies of the Jacobian factors of a block of inputs of a Linear-only network: per layer the inputs
+    a~ [rows, n_l + 1] and, per requested output c, g_c [rows, m_l]."""
+
+    def __init__(self, net, layers, n_out, rows, device):
+        self.layers = layers
+        self.A = [_SplitRows(rows, d, device) for (_, d, _, _) in layers]
+        self.G = [[_SplitRows(rows, m, device) for _ in range(n_out)] for (_, _, _, m) in layers]
+
+    def fill(self, net, pl, ws, n, r0, outputs):
+        base = ws.data_ptr()
+        K = net.K
+        for li, (col, d, unit, m) in enumerate(self.layers):
+            a = base + 4 * (int(pl.acat_off) + col)
+            check(lib.bnnp_split_bf16_rows(a, int(pl.Dtot), n, d, self.A[li].pitch, self.A[li].hi.data_ptr() + 2 * r0 * self.A[li].pitch,
+                                           self.A[li].lo.data_ptr() + 2 * r0 * self.A[li].pitch, stream()), 'bnnp_split_bf16_rows')
+            for oi, c in enumerate(outputs):
+                g = base + 4 * (int(pl.gcat_off) + c * int(pl.Mtot) + unit)          # rows (n, v = c) of G_cat
+                G = self.G[li][oi]
+                check(lib.bnnp_split_bf16_rows(g, K * int(pl.Mtot), n, m, G.pitch, G.hi.data_ptr() + 2 * r0 * G.pitch,
+                                               G.lo.data_ptr() + 2 * r0 * G.pitch, stream()), 'bnnp_split_bf16_rows')
+
+
+def _linear_layers(net):
+    """[(first A_cat column, fan-in incl. the bias column, first G_cat unit, fan-out)] of a Linear-only network, else None."""
+    pl = net.plan(1, net.K)
+    layers = []
+    for i in range(net.n_ops):
+        op = net.ops[i]
+        if op.kind == cabi.OP_CONV2D:
+            return None
+        if op.kind == cabi.OP_LINEAR:
+            d = op.in_c + (1 if op.has_bias else 0)
+            if d > KSEG or op.out_c > KSEG:
+                return None
+            layers.append((int(pl.op[i].lin_col), d, int(pl.op[i].lin_unit), int(op.out_c)))
+    return layers or None
+
+
+def _structured(net, model, X_train, X_test, outputs, theta, scale, out):
+    """Fill K_train / K_train_test / K_test (diagonal) / f_gp / f_star in ``out`` for a Linear-only network (one kernel slot)."""
+    dev = net.device
+    n, m = len(X_train), (len(X_test) if X_test is not None else 0)
+    C_ = len(outputs)
+    chunk = 2048
+    layers = None
+
+    def factors(X, s, F, r0):
+        nonlocal layers
+        X2d, pl, ws, f = net.jacobian_factors(X[s:s + chunk])
+        k = X2d.shape[0]
+        if layers is None:
+            layers = _linear_layers(net)
+        if F is None:
+            F = _Factors(net, layers, C_, n if r0 is not None else min(chunk, max(m, 1)), dev)
+        F.fill(net, pl, ws, k, r0 if r0 is not None else 0, outputs)
+        fm = torch.empty(k, net.K, dtype=torch.float32, device=dev)
+        check(lib.bnnp_glm_fmu(net.ops, net.n_ops, ct.byref(pl), k, ptr(X2d), ptr(ws), ptr(f), ptr(theta), ptr(fm), stream()),
+              'bnnp_glm_fmu')
+        Av = ws[int(pl.acat_off):int(pl.acat_off) + k * int(pl.Dtot)].view(k, int(pl.Dtot))
+        Gv = ws[int(pl.gcat_off):int(pl.gcat_off) + k * net.K * int(pl.Mtot)].view(k, net.K, int(pl.Mtot))
+        diag = None
+        if r0 is None:            # test block: the diagonal of its own kernel, sum_l |g_c|^2 |a~|^2
+            diag = torch.zeros(C_, k, dtype=torch.float32, device=dev)
+            for (col, d, unit, mm) in layers:
+                a2 = (Av[:, col:col + d] ** 2).sum(1)
+                g2 = (Gv[:, outputs, unit:unit + mm] ** 2).sum(2)
+                diag += (g2 * a2.unsqueeze(1)).t()
+        return F, k, f, (fm - f), diag
+
+    def products(Fr, nr, Fc, nc, dst, col0, ldc, tmp):
+        """dst[c][:, col0:col0+nc] = sum_l (G_c G_c^T) o (A~ A~^T) for the row block Fr and the column block Fc."""
+        AA = tmp[:nr * nc].view(nr, nc)
+        for li in range(len(layers)):
+            d, mm = layers[li][1], layers[li][3]
+            Ar, Ac = Fr.A[li], Fc.A[li]
+            check(lib.bnnp_gemm_nt_split(nr, nc, d, 1.0, Ar.hi.data_ptr(), Ar.lo.data_ptr(), Ar.pitch, Ac.hi.data_ptr(),
+                                         Ac.lo.data_ptr(), Ac.pitch, 0.0, AA.data_ptr(), nc, None, stream()), 'bnnp_gemm_nt_split')
+            for oi in range(C_):
+                Gr, Gc = Fr.G[li][oi], Fc.G[li][oi]
+                check(lib.bnnp_gemm_nt_split_had(nr, nc, mm, scale, Gr.hi.data_ptr(), Gr.lo.data_ptr(), Gr.pitch,
+                                                 Gc.hi.data_ptr(), Gc.lo.data_ptr(), Gc.pitch, 0.0 if li == 0 else 1.0,
+                                                 dst[oi].data_ptr() + 4 * col0, ldc, AA.data_ptr(), nc, stream()),
+                      'bnnp_gemm_nt_split_had')
+
+    Ftr = None
+    for s in range(0, n, chunk):
+        Ftr, k, f, fgp, _ = factors(X_train, s, Ftr, s)
+        out['f_star_train'][:, s:s + k] = f.t()[outputs]
+        out['f_gp_train'][:, s:s + k] = fgp.t()[outputs]
+    tmp = torch.empty(max(n, 1) * max(n, min(chunk, max(m, 1))), dtype=torch.float32, device=dev)
+    products(Ftr, n, Ftr, n, [out['K_train'][c, 0] for c in range(C_)], 0, n, tmp)
+    if X_test is None:
+        return
+    Fte = None
+    for s in range(0, m, chunk):
+        Fte, k, f, fgp, diag = factors(X_test, s, Fte, None)
+        out['f_star_test'][:, s:s + k] = f.t()[outputs]
+        out['f_gp_test'][:, s:s + k] = fgp.t()[outputs]
+        out['K_test'][:, 0, s:s + k] = scale * diag
+        products(Ftr, n, Fte, k, [out['K_train_test'][c, 0] for c in range(C_)], s, m, tmp)
+
+
 def gp_quantities_device(model, X_train, X_test=None, outputs=-1, optimize_params=(), only_pred_var=True,
                          collapse_groups=False, with_prior_prec=True, max_ram_gb=10):
     """``gp_quantities`` with every tensor left on the model's device (``FunctionaLaplace`` keeps them there)."""
@@ -139,6 +252,23 @@ def gp_quantities_device(model, X_train, X_test=None, outputs=-1, optimize_param
         K_train_test = torch.zeros(C, n_slots, n, m, **f32)
         K_test = torch.zeros(*((C, n_slots, m) if only_pred_var else (C, n_slots, m, m)), **f32)
         f_gp_test, f_star_test = torch.ones(C, m, **f32), torch.ones(C, m, **f32)
+    uniform = None            # the prior-variance scale when it is one number for the whole kernel
+    if n_slots == 1:
+        scs = set(sc for _, sc, _, _ in slots)
+        if not with_prior_prec or scs == {None}:
+            uniform = 1.0
+        elif len(scs) == 1:
+            uniform = float(next(iter(scs)))
+    net.prepare(cabi.f32(X_train[:1], dev))
+    if STRUCTURED and uniform is not None and only_pred_var and _linear_layers(net) is not None:
+        res = {'K_train': K_train, 'f_gp_train': f_gp_train, 'f_star_train': f_star_train}
+        if X_test is not None:
+            res.update({'K_train_test': K_train_test, 'K_test': K_test, 'f_gp_test': f_gp_test, 'f_star_test': f_star_test})
+        _structured(net, model, X_train, X_test, outputs, theta, uniform, res)
+        net.release()
+        return _finish(K_train, K_train_test if X_test is not None else None, K_test if X_test is not None else None,
+                       f_gp_train, f_star_train, f_gp_test if X_test is not None else None,
+                       f_star_test if X_test is not None else None, all_vars, opt_vars, collapse_groups)
     chunk = max(1, min(1024, JAC_CHUNK_FLOATS // max(P, 1)))
     # one plane set per kernel slot (a single one unless optimize_params separates prior-variance groups)
     Jtr = [_SplitRows(n, P, dev) for _ in range(n_slots)]
@@ -192,7 +322,13 @@ def gp_quantities_device(model, X_train, X_test=None, outputs=-1, optimize_param
                 _nt(Jtr[g], n, Jte[g], m, K_train_test[idx, g])
                 _nt(Jte[g], m, Jte[g], m, K_test[idx, g])
     net.release()
+    return _finish(K_train, K_train_test if X_test is not None else None, K_test if X_test is not None else None,
+                   f_gp_train, f_star_train, f_gp_test if X_test is not None else None,
+                   f_star_test if X_test is not None else None, all_vars, opt_vars, collapse_groups)
 
+
+def _finish(K_train, K_train_test, K_test, f_gp_train, f_star_train, f_gp_test, f_star_test, all_vars, opt_vars,
+            collapse_groups):
     def collapse(K):
         # preds/gps.py:894-908
         if len(opt_vars) > 0:
@@ -209,7 +345,7 @@ def gp_quantities_device(model, X_train, X_test=None, outputs=-1, optimize_param
     q = {'K_train': collapse(K_train) if collapse_groups else K_train,
          'f_gp_train': f_gp_train, 'f_star_train': f_star_train,
          'prior_var': (float(all_vars[0].exp().item()) if len(all_vars) == 1 else None) if collapse_groups else None}
-    if X_test is not None:
+    if K_train_test is not None:
         q['K_train_test'] = collapse(K_train_test) if collapse_groups else K_train_test
         q['K_test'] = collapse(K_test) if collapse_groups else K_test
         q['f_gp_test'] = f_gp_test

@@ -355,6 +355,12 @@ int bnnp_gemm_nt_split(int64_t M, int64_t N, int64_t K, float alpha, const void*
                        float* scratch, void* stream);
 int bnnp_split_bf16_t(const float* src, int64_t ld_src, int64_t rows, int64_t cols, int64_t pitch, void* hi, void* lo,
                       void* stream);
+/* bnnp_gemm_nt_split (K <= 4096) whose product is multiplied elementwise by had[m, n] (row pitch ldh) before it enters C:
+ * C = alpha * (A B^T) o had + beta * C.  One layer's term of the function-space kernel of a Linear network,
+ * K_c += (G_c G_c^T) o (A~ A~^T)  (preds/gps.py:56-88 contracts the materialised Jacobians instead). */
+int bnnp_gemm_nt_split_had(int64_t M, int64_t N, int64_t K, float alpha, const void* Ah, const void* Al, int64_t lda,
+                           const void* Bh, const void* Bl, int64_t ldb, float beta, float* C, int64_t ldc,
+                           const float* had, int64_t ldh, void* stream);
 /* bnnp_split_bf16 with an explicit destination pitch (>= cols, multiple of 8; columns cols..pitch-1 are zeroed): rows that
  * start on 128-byte lines keep the 64-byte rows of the TMA boxes inside one sector pair (function-space kernels,
  * preds/gps.py:56-88). */

@@ -20,8 +20,19 @@ def _setup(name):
     return g, model.cuda(), preds_b200
 
 
+@pytest.fixture(params=[True, False], ids=['structured', 'materialised'])
+def ntk_route(request):
+    """Linear-only networks have two routes to the kernels (Hadamard of short Grams / materialised one-column Jacobians);
+    conv nets always take the second."""
+    from preds_b200 import gps
+    old = gps.STRUCTURED
+    gps.STRUCTURED = request.param
+    yield request.param
+    gps.STRUCTURED = old
+
+
 @pytest.mark.parametrize('name', cases.GP_CASES)
-def test_functional_laplace_against_reference_golden(name):
+def test_functional_laplace_against_reference_golden(name, ntk_route):
     g, model, pb = _setup(name)
     Xa, Xb, Xte = (torch.from_numpy(g[k]) for k in ('Xa', 'Xb', 'Xte'))
     prior = float(g['prior'])
@@ -73,7 +84,7 @@ def test_gp_quantities_option_paths(name):
     assert 'K_test' not in only_train and cases.rel_err(only_train['K_train'][:, 0], g['q_K_train']) < TOL
 
 
-def test_gp_kernels_over_several_k_segments_and_prior_groups():
+def test_gp_kernels_over_several_k_segments_and_prior_groups(ntk_route):
     """P = 10 309 (three 4096-wide segments of the tensor-core product), 300 x 200 inputs, against the oracle; then two
     prior-variance groups of which one is 'optimised' (own kernel slot, unscaled) against a float64 evaluation from the
     oracle's Jacobians."""
