@@ -194,11 +194,6 @@ def inverse_from_chol(L, shared=False):
     return S
 
 
-def planes_bytes(P):
-    """Peak extra device memory of ``inverse_from_chol`` beside L and Sigma (the planes of Y and the block temporaries)."""
-    return 6 * P * (_up8(P) + 56) + 6 * NB * (_up8(P) + 56) + 6 * P * NB + 6 * NB * NB + 4 * P * NB
-
-
 def use_tc(P):
     return ENGINE == 'tc' and P >= MIN_P
 

@@ -44,10 +44,6 @@ STRUCTURED = True              # Linear-only networks: Hadamard-of-Grams kernels
 JAC_CHUNK_FLOATS = 1 << 29     # fp32 Jacobian of one chunk of inputs (2 GB)
 
 
-def _up8(v):
-    return (v + 7) // 8 * 8
-
-
 class _SplitRows:
     """bf16 hi / lo copies of a [rows, P] matrix (rows k-contiguous, pitch a multiple of 64 elements = 128-byte lines)."""
 
@@ -407,7 +403,9 @@ def gp_predictive_moments(q, prior_prec, indep=False):
         for c in range(C):
             B = w_sqrt[c].unsqueeze(1) * K_nn[c] * w_sqrt[c].unsqueeze(0)
             B.diagonal().add_(1.0)
-            Kinv = w_sqrt[c].unsqueeze(1) * torch.inverse(B) * w_sqrt[c].unsqueeze(0)
+            # B = I + W^1/2 K W^1/2 is symmetric positive definite: its inverse through a Cholesky factorisation
+            # (the reference calls torch.inverse, an LU with pivoting, preds/laplace.py:193)
+            Kinv = w_sqrt[c].unsqueeze(1) * torch.cholesky_inverse(torch.linalg.cholesky(B)) * w_sqrt[c].unsqueeze(0)
             _mm(0, 0, Kinv.contiguous(), K_nm[c], T)
             f_var[:, c, c] = K_m[c] - (K_nm[c] * T).sum(0)
         return f_mu, f_var
