@@ -570,9 +570,36 @@ def other_configs(dev):
             lap.infer(batches, cov_type=cov)
             lap.predictive_samples_glm(Xte[:64], n_samples=8, seed=1)
             glm_ms = timed(lambda: lap.predictive_samples_glm(Xte, n_samples=S, seed=2), reps=2)
+            # SURVEY 8d work per unit: layer widths (n_l -> m_l) of the cfg3 MLP, K = 10
+            dims = [(784, 1024), (1024, 512), (512, 256), (256, 128), (128, 10)]
+            Kc = 10
+            fwd = 2.0 * sum(n * m for n, m in dims)
+            bwd = 2.0 * Kc * sum(n * m for n, m in dims[1:])
+            fbytes = 4.0 * sum(n + Kc * m for n, m in dims)                       # 4 sum(size a + K size g) per example / input
+            pkk, _ = peaks()
+            tc_peak = pkk.get('bf16_tflops_sustained', pkk['bf16_tflops']) / 3.0      # fp32-grade = 3 bf16 MMA passes
+            if cov == 'kron':
+                acc_flop = sum(2.0 * n * n + 2.0 * Kc * m * m for n, m in dims) + fwd + bwd
+                glm_flop = sum(2.0 * n * n + 2.0 * Kc * m * m + 2.0 * m * n + Kc * Kc * m for n, m in dims) + fwd + bwd
+            else:
+                acc_flop = sum(2.0 * m * n for n, m in dims) + fwd + bwd
+                glm_flop = acc_flop
+            acc_tf = acc_flop * N / (acc_ms * 1e-3) / 1e12
+            glm_tf = glm_flop * nte / (glm_ms * 1e-3) / 1e12
+            roof = {'accum': {'bound': 'tensor', 'achieved': acc_tf, 'peak': tc_peak, 'unit': 'TFLOP/s fp32-equivalent',
+                              'frac': acc_tf / tc_peak, 'flop_per_example': acc_flop},
+                    'glm': {'bound': 'tensor', 'achieved': glm_tf, 'peak': tc_peak, 'unit': 'TFLOP/s fp32-equivalent',
+                            'frac': glm_tf / tc_peak, 'flop_per_input': glm_flop}}
+            if cov == 'diag':           # north star: HBM-bound on the factor stream -- report against both rooflines
+                roof['accum_hbm'] = {'bound': 'hbm', 'achieved': fbytes * N / (acc_ms * 1e-3) / 1e9, 'peak': pkk['hbm_gbs'],
+                                     'unit': 'GB/s', 'frac': fbytes * N / (acc_ms * 1e-3) / 1e9 / pkk['hbm_gbs'],
+                                     'bytes_per_example': fbytes}
+                roof['glm_hbm'] = {'bound': 'hbm', 'achieved': fbytes * nte / (glm_ms * 1e-3) / 1e9, 'peak': pkk['hbm_gbs'],
+                                   'unit': 'GB/s', 'frac': fbytes * nte / (glm_ms * 1e-3) / 1e9 / pkk['hbm_gbs'],
+                                   'bytes_per_input': fbytes}
             out.append({'config': 'cfg3 MLP 784-1024-512-256-128-10 (P=1494154), loader batch 256', 'cov_type': cov,
                         'accum_examples_per_s': N / acc_ms * 1e3, 'glm_input_samples_per_s': nte * S / glm_ms * 1e3,
-                        'glm_inputs': nte, 'glm_samples': S})
+                        'glm_inputs': nte, 'glm_samples': S, 'roofline': roof})
         del model, lap, batches, Xte
         torch.manual_seed(71)
         model = CIFAR10Net(3, 10, use_tanh=True).to(dev)
@@ -583,8 +610,14 @@ def other_configs(dev):
         lap = Laplace(model, 1.0, CategoricalLh())
         lap.infer(batches[:2], cov_type='kron', factorise=False)
         acc_ms = timed(lambda: lap.infer(batches, cov_type='kron', factorise=False))
+        pkk, _ = peaks()
+        tc_peak = pkk.get('bf16_tflops_sustained', pkk['bf16_tflops']) / 3.0
+        c4_tf = 0.53e9 * N / (acc_ms * 1e-3) / 1e12                                 # ~0.53 GFLOP per example
         out.append({'config': 'cfg4 CIFAR10Net(3,10) (P=895210), loader batch 256', 'cov_type': 'kron',
-                    'accum_examples_per_s': N / acc_ms * 1e3})
+                    'accum_examples_per_s': N / acc_ms * 1e3,
+                    'roofline': {'accum': {'bound': 'tensor', 'achieved': c4_tf, 'peak': tc_peak, 'unit': 'TFLOP/s fp32-equivalent',
+                                           'frac': c4_tf / tc_peak, 'flop_per_example': 0.53e9},
+                                 'input_stream_GBs': 3 * 32 * 32 * 4.0 * N / (acc_ms * 1e-3) / 1e9}})
         del model, lap, batches
         torch.cuda.empty_cache()
         # function-space inference (experiments/imginference.py:343-372: subset of M training inputs against

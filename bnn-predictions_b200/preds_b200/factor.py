@@ -22,9 +22,6 @@ MIN_P = 4096         # below this the library calls are used as they are
 ENGINE = 'tc'        # 'library': cuSOLVER / cuBLAS through torch whatever the size (A/B timing, scripts/factor_check.py)
 
 
-def _up8(v):
-    return (v + 7) // 8 * 8
-
 
 class _Planes:
     """Three bf16 planes (hi, mid, lo) of a [rows, cols] matrix, rows k-contiguous; the pitch is a multiple of 64 elements so
