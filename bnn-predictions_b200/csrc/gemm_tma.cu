@@ -26,8 +26,10 @@ constexpr int A_TERM = TILE_M * BK * 2, A_STAGE = 2 * A_TERM;      // hi + lo: 1
 constexpr int B_TERM = MAX_N * BK * 2, B_STAGE = 2 * B_TERM;       // 32 KB
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;                     // 48 KB
 constexpr int EPI_TILE_BYTES = 32 * 33 * 4 + 32;                   // per epilogue warp: [32][33] fp32 transpose tile
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_TILE_BYTES;
-constexpr int NUM_THREADS = 256;      // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-7: epilogue (one per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;          // two per TMEM lane quarter, each draining half of the tile's columns: with K of a few
+                                      // hundred (the K-column backward products) a tile's epilogue outlasts its MMAs
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_WARPS * EPI_TILE_BYTES;
+constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;   // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warps 4-11: epilogue
 constexpr int EPI_WARP0 = 4;
 constexpr int kMaxChunksPerAccum = 128;
 
@@ -59,7 +61,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -126,8 +128,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       // transpose turns that into lane = column, so that every store instruction of the warp writes 128 contiguous
       // bytes of one output row (thread-per-row stores touch 32 cache lines per instruction: measured 41 us per
       // 128 x 256 tile against 6.6 us of MMA time on the K = 512 backward product)
-      const int q = warp - EPI_WARP0;
-      float* sc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + q * EPI_TILE_BYTES);
+      const int q = (warp - EPI_WARP0) & 3;                   // TMEM lane quarter (= warp index modulo 4)
+      const int half = (warp - EPI_WARP0) >> 2;               // which half of the tile's 32-column blocks
+      float* sc = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256 + (warp - EPI_WARP0) * EPI_TILE_BYTES);
       mbar_wait(&acc_full[buf], buf_phase);
       tc_fence_after();
       if (args.ct_L > 0) {
@@ -136,7 +139,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
         const long long m = m0 + q * 32 + lane;
         const int ncols_t = (int)(args.N - n0 < args.wn ? args.N - n0 : args.wn);
         float* pt = args.C + ((m / args.ct_L) * args.N + n0) * args.ct_L + (m % args.ct_L);
-        for (int c0 = 0; c0 < ncols_t; c0 += 32) {
+        for (int c0 = half * 32; c0 < ncols_t; c0 += 64) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
           if (m < args.M) {
@@ -156,7 +159,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constan
       const long long rbase = m0 + q * 32;
       int nrows = (int)(args.M - rbase < 32 ? (args.M - rbase < 0 ? 0 : args.M - rbase) : 32);
       const int ncols = (int)(args.N - n0 < args.wn ? args.N - n0 : args.wn);
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      for (int c0 = half * 32; c0 < ncols; c0 += 64) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
         __syncwarp();
