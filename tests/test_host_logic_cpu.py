@@ -93,3 +93,69 @@ def test_new_entry_points_fail_loudly_without_a_gpu():
                  lambda: nll_cls(torch.full((6, 3), 1 / 3), y, lh)):
         with pytest.raises(pkg._cabi.BnnpError):
             call()
+
+
+def test_function_space_host_logic_and_loud_failure():
+    """Prior-variance groups of gp_quantities (preds/gps.py:700-735: one kernel slot per optimised log-variance tensor, the
+    rest summed into the last slot with its prior variance as a scale; contiguous parameter ranges merged), the
+    constructor side effects of FunctionaLaplace (preds/laplace.py:140-160), and no CPU fallback."""
+    pkg = _pkg()
+    from preds_b200 import gps
+    model = pkg.MLPS(3, [4], 2, 'tanh')
+    params = list(model.parameters())                           # w1 (12), b1 (4), w2 (8), b2 (2)
+    va, vb = torch.tensor(0.5), torch.tensor(-1.0)
+    for i, p in enumerate(params):
+        p.log_prior_var = va if i in (0, 1, 3) else vb
+    all_vars, opt_vars, n_slots, slots, P = gps._groups(model, ())
+    assert P == 26 and len(all_vars) == 2 and opt_vars == [] and n_slots == 1
+    assert [(s, lo, hi) for s, _, lo, hi in slots] == [(0, 0, 16), (0, 16, 24), (0, 24, 26)]
+    assert abs(slots[0][1] - float(va.exp())) < 1e-6 and abs(slots[1][1] - float(vb.exp())) < 1e-6
+    all_vars, opt_vars, n_slots, slots, P = gps._groups(model, {va})
+    assert n_slots == 2 and len(opt_vars) == 1 and opt_vars[0] is va
+    assert [(s, sc is None, lo, hi) for s, sc, lo, hi in slots] == [(0, True, 0, 16), (1, False, 16, 24), (0, True, 24, 26)]
+    all_vars, opt_vars, n_slots, slots, P = gps._groups(model, va)                 # a bare tensor is accepted too
+    assert n_slots == 2
+    all_vars, opt_vars, n_slots, slots, P = gps._groups(model, {va, vb})           # everything optimised: no rest slot
+    assert n_slots == 2 and all(sc is None for _, sc, _, _ in slots)
+    params[0].requires_grad_(False)
+    with pytest.raises(pkg._cabi.BnnpError):
+        gps._groups(model, ())
+    params[0].requires_grad_(True)
+
+    lh = pkg.CategoricalLh()
+    lap = pkg.FunctionaLaplace(model, 0.25, lh)
+    assert lap.P == 26 and not lap.inferred and model.likelihood is lh
+    assert all(p.log_prior_var is params[0].log_prior_var for p in params)
+    assert abs(float(params[0].log_prior_var) - float(-torch.log(torch.tensor(0.25)))) < 1e-7
+    with pytest.raises(ValueError):
+        lap.predictive_samples()
+    with pytest.raises(AssertionError):
+        pkg.FunctionaLaplace(model, torch.ones(26), lh)                          # np.isscalar(prior_prec)
+    if not torch.cuda.is_available():
+        with pytest.raises(pkg._cabi.BnnpError):
+            lap.infer([(torch.randn(4, 3), None)], [(torch.randn(2, 3), None)])
+        with pytest.raises(pkg._cabi.BnnpError):
+            pkg.gp_quantities(model, torch.randn(4, 3))
+    with pytest.raises(NotImplementedError):
+        pkg.gp_quantities(model, torch.randn(4, 3), save_jacobians=True)
+
+
+def test_factorisation_host_logic():
+    """Tile ownership of the shared factorisation (128-column strips dealt out cyclically in GLOBAL coordinates) and the
+    engine switch."""
+    from preds_b200 import factor
+    m = factor._own_cols_mask(1024, 300, 1, 4, 'cpu')
+    cols = torch.arange(1024, 1324)
+    assert torch.equal(m, (((cols // 128) % 4) == 1).float())
+    total = sum(factor._own_cols_mask(2048, 1000, r, 3, 'cpu') for r in range(3))
+    assert torch.equal(total, torch.ones(1000))                                  # every column has exactly one owner
+    assert factor.use_tc(factor.MIN_P) and not factor.use_tc(factor.MIN_P - 1)
+    old = factor.ENGINE
+    factor.ENGINE = 'library'
+    try:
+        assert not factor.use_tc(100000)
+    finally:
+        factor.ENGINE = old
+    assert factor._group(False) == (None, 0, 1) and factor._group(True) == (None, 0, 1)      # no process group here
+    A = torch.eye(8) * 4
+    assert torch.equal(factor.cholesky(A), torch.eye(8) * 2)                     # below MIN_P: the library call
