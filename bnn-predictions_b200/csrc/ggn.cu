@@ -9,6 +9,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tma.cuh"
 #include "gram_tc.cuh"
+#include "conv_diag_tc.cuh"
 
 namespace bnnp {
 
@@ -16,17 +17,7 @@ namespace bnnp {
 // shared functors
 // ------------------------------------------------------------------------------------------
 // implicit im2col of a conv input: U(pos, e) with e = (ci, a, b), pos = (oh, ow); batch b -> example b / V
-struct Im2col {
-  const float* in; int64_t ild; int V;
-  int Cin, H, W, OW, kh, kw, sh, sw, pl, pt;
-  __device__ float at(int64_t n, int pos, int e) const {
-    int b = e % kw, a = (e / kw) % kh, ci = e / (kw * kh);
-    int oh = pos / OW, ow = pos % OW;
-    int ih = oh * sh - pt + a, iw = ow * sw - pl + b;
-    if (ih < 0 || ih >= H || iw < 0 || iw >= W) return 0.f;
-    return in[n * ild + ((int64_t)ci * H + ih) * W + iw];
-  }
-};
+using Im2col = ConvGeom;      // (conv_diag_tc.cuh)
 static Im2col make_im2col(const bnnp_op_t& o, const float* in, int64_t ild, int V) {
   return Im2col{in, ild, V, o.in_c, o.in_h, o.in_w, o.out_w, o.kh, o.kw, o.stride_h, o.stride_w,
                 o.pad_l, o.pad_t};
@@ -569,6 +560,9 @@ extern "C" int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops,
       int64_t E = (int64_t)ops[i].in_c * ops[i].kh * ops[i].kw, L = (int64_t)ops[i].out_h * ops[i].out_w;
       int64_t v = N * V * ops[i].out_c + 64 + 256LL * ((ops[i].out_c + 31) / 32 * 32) * E + 64 + N * L * ((E + 3) / 4 * 4) + 64;
       need = need > v ? need : v;
+      // TMA-fed variant: bf16 planes of the gradients and of the unfolded input + per-CTA sums
+      v = N * V * ops[i].out_c + 64 + conv_diag_tma_scratch_floats(N, V, ops[i].out_c, (int)L, (int)E) + 64;
+      need = need > v ? need : v;
     }
     if (ops[i].kind == BNNP_OP_LINEAR) {
       int64_t mm = ops[i].out_c, nn = ops[i].in_c + 1;
@@ -645,7 +639,12 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
     const float* G = ws + q.grad_off;
     float* partial = scratch + N * V * (int64_t)o.out_c + 64;
-    if (!g_bnnp_opt.net_simt && (long long)N * V * o.out_c * L * E >= kTcMinMacsG && N * V <= 0x7fffffff) {
+    if (!g_bnnp_opt.net_simt && g_bnnp_opt.gemm_generated == 0 && (long long)N * V * o.out_c * L * E >= kTcMinMacsG &&
+        conv_diag_tma_ok(o.out_c, L, N * V)) {
+      int rc = conv_diag_tma(make_im2col(o, in, ild, 1), G, q.grad_ld, N, V, o.out_c, L, E, factor, diag + o.theta_off_w,
+                             partial, st);
+      if (rc) return rc;
+    } else if (!g_bnnp_opt.net_simt && (long long)N * V * o.out_c * L * E >= kTcMinMacsG && N * V <= 0x7fffffff) {
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
