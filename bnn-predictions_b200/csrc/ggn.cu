@@ -365,13 +365,23 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nz
 }
 
 // d[offb + co] += factor * sum_r s[r, co]^2
+// block (32, 32): 32 columns x 32 row phases, combined in a fixed order (one thread per column walking all R rows took
+// 0.29 ms per conv layer at R = 5120: 9 % of the cfg4 diag pass for a 1.3 MB input)
 __global__ void colsq_accum_kernel(const float* __restrict__ s, int64_t R, int C, float factor,
                                    float* __restrict__ d) {
-  int co = blockIdx.x * blockDim.x + threadIdx.x;
-  if (co >= C) return;
+  __shared__ float red[32][33];
+  const int co = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int64_t r = 0; r < R; ++r) { float v = s[r * C + co]; acc = fmaf(v, v, acc); }
-  d[co] += factor * acc;
+  if (co < C)
+    for (int64_t r = threadIdx.y; r < R; r += 32) { const float v = s[r * C + co]; acc = fmaf(v, v, acc); }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && co < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += red[j][threadIdx.x];
+    d[co] += factor * t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -678,8 +688,8 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
       conv_possum_kernel<<<(unsigned)ceil_div64(R * o.out_c * 32, 256), 256, 0, st>>>(G, q.grad_ld, R, o.out_c, L,
                                                                                        scratch, o.out_c);
       BNNP_LAUNCH_CHECK();
-      colsq_accum_kernel<<<(unsigned)ceil_div64(o.out_c, 64), 64, 0, st>>>(scratch, R, o.out_c, factor,
-                                                                          diag + o.theta_off_b);
+      colsq_accum_kernel<<<(unsigned)ceil_div64(o.out_c, 32), dim3(32, 32), 0, st>>>(scratch, R, o.out_c, factor,
+                                                                                    diag + o.theta_off_b);
       BNNP_LAUNCH_CHECK();
     }
   }
