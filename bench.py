@@ -610,8 +610,19 @@ def other_configs(dev):
         lap = Laplace(model, 1.0, CategoricalLh())
         lap.infer(batches[:2], cov_type='kron', factorise=False)
         acc_ms = timed(lambda: lap.infer(batches, cov_type='kron', factorise=False))
+        lap.infer(batches[:2], cov_type='diag', factorise=False)
+        dacc_ms = timed(lambda: lap.infer(batches, cov_type='diag', factorise=False))
         pkk, _ = peaks()
         tc_peak = pkk.get('bf16_tflops_sustained', pkk['bf16_tflops']) / 3.0
+        # SURVEY 8d, diag: per-example conv flops 2 K L m n (conv1 64x75 L=784, conv2 96x576 L=144, conv3 128x864 L=36) + dense
+        d4_flop = 2.0 * 10 * (784 * 64 * 75 + 144 * 96 * 576 + 36 * 128 * 864) + 2.0 * (1152 * 512 + 512 * 256 + 256 * 10)
+        d4_tf = d4_flop * N / (dacc_ms * 1e-3) / 1e12
+        out.append({'config': 'cfg4 CIFAR10Net(3,10) (P=895210), loader batch 256', 'cov_type': 'diag',
+                    'accum_examples_per_s': N / dacc_ms * 1e3,
+                    'roofline': {'accum': {'bound': 'tensor', 'achieved': d4_tf, 'peak': tc_peak, 'unit': 'TFLOP/s fp32-equivalent',
+                                           'frac': d4_tf / tc_peak, 'flop_per_example': d4_flop,
+                                           'note': 'per-row weight-Jacobian products only (2 K L m n); the forward / K-column '
+                                                   'backward passes that feed them are not counted'}}})
         c4_tf = 0.53e9 * N / (acc_ms * 1e-3) / 1e12                                 # ~0.53 GFLOP per example
         out.append({'config': 'cfg4 CIFAR10Net(3,10) (P=895210), loader batch 256', 'cov_type': 'kron',
                     'accum_examples_per_s': N / acc_ms * 1e3,
