@@ -79,11 +79,11 @@ def test_gemm3_lower_and_triangular_k():
     assert bool((C[above] == 7.0).all())
 
 
-@pytest.mark.parametrize('P', [4099, 6000])
+@pytest.mark.parametrize('P', [4097, 4099, 6000])
 def test_factorisation_chain_against_library(P):
     """cholesky_lower / inverse_from_chol against torch.linalg.cholesky / cholesky_inverse on an SPD matrix with a
     prior-dominated spectrum: the factors are no further from a float64 factorisation than 2x the library's, and so is the
-    residual |H Sigma - I|."""
+    residual |H Sigma - I|.  P = 4097: a last panel of a single row / column (K = 1 products, 1 x 1 diagonal block)."""
     from preds_b200 import factor
     g = torch.Generator(device='cuda').manual_seed(1)
     A = torch.randn(P, 512, device='cuda', generator=g)

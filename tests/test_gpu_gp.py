@@ -124,3 +124,24 @@ def test_gp_kernels_over_several_k_segments_and_prior_groups(ntk_route):
     assert cases.rel_err(q['K_test'][0, 0], (Jt[:, :n0] ** 2).sum(1)) < TOL
     qc = pb.gp_quantities(model, Xtr[:40], Xte[:30], outputs=[2], optimize_params={va}, collapse_groups=True)
     assert cases.rel_err(qc['K_train'][0], float(va.exp()) * want0 + want1) < TOL
+
+
+def test_gp_quantities_single_output_model(ntk_route):
+    """K = 1 (regression-style network, MLPS(..., 1)): gp_quantities has one output slot; against the oracle, ragged sizes."""
+    import preds_b200 as pb
+    torch.manual_seed(9)
+    model = pb.MLPS(7, [11, 5], 1, 'tanh')
+    omodel = port.make_mlps(7, [11, 5], 1, 'tanh')
+    port.set_theta(omodel, port.get_theta(model))
+    g = torch.Generator().manual_seed(10)
+    Xtr, Xte = torch.randn(37, 7, generator=g), torch.randn(13, 7, generator=g)
+    model = model.cuda()
+    log_var = torch.tensor(0.0)
+    for p in model.parameters():
+        p.log_prior_var = log_var
+    q = pb.gp_quantities(model, Xtr, Xte, collapse_groups=True, with_prior_prec=False)
+    oq = port.gp_quantities(omodel, Xtr, Xte)
+    for k, v in oq.items():
+        assert tuple(q[k].shape) == tuple(v.shape), k
+        assert cases.rel_err(q[k], v) < TOL, k
+    assert q['prior_var'] == 1.0
