@@ -58,13 +58,25 @@ class _SplitRows:
                                        stream()), 'bnnp_split_bf16_rows')
 
 
+SPLITK_SCRATCH_FLOATS = 1 << 28       # 1 GB of deterministic split-K partials per product call
+
+
 def _nt(A, an, B, bn, out):
-    """out [an, bn] (fp32, row stride out.stride(0)) = A[:an] B[:bn]^T over all P columns, P walked in KSEG segments."""
-    for s in range(0, A.P, KSEG):
-        kk = min(KSEG, A.P - s)
+    """out [an, bn] (fp32, row stride out.stride(0)) = A[:an] B[:bn]^T over all P columns.  One tensor-core accumulation
+    never spans more than KSEG columns; a small output with a long P (a few output tiles, hundreds of segments) is ONE call
+    whose segments run in parallel as split-K partials (summed in a fixed order), a large output walks P in as many
+    segments per call as the partial buffer allows."""
+    per_call = max(1, min((A.P + KSEG - 1) // KSEG, SPLITK_SCRATCH_FLOATS // max(1, an * bn)))
+    kcall = per_call * KSEG
+    scratch = None
+    if per_call > 1:
+        scratch = torch.empty(int(lib.bnnp_gemm_nt_scratch_floats(an, bn, min(kcall, A.P))) + 64, dtype=torch.float32,
+                              device=out.device)
+    for s in range(0, A.P, kcall):
+        kk = min(kcall, A.P - s)
         check(lib.bnnp_gemm_nt_split(an, bn, kk, 1.0, A.hi.data_ptr() + 2 * s, A.lo.data_ptr() + 2 * s, A.pitch,
                                      B.hi.data_ptr() + 2 * s, B.lo.data_ptr() + 2 * s, B.pitch,
-                                     0.0 if s == 0 else 1.0, out.data_ptr(), out.stride(0), None, stream()),
+                                     0.0 if s == 0 else 1.0, out.data_ptr(), out.stride(0), ptr(scratch), stream()),
               'bnnp_gemm_nt_split')
 
 
