@@ -193,23 +193,28 @@ __global__ void split_conv_grad_rows_kernel(const float* __restrict__ g, long lo
   *reinterpret_cast<uint4*>(lo + rc * Lp + pos) = l;
 }
 
-// planes[(n * E + e), pos] <- bf16 hi / lo of unfold(in[n])[e, pos]
-__global__ void im2col_rows_split_kernel(ConvGeom u, long long N, int L, int E, int Lp, __nv_bfloat16* __restrict__ hi,
+// planes[(n * E + e), pos] <- bf16 hi / lo of unfold(in[n])[e, pos]        grid (ceil(E * p8 / 256), N)
+__global__ void im2col_rows_split_kernel(ConvUnfold u, int L, int E, int Lp, __nv_bfloat16* __restrict__ hi,
                                          __nv_bfloat16* __restrict__ lo) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int p8 = (L + 7) >> 3;
-  if (i >= N * E * p8) return;
-  const int pos = (int)(i % p8) << 3;
-  const long long ne = i / p8;
-  const long long n = ne / E;
-  const int e = (int)(ne % E);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= E * p8) return;
+  const long long n = blockIdx.y;
+  const int e = j / p8, pos = (j - e * p8) << 3;
+  const int b = e % u.kw, t = e / u.kw, a = t % u.kh, ci = t / u.kh;
+  int oh = pos / u.OW, ow = pos - oh * u.OW;
+  const float* xn = u.in + n * u.ild;
   float v[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = pos + k < L ? u.at(n, pos + k, e) : 0.f;
+  for (int k = 0; k < 8; ++k) {
+    v[k] = pos + k < L ? u.at_dec(xn, ci, a, b, oh, ow) : 0.f;
+    if (++ow == u.OW) { ow = 0; ++oh; }
+  }
   uint4 h, l;
   split8(v, h, l);
-  *reinterpret_cast<uint4*>(hi + ne * Lp + pos) = h;
-  *reinterpret_cast<uint4*>(lo + ne * Lp + pos) = l;
+  const long long o = (n * E + e) * Lp + pos;
+  *reinterpret_cast<uint4*>(hi + o) = h;
+  *reinterpret_cast<uint4*>(lo + o) = l;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -253,7 +258,9 @@ static inline int pick_ipt(int Cout, int V) {
 
 }  // namespace cd
 
-bool conv_diag_tma_ok(int Cout, int L, long long R) { return Cout >= 1 && Cout <= cd::TILE && L >= 1 && R * Cout < (1LL << 31); }
+bool conv_diag_tma_ok(int Cout, int L, long long N, int V) {
+  return Cout >= 1 && Cout <= cd::TILE && L >= 1 && N * V * Cout < (1LL << 31) && N <= 65535;   // (N: grid.y of the unfold pass)
+}
 
 int64_t conv_diag_tma_scratch_floats(int64_t N, int V, int Cout, int L, int E) {
   const int64_t Lp = cd::up64(L);
@@ -261,11 +268,11 @@ int64_t conv_diag_tma_scratch_floats(int64_t N, int V, int Cout, int L, int E) {
   return cd::up64(N * V * Cout * Lp) + cd::up64(N * E * Lp) + 160LL * cd::TILE * cd::TILE + 256;
 }
 
-int conv_diag_tma(const ConvGeom& u, const float* G, int64_t gld, int64_t N, int V, int Cout, int L, int E, float factor,
+int conv_diag_tma(const ConvUnfold& u, const float* G, int64_t gld, int64_t N, int V, int Cout, int L, int E, float factor,
                   float* d_w, float* scratch, cudaStream_t st) {
   using namespace cd;
   const int64_t R = N * V;
-  if (!conv_diag_tma_ok(Cout, L, R)) return BNNP_ERR_UNSUPPORTED;
+  if (!conv_diag_tma_ok(Cout, L, N, V)) return BNNP_ERR_UNSUPPORTED;
   const int Lp = (int)up64(L);
   float* base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 127) & ~uintptr_t(127));
   __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base);
@@ -276,7 +283,7 @@ int conv_diag_tma(const ConvGeom& u, const float* G, int64_t gld, int64_t N, int
   const int p8 = (L + 7) >> 3;
   split_conv_grad_rows_kernel<<<(unsigned)ceil_div64(R * Cout * p8, 256), 256, 0, st>>>(G, gld, R, Cout, L, Lp, ah, al);
   BNNP_LAUNCH_CHECK();
-  im2col_rows_split_kernel<<<(unsigned)ceil_div64(N * E * p8, 256), 256, 0, st>>>(u, N, L, E, Lp, bh, bl);
+  im2col_rows_split_kernel<<<dim3((unsigned)ceil_div64((int64_t)E * p8, 256), (unsigned)N), 256, 0, st>>>(u, L, E, Lp, bh, bl);
   BNNP_LAUNCH_CHECK();
   Args a;
   a.R = R; a.V = V; a.Cout = Cout; a.E = E; a.L = L;

@@ -17,7 +17,7 @@ namespace bnnp {
 // shared functors
 // ------------------------------------------------------------------------------------------
 // implicit im2col of a conv input: U(pos, e) with e = (ci, a, b), pos = (oh, ow); batch b -> example b / V
-using Im2col = ConvGeom;      // (conv_diag_tc.cuh)
+using Im2col = ConvUnfold;      // (conv_diag_tc.cuh)
 static Im2col make_im2col(const bnnp_op_t& o, const float* in, int64_t ild, int V) {
   return Im2col{in, ild, V, o.in_c, o.in_h, o.in_w, o.out_w, o.kh, o.kw, o.stride_h, o.stride_w,
                 o.pad_l, o.pad_t};
@@ -231,16 +231,21 @@ __global__ void im2col_kernel(Im2col u, int64_t N, int L, int E, int Epad, float
 // One thread per 8 consecutive rp (16-byte stores).
 __global__ void im2col_t_split_kernel(Im2col u, int64_t N, int L, int E, int64_t NLp, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t p8 = NLp >> 3;
-  if (i >= (int64_t)E * p8) return;
-  const int e = (int)(i / p8);
-  const int64_t rp0 = (i % p8) << 3;
+  // grid (ceil(NLp / 8 / 256), E): e is uniform per block, (n, oh, ow) of the first of a thread's 8 positions come from two
+  // 32-bit divisions and are advanced incrementally (u.at() per element: eight divisions, three of them 64-bit)
+  const int e = blockIdx.y;
+  const int64_t rp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) << 3;
+  if (rp0 >= NLp) return;
+  const int b = e % u.kw, t = e / u.kw, a = t % u.kh, ci = t / u.kh;
+  int64_t n = rp0 / L;
+  int pos = (int)(rp0 - n * L);
+  int oh = pos / u.OW, ow = pos - oh * u.OW;
   float v[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int64_t rp = rp0 + k;
-    v[k] = rp < N * L ? u.at(rp / L, (int)(rp % L), e) : 0.f;
+    v[k] = n < N ? u.at_dec(u.in + n * u.ild, ci, a, b, oh, ow) : 0.f;
+    if (++ow == u.OW) { ow = 0; ++oh; }
+    if (++pos == L) { pos = 0; oh = 0; ow = 0; ++n; }
   }
   uint4 h, l;
   tcp::split8(v, h, l);
@@ -650,7 +655,7 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     const float* G = ws + q.grad_off;
     float* partial = scratch + N * V * (int64_t)o.out_c + 64;
     if (!g_bnnp_opt.net_simt && g_bnnp_opt.gemm_generated == 0 && (long long)N * V * o.out_c * L * E >= kTcMinMacsG &&
-        conv_diag_tma_ok(o.out_c, L, N * V)) {
+        conv_diag_tma_ok(o.out_c, L, N, V)) {
       int rc = conv_diag_tma(make_im2col(o, in, ild, 1), G, q.grad_ld, N, V, o.out_c, L, E, factor, diag + o.theta_off_w,
                              partial, st);
       if (rc) return rc;
@@ -819,7 +824,8 @@ extern "C" int bnnp_kfac_accum_ex(const bnnp_op_t* ops, int n_ops, const bnnp_pl
         __nv_bfloat16* uh = reinterpret_cast<__nv_bfloat16*>(base);
         __nv_bfloat16* ul = uh + (int64_t)E * NLp;
         float* part = base + ((int64_t)E * NLp + 63) / 64 * 64;
-        im2col_t_split_kernel<<<(unsigned)ceil_div64((int64_t)E * (NLp >> 3), 256), 256, 0, st>>>(u, N, L, E, NLp, uh, ul);
+        if (E > 65535) return BNNP_ERR_UNSUPPORTED;
+        im2col_t_split_kernel<<<dim3((unsigned)ceil_div64(NLp >> 3, 256), (unsigned)E), 256, 0, st>>>(u, N, L, E, NLp, uh, ul);
         BNNP_LAUNCH_CHECK();
         rc = gemm_tma_nt(E, E, NL, batch_factor / (float)N, uh, ul, NLp, uh, ul, NLp, 1.f, Af, E, part, st);
       } else if (!g_bnnp_opt.net_simt && (long long)E * E * N * L >= kTcMinMacsG) {

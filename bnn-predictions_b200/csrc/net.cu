@@ -416,21 +416,32 @@ __global__ void col2im_gather_kernel(const float* __restrict__ dUt, float* __res
 }
 
 // ---- convolution forward on tensor cores: out[(n,pos), co] = sum_e U[(n,pos), e] W[co, e] + bias ----
+// grid (ceil(L / 16), N), 256 threads along e: (ci, a, b) of e are decomposed once per thread, the 16 positions of the block
+// walked incrementally (a flat one-thread-per-element index needs eight integer divisions per element, three of them
+// 64-bit: the pass was compute-bound at 0.5 TB/s of stores); stores are e-contiguous per position
 __global__ void im2col_fwd_kernel(const float* __restrict__ in, int64_t ild, int64_t N, ConvGeom g, int E, int Epad,
                                   float* __restrict__ U) {
   const int L = g.OH * g.OW;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * L * Epad) return;
-  const int e = (int)(i % Epad);
-  const int64_t rp = i / Epad;
-  float v = 0.f;
-  if (e < E) {
-    const int b = e % g.kw, a = (e / g.kw) % g.kh, ci = e / (g.kw * g.kh);
-    const int pos = (int)(rp % L), oh = pos / g.OW, ow = pos % g.OW;
-    const int ih = oh * g.sh - g.pt + a, iw = ow * g.sw - g.pl + b;
-    if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = in[(rp / L) * ild + ((int64_t)ci * g.H + ih) * g.W + iw];
+  const int64_t n = blockIdx.y;
+  const int pos0 = blockIdx.x * 16;
+  const int npos = L - pos0 < 16 ? L - pos0 : 16;
+  const int oh0 = pos0 / g.OW, ow0 = pos0 - oh0 * g.OW;
+  const float* xn = in + n * ild;
+  float* Un = U + (n * L + pos0) * (int64_t)Epad;
+  for (int e = threadIdx.x; e < Epad; e += blockDim.x) {
+    const int b = e % g.kw, t = e / g.kw, a = t % g.kh, ci = t / g.kh;
+    const float* xc = xn + (int64_t)ci * g.H * g.W;
+    int oh = oh0, ow = ow0;
+    for (int p = 0; p < npos; ++p) {
+      float v = 0.f;
+      if (e < E) {
+        const int ih = oh * g.sh - g.pt + a, iw = ow * g.sw - g.pl + b;
+        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v = __ldg(xc + ih * g.W + iw);
+      }
+      Un[(int64_t)p * Epad + e] = v;
+      if (++ow == g.OW) { ow = 0; ++oh; }
+    }
   }
-  U[i] = v;
 }
 struct ConvStoreOutT : tcg::TcNoState {   // out[n*old + co*L + pos] = acc(m = (n,pos), co) + bias[co]
   float* out; long long old; const float* bias; int L;
@@ -608,11 +619,10 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
       }
       case BNNP_OP_CONV2D: {
         const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
-        if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)N * L * E * o.out_c >= kTcMinMacs) {
+        if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)N * L * E * o.out_c >= kTcMinMacs && N <= 65535) {
           const int Epad = (E + 3) / 4 * 4;
           float* U = ws + plan->conv_scratch_off;
-          im2col_fwd_kernel<<<(unsigned)ceil_div64(N * L * (int64_t)Epad, 256), 256, 0, st>>>(in, ild, N, geom_of(o), E,
-                                                                                            Epad, U);
+          im2col_fwd_kernel<<<dim3((unsigned)ceil_div64(L, 16), (unsigned)N), 256, 0, st>>>(in, ild, N, geom_of(o), E, Epad, U);
           BNNP_LAUNCH_CHECK();
           int rc = tcg::gemm_tc(N * L, o.out_c, E, 1, tcg::TcRowMajor{U, Epad, 0}, tcg::TcRowMajor{o.weight, E, 0},
                                 ConvStoreOutT(out, q.act_ld, o.has_bias ? o.bias : nullptr, L), 1, st);
