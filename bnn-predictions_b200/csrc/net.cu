@@ -213,7 +213,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
   idx[n * per + r] = bi;
 }
 
-// grid: (ceil(H*W/256), C, z): the candidate windows of a position are found once and reused for all rows.
+// grid: (ceil(C*H*W/256), 1, z): the candidate windows of a position are found once and reused for all rows.
 // FUSE != 0: the op in front of the pool is an elementwise activation whose (in-place) output `act` is the pool's
 // input; its backward  g *= act'(out)  is applied to the value before the single store, which removes one full
 // read-modify-write pass over the [R, C*H*W] gradient (the K-column backward of a conv net is HBM-bound).
@@ -222,10 +222,12 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
                                    float* __restrict__ gin, int64_t gild,
                                    const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g,
                                    const float* __restrict__ act, int64_t actld, int act_kind) {
-  const int me = blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread per input element (c, ih, iw), flattened over channels so that small feature maps (12 x 12, 6 x 6) fill
+  // their blocks (one block row per channel left 44 % / 86 % of the threads idle there)
   const int HW = g.H * g.W;
-  if (me >= HW) return;
-  const int c = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.Cin * HW) return;
+  const int c = j / HW, me = j - c * HW;
   const int ih = me / g.W, iw = me - ih * g.W;
   const int OL = g.OH * g.OW;
   const int64_t operp = (int64_t)g.Cout * OL;
@@ -384,34 +386,41 @@ struct ConvStoreDUt : tcg::TcNoState {    // dUt[(r*E + e)*L + pos] = acc(m = (r
       if (e < nvalid) q[(long long)e * L] = v[e];
   }
 };
+// One thread per input element (ci, ih, iw) -- flattened, so that small feature maps (6 x 6, 14 x 14) fill their blocks --
+// with the (at most KH x KW) contributing taps resolved once into registers (compile-time indexed: a dynamically indexed
+// offset list lives in local memory and costs a load per tap and row); rows r in the outer loop.
+template <int KH, int KW>
 __global__ void col2im_gather_kernel(const float* __restrict__ dUt, float* __restrict__ gin, int64_t gild,
                                      int64_t R, ConvGeom g) {
-  const int me = blockIdx.x * blockDim.x + threadIdx.x;      // grid: (ceil(H*W/256), Cin, rows)
   const int HW = g.H * g.W;
-  if (me >= HW) return;
-  const int ci = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;       // grid: (ceil(Cin*H*W/256), row slices)
+  if (j >= g.Cin * HW) return;
+  const int ci = j / HW, me = j - ci * HW;
   const int ih = me / g.W, iw = me - ih * g.W;
-  const int L = g.OH * g.OW, kk = g.kh * g.kw;
-  int off[25];
-  int noff = 0;
-  for (int a = 0; a < g.kh; ++a) {
+  const int L = g.OH * g.OW;
+  int off[KH * KW];
+  bool ok[KH * KW];
+#pragma unroll
+  for (int a = 0; a < KH; ++a) {
     const int th = ih + g.pt - a;
-    if (th < 0 || th % g.sh) continue;
-    const int oh = th / g.sh;
-    if (oh >= g.OH) continue;
-    for (int b = 0; b < g.kw; ++b) {
+    const bool vh = a < g.kh && th >= 0 && th % g.sh == 0 && th / g.sh < g.OH;
+#pragma unroll
+    for (int b = 0; b < KW; ++b) {
       const int tw = iw + g.pl - b;
-      if (tw < 0 || tw % g.sw) continue;
-      const int ow = tw / g.sw;
-      if (ow >= g.OW || noff >= 25) continue;
-      off[noff++] = (a * g.kw + b) * L + oh * g.OW + ow;
+      const bool vw = b < g.kw && tw >= 0 && tw % g.sw == 0 && tw / g.sw < g.OW;
+      ok[a * KW + b] = vh && vw;
+      off[a * KW + b] = vh && vw ? (a * g.kw + b) * L + (th / g.sh) * g.OW + tw / g.sw : 0;
     }
   }
-  for (int64_t r = blockIdx.z; r < R; r += gridDim.z) {
-    const float* base = dUt + (r * ((int64_t)g.Cin * kk) + (int64_t)ci * kk) * L;
+  const int64_t per_row = (int64_t)g.Cin * g.kh * g.kw * L;
+  const float* base0 = dUt + (int64_t)ci * g.kh * g.kw * L;
+  for (int64_t r = blockIdx.y; r < R; r += gridDim.y) {
+    const float* base = base0 + r * per_row;
     float acc = 0.f;
-    for (int t = 0; t < noff; ++t) acc += base[off[t]];
-    gin[r * gild + (int64_t)ci * HW + me] = acc;
+#pragma unroll
+    for (int t = 0; t < KH * KW; ++t)
+      if (ok[t]) acc += base[off[t]];
+    gin[r * gild + j] = acc;
   }
 }
 
@@ -741,14 +750,17 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
             rc = tcg::gemm_tc(R * L, E, o.out_c, 1, ConvGoutRowsA{gout, q.grad_ld, L}, tcg::TcColMajor{o.weight, E, 0},
                               ConvStoreDUt(dUt, E, L), 1, st);
           if (rc) return rc;
-          if (o.kh * o.kw > 25) return BNNP_ERR_UNSUPPORTED;
+          if (o.kh > 5 || o.kw > 5) return BNNP_ERR_UNSUPPORTED;
           {
-            // few z-blocks: the tap offsets depend on (channel, position) only and are reused across rows
-            const int64_t bxy = ceil_div64((int64_t)o.in_h * o.in_w, 256) * o.in_c;
-            int64_t gz = ceil_div64(4096, bxy);
-            gz = gz < 1 ? 1 : (gz > R ? R : gz);
-            col2im_gather_kernel<<<dim3((unsigned)ceil_div64((int64_t)o.in_h * o.in_w, 256), (unsigned)o.in_c, (unsigned)gz),
-                                   256, 0, st>>>(dUt, gin, qp.grad_ld, R, geom_of(o));
+            // few row slices: the tap offsets depend on (channel, position) only and are reused across rows
+            const int64_t bx = ceil_div64((int64_t)o.in_c * o.in_h * o.in_w, 256);
+            int64_t gy = ceil_div64(8192, bx);
+            gy = gy < 1 ? 1 : (gy > R ? R : (gy > 65535 ? 65535 : gy));
+            const dim3 grid((unsigned)bx, (unsigned)gy);
+            if (o.kh <= 3 && o.kw <= 3)
+              col2im_gather_kernel<3, 3><<<grid, 256, 0, st>>>(dUt, gin, qp.grad_ld, R, geom_of(o));
+            else
+              col2im_gather_kernel<5, 5><<<grid, 256, 0, st>>>(dUt, gin, qp.grad_ld, R, geom_of(o));
           }
           BNNP_LAUNCH_CHECK();
         } else if (R <= 65535) {
@@ -765,10 +777,10 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
         if (o.kh > 3 || o.kw > 3) return BNNP_ERR_UNSUPPORTED;
         {
           // few z-blocks: the candidate windows depend on (channel, position) only and are reused across examples
-          const int64_t bxy = ceil_div64((int64_t)o.in_h * o.in_w, 256) * o.in_c;
+          const int64_t bxy = ceil_div64((int64_t)o.in_h * o.in_w * o.in_c, 256);
           int64_t gz = ceil_div64(4096, bxy);
           gz = gz < 1 ? 1 : (gz > N ? N : gz);
-          const dim3 grid((unsigned)ceil_div64((int64_t)o.in_h * o.in_w, 256), (unsigned)o.in_c, (unsigned)gz);
+          const dim3 grid((unsigned)bxy, 1, (unsigned)gz);
           const int32_t* idxp = reinterpret_cast<const int32_t*>(ws) + q.idx_off;
           // position sums only for the first conv (KFAC): see maxpool_bwd_possum_kernel
           const bool act_before = i - 1 > first_param && is_elementwise_op(ops[i - 1]);
