@@ -276,6 +276,92 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
   }
 }
 
+// The same for stride >= 2 and windows <= 3 x 3 (every position lies in at most 2 x 2 windows), four consecutive positions
+// per thread and one 16-byte store per row (requires W % 4 == 0 and 16-byte aligned rows).  The general kernel is
+// instruction-bound, not memory-bound (ncu on the [5120, 64, 28, 28] gradient of CIFAR10Net's first pool: 1.09e9 warp
+// instructions of which 63 % are IMAD / LEA / IADD3, issue slots 63 % busy, DRAM 11 %): with overlapping windows a local maximum
+// wins SEVERAL windows, so most threads walk all nine predicated (address, load, add) candidates for each of the V rows.  Here
+// the at most four candidate windows of a position are compacted once per thread into register-resident offsets; the row loop
+// is sixteen predicated loads on precomputed offsets and one store.
+template <int FUSE>
+__global__ void maxpool_bwd4_kernel(const float* __restrict__ gout, int64_t gold,
+                                    float* __restrict__ gin, int64_t gild,
+                                    const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g,
+                                    const float* __restrict__ act, int64_t actld, int act_kind) {
+  const int HW = g.H * g.W, W4 = g.W >> 2;
+  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per 4 consecutive positions of a row
+  if (j4 >= g.Cin * g.H * W4) return;
+  const int c = j4 / (g.H * W4), rem = j4 - c * (g.H * W4);
+  const int ih = rem / W4, iw0 = (rem - ih * W4) << 2;
+  const int me0 = ih * g.W + iw0;
+  const int OL = g.OH * g.OW;
+  const int64_t operp = (int64_t)g.Cout * OL;
+  // candidate output rows of this input row (at most two for stride >= 2), as row offsets into the pooled map
+  int orow[2] = {0, 0};
+  int na = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const int th = ih + g.pt - a;
+    if (a < g.kh && th >= 0 && th % g.sh == 0 && th / g.sh < g.OH) {
+      if (na == 0) orow[0] = (th / g.sh) * g.OW; else orow[1] = (th / g.sh) * g.OW;
+      ++na;
+    }
+  }
+  // candidate windows (i, j) of each of the four positions: offsets into the pooled map, -1 = none
+  int off[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    int ocol[2] = {0, 0};
+    int nb = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int tw = iw0 + p + g.pl - b;
+      if (b < g.kw && tw >= 0 && tw % g.sw == 0 && tw / g.sw < g.OW) {
+        if (nb == 0) ocol[0] = tw / g.sw; else ocol[1] = tw / g.sw;
+        ++nb;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) off[p][i * 2 + jj] = (i < na && jj < nb) ? orow[i] + ocol[jj] : -1;
+  }
+  for (int64_t n = blockIdx.z; n < N; n += gridDim.z) {
+    const int32_t* id = idx + n * operp + (int64_t)c * OL;
+    unsigned hit = 0;                                              // bit p * 4 + k: position p won its candidate window k
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (off[p][k] >= 0 && __ldg(id + off[p][k]) == me0 + p) hit |= 1u << (p * 4 + k);
+    float* gp = gin + n * V * gild + (int64_t)c * HW + me0;
+    if (hit == 0u) {                                               // four zeros per row
+      for (int v = 0; v < V; ++v, gp += gild) *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    float d[4] = {1.f, 1.f, 1.f, 1.f};
+    if (FUSE) {
+      const float4 o4 = __ldg(reinterpret_cast<const float4*>(act + n * actld + (int64_t)c * HW + me0));
+      const float o[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        d[p] = act_kind == BNNP_OP_RELU ? (o[p] > 0.f ? 1.f : 0.f) : (act_kind == BNNP_OP_TANH ? 1.f - o[p] * o[p] : o[p] * (1.f - o[p]));
+    }
+    const float* go = gout + n * V * gold + (int64_t)c * OL;
+    for (int v = 0; v < V; ++v, gp += gild, go += gold) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (hit & (1u << (p * 4 + k))) acc[p] += __ldg(go + off[p][k]);
+        if (FUSE) acc[p] *= d[p];
+      }
+      *reinterpret_cast<float4*>(gp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+  }
+}
+
 // KFAC needs only the POSITION SUMS of the gradient at a conv layer's output (BackPACK KFLR: G = sum (sum_pos g)(sum_pos
 // g)^T, preds/laplace.py:73-78).  For the first parameterised layer nothing upstream needs the full gradient either, so
 // when it is followed by (activation,) max-pool the [R, C, H, W] gradient (2 MB per example at CIFAR10Net's conv1 and
@@ -794,14 +880,30 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
           }
           // an elementwise activation right in front of the pool (conv -> relu -> pool): its backward is folded into
           // this kernel's store and the op is skipped below
-          if (i - 1 > first_param && is_elementwise_op(ops[i - 1])) {
+          const bool fuse_act = i - 1 > first_param && is_elementwise_op(ops[i - 1]);
+          const float* actp = fuse_act ? ws + qp.act_off : nullptr;
+          // stride >= 2: four positions per thread, compacted candidate windows, 16-byte stores (aligned rows)
+          const bool vec4 = o.in_w % 4 == 0 && o.stride_h >= 2 && o.stride_w >= 2 && qp.grad_ld % 4 == 0 &&
+                            (reinterpret_cast<uintptr_t>(gin) & 15) == 0 &&
+                            (!fuse_act || (qp.act_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(actp) & 15) == 0));
+          if (vec4) {
+            const int64_t b4 = ceil_div64((int64_t)o.in_h * (o.in_w / 4) * o.in_c, 128);
+            int64_t gz4 = ceil_div64(8192, b4);
+            gz4 = gz4 < 1 ? 1 : (gz4 > N ? N : gz4);
+            const dim3 grid4((unsigned)b4, 1, (unsigned)gz4);
+            if (fuse_act)
+              maxpool_bwd4_kernel<1><<<grid4, 128, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o), actp,
+                                                          qp.act_ld, ops[i - 1].kind);
+            else
+              maxpool_bwd4_kernel<0><<<grid4, 128, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o), nullptr, 0, 0);
+          } else if (fuse_act) {
             maxpool_bwd_kernel<1><<<grid, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o),
-                                                        ws + qp.act_off, qp.act_ld, ops[i - 1].kind);
-            fused_prev = true;
+                                                        actp, qp.act_ld, ops[i - 1].kind);
           } else {
             maxpool_bwd_kernel<0><<<grid, 256, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o),
                                                         nullptr, 0, 0);
           }
+          fused_prev = fuse_act;
         }
         BNNP_LAUNCH_CHECK();
         break;
