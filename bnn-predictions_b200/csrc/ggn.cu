@@ -33,25 +33,23 @@ static const float* op_input(const bnnp_op_t* ops, const bnnp_plan_t* plan, int 
 // ------------------------------------------------------------------------------------------
 // Jacobian materialisation  Js[n, p, v]
 // ------------------------------------------------------------------------------------------
+// grid (ceil(per / 256), N): the example is the block row and the parameter index a 32-bit quantity (a flat 64-bit element
+// index costs three 64-bit divisions per element and made this pass instruction-bound)
 __global__ void jac_linear_kernel(const float* __restrict__ G, int64_t gld, const float* __restrict__ A,
                                   int64_t ald, int64_t N, int V, int m, int nin, int has_bias,
                                   int64_t offw, int64_t offb, int64_t P, float* __restrict__ Js) {
-  int64_t per = (int64_t)m * (nin + (has_bias ? 1 : 0));
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * per * V) return;
-  int v = (int)(i % V);
-  int64_t e = (i / V) % per, n = i / (V * per);
-  int64_t p; float val;
-  if (e < (int64_t)m * nin) {
-    int u = (int)(e / nin), j = (int)(e % nin);
-    p = offw + e;
-    val = G[(n * V + v) * gld + u] * A[n * ald + j];
-  } else {
-    int u = (int)(e - (int64_t)m * nin);
-    p = offb + u;
-    val = G[(n * V + v) * gld + u];
-  }
-  Js[(n * P + p) * V + v] = val;
+  const int per = m * (nin + (has_bias ? 1 : 0));
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= per) return;
+  const int64_t n = blockIdx.y;
+  int u, j = -1;
+  int64_t p;
+  if (e < m * nin) { u = e / nin; j = e - u * nin; p = offw + e; }
+  else { u = e - m * nin; p = offb + u; }
+  const float a = j >= 0 ? A[n * ald + j] : 1.f;
+  const float* g = G + n * V * gld + u;
+  float* out = Js + (n * P + p) * V;
+  for (int v = 0; v < V; ++v) out[v] = g[v * gld] * a;
 }
 
 struct ConvGradA {     // A(co, pos) = gout[r, co, pos]
@@ -464,7 +462,8 @@ extern "C" int bnnp_jacobians_cols(const bnnp_op_t* ops, int n_ops, const bnnp_p
     const float* G = ws + q.grad_off;
     if (o.kind == BNNP_OP_LINEAR) {
       int64_t per = (int64_t)o.out_c * (o.in_c + (o.has_bias ? 1 : 0));
-      jac_linear_kernel<<<(unsigned)ceil_div64(N * per * V, 256), 256, 0, st>>>(
+      if (N > 65535 || per >= (1LL << 31)) return BNNP_ERR_UNSUPPORTED;
+      jac_linear_kernel<<<dim3((unsigned)ceil_div64(per, 256), (unsigned)N), 256, 0, st>>>(
           G, q.grad_ld, ws + plan->acat_off + q.lin_col, plan->Dtot, N, V, o.out_c, o.in_c, o.has_bias,
           o.theta_off_w, o.theta_off_b, plan->P, Js);
       BNNP_LAUNCH_CHECK();
