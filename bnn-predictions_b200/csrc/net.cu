@@ -29,18 +29,21 @@ __global__ void act_fwd_kernel(float* __restrict__ x, int64_t rows, int64_t cols
   *p = v;
 }
 
-// g[(n,v), c] *= act'(out[n, c])      grid: (ceil(cols/256), rows) -- no per-element index division
+// g[(n,v), c] *= act'(out[n, c])      grid: (ceil(cols/256), example slices): the derivative is computed once per example and
+// applied to its V rows (a row loop with r / V costs a 64-bit division per element and an activation load per row)
 __global__ void act_bwd_kernel(float* __restrict__ g, int64_t gld, const float* __restrict__ out,
                                int64_t old, int64_t R, int V, int64_t cols, int kind) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
-  for (int64_t r = blockIdx.y; r < R; r += gridDim.y) {
-    const float o = out[(r / V) * old + c];
+  const int64_t N = R / V;
+  for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+    const float o = out[n * old + c];
     float d;
     if (kind == BNNP_OP_RELU) d = o > 0.f ? 1.f : 0.f;
     else if (kind == BNNP_OP_TANH) d = 1.f - o * o;
     else d = o * (1.f - o);
-    g[r * gld + c] *= d;
+    float* p = g + n * V * gld + c;
+    for (int v = 0; v < V; ++v, p += gld) *p *= d;
   }
 }
 
@@ -914,7 +917,8 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
       case BNNP_OP_RELU: case BNNP_OP_TANH: case BNNP_OP_SIGMOID:
         {
           int64_t gy = ceil_div64(8192, ceil_div64(isz, 256));
-          gy = gy < 1 ? 1 : (gy > R ? R : gy);
+          gy = gy < 1 ? 1 : (gy > R / V ? R / V : gy);
+          if (gy < 1) gy = 1;
           act_bwd_kernel<<<dim3((unsigned)ceil_div64(isz, 256), (unsigned)gy), 256, 0, st>>>(
               gout, q.grad_ld, ws + q.act_off, q.act_ld, R, V, isz, o.kind);
         }
