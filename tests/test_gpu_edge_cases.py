@@ -236,3 +236,38 @@ def test_descriptor_verification_catches_small_functional_changes():
     torch.manual_seed(0)
     with pytest.raises(BnnpError):
         Jacobians(Scaled().cuda(), torch.randn(4, 6).cuda())
+
+
+def test_smooth_conv_net_on_the_tensor_core_branches_against_the_oracle():
+    """A conv net WITHOUT discrete decisions (tanh, no pooling), so that diag / KFLR agree with the oracle to 1e-4 with no
+    routing injected, sized to take the tensor-core conv branches with shapes CIFAR10Net does not have: C_out = 32 and 20
+    (three rows r of an example per 128-row tile of the diag product since V = 3), E = 27 / 288 (ragged 128-wide e blocks),
+    L = 100 / 64, 12 x 12 inputs (hoisted-index unfold passes on odd sizes), K = 3."""
+    import copy
+    from preds_b200 import Laplace, CategoricalLh
+    torch.manual_seed(21)
+    net = nn.Sequential(nn.Conv2d(3, 32, 3), nn.Tanh(), nn.Conv2d(32, 20, 3), nn.Tanh(), nn.Flatten(), nn.Linear(20 * 8 * 8, 3))
+    net.output_size = 3
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(0.5)
+    onet = copy.deepcopy(net)
+    g = torch.Generator().manual_seed(22)
+    X, y = torch.randn(192, 3, 12, 12, generator=g), torch.randint(3, (192,), generator=g)
+    batches = [(X[:100], y[:100]), (X[100:], y[100:])]
+    net = net.cuda()
+    for cov in ('diag', 'kron'):
+        post = port.infer(onet, 0.9, port.CategoricalLh(), batches, cov)
+        lap = Laplace(net, 0.9, CategoricalLh())
+        lap.infer(batches, cov_type=cov)
+        if cov == 'diag':
+            got, want = lap.precision.cpu(), post['precision']
+            off = 0
+            for p in onet.parameters():            # per parameter tensor, relative to its own scale
+                a, b = got[off:off + p.numel()], want[off:off + p.numel()]
+                assert cases.rel_err(a, b) < TOL, tuple(p.shape)
+                off += p.numel()
+        else:
+            for qa, qb in zip(lap.Sigma_chol.qhs, post['kron'].qhs):
+                for a, b in zip(qa, qb):
+                    assert cases.rel_err(a.cpu(), b) < TOL, tuple(b.shape)
