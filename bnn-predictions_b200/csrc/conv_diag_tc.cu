@@ -72,6 +72,9 @@ conv_diag_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
+      // the gradient planes stream through once, the (small) unfolded input of an example is re-used by its V rows: without
+      // the hints the stream evicts it first (ncu on conv1: L2 hit rate 28 %, 1.9 GB of DRAM reads for 1.2 GB of operands)
+      const uint64_t pol_a = l2_policy_evict_first(), pol_b = l2_policy_evict_last();
       for (long long t = t_beg; t < t_end; ++t) {
         const long long r0 = t * args.ipt;
         const long long n = r0 / args.V;
@@ -79,10 +82,15 @@ conv_diag_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_consta
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* base = smem + s * STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], (uint32_t)STAGE_BYTES);
-          tma_load_2d(&map_ah, &full[s], base, c * BK, (int)(t * rows_tile));
-          tma_load_2d(&map_al, &full[s], base + TERM, c * BK, (int)(t * rows_tile));
-          tma_load_2d(&map_bh, &full[s], base + 2 * TERM, c * BK, (int)(n * args.E + (long long)et * TILE));
-          tma_load_2d(&map_bl, &full[s], base + 3 * TERM, c * BK, (int)(n * args.E + (long long)et * TILE));
+          if (args.n_et == 1) {           // a single e block: every gradient tile is read exactly once
+            tma_load_2d_hint(&map_ah, &full[s], base, c * BK, (int)(t * rows_tile), pol_a);
+            tma_load_2d_hint(&map_al, &full[s], base + TERM, c * BK, (int)(t * rows_tile), pol_a);
+          } else {                        // the CTAs of the other e blocks read the same tile: leave it to the default policy
+            tma_load_2d(&map_ah, &full[s], base, c * BK, (int)(t * rows_tile));
+            tma_load_2d(&map_al, &full[s], base + TERM, c * BK, (int)(t * rows_tile));
+          }
+          tma_load_2d_hint(&map_bh, &full[s], base + 2 * TERM, c * BK, (int)(n * args.E + (long long)et * TILE), pol_b);
+          tma_load_2d_hint(&map_bl, &full[s], base + 3 * TERM, c * BK, (int)(n * args.E + (long long)et * TILE), pol_b);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
