@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'lib')
 SO = os.path.join(LIB, 'libbnnp_b200.so')
 SOURCES = ['net.cu', 'lik.cu', 'ggn.cu', 'gram_tc.cu', 'gemm_tc.cu', 'glm.cu', 'glm_tc.cu', 'bnn.cu', 'linpred.cu', 'metrics.cu',
-           'exchange.cu', 'wide_k.cu', 'gemm_tma.cu', 'gemm3.cu', 'conv_diag_tc.cu']
+           'exchange.cu', 'wide_k.cu', 'gemm_tma.cu', 'gemm3.cu', 'conv_diag_tc.cu', 'conv_bwd_tc.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Wno-deprecated-gpu-targets']
 # BNNP_EXPERIMENTS=1 at build time also compiles the kernels kept only for A/B timing (never part of the default build)

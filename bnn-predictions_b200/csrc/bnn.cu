@@ -358,7 +358,7 @@ extern "C" const char* bnnp_strerror(int code) {
   }
 }
 unsigned long long g_bnnp_launches = 0;
-BnnpOptions g_bnnp_opt = {0, 0, 0, 0, 0, 0};
+BnnpOptions g_bnnp_opt = {0, 0, 0, 0, 0, 0, 0};
 static int* option_slot(const char* name) {
   if (!name) return nullptr;
   if (!strcmp(name, "gram_kernel")) return &g_bnnp_opt.gram_kernel;
@@ -367,6 +367,7 @@ static int* option_slot(const char* name) {
   if (!strcmp(name, "debug_sync")) return &g_bnnp_opt.debug_sync;
   if (!strcmp(name, "net_simt")) return &g_bnnp_opt.net_simt;
   if (!strcmp(name, "gemm_generated")) return &g_bnnp_opt.gemm_generated;
+  if (!strcmp(name, "conv_bwd_explicit")) return &g_bnnp_opt.conv_bwd_explicit;
   return nullptr;
 }
 extern "C" int bnnp_set_option(const char* name, int value) {

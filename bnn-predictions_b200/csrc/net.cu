@@ -11,6 +11,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tma.cuh"
+#include "conv_bwd_tc.cuh"
 
 namespace bnnp {
 
@@ -655,6 +656,8 @@ extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, 
         // backward-data: dU^T [N*V, E, L] + the transposed bf16 hi/lo gradients and weights of the TMA-fed product
         const int64_t bwd = (N * V * E * L + 63) / 64 * 64 + conv_bwd_tma_scratch_floats(N * V, ops[i].out_c, L, E);
         if (i > first_param && bwd > v) v = bwd;
+        const int64_t bwi = conv_bwd_implicit_scratch_floats(N * V, ops[i].out_c, (int)L, ops[i].in_c, ops[i].kh * ops[i].kw) + 64;
+        if (i > first_param && bwi > v) v = bwi;
         need = need > v ? need : v;
       }
     // bf16 hi/lo operand copies of the TMA-fed Linear-layer products (forward over N rows, backward over N*V rows)
@@ -833,6 +836,15 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
           const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
           float* dUt = ws + plan->conv_scratch_off;
           int rc;
+          if (g_bnnp_opt.gemm_generated == 0 && g_bnnp_opt.conv_bwd_explicit == 0 &&
+              conv_bwd_implicit_ok(o.in_c, o.out_c, o.in_h, o.in_w, o.out_h, o.out_w, o.kh, o.kw, o.stride_h, o.stride_w, R)) {
+            // implicit GEMM: the gradient planes are fetched per filter tap by 4-D TMA boxes (out-of-range = padding); neither
+            // the [R, E, L] product nor the col2im gather exists
+            rc = conv_bwd_implicit(gout, q.grad_ld, R, o.in_c, o.out_c, o.in_h, o.in_w, o.out_h, o.out_w, o.kh, o.kw, o.pad_l,
+                                   o.pad_t, o.weight, gin, qp.grad_ld, dUt, st);
+            if (rc) return rc;
+            break;
+          }
           if (g_bnnp_opt.gemm_generated == 0 && R <= 65535)
             rc = conv_bwd_tma(gout, q.grad_ld, R, o.out_c, L, o.weight, E, dUt, dUt + ((int64_t)R * E * L + 63) / 64 * 64, st);
           else
