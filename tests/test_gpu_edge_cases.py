@@ -271,3 +271,35 @@ def test_smooth_conv_net_on_the_tensor_core_branches_against_the_oracle():
             for qa, qb in zip(lap.Sigma_chol.qhs, post['kron'].qhs):
                 for a, b in zip(qa, qb):
                     assert cases.rel_err(a.cpu(), b) < TOL, tuple(b.shape)
+
+
+def test_implicit_conv_backward_on_ragged_shapes_against_autograd():
+    """Backward-data of the stride-1 convs on the implicit-GEMM kernel (csrc/conv_bwd_tc.cu) with shapes that leave every
+    tile ragged: 9 x 11 maps (boxes of 16 x 8 pixels), C_in = 5 / 7 (MMA N padded to 16), C_out = 7 / 4 (< one 32-channel
+    chunk), a 3 x 2 filter, asymmetric ZeroPad2d padding folded into the conv, a 1 x 1 conv; per-output autograd in fp32 on
+    the CPU is the reference (tests/test_jacobians.py:60-66 of the reference), and the product + col2im route
+    (option conv_bwd_explicit) must give the same Jacobians."""
+    from preds_b200 import Jacobians
+    from preds_b200._cabi import lib
+    torch.manual_seed(33)
+    net = nn.Sequential(nn.Conv2d(3, 5, 3, padding=1), nn.Tanh(), nn.ZeroPad2d((2, 0, 1, 3)), nn.Conv2d(5, 7, (3, 2)), nn.Tanh(),
+                        nn.Conv2d(7, 4, 1), nn.Tanh(), nn.Flatten(), nn.Linear(4 * 11 * 12, 3))
+    net.output_size = 3
+    X = torch.randn(5, 3, 9, 11)
+    out = net(X)
+    params = list(net.parameters())
+    naive = torch.empty(5, sum(p.numel() for p in params), 3)
+    for i in range(5):
+        for k in range(3):
+            g = torch.autograd.grad(out[i, k], params, retain_graph=True)
+            naive[i, :, k] = torch.cat([t.reshape(-1) for t in g])
+    net = net.cuda()
+    Js, f = Jacobians(net, X)
+    assert torch.allclose(out.detach(), f.cpu(), atol=1e-5)
+    assert torch.abs(Js.cpu() - naive).max() < 5e-6 * max(1.0, float(naive.abs().max()))
+    assert lib.bnnp_set_option(b'conv_bwd_explicit', 1) == 0
+    try:
+        Js2, _ = Jacobians(net, X)
+    finally:
+        lib.bnnp_set_option(b'conv_bwd_explicit', 0)
+    assert torch.abs(Js2 - Js).max() < 5e-6 * max(1.0, float(naive.abs().max()))
