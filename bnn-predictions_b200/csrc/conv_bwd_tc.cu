@@ -28,6 +28,7 @@ constexpr int NSTG = 4;
 
 struct Args {
   int R, H, W, Cin, Nt;            // Nt = up16(Cin): MMA N
+  int wide;                        // 1 (Nt <= 128): hi and lo weight planes side by side as ONE N = 2 Nt operand
   int kh, kw, pl, pt;
   int BX, BY, BR;                  // box of output pixels: BX * BY * BR = 128
   int tiles_y;                     // ceil(H / BY)
@@ -87,7 +88,7 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constan
             tma_load_4d(&map_gh, &full[s], base, c * BK, cx, cy, r0);
             tma_load_4d(&map_gl, &full[s], base + A_TERM, c * BK, cx, cy, r0);
             tma_load_2d(&map_wh, &full[s], base + 2 * A_TERM, c * BK, t * args.Cin);
-            tma_load_2d(&map_wl, &full[s], base + 2 * A_TERM + B_TERM, c * BK, t * args.Cin);
+            tma_load_2d(&map_wl, &full[s], base + 2 * A_TERM + args.Nt * 64, c * BK, t * args.Cin);
             if (++s == NSTG) { s = 0; ph ^= 1; }
           }
         }
@@ -96,7 +97,11 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t s = 0, ph = 0, it = 0;
-      const uint32_t idesc = umma_idesc_bf16(args.Nt);
+      // wide: g_hi x [W_hi; W_lo] is one MMA of N = 2 Nt (the lo plane follows the hi plane in shared memory) into columns
+      // [0, Nt) and [Nt, 2 Nt), g_lo x W_hi adds into [0, Nt); the epilogue sums the two ranges.  Two reads of the 128-row
+      // gradient tile per k step instead of three: these narrow-N MMAs are bound by their shared-memory operand reads.
+      const uint32_t idesc = umma_idesc_bf16(args.Nt), idesc2 = umma_idesc_bf16(2 * args.Nt);
+      const uint32_t b_lo = (uint32_t)args.Nt * 64;
       for (long long tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++it) {
         const uint32_t buf = it & 1;
         mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -109,9 +114,13 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constan
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t dah = umma_desc_sw64(a0 + kk * 32), dal = umma_desc_sw64(a0 + A_TERM + kk * 32);
-            const uint64_t dbh = umma_desc_sw64(b0 + kk * 32), dbl = umma_desc_sw64(b0 + B_TERM + kk * 32);
-            umma_bf16(d, dah, dbh, idesc, (c | kk) ? 1u : 0u);
-            umma_bf16(d, dah, dbl, idesc, 1u);
+            const uint64_t dbh = umma_desc_sw64(b0 + kk * 32);
+            if (args.wide) {
+              umma_bf16(d, dah, dbh, idesc2, (c | kk) ? 1u : 0u);
+            } else {
+              umma_bf16(d, dah, dbh, idesc, (c | kk) ? 1u : 0u);
+              umma_bf16(d, dah, umma_desc_sw64(b0 + b_lo + kk * 32), idesc, 1u);
+            }
             umma_bf16(d, dal, dbh, idesc, 1u);
           }
           umma_commit(&empty[s]);
@@ -138,6 +147,12 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constan
       for (int c0 = 0; c0 < args.Cin; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + c0), v);
+        if (args.wide) {
+          uint32_t w[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MAX_N + args.Nt + c0), w);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+        }
         if (ok) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
@@ -251,6 +266,7 @@ int conv_bwd_implicit(const float* gout, int64_t gld, int64_t R, int Cin, int Co
 
   Args a;
   a.R = (int)R; a.H = H; a.W = W; a.Cin = Cin; a.Nt = (Cin + 15) / 16 * 16;
+  a.wide = a.Nt <= 128 ? 1 : 0;
   a.kh = kh; a.kw = kw; a.pl = pl; a.pt = pt;
   a.BX = pow2_ge(W);
   a.BY = pow2_ge(H) < TILE_M / a.BX ? pow2_ge(H) : TILE_M / a.BX;
