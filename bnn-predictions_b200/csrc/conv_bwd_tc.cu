@@ -35,6 +35,7 @@ struct Args {
   long long n_tiles;               // tiles_y * ceil(R / BR)
   int n_cc;                        // Cout chunks of 32
   float* dX; long long ld;         // dX[r * ld + ci * H * W + y * W + x]
+  const float* bias;               // [Cin] added in the epilogue (forward convolution), or nullptr
 };
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
@@ -156,7 +157,8 @@ conv_bwd_kernel(const __grid_constant__ CUtensorMap map_gh, const __grid_constan
         if (ok) {
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (c0 + e < args.Cin) out[(long long)(c0 + e) * HW] = __uint_as_float(v[e]);
+            if (c0 + e < args.Cin)
+              out[(long long)(c0 + e) * HW] = __uint_as_float(v[e]) + (args.bias ? __ldg(args.bias + c0 + e) : 0.f);
         }
       }
       tc_fence_before();
@@ -217,12 +219,15 @@ split_grad_nhwc_slab_kernel(const float* __restrict__ g, long long gld, int Cout
   }
 }
 // planes[(t * Cin + ci), co] <- bf16 hi / lo of W[co, ci, a, b], t = a * kw + b   (co >= Cout zero)
-__global__ void split_weight_taps_kernel(const float* __restrict__ W, int Cout, int Cin, int taps, int Cp,
+// fwd: the forward convolution through the same kernel -- the roles of the channel axes swap and the taps are mirrored:
+// planes[(t * Cin + ci), co] <- W[ci, co, taps - 1 - t]  (W stored [Cin][Cout][taps] in the kernel's naming)
+__global__ void split_weight_taps_kernel(const float* __restrict__ W, int Cout, int Cin, int taps, int Cp, int fwd,
                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= taps * Cin * Cp) return;
   const int co = i % Cp, row = i / Cp, ci = row % Cin, t = row / Cin;
-  const float v = co < Cout ? W[((long long)co * Cin + ci) * taps + t] : 0.f;
+  const float v = co >= Cout ? 0.f
+                             : (fwd ? W[((long long)ci * Cout + co) * taps + (taps - 1 - t)] : W[((long long)co * Cin + ci) * taps + t]);
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[i] = h;
   lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -273,7 +278,8 @@ int64_t conv_bwd_implicit_scratch_floats(int64_t R, int Cout, int L, int Cin, in
 }
 
 int conv_bwd_implicit(const float* gout, int64_t gld, int64_t R, int Cin, int Cout, int H, int W, int OH, int OW, int kh, int kw,
-                      int pl, int pt, const float* Wt, float* dX, int64_t dld, float* scratch, cudaStream_t st) {
+                      int pl, int pt, const float* Wt, float* dX, int64_t dld, float* scratch, cudaStream_t st, int fwd,
+                      const float* bias) {
   using namespace cb;
   if (!conv_bwd_implicit_ok(Cin, Cout, H, W, OH, OW, kh, kw, 1, 1, R)) return BNNP_ERR_UNSUPPORTED;
   const int L = OH * OW, taps = kh * kw;
@@ -293,7 +299,7 @@ int conv_bwd_implicit(const float* gout, int64_t gld, int64_t R, int Cin, int Co
         gout, gld, Cout, L, Cp, gh, gl);
   }
   BNNP_LAUNCH_CHECK();
-  split_weight_taps_kernel<<<(unsigned)ceil_div64((int64_t)taps * Cin * Cp, 256), 256, 0, st>>>(Wt, Cout, Cin, taps, Cp, wh, wl);
+  split_weight_taps_kernel<<<(unsigned)ceil_div64((int64_t)taps * Cin * Cp, 256), 256, 0, st>>>(Wt, Cout, Cin, taps, Cp, fwd, wh, wl);
   BNNP_LAUNCH_CHECK();
 
   Args a;
@@ -306,7 +312,7 @@ int conv_bwd_implicit(const float* gout, int64_t gld, int64_t R, int Cin, int Co
   a.tiles_y = (H + a.BY - 1) / a.BY;
   a.n_tiles = (long long)a.tiles_y * ((R + a.BR - 1) / a.BR);
   a.n_cc = (Cout + BK - 1) / BK;
-  a.dX = dX; a.ld = dld;
+  a.dX = dX; a.ld = dld; a.bias = bias;
 
   CUtensorMap mgh, mgl, mwh, mwl;
   {

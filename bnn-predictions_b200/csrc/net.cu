@@ -658,6 +658,10 @@ extern "C" int bnnp_net_plan(const bnnp_op_t* ops, int n_ops, int64_t N, int V, 
         if (i > first_param && bwd > v) v = bwd;
         const int64_t bwi = conv_bwd_implicit_scratch_floats(N * V, ops[i].out_c, (int)L, ops[i].in_c, ops[i].kh * ops[i].kw) + 64;
         if (i > first_param && bwi > v) v = bwi;
+        // forward as the same implicit GEMM: planes of the layer input [N, in_h * in_w, C_in] and of the mirrored weights
+        const int64_t fwi = conv_bwd_implicit_scratch_floats(N, ops[i].in_c, ops[i].in_h * ops[i].in_w, ops[i].out_c,
+                                                             ops[i].kh * ops[i].kw) + 64;
+        if (fwi > v) v = fwi;
         need = need > v ? need : v;
       }
     // bf16 hi/lo operand copies of the TMA-fed Linear-layer products (forward over N rows, backward over N*V rows)
@@ -720,7 +724,17 @@ extern "C" int bnnp_net_forward(const bnnp_op_t* ops, int n_ops, const bnnp_plan
       }
       case BNNP_OP_CONV2D: {
         const int E = o.in_c * o.kh * o.kw, L = o.out_h * o.out_w;
-        if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)N * L * E * o.out_c >= kTcMinMacs && N <= 65535) {
+        if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)N * L * E * o.out_c >= kTcMinMacs &&
+            g_bnnp_opt.gemm_generated == 0 && g_bnnp_opt.conv_bwd_explicit == 0 && o.in_c >= 16 &&
+            conv_bwd_implicit_ok(o.out_c, o.in_c, o.out_h, o.out_w, o.in_h, o.in_w, o.kh, o.kw, o.stride_h, o.stride_w, N)) {
+          // implicit GEMM on 4-D TMA boxes of the NHWC bf16 hi / lo input (conv_bwd_tc.cu with the channel roles swapped and the
+          // taps mirrored): no unfolded input.  Not for a few input channels (an RGB first layer): the kernel's reduction axis is the
+          // channel axis in chunks of 32 per tap, so C_in = 3 would run at 10 % useful MMA work (measured slower than the unfold).
+          int rc = conv_bwd_implicit(in, ild, N, o.out_c, o.in_c, o.out_h, o.out_w, o.in_h, o.in_w, o.kh, o.kw, o.kw - 1 - o.pad_l,
+                                     o.kh - 1 - o.pad_t, o.weight, out, q.act_ld, ws + plan->conv_scratch_off, st, 1,
+                                     o.has_bias ? o.bias : nullptr);
+          if (rc) return rc;
+        } else if (plan->conv_scratch_off >= 0 && !g_bnnp_opt.net_simt && (long long)N * L * E * o.out_c >= kTcMinMacs && N <= 65535) {
           const int Epad = (E + 3) / 4 * 4;
           float* U = ws + plan->conv_scratch_off;
           im2col_fwd_kernel<<<dim3((unsigned)ceil_div64(L, 16), (unsigned)N), 256, 0, st>>>(in, ild, N, geom_of(o), E, Epad, U);

@@ -303,3 +303,33 @@ def test_implicit_conv_backward_on_ragged_shapes_against_autograd():
     finally:
         lib.bnnp_set_option(b'conv_bwd_explicit', 0)
     assert torch.abs(Js2 - Js).max() < 5e-6 * max(1.0, float(naive.abs().max()))
+
+
+def test_implicit_conv_forward_on_ragged_shapes_against_torch():
+    """The forward convolution on the implicit-GEMM kernel (conv_bwd_tc.cu with the channel roles swapped and the taps
+    mirrored): same ragged network as above (asymmetric folded padding, 3 x 2 and 1 x 1 filters, 17 / 21 input channels on
+    the implicit route (>= 16; the 3-channel first conv stays on the unfolded-input GEMM), biases), at N = 4096 so that every conv is
+    above the tensor-core threshold; torch's fp32 CPU forward is the reference,
+    and the unfolded-input GEMM route (option conv_bwd_explicit) must agree."""
+    from preds_b200._engine import net_for
+    from preds_b200._cabi import lib
+    torch.manual_seed(34)
+    net = nn.Sequential(nn.Conv2d(3, 17, 3, padding=1), nn.Tanh(), nn.ZeroPad2d((2, 0, 1, 3)), nn.Conv2d(17, 21, (3, 2)), nn.Tanh(),
+                        nn.Conv2d(21, 4, 1), nn.Tanh(), nn.Flatten(), nn.Linear(4 * 11 * 12, 3))
+    net.output_size = 3
+    X = torch.randn(4096, 3, 9, 11)
+    with torch.no_grad():
+        want = net(X)
+    net = net.cuda()
+    eng = net_for(net)
+    got = {}
+    for opt in (0, 1):
+        assert lib.bnnp_set_option(b'conv_bwd_explicit', opt) == 0
+        try:
+            _, _, f = eng.forward(eng.prepare(X), 3)
+            got[opt] = f.cpu()
+        finally:
+            lib.bnnp_set_option(b'conv_bwd_explicit', 0)
+    scale = float(want.abs().max())
+    assert float((got[0] - want).abs().max()) < 1e-5 * scale
+    assert float((got[1] - want).abs().max()) < 1e-5 * scale
