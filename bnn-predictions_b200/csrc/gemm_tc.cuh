@@ -342,8 +342,11 @@ struct TcStoreAxpby : TcNoState {      // C = alpha*acc + beta*C
 #pragma unroll
       for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = alpha * v[e];
     } else {
+      float old[32];                     // loads before stores: interleaved on the same array they serialise
 #pragma unroll
-      for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = alpha * v[e] + beta * q[e];
+      for (int e = 0; e < 32; ++e) old[e] = e < nvalid ? q[e] : 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) if (e < nvalid) q[e] = alpha * v[e] + beta * old[e];
     }
   }
 };
