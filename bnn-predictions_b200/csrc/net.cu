@@ -401,6 +401,48 @@ __global__ void maxpool_bwd_possum_kernel(const float* __restrict__ gout, int64_
   if (lane == 0) S[r * C + c] = acc;
 }
 
+// The same with one warp per (example, channel) for pooled maps of at most 256 positions: the winner index and the activation
+// derivative of a window depend on the example only, so they are gathered ONCE into registers and the V rows of the example are
+// streamed against them (the per-row kernel repeats the dependent index -> activation gathers for each of the V rows).
+__global__ void maxpool_bwd_possum_rows_kernel(const float* __restrict__ gout, int64_t gold, float* __restrict__ S,
+                                               const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g,
+                                               const float* __restrict__ act, int64_t actld, int act_kind) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int C = g.Cout, OL = g.OH * g.OW, HW = g.H * g.W;
+  if (w >= N * C) return;
+  const int c = (int)(w % C);
+  const int64_t n = w / C;
+  const int32_t* id = idx + (n * C + c) * (int64_t)OL;
+  const float* a = act ? act + n * actld + (int64_t)c * HW : nullptr;
+  float d[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = lane + 32 * k;
+    const int win = i < OL ? __ldg(id + i) : -1;
+    d[k] = 0.f;
+    if (win >= 0) {
+      d[k] = 1.f;
+      if (a) {
+        const float o = __ldg(a + win);
+        d[k] = act_kind == BNNP_OP_RELU ? (o > 0.f ? 1.f : 0.f) : (act_kind == BNNP_OP_TANH ? 1.f - o * o : o * (1.f - o));
+      }
+    }
+  }
+  for (int v = 0; v < V; ++v) {
+    const int64_t r = n * V + v;
+    const float* go = gout + r * gold + (int64_t)c * OL;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = lane + 32 * k;
+      if (i < OL) acc = fmaf(__ldg(go + i), d[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) S[r * C + c] = acc;
+  }
+}
+
 __global__ void avgpool_fwd_kernel(const float* __restrict__ in, int64_t ild,
                                    float* __restrict__ out, int64_t old, int64_t N, ConvGeom g) {
   int64_t per = (int64_t)g.Cout * g.OH * g.OW;
@@ -901,9 +943,14 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
           const bool act_before = i - 1 > first_param && is_elementwise_op(ops[i - 1]);
           if ((flags & BNNP_BWD_FIRST_CONV_POSSUM) && (act_before ? i - 2 : i - 1) == first_param) {
             const bnnp_op_plan_t& qc = plan->op[first_param];
-            maxpool_bwd_possum_kernel<<<(unsigned)ceil_div64(R * o.in_c * 32, 256), 256, 0, st>>>(
-                gout, q.grad_ld, ws + qc.grad_off, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr,
-                qp.act_ld, act_before ? ops[i - 1].kind : 0);
+            if (o.out_h * o.out_w <= 256)
+              maxpool_bwd_possum_rows_kernel<<<(unsigned)ceil_div64(N * o.in_c * 32, 256), 256, 0, st>>>(
+                  gout, q.grad_ld, ws + qc.grad_off, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr,
+                  qp.act_ld, act_before ? ops[i - 1].kind : 0);
+            else
+              maxpool_bwd_possum_kernel<<<(unsigned)ceil_div64(R * o.in_c * 32, 256), 256, 0, st>>>(
+                  gout, q.grad_ld, ws + qc.grad_off, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr,
+                  qp.act_ld, act_before ? ops[i - 1].kind : 0);
             BNNP_LAUNCH_CHECK();
             return BNNP_OK;                  // nothing upstream of the first parameterised layer
           }
