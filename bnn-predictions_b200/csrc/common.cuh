@@ -32,7 +32,7 @@ struct BnnpOptions {
   int debug_sync;      // synchronise and report after every GLM TMA launch
   int net_simt;        // forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size (parity bisection)
   int gemm_generated;  // 1: Linear-layer products / KFAC Grams on the generated-operand tensor-core GEMM instead of the TMA-fed one (A/B timing)
-  int conv_bwd_explicit;  // 1: conv backward-data as product + col2im gather instead of the implicit GEMM (A/B timing, parity)
+  int conv_bwd_explicit;  // 1: conv backward-data as product + col2im gather and conv forward as unfold + GEMM instead of the implicit GEMM (A/B timing, parity)
 };
 extern BnnpOptions g_bnnp_opt;
 

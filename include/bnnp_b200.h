@@ -401,7 +401,9 @@ uint64_t bnnp_launch_count(void);
  * "glm_single" 1 = single-CTA full-covariance GLM kernel, "glm_simt" 1 = kron / diag GLM contractions on the fp32
  * SIMT kernels, "debug_sync" 1 = synchronise after every GLM TMA launch,
  * "net_simt" 1 = forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size,
- * "gemm_generated" 1 = Linear-layer products / KFAC Grams on the generated-operand GEMM instead of the TMA-fed one.  Unknown name: BNNP_ERR_INVALID. */
+ * "gemm_generated" 1 = Linear-layer products / KFAC Grams on the generated-operand GEMM instead of the TMA-fed one;
+ * "conv_bwd_explicit" 1 = stride-1 conv backward-data as product + col2im gather and conv forward as unfold + GEMM instead of
+ * the implicit-GEMM kernel (csrc/conv_bwd_tc.cu).  Unknown name: BNNP_ERR_INVALID. */
 int bnnp_set_option(const char* name, int value);
 int bnnp_get_option(const char* name);
 int bnnp_prof_enable(int on);
