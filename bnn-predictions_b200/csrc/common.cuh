@@ -32,7 +32,7 @@ struct BnnpOptions {
   int debug_sync;      // synchronise and report after every GLM TMA launch
   int net_simt;        // forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size (parity bisection)
   int gemm_generated;  // 1: Linear-layer products / KFAC Grams on the generated-operand tensor-core GEMM instead of the TMA-fed one (A/B timing)
-  int conv_bwd_explicit;  // 1: conv backward-data as product + col2im gather and conv forward as unfold + GEMM instead of the implicit GEMM (A/B timing, parity)
+  int conv_bwd_explicit;  // 1: conv backward-data as product + col2im gather and conv forward as unfold + GEMM instead of the implicit GEMM, fp32 first-conv gradient + split pass in the diag path (A/B timing, parity)
 };
 extern BnnpOptions g_bnnp_opt;
 
@@ -61,5 +61,10 @@ static inline bool is_param_op(const bnnp_op_t& o) {
 static inline bool is_elementwise_op(const bnnp_op_t& o) {
   return o.kind == BNNP_OP_RELU || o.kind == BNNP_OP_TANH || o.kind == BNNP_OP_SIGMOID;
 }
+// net.cu: first conv followed by ([activation,] max-pool) -- helpers shared with ggn.cu
+int net_first_conv_possum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V, const float* ws,
+                          float* S, cudaStream_t st);
+bool net_first_conv_planes_structure_ok(const bnnp_op_t* ops, int n_ops);
+
 static inline int64_t op_in_size(const bnnp_op_t& o) { return (int64_t)o.in_c * o.in_h * o.in_w; }
 static inline int64_t op_out_size(const bnnp_op_t& o) { return (int64_t)o.out_c * o.out_h * o.out_w; }

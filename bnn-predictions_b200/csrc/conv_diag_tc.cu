@@ -277,7 +277,7 @@ int64_t conv_diag_tma_scratch_floats(int64_t N, int V, int Cout, int L, int E) {
 }
 
 int conv_diag_tma(const ConvUnfold& u, const float* G, int64_t gld, int64_t N, int V, int Cout, int L, int E, float factor,
-                  float* d_w, float* scratch, cudaStream_t st) {
+                  float* d_w, float* scratch, cudaStream_t st, const __nv_bfloat16* pre_hi, const __nv_bfloat16* pre_lo) {
   using namespace cd;
   const int64_t R = N * V;
   if (!conv_diag_tma_ok(Cout, L, N, V)) return BNNP_ERR_UNSUPPORTED;
@@ -289,8 +289,12 @@ int conv_diag_tma(const ConvUnfold& u, const float* G, int64_t gld, int64_t N, i
   __nv_bfloat16* bl = bh + N * E * (int64_t)Lp;
   float* part = base + up64(R * Cout * Lp) + up64(N * E * (int64_t)Lp);
   const int p8 = (L + 7) >> 3;
-  split_conv_grad_rows_kernel<<<(unsigned)ceil_div64(R * Cout * p8, 256), 256, 0, st>>>(G, gld, R, Cout, L, Lp, ah, al);
-  BNNP_LAUNCH_CHECK();
+  if (pre_hi) {            // the planes were made by the producer of the gradient (row pitch L, L % 8 == 0)
+    if (!pre_lo || (L & 7)) return BNNP_ERR_INVALID;
+  } else {
+    split_conv_grad_rows_kernel<<<(unsigned)ceil_div64(R * Cout * p8, 256), 256, 0, st>>>(G, gld, R, Cout, L, Lp, ah, al);
+    BNNP_LAUNCH_CHECK();
+  }
   im2col_rows_split_kernel<<<dim3((unsigned)ceil_div64((int64_t)E * p8, 256), (unsigned)N), 256, 0, st>>>(u, L, E, Lp, bh, bl);
   BNNP_LAUNCH_CHECK();
   Args a;
@@ -313,8 +317,8 @@ int conv_diag_tma(const ConvUnfold& u, const float* G, int64_t gld, int64_t N, i
   a.part = part;
   CUtensorMap mah, mal, mbh, mbl;
   int rc;
-  if ((rc = make_map(&mah, ah, R * Cout, L, Lp))) return rc;
-  if ((rc = make_map(&mal, al, R * Cout, L, Lp))) return rc;
+  if ((rc = make_map(&mah, pre_hi ? pre_hi : ah, R * Cout, L, pre_hi ? L : Lp))) return rc;
+  if ((rc = make_map(&mal, pre_hi ? pre_lo : al, R * Cout, L, pre_hi ? L : Lp))) return rc;
   if ((rc = make_map(&mbh, bh, N * E, L, Lp))) return rc;
   if ((rc = make_map(&mbl, bl, N * E, L, Lp))) return rc;
   static bool attr = false;

@@ -30,6 +30,8 @@ struct ConvUnfold {
 bool conv_diag_tma_ok(int Cout, int L, long long N, int V);
 int64_t conv_diag_tma_scratch_floats(int64_t N, int V, int Cout, int L, int E);
 int conv_diag_tma(const ConvUnfold& u, const float* G, int64_t gld, int64_t N, int V, int Cout, int L, int E, float factor,
-                  float* d_w, float* scratch, cudaStream_t st);
+                  float* d_w, float* scratch, cudaStream_t st, const __nv_bfloat16* pre_hi = nullptr,
+                  const __nv_bfloat16* pre_lo = nullptr);
+// pre_hi / pre_lo: the gradient already as bf16 hi / lo planes [(r, co), pos] with row pitch L (L % 8 == 0); G is then unused
 
 }  // namespace bnnp

@@ -617,10 +617,30 @@ extern "C" int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops,
   return need + lin + 64;
 }
 
+// whether the first conv's weight diagonal takes the TMA-fed kernel (the only consumer of pre-split gradient planes)
+static bool conv_diag_on_tma(const bnnp_op_t& o, int64_t N, int V) {
+  const int L = o.out_h * o.out_w, E = o.in_c * o.kh * o.kw;
+  return !g_bnnp_opt.net_simt && g_bnnp_opt.gemm_generated == 0 && (long long)N * V * o.out_c * L * E >= kTcMinMacsG &&
+         conv_diag_tma_ok(o.out_c, L, N, V);
+}
+extern "C" int bnnp_net_first_conv_planes_ok(const bnnp_op_t* ops, int n_ops, int64_t N, int V) {
+  if (!ops || N <= 0 || V <= 0 || g_bnnp_opt.conv_bwd_explicit || !net_first_conv_planes_structure_ok(ops, n_ops)) return 0;
+  for (int i = 0; i < n_ops; ++i)
+    if (is_param_op(ops[i])) return conv_diag_on_tma(ops[i], N, V) ? 1 : 0;
+  return 0;
+}
 extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                                    int V, const float* X, const float* ws, float factor, float* diag,
                                    float* scratch, void* stream) {
+  return bnnp_ggn_diag_accum_ex(ops, n_ops, plan, N, V, X, ws, factor, diag, scratch, 0, stream);
+}
+extern "C" int bnnp_ggn_diag_accum_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                                      int V, const float* X, const float* ws, float factor, float* diag,
+                                      float* scratch, int flags, void* stream) {
   if (!ops || !plan || !ws || !diag || !scratch || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
+  int first_param = -1;
+  for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { first_param = i; break; }
+  if ((flags & BNNP_BWD_FIRST_CONV_PLANES) && !bnnp_net_first_conv_planes_ok(ops, n_ops, N, V)) return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
   const int M = plan->Mtot;
   if (M > 0) {
@@ -681,8 +701,11 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     float* partial = scratch + N * V * (int64_t)o.out_c + 64;
     if (!g_bnnp_opt.net_simt && g_bnnp_opt.gemm_generated == 0 && (long long)N * V * o.out_c * L * E >= kTcMinMacsG &&
         conv_diag_tma_ok(o.out_c, L, N, V)) {
+      // flags & BNNP_BWD_FIRST_CONV_PLANES: the pool backward left this layer's gradient as the kernel's bf16 planes
+      const bool planes = (flags & BNNP_BWD_FIRST_CONV_PLANES) && i == first_param;
+      const __nv_bfloat16* ph = planes ? reinterpret_cast<const __nv_bfloat16*>(G) : nullptr;
       int rc = conv_diag_tma(make_im2col(o, in, ild, 1), G, q.grad_ld, N, V, o.out_c, L, E, factor, diag + o.theta_off_w,
-                             partial, st);
+                             partial, st, ph, planes ? ph + N * V * q.grad_ld : nullptr);
       if (rc) return rc;
     } else if (!g_bnnp_opt.net_simt && (long long)N * V * o.out_c * L * E >= kTcMinMacsG && N * V <= 0x7fffffff) {
       int dev = 0, sms = 148;
@@ -715,7 +738,12 @@ extern "C" int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_p
     }
     if (o.has_bias) {
       int64_t R = N * V;
-      launch_conv_possum(G, q.grad_ld, R, o.out_c, L, scratch, o.out_c, st);
+      if ((flags & BNNP_BWD_FIRST_CONV_PLANES) && i == first_param) {      // no fp32 gradient: position sums from the pooled one
+        int rc = net_first_conv_possum(ops, n_ops, plan, N, V, ws, scratch, st);
+        if (rc) return rc;
+      } else {
+        launch_conv_possum(G, q.grad_ld, R, o.out_c, L, scratch, o.out_c, st);
+      }
       BNNP_LAUNCH_CHECK();
       colsq_accum_kernel<<<(unsigned)ceil_div64(o.out_c, 32), dim3(32, 32), 0, st>>>(scratch, R, o.out_c, factor,
                                                                                     diag + o.theta_off_b);

@@ -287,11 +287,15 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ gout, int64_t gold,
 // wins SEVERAL windows, so most threads walk all nine predicated (address, load, add) candidates for each of the V rows.  Here
 // the at most four candidate windows of a position are compacted once per thread into register-resident offsets; the row loop
 // is sixteen predicated loads on precomputed offsets and one store.
-template <int FUSE>
+// PLANES != 0: the gradient leaves as the bf16 hi / lo planes [(r, c), pos] of the conv-weight diagonal kernel (conv_diag_tc.cu;
+// row pitch H * W, lo plane `plane_elems` elements behind the hi plane, both inside the fp32 gradient buffer they replace)
+// instead of fp32 -- the 1 GB gradient of CIFAR10Net's first conv was written here, re-read by the split pass and re-written as
+// planes.
+template <int FUSE, int PLANES = 0>
 __global__ void maxpool_bwd4_kernel(const float* __restrict__ gout, int64_t gold,
                                     float* __restrict__ gin, int64_t gild,
                                     const int32_t* __restrict__ idx, int64_t N, int V, ConvGeom g,
-                                    const float* __restrict__ act, int64_t actld, int act_kind) {
+                                    const float* __restrict__ act, int64_t actld, int act_kind, int64_t plane_elems = 0) {
   const int HW = g.H * g.W, W4 = g.W >> 2;
   const int j4 = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per 4 consecutive positions of a row
   if (j4 >= g.Cin * g.H * W4) return;
@@ -339,8 +343,16 @@ __global__ void maxpool_bwd4_kernel(const float* __restrict__ gout, int64_t gold
       for (int k = 0; k < 4; ++k)
         if (off[p][k] >= 0 && __ldg(id + off[p][k]) == me0 + p) hit |= 1u << (p * 4 + k);
     float* gp = gin + n * V * gild + (int64_t)c * HW + me0;
+    __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(gin) + n * V * gild + (int64_t)c * HW + me0;
     if (hit == 0u) {                                               // four zeros per row
-      for (int v = 0; v < V; ++v, gp += gild) *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (PLANES) {
+        for (int v = 0; v < V; ++v, hp += gild) {
+          *reinterpret_cast<uint2*>(hp) = make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(hp + plane_elems) = make_uint2(0u, 0u);
+        }
+      } else {
+        for (int v = 0; v < V; ++v, gp += gild) *reinterpret_cast<float4*>(gp) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       continue;
     }
     float d[4] = {1.f, 1.f, 1.f, 1.f};
@@ -352,7 +364,7 @@ __global__ void maxpool_bwd4_kernel(const float* __restrict__ gout, int64_t gold
         d[p] = act_kind == BNNP_OP_RELU ? (o[p] > 0.f ? 1.f : 0.f) : (act_kind == BNNP_OP_TANH ? 1.f - o[p] * o[p] : o[p] * (1.f - o[p]));
     }
     const float* go = gout + n * V * gold + (int64_t)c * OL;
-    for (int v = 0; v < V; ++v, gp += gild, go += gold) {
+    for (int v = 0; v < V; ++v, gp += gild, hp += gild, go += gold) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -361,7 +373,16 @@ __global__ void maxpool_bwd4_kernel(const float* __restrict__ gout, int64_t gold
           if (hit & (1u << (p * 4 + k))) acc[p] += __ldg(go + off[p][k]);
         if (FUSE) acc[p] *= d[p];
       }
-      *reinterpret_cast<float4*>(gp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (PLANES) {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(acc[0] - __low2float(h0), acc[1] - __high2float(h0));
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(acc[2] - __low2float(h1), acc[3] - __high2float(h1));
+        *reinterpret_cast<uint2*>(hp) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(hp + plane_elems) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+      } else {
+        *reinterpret_cast<float4*>(gp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
     }
   }
 }
@@ -842,10 +863,58 @@ extern "C" int bnnp_net_first_conv_possum_ok(const bnnp_op_t* ops, int n_ops) {
   if (j < n_ops && is_elementwise_op(ops[j])) ++j;
   return j < n_ops && ops[j].kind == BNNP_OP_MAXPOOL2D && ops[j].kh <= 3 && ops[j].kw <= 3 ? 1 : 0;
 }
+// index of the max-pool behind the first conv (conv [-> activation] -> max-pool), its activation flag
+static int first_conv_pool(const bnnp_op_t* ops, int n_ops, int* first_param, bool* act_before) {
+  int fp = -1;
+  for (int i = 0; i < n_ops; ++i) if (is_param_op(ops[i])) { fp = i; break; }
+  if (fp < 0 || ops[fp].kind != BNNP_OP_CONV2D) return -1;
+  int j = fp + 1;
+  const bool act = j < n_ops && is_elementwise_op(ops[j]);
+  if (act) ++j;
+  if (j >= n_ops || ops[j].kind != BNNP_OP_MAXPOOL2D || ops[j].kh > 3 || ops[j].kw > 3) return -1;
+  *first_param = fp; *act_before = act;
+  return j;
+}
+// S[r, c] = sum_pos of the first conv's output gradient, straight from the pooled gradient (maxpool_bwd_possum kernels)
+int net_first_conv_possum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N, int V, const float* ws,
+                          float* S, cudaStream_t st) {
+  int fp; bool act_before;
+  const int j = first_conv_pool(ops, n_ops, &fp, &act_before);
+  if (j < 0) return BNNP_ERR_INVALID;
+  const bnnp_op_t& o = ops[j];
+  const bnnp_op_plan_t& q = plan->op[j];
+  const bnnp_op_plan_t& qp = plan->op[j - 1];
+  const int64_t R = N * V;
+  const int32_t* idxp = reinterpret_cast<const int32_t*>(ws) + q.idx_off;
+  const float* gout = ws + q.grad_off;
+  if (o.out_h * o.out_w <= 256)
+    maxpool_bwd_possum_rows_kernel<<<(unsigned)ceil_div64(N * o.in_c * 32, 256), 256, 0, st>>>(
+        gout, q.grad_ld, S, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr, qp.act_ld,
+        act_before ? ops[j - 1].kind : 0);
+  else
+    maxpool_bwd_possum_kernel<<<(unsigned)ceil_div64(R * o.in_c * 32, 256), 256, 0, st>>>(
+        gout, q.grad_ld, S, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr, qp.act_ld,
+        act_before ? ops[j - 1].kind : 0);
+  BNNP_LAUNCH_CHECK();
+  return BNNP_OK;
+}
+// structural half of bnnp_net_first_conv_planes_ok (ggn.cu adds the conditions of the diag kernel)
+bool net_first_conv_planes_structure_ok(const bnnp_op_t* ops, int n_ops) {
+  int fp; bool act_before;
+  const int j = first_conv_pool(ops, n_ops, &fp, &act_before);
+  if (j < 0) return false;
+  const bnnp_op_t& o = ops[j];
+  const int64_t isz = (int64_t)o.in_c * o.in_h * o.in_w;
+  return o.in_w % 4 == 0 && o.stride_h >= 2 && o.stride_w >= 2 && isz % 4 == 0 && (o.in_h * o.in_w) % 8 == 0;
+}
+
 extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                     const float* seed, int64_t N, int V, float* ws, int flags, void* stream) {
   if (!ops || !plan || !seed || !ws || N <= 0 || V <= 0) return BNNP_ERR_INVALID;
   if ((flags & BNNP_BWD_FIRST_CONV_POSSUM) && !bnnp_net_first_conv_possum_ok(ops, n_ops)) return BNNP_ERR_INVALID;
+  if ((flags & BNNP_BWD_FIRST_CONV_PLANES) &&
+      ((flags & BNNP_BWD_FIRST_CONV_POSSUM) || !net_first_conv_planes_structure_ok(ops, n_ops)))
+    return BNNP_ERR_INVALID;
   cudaStream_t st = as_stream(stream);
   const int K = plan->K;
   const int64_t R = N * V;
@@ -942,16 +1011,8 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
           // position sums only for the first conv (KFAC): see maxpool_bwd_possum_kernel
           const bool act_before = i - 1 > first_param && is_elementwise_op(ops[i - 1]);
           if ((flags & BNNP_BWD_FIRST_CONV_POSSUM) && (act_before ? i - 2 : i - 1) == first_param) {
-            const bnnp_op_plan_t& qc = plan->op[first_param];
-            if (o.out_h * o.out_w <= 256)
-              maxpool_bwd_possum_rows_kernel<<<(unsigned)ceil_div64(N * o.in_c * 32, 256), 256, 0, st>>>(
-                  gout, q.grad_ld, ws + qc.grad_off, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr,
-                  qp.act_ld, act_before ? ops[i - 1].kind : 0);
-            else
-              maxpool_bwd_possum_kernel<<<(unsigned)ceil_div64(R * o.in_c * 32, 256), 256, 0, st>>>(
-                  gout, q.grad_ld, ws + qc.grad_off, idxp, N, V, geom_of(o), act_before ? ws + qp.act_off : nullptr,
-                  qp.act_ld, act_before ? ops[i - 1].kind : 0);
-            BNNP_LAUNCH_CHECK();
+            int rc = net_first_conv_possum(ops, n_ops, plan, N, V, ws, ws + plan->op[first_param].grad_off, st);
+            if (rc) return rc;
             return BNNP_OK;                  // nothing upstream of the first parameterised layer
           }
           // an elementwise activation right in front of the pool (conv -> relu -> pool): its backward is folded into
@@ -962,12 +1023,20 @@ extern "C" int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_
           const bool vec4 = o.in_w % 4 == 0 && o.stride_h >= 2 && o.stride_w >= 2 && qp.grad_ld % 4 == 0 &&
                             (reinterpret_cast<uintptr_t>(gin) & 15) == 0 &&
                             (!fuse_act || (qp.act_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(actp) & 15) == 0));
+          if ((flags & BNNP_BWD_FIRST_CONV_PLANES) && (fuse_act ? i - 2 : i - 1) == first_param && !vec4) return BNNP_ERR_INVALID;
           if (vec4) {
             const int64_t b4 = ceil_div64((int64_t)o.in_h * (o.in_w / 4) * o.in_c, 128);
             int64_t gz4 = ceil_div64(8192, b4);
             gz4 = gz4 < 1 ? 1 : (gz4 > N ? N : gz4);
             const dim3 grid4((unsigned)b4, 1, (unsigned)gz4);
-            if (fuse_act)
+            const bool planes = (flags & BNNP_BWD_FIRST_CONV_PLANES) && (fuse_act ? i - 2 : i - 1) == first_param;
+            if (planes && fuse_act)
+              maxpool_bwd4_kernel<1, 1><<<grid4, 128, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o), actp,
+                                                             qp.act_ld, ops[i - 1].kind, R * qp.grad_ld);
+            else if (planes)
+              maxpool_bwd4_kernel<0, 1><<<grid4, 128, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o), nullptr, 0, 0,
+                                                             R * qp.grad_ld);
+            else if (fuse_act)
               maxpool_bwd4_kernel<1><<<grid4, 128, 0, st>>>(gout, q.grad_ld, gin, qp.grad_ld, idxp, N, V, geom_of(o), actp,
                                                           qp.act_ld, ops[i - 1].kind);
             else

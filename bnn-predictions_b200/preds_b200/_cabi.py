@@ -18,6 +18,7 @@ MAX_K_WIDE = 128      # BNNP_MAX_K_WIDE: likelihood terms / GLM sampler beyond t
 OP_LINEAR, OP_CONV2D, OP_RELU, OP_TANH, OP_MAXPOOL2D, OP_AVGPOOL2D, OP_FLATTEN, OP_SIGMOID = range(1, 9)
 LIK_CATEGORICAL, LIK_GAUSSIAN, LIK_BERNOULLI = 0, 1, 2
 BWD_FIRST_CONV_POSSUM = 1
+BWD_FIRST_CONV_PLANES = 2
 ERR_INVALID = -1
 
 
@@ -79,6 +80,8 @@ _SIGS = {
     'bnnp_pack_lower': (_I, [_P, _L, _L, _L, _P, _V]),
     'bnnp_unpack_lower': (_I, [_P, _L, _L, _L, _P, _P, _F, _V]),
     'bnnp_ggn_diag_accum': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _P, _P, _V]),
+    'bnnp_ggn_diag_accum_ex': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _P, _P, _I, _V]),
+    'bnnp_net_first_conv_planes_ok': (_I, [_OPS, _I, _L, _I]),
     'bnnp_ggn_diag_scratch_floats': (_L, [_OPS, _I, _PLAN, _L, _I]),
     'bnnp_kfac_accum': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _F, C.POINTER(_P), _P, _V]),
     'bnnp_kfac_accum_ex': (_I, [_OPS, _I, _PLAN, _L, _I, _P, _P, _F, _F, C.POINTER(_P), _P, _I, _V]),

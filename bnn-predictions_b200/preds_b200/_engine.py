@@ -315,18 +315,24 @@ class Net:
         self.backward(pl, ws, self.identity_seed(N), N, self.K)
         return X2d, pl, ws, f
 
-    def sqrt_factors(self, X, lik_code, kfac_only=False):
+    def sqrt_factors(self, X, lik_code, kfac_only=False, diag_only=False):
         """forward + backward seeded with the loss-Hessian square root (BackPACK convention).  ``kfac_only``: the
-        consumer is the KFAC accumulation, which needs only position sums at a first conv layer; returns the flags to
-        hand to ``bnnp_kfac_accum_ex`` as a fifth element."""
+        consumer is the KFAC accumulation, which needs only position sums at a first conv layer; ``diag_only``: the
+        consumer is the diagonal accumulation, which takes a first conv layer's gradient as the bf16 planes of its
+        tensor-core kernel.  Either returns the flags to hand to ``bnnp_kfac_accum_ex`` / ``bnnp_ggn_diag_accum_ex`` as
+        a fifth element."""
         X2d = self.prepare(X)
-        flags = cabi.BWD_FIRST_CONV_POSSUM if kfac_only and lib.bnnp_net_first_conv_possum_ok(self.ops, self.n_ops) else 0
         N = X2d.shape[0]
+        flags = 0
+        if kfac_only and lib.bnnp_net_first_conv_possum_ok(self.ops, self.n_ops):
+            flags = cabi.BWD_FIRST_CONV_POSSUM
+        elif diag_only and lib.bnnp_net_first_conv_planes_ok(self.ops, self.n_ops, N, self.K):
+            flags = cabi.BWD_FIRST_CONV_PLANES
         pl, ws, f = self.forward(X2d, self.K)
         seed = torch.empty(N, self.K, self.K, dtype=torch.float32, device=self.device)
         check(lib.bnnp_lik_sqrt_seed(lik_code, ptr(f), N, self.K, ptr(seed), stream()), 'bnnp_lik_sqrt_seed')
         self.backward(pl, ws, seed, N, self.K, flags)
-        if kfac_only:
+        if kfac_only or diag_only:
             return X2d, pl, ws, f, flags
         return X2d, pl, ws, f
 

@@ -320,11 +320,11 @@ class Laplace:
     def _accumulate_diag(self, batches, diag, hess_factor):
         net = net_for(self.model)
         for X, _ in self._superbatches(batches):
-            X2d, pl, ws, f = net.sqrt_factors(X, self.likelihood.code)
+            X2d, pl, ws, f, flags = net.sqrt_factors(X, self.likelihood.code, diag_only=True)
             N = X2d.shape[0]
             sc = net.scratch(lib.bnnp_ggn_diag_scratch_floats(net.ops, net.n_ops, C.byref(pl), N, net.K))
-            check(lib.bnnp_ggn_diag_accum(net.ops, net.n_ops, C.byref(pl), N, net.K, ptr(X2d), ptr(ws),
-                                          hess_factor, ptr(diag), ptr(sc), stream()), 'bnnp_ggn_diag_accum')
+            check(lib.bnnp_ggn_diag_accum_ex(net.ops, net.n_ops, C.byref(pl), N, net.K, ptr(X2d), ptr(ws),
+                                             hess_factor, ptr(diag), ptr(sc), flags, stream()), 'bnnp_ggn_diag_accum_ex')
 
     def _accumulate_kron(self, batches, kron, hess_factor, N_total):
         net = net_for(self.model)

@@ -107,6 +107,13 @@ int bnnp_net_backward(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
  * bnnp_kfac_accum_ex with the same flag.  bnnp_net_first_conv_possum_ok() says whether the network qualifies. */
 #define BNNP_BWD_FIRST_CONV_POSSUM 1
 int bnnp_net_first_conv_possum_ok(const bnnp_op_t* ops, int n_ops);
+/* BNNP_BWD_FIRST_CONV_PLANES (diagonal GGN only; not together with ..._POSSUM): when the first parameterised layer is a conv
+ * followed by ([activation,] a stride >= 2 max-pool), the pool backward leaves that conv's output gradient as the bf16 hi / lo
+ * planes [(r, c), pos] the conv-weight diagonal kernel streams (inside the fp32 gradient buffer they replace) instead of fp32;
+ * consumed by bnnp_ggn_diag_accum_ex with the same flag.  bnnp_net_first_conv_planes_ok() says whether network and batch
+ * qualify (preds/laplace.py:52-59 is the loop this serves). */
+#define BNNP_BWD_FIRST_CONV_PLANES 2
+int bnnp_net_first_conv_planes_ok(const bnnp_op_t* ops, int n_ops, int64_t N, int V);
 int bnnp_net_backward_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                          const float* seed, int64_t N, int V, float* ws, int flags, void* stream);
 
@@ -193,6 +200,10 @@ int bnnp_unpack_lower(const float* packed, int64_t P, int64_t row0, int64_t row1
 int bnnp_ggn_diag_accum(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
                         int V, const float* X, const float* ws, float factor, float* diag,
                         float* scratch, void* stream);
+/* The same with the flags the backward ran with (0 or BNNP_BWD_FIRST_CONV_PLANES). */
+int bnnp_ggn_diag_accum_ex(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan, int64_t N,
+                           int V, const float* X, const float* ws, float factor, float* diag,
+                           float* scratch, int flags, void* stream);
 int64_t bnnp_ggn_diag_scratch_floats(const bnnp_op_t* ops, int n_ops, const bnnp_plan_t* plan,
                                      int64_t N, int V);
 
@@ -403,7 +414,7 @@ uint64_t bnnp_launch_count(void);
  * "net_simt" 1 = forward / backward / diag / KFAC contractions on the fp32 SIMT kernels whatever their size,
  * "gemm_generated" 1 = Linear-layer products / KFAC Grams on the generated-operand GEMM instead of the TMA-fed one;
  * "conv_bwd_explicit" 1 = stride-1 conv backward-data as product + col2im gather and conv forward as unfold + GEMM instead of
- * the implicit-GEMM kernel (csrc/conv_bwd_tc.cu).  Unknown name: BNNP_ERR_INVALID. */
+ * the implicit-GEMM kernel (csrc/conv_bwd_tc.cu), and bnnp_net_first_conv_planes_ok() answers 0.  Unknown name: BNNP_ERR_INVALID. */
 int bnnp_set_option(const char* name, int value);
 int bnnp_get_option(const char* name);
 int bnnp_prof_enable(int on);

@@ -333,3 +333,36 @@ def test_implicit_conv_forward_on_ragged_shapes_against_torch():
     scale = float(want.abs().max())
     assert float((got[0] - want).abs().max()) < 1e-5 * scale
     assert float((got[1] - want).abs().max()) < 1e-5 * scale
+
+
+def test_first_conv_gradient_planes_match_the_fp32_route():
+    """Diagonal GGN of CIFAR10Net (conv -> relu -> stride-2 max-pool first): by default the pool backward leaves the first conv's
+    output gradient as the bf16 hi / lo planes of the conv-weight diagonal kernel and the bias position sums come from the
+    pooled gradient (BNNP_BWD_FIRST_CONV_PLANES); with option conv_bwd_explicit the fp32 gradient + split pass + product /
+    col2im conv route of the round-2 start runs.  Same diagonal per parameter tensor (2e-4 of its own scale; the two routes
+    differ in fp32 summation order only), and the flag is really taken."""
+    from preds_b200 import Laplace, CategoricalLh, CIFAR10Net
+    from preds_b200._cabi import lib
+    from preds_b200._engine import net_for
+    torch.manual_seed(5)
+    model = CIFAR10Net(3, 10, use_tanh=True).cuda()
+    g = torch.Generator().manual_seed(6)
+    X, y = torch.randn(64, 3, 32, 32, generator=g).cuda(), torch.randint(10, (64,), generator=g).cuda()
+    eng = net_for(model)
+    eng.prepare(X)
+    assert lib.bnnp_net_first_conv_planes_ok(eng.ops, eng.n_ops, 64, 10) == 1
+    got = {}
+    for opt in (0, 1):
+        assert lib.bnnp_set_option(b'conv_bwd_explicit', opt) == 0
+        try:
+            assert lib.bnnp_net_first_conv_planes_ok(eng.ops, eng.n_ops, 64, 10) == 1 - opt
+            lap = Laplace(model, 1.0, CategoricalLh())
+            lap.infer([(X, y)], cov_type='diag')
+            got[opt] = lap.precision.clone()
+        finally:
+            lib.bnnp_set_option(b'conv_bwd_explicit', 0)
+    off = 0
+    for p in model.parameters():
+        a, b = got[0][off:off + p.numel()], got[1][off:off + p.numel()]
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()), tuple(p.shape)
+        off += p.numel()
