@@ -162,3 +162,69 @@ def test_shard_bounds():
         assert all(a[1] == b[0] for a, b in zip(blocks[:-1], blocks[1:]))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _conv_pool_ops(in_c=3, hw=32, out_c=64, k=5, pool_k=3, pool_s=2, relu=True):
+    """conv (valid) [-> relu] -> max-pool ('same' zero padding) -> flatten -> linear, as CIFAR10Net's first stage."""
+    from preds_b200 import _cabi
+    oh = hw - k + 1
+    ph = -(-oh // pool_s)
+    pad = max((ph - 1) * pool_s + pool_k - oh, 0)
+    ops = []
+    c = _cabi.Op()
+    c.kind, c.in_c, c.in_h, c.in_w, c.out_c, c.out_h, c.out_w = _cabi.OP_CONV2D, in_c, hw, hw, out_c, oh, oh
+    c.kh = c.kw = k
+    c.stride_h = c.stride_w = 1
+    c.has_bias, c.weight, c.bias = 1, 1 << 20, 1 << 21
+    c.theta_off_w, c.theta_off_b = 0, out_c * in_c * k * k
+    ops.append(c)
+    if relu:
+        r = _cabi.Op()
+        r.kind, r.in_c, r.in_h, r.in_w, r.out_c, r.out_h, r.out_w = _cabi.OP_RELU, out_c, oh, oh, out_c, oh, oh
+        ops.append(r)
+    p = _cabi.Op()
+    p.kind, p.in_c, p.in_h, p.in_w, p.out_c, p.out_h, p.out_w = _cabi.OP_MAXPOOL2D, out_c, oh, oh, out_c, ph, ph
+    p.kh = p.kw = pool_k
+    p.stride_h = p.stride_w = pool_s
+    p.pad_l, p.pad_r = pad // 2, pad - pad // 2
+    p.pad_t, p.pad_b = pad // 2, pad - pad // 2
+    ops.append(p)
+    f = _cabi.Op()
+    f.kind, f.in_c, f.in_h, f.in_w, f.out_c, f.out_h, f.out_w = _cabi.OP_FLATTEN, out_c, ph, ph, out_c, ph, ph
+    ops.append(f)
+    return (_cabi.Op * len(ops))(*ops)
+
+
+def test_first_conv_shortcuts_are_offered_only_where_they_apply():
+    """Host logic of the two first-conv shortcuts of the factor passes (no device work): BNNP_BWD_FIRST_CONV_POSSUM (KFAC) needs
+    conv [-> activation] -> max-pool with windows <= 3 x 3; BNNP_BWD_FIRST_CONV_PLANES (diag) additionally a stride >= 2 pool
+    on maps whose width is a multiple of 4 and whose size is a multiple of 8, a batch large enough for the TMA-fed diagonal
+    kernel, and none of the routing options that move the conv paths elsewhere."""
+    from preds_b200 import _cabi
+    lib = _cabi.lib
+    ops = _conv_pool_ops()                                   # CIFAR10Net's first stage: 28 x 28 maps, 3 x 3 / stride-2 pool
+    assert lib.bnnp_net_first_conv_possum_ok(ops, len(ops)) == 1
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 256, 10) == 1
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 1, 1) == 0          # below the tensor-core threshold
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 0, 10) == 0
+    for name in (b'conv_bwd_explicit', b'net_simt', b'gemm_generated'):
+        assert lib.bnnp_set_option(name, 1) == 0
+        try:
+            assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 256, 10) == 0, name
+        finally:
+            lib.bnnp_set_option(name, 0)
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 256, 10) == 1
+    ops = _conv_pool_ops(hw=30)                              # 26 x 26 maps: width not a multiple of 4
+    assert lib.bnnp_net_first_conv_possum_ok(ops, len(ops)) == 1
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 256, 10) == 0
+    ops = _conv_pool_ops(pool_s=1)                           # stride-1 pool: four-wide pool backward does not apply
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 256, 10) == 0
+    ops = _conv_pool_ops(pool_k=5)                           # 5 x 5 window: neither shortcut
+    assert lib.bnnp_net_first_conv_possum_ok(ops, len(ops)) == 0
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 256, 10) == 0
+    ops = _conv_pool_ops(relu=False)
+    assert lib.bnnp_net_first_conv_possum_ok(ops, len(ops)) == 1
+    assert lib.bnnp_net_first_conv_planes_ok(ops, len(ops), 256, 10) == 1
+    mlp, _ = _mlp_ops([784, 75, 10])
+    assert lib.bnnp_net_first_conv_possum_ok(mlp, len(mlp)) == 0
+    assert lib.bnnp_net_first_conv_planes_ok(mlp, len(mlp), 4096, 10) == 0
